@@ -1,0 +1,69 @@
+"""ctypes binding of libgsrigid.so (include/gsrigid.h).  There is NO fallback: if the CUDA library cannot be loaded the
+rigid path raises, it never degrades to a CPU or PyTorch implementation."""
+
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libgsrigid.so")
+_lib = None
+
+EXPORTS = (
+    "gsr_model_begin", "gsr_model_set_f32", "gsr_model_set_i32", "gsr_model_set_scalar", "gsr_model_commit", "gsr_model_refresh",
+    "gsr_state_sizes", "gsr_field_count", "gsr_field_info", "gsr_bind", "gsr_init_state", "gsr_step",
+    "gsr_forward_kinematics", "gsr_reset_envs", "gsr_step_host", "gsr_launch_count", "gsr_kernel_info",
+    "gsr_last_error", "gsr_version", "gsr_destroy",
+)
+
+
+class GsrError(RuntimeError):
+    pass
+
+
+def build(force=False):
+    """Compile libgsrigid.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    if force or not os.path.exists(LIB_PATH):
+        subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc")] + (["-B"] if force else []))
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GsrError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)"
+            )
+        L = ctypes.CDLL(LIB_PATH)
+        vp, cp, i, sz = ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_size_t
+        L.gsr_model_begin.argtypes = [ctypes.POINTER(vp)]
+        L.gsr_model_set_f32.argtypes = [vp, cp, vp, sz]
+        L.gsr_model_set_i32.argtypes = [vp, cp, vp, sz]
+        L.gsr_model_set_scalar.argtypes = [vp, cp, ctypes.c_double]
+        L.gsr_model_commit.argtypes = [vp, i, i]
+        L.gsr_model_refresh.argtypes = [vp]
+        L.gsr_state_sizes.argtypes = [vp, ctypes.POINTER(sz), ctypes.POINTER(sz)]
+        L.gsr_field_count.argtypes = [vp]
+        L.gsr_field_info.argtypes = [vp, i, ctypes.POINTER(cp), ctypes.POINTER(i), ctypes.POINTER(sz), ctypes.POINTER(sz)]
+        L.gsr_bind.argtypes = [vp, vp, vp]
+        L.gsr_init_state.argtypes = [vp, vp]
+        L.gsr_step.argtypes = [vp, i, vp]
+        L.gsr_forward_kinematics.argtypes = [vp, vp, vp]
+        L.gsr_reset_envs.argtypes = [vp, vp, vp]
+        L.gsr_step_host.argtypes = [vp, i, vp, vp, vp, vp]
+        L.gsr_launch_count.argtypes = [vp]
+        L.gsr_launch_count.restype = ctypes.c_longlong
+        L.gsr_kernel_info.argtypes = [vp, i, ctypes.POINTER(cp), ctypes.POINTER(ctypes.c_longlong)]
+        L.gsr_last_error.argtypes = [vp]
+        L.gsr_last_error.restype = cp
+        L.gsr_version.restype = cp
+        L.gsr_destroy.argtypes = [vp]
+        _lib = L
+    return _lib
+
+
+def check(handle, rc):
+    if rc != 0:
+        msg = lib().gsr_last_error(handle)
+        raise GsrError(f"gsrigid error {rc}: {msg.decode() if msg else ''}")

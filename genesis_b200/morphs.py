@@ -1,0 +1,51 @@
+"""Morph descriptions accepted by Scene.add_entity (subset of genesis/options/morphs.py:186,415,795,916)."""
+
+from dataclasses import dataclass
+
+
+@dataclass
+class Morph:
+    pos: tuple | None = None
+    quat: tuple | None = None
+    collision: bool = True
+    visualization: bool = False
+
+
+@dataclass
+class Plane(Morph):
+    normal: tuple = (0.0, 0.0, 1.0)
+    plane_size: tuple = (1e3, 1e3)
+    fixed: bool = True
+
+
+@dataclass
+class Box(Morph):
+    size: tuple = (1.0, 1.0, 1.0)
+    fixed: bool = False
+
+
+@dataclass
+class Sphere(Morph):
+    radius: float = 0.5
+    fixed: bool = False
+
+
+@dataclass
+class MJCF(Morph):
+    file: str = ""
+    scale: float = 1.0
+    default_armature: float | None = 0.1
+    convexify: bool | None = None
+    decimate: bool = True
+    decimate_face_num: int = 500
+
+
+@dataclass
+class URDF(Morph):
+    file: str = ""
+    scale: float = 1.0
+    fixed: bool = False
+    merge_fixed_links: bool = True
+    links_to_keep: tuple = ()
+    default_armature: float | None = 0.1
+    convexify: bool | None = None

@@ -1,0 +1,560 @@
+"""Host-side RigidSolver: the drop-in for genesis/engine/solvers/rigid/rigid_solver.py on the batched step path.
+
+All state lives in two torch tensors (float32 / int32) on the CUDA device whose layout is dictated by libgsrigid
+(include/gsrigid.h); this class only creates views, forwards `substep` to the C ABI and implements the accessor
+surface (get_*/set_*/control_dofs_*) with the reference's argument conventions (rigid_solver.py:1902-2580,
+kinematic_solver.py:940-1003): inputs broadcast to (len(envs_idx), len(idx)), `envs_idx=None` means all envs,
+returned tensors are (B, n) copies on `gs.device`.  There is no CPU path: building a scene requires CUDA.
+"""
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .constants import CTRL_MODE, ErrorCode
+from .model import ModelBuilder, box_l_infos, parse_mjcf, parse_urdf, plane_l_infos, sphere_l_infos
+from .model.compiled import load_compiled, resolve_asset
+from . import morphs as _morphs
+
+RATE_CHECK_ERRNO = 10  # genesis/engine/simulator.py:47
+
+
+class GenesisException(Exception):
+    pass
+
+
+def _morph_to_infos(morph):
+    """Returns (l_infos, eqs_info, is_robot, local_collision_mask)."""
+    if isinstance(morph, _morphs.Plane):
+        return plane_l_infos(morph.pos or (0, 0, 0), morph.quat or (1, 0, 0, 0), morph.normal, morph.plane_size), [], False, False
+    if isinstance(morph, _morphs.Box):
+        return box_l_infos(morph.size, morph.pos or (0, 0, 0), morph.quat or (1, 0, 0, 0), morph.fixed), [], False, False
+    if isinstance(morph, _morphs.Sphere):
+        return sphere_l_infos(morph.radius, morph.pos or (0, 0, 0), morph.fixed), [], False, False
+    if isinstance(morph, (_morphs.MJCF, _morphs.URDF)):
+        is_mjcf = isinstance(morph, _morphs.MJCF)
+        path = resolve_asset(morph.file)
+        if path is not None:
+            if is_mjcf:
+                l_infos, eqs = parse_mjcf(path, default_armature=morph.default_armature, scale=morph.scale)
+            else:
+                l_infos, eqs = parse_urdf(path, merge_fixed_links=morph.merge_fixed_links, links_to_keep=morph.links_to_keep,
+                                          default_armature=morph.default_armature, scale=morph.scale, fixed=morph.fixed)
+        else:
+            loaded = load_compiled(morph.file)
+            if loaded is None:
+                raise GenesisException(f"Asset '{morph.file}' not found and no pre-compiled model is bundled for it.")
+            l_infos, eqs = loaded
+        _apply_morph_pose(l_infos, morph)
+        return l_infos, eqs, True, is_mjcf
+    raise GenesisException(f"Unsupported morph: {morph!r}")
+
+
+def _apply_morph_pose(l_infos, morph):
+    """rigid_entity.py:744-767: offset the base link pose by morph.pos / morph.quat."""
+    from .model import geom_np as gn
+    from .constants import JOINT_TYPE
+
+    if morph.pos is None and morph.quat is None:
+        return
+    for li in l_infos:
+        if li["parent_idx"] < 0:
+            pos_off = np.zeros(3) if morph.pos is None else np.asarray(morph.pos, float)
+            quat_off = np.array([1.0, 0, 0, 0]) if morph.quat is None else np.asarray(morph.quat, float)
+            li["pos"], li["quat"] = gn.transform_pos_quat(li["pos"], li["quat"], pos_off, quat_off)
+            for j in li["joints"]:
+                if j["type"] == JOINT_TYPE.FREE:
+                    j["init_qpos"] = np.concatenate([li["pos"], li["quat"]])
+
+
+class RigidSolver:
+    def __init__(self, scene, sim_options, rigid_options):
+        self._scene = scene
+        self._sim_options = sim_options
+        self._options = rigid_options
+        self._entities = []
+        self._morphs = []
+        self._is_built = False
+        self._substep_dt = (rigid_options.dt or sim_options.dt) / max(1, sim_options.substeps)
+        self._gravity = rigid_options.gravity or sim_options.gravity
+        self._handle = None
+        self._n_substeps_total = 0
+        self.model = None
+
+    # ------------------------------------------------------------------ build
+    def add_entity(self, morph, material=None):
+        from .rigid_entity import RigidEntity
+
+        entity = RigidEntity(self, morph, material, len(self._entities))
+        self._entities.append(entity)
+        return entity
+
+    def build_model(self):
+        o = self._options
+        if o.use_contact_island or o.use_hibernation or o.noslip_iterations or o.enable_mujoco_compatibility or o.use_gjk_collision:
+            raise GenesisException(
+                "contact islands, hibernation, noslip, mujoco-compatibility and GJK-first collision are outside the "
+                "hot-path scope of this build (DESIGN.md 'Out of scope')."
+            )
+        b = ModelBuilder(
+            dt=self._substep_dt, gravity=self._gravity, constraint_timeconst=o.constraint_timeconst,
+            enable_self_collision=o.enable_self_collision, enable_adjacent_collision=o.enable_adjacent_collision,
+            max_collision_pairs=o.max_collision_pairs, multiplier_collision_broad_phase=o.multiplier_collision_broad_phase,
+            max_dynamic_constraints=o.max_dynamic_constraints,
+        )
+        b.enable_neutral_collision = o.enable_neutral_collision
+        for ent in self._entities:
+            l_infos, eqs, is_robot, local_mask = _morph_to_infos(ent.morph)
+            rho = getattr(ent.material, "rho", None)
+            friction = getattr(ent.material, "friction", None)
+            ent._info = b.add_entity(type(ent.morph).__name__.lower(), l_infos, eqs, is_robot=is_robot, rho=rho,
+                                     friction=friction, local_collision_mask=local_mask)
+            ent._info.gravity_compensation = getattr(ent.material, "gravity_compensation", 0.0)
+        self.model = b.build()
+        return self.model
+
+    def model_options(self):
+        o = self._options
+        return dict(iterations=o.iterations, ls_iterations=o.ls_iterations, tolerance=o.tolerance, ls_tolerance=o.ls_tolerance,
+                    integrator=int(o.integrator), solver_type=int(o.constraint_solver), enable_collision=int(o.enable_collision),
+                    enable_joint_limit=int(o.enable_joint_limit), enable_multi_contact=int(o.enable_multi_contact),
+                    sort_contacts=1)
+
+    def build(self, n_envs, device):
+        if not torch.cuda.is_available():
+            raise GenesisException("genesis_b200 has no CPU fallback: a CUDA device (B200, sm_100a) is required to build a scene.")
+        self.n_envs = n_envs
+        self._B = max(1, n_envs)
+        self.device = torch.device(device)
+        m = self.model if self.model is not None else self.build_model()
+        L = _lib.lib()
+        h = ctypes.c_void_p()
+        _lib.check(None, L.gsr_model_begin(ctypes.byref(h)))
+        self._handle = h
+        self._upload_model_arrays()
+        for k, v in self.model_options().items():
+            L.gsr_model_set_scalar(h, f"cfg_{k}".encode(), float(v))
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        _lib.check(h, L.gsr_model_commit(h, dev_index, self._B))
+        nf, ni = ctypes.c_size_t(), ctypes.c_size_t()
+        _lib.check(h, L.gsr_state_sizes(h, ctypes.byref(nf), ctypes.byref(ni)))
+        with torch.cuda.device(self.device):
+            self._F = torch.zeros(nf.value, dtype=torch.float32, device=self.device)
+            self._I = torch.zeros(ni.value, dtype=torch.int32, device=self.device)
+        _lib.check(h, L.gsr_bind(h, self._F.data_ptr(), self._I.data_ptr()))
+        self._fields = {}
+        name, is_int, off, items = ctypes.c_char_p(), ctypes.c_int(), ctypes.c_size_t(), ctypes.c_size_t()
+        for i in range(L.gsr_field_count(h)):
+            _lib.check(h, L.gsr_field_info(h, i, ctypes.byref(name), ctypes.byref(is_int), ctypes.byref(off), ctypes.byref(items)))
+            buf = self._I if is_int.value else self._F
+            self._fields[name.value.decode()] = buf[off.value * self._B: (off.value + items.value) * self._B].view(items.value, self._B)
+        _lib.check(h, L.gsr_init_state(h, self._stream()))
+        self._is_built = True
+        self._init_qpos = self._fields["qpos"].clone()
+        self._envs_all = torch.arange(self._B, device=self.device)
+        m_ = self.model
+        self._dofs_limit = torch.tensor(m_.dofs_limit, dtype=torch.float32, device=self.device).reshape(-1, 2)
+
+    def _upload_model_arrays(self):
+        L, h, m = _lib.lib(), self._handle, self.model
+        self._model_keepalive = []
+        for k, v in m.__dict__.items():
+            if isinstance(v, np.ndarray):
+                if v.dtype.kind == "f":
+                    a = np.ascontiguousarray(v, dtype=np.float32)
+                    L.gsr_model_set_f32(h, k.encode(), a.ctypes.data, a.size)
+                elif v.dtype.kind in "iub":
+                    a = np.ascontiguousarray(v, dtype=np.int32)
+                    L.gsr_model_set_i32(h, k.encode(), a.ctypes.data, a.size)
+        for k in ("n_links", "n_joints", "n_dofs", "n_qs", "n_geoms", "n_entities", "n_equalities", "n_pairs", "n_verts",
+                  "max_contact_pairs", "max_broad_pairs", "n_contacts_per_pair", "len_constraints", "meaninertia", "dt"):
+            L.gsr_model_set_scalar(h, k.encode(), float(getattr(m, k)))
+        for i, ax in enumerate("xyz"):
+            L.gsr_model_set_scalar(h, f"gravity_{ax}".encode(), float(m.gravity[i]))
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def field(self, name):
+        """Zero-copy (rows, B) torch view of a state field (the reference's zero-copy qd_to_torch views)."""
+        return self._fields[name]
+
+    # ------------------------------------------------------------------ stepping
+    def substep(self, n=1):
+        _lib.check(self._handle, _lib.lib().gsr_step(self._handle, n, self._stream()))
+        self._n_substeps_total += n
+
+    def step_host(self, ctrl_pos_host, qpos_host, vel_host, n=1):
+        """Reference-facing host-buffer call (bench.py e2e): numpy (B, n) float32 arrays in / out."""
+        p = lambda a: ctypes.c_void_p(a.ctypes.data) if a is not None else None
+        _lib.check(self._handle, _lib.lib().gsr_step_host(self._handle, n, p(ctrl_pos_host), p(qpos_host), p(vel_host), self._stream()))
+        self._n_substeps_total += n
+
+    def launch_count(self):
+        return int(_lib.lib().gsr_launch_count(self._handle))
+
+    def kernel_launches(self):
+        out = {}
+        name, cnt = ctypes.c_char_p(), ctypes.c_longlong()
+        i = 0
+        while _lib.lib().gsr_kernel_info(self._handle, i, ctypes.byref(name), ctypes.byref(cnt)) == 0:
+            out[name.value.decode()] = cnt.value
+            i += 1
+        return out
+
+    def get_error_envs_mask(self):
+        return self._fields["errno_"][0] > 0
+
+    def check_errno(self):
+        """rigid_solver.py:985-1009 (polled every RATE_CHECK_ERRNO substeps by Scene.step)."""
+        errno = int(torch.bitwise_or(self._fields["errno_"][0], 0).max().item()) if self._B else 0
+        if errno == 0:
+            return
+        bits = int(np.bitwise_or.reduce(self._fields["errno_"][0].cpu().numpy()))
+        if bits & ErrorCode.OVERFLOW_CANDIDATE_CONTACTS:
+            raise GenesisException(f"Exceeding max number of broad phase candidate contact pairs ({self.model.max_broad_pairs}). "
+                                   "Please increase the value of RigidSolver's option 'multiplier_collision_broad_phase'.")
+        if bits & ErrorCode.OVERFLOW_COLLISION_PAIRS:
+            raise GenesisException(f"Exceeding max number of contact pairs ({self.model.max_contact_pairs}). Please increase the "
+                                   "value of RigidSolver's option 'max_collision_pairs'.")
+        if bits & ErrorCode.INVALID_FORCE_NAN:
+            raise GenesisException("Invalid constraint forces causing 'nan'. Please decrease Rigid simulation timestep.")
+        if bits & ErrorCode.INVALID_ACC_NAN:
+            raise GenesisException("Invalid accelerations causing 'nan'. Please decrease Rigid simulation timestep.")
+
+    # ------------------------------------------------------------------ index helpers
+    def _envs(self, envs_idx):
+        if envs_idx is None:
+            return None
+        if isinstance(envs_idx, torch.Tensor) and envs_idx.dtype == torch.bool:
+            return torch.nonzero(envs_idx.to(self.device), as_tuple=False)[:, 0]
+        return torch.as_tensor(envs_idx, device=self.device, dtype=torch.long).reshape(-1)
+
+    def _idx(self, idx, n):
+        if idx is None:
+            return torch.arange(n, device=self.device)
+        if isinstance(idx, slice):
+            return torch.arange(n, device=self.device)[idx]
+        if isinstance(idx, range):
+            return torch.as_tensor(list(idx), device=self.device, dtype=torch.long)
+        return torch.as_tensor(idx, device=self.device, dtype=torch.long).reshape(-1)
+
+    def _get(self, name, idx, envs_idx, n, comps=1):
+        """(B, len(idx)[, comps]) copy of field rows."""
+        f = self._fields[name]
+        idx = self._idx(idx, n)
+        if comps > 1:
+            f = f.view(-1, comps, self._B)[idx]  # (n, comps, B)
+            out = f.permute(2, 0, 1)
+        else:
+            out = f[idx].permute(1, 0)
+        envs = self._envs(envs_idx)
+        out = out if envs is None else out[envs]
+        out = out.clone() if out.dtype != torch.int32 or True else out
+        if self.n_envs == 0:
+            out = out[0]
+        return out
+
+    def _set(self, name, value, idx, envs_idx, n, dtype=torch.float32):
+        f = self._fields[name]
+        idx = self._idx(idx, n)
+        envs = self._envs(envs_idx)
+        nb = self._B if envs is None else len(envs)
+        value = torch.as_tensor(value, dtype=dtype, device=self.device)
+        if self.n_envs == 0 and value.ndim <= 1:
+            value = value.reshape(1, -1) if value.ndim == 1 else value
+        value = torch.broadcast_to(value, (nb, len(idx)))
+        if envs is None:
+            f[idx] = value.T.to(f.dtype)
+        else:
+            f[idx[:, None], envs[None, :]] = value.T.to(f.dtype)
+
+    def _env_mask(self, envs_idx):
+        envs = self._envs(envs_idx)
+        if envs is None:
+            return None
+        mask = torch.zeros(self._B, dtype=torch.uint8, device=self.device)
+        mask[envs] = 1
+        return mask
+
+    def _forward(self, envs_idx=None):
+        mask = self._env_mask(envs_idx)
+        ptr = ctypes.c_void_p(mask.data_ptr()) if mask is not None else None
+        _lib.check(self._handle, _lib.lib().gsr_forward_kinematics(self._handle, ptr, self._stream()))
+
+    # ------------------------------------------------------------------ setters (rigid_solver.py:1902-2287)
+    def set_qpos(self, qpos, qs_idx=None, envs_idx=None, *, skip_forward=False):
+        self._set("qpos", qpos, qs_idx, envs_idx, self.model.n_qs)
+        self._reset_warmstart(envs_idx)
+        if not skip_forward:
+            self._forward(envs_idx)
+
+    def set_dofs_velocity(self, velocity, dofs_idx=None, envs_idx=None, *, skip_forward=False):
+        if velocity is None:
+            velocity = 0.0
+        self._set("vel", velocity, dofs_idx, envs_idx, self.model.n_dofs)
+        if not skip_forward:
+            self._forward(envs_idx)
+
+    def set_dofs_position(self, position, dofs_idx=None, envs_idx=None):
+        """dofs_state.pos -> qpos (rigid_solver.py set_dofs_position / kernel_set_dofs_position)."""
+        from .constants import JOINT_TYPE
+
+        m = self.model
+        dofs = self._idx(dofs_idx, m.n_dofs)
+        envs = self._envs(envs_idx)
+        nb = self._B if envs is None else len(envs)
+        pos = torch.broadcast_to(torch.as_tensor(position, dtype=torch.float32, device=self.device), (nb, len(dofs)))
+        cur = self._fields["dofs_pos"].T.clone()  # (B, nD)
+        sel = cur if envs is None else cur[envs]
+        sel[:, dofs] = pos
+        qpos = self._fields["qpos"].T.clone()
+        qsel = qpos if envs is None else qpos[envs]
+        for j in range(m.n_joints):
+            t, qs, ds = int(m.joints_type[j]), int(m.joints_q_start[j]), int(m.joints_dof_start[j])
+            if t in (JOINT_TYPE.REVOLUTE, JOINT_TYPE.PRISMATIC):
+                qsel[:, qs] = sel[:, ds] + float(m.qpos0[qs])
+            elif t == JOINT_TYPE.FREE:
+                qsel[:, qs: qs + 3] = sel[:, ds: ds + 3]
+                qsel[:, qs + 3: qs + 7] = _xyz_to_quat_torch(sel[:, ds + 3: ds + 6])
+        self.set_qpos(qsel, None, envs_idx)
+
+    def _reset_warmstart(self, envs_idx):
+        mask = self._env_mask(envs_idx)
+        ptr = ctypes.c_void_p(mask.data_ptr()) if mask is not None else None
+        _lib.check(self._handle, _lib.lib().gsr_reset_envs(self._handle, ptr, self._stream()))
+
+    def control_dofs_position(self, position, dofs_idx=None, envs_idx=None):
+        n = self.model.n_dofs
+        self._set("ctrl_mode", int(CTRL_MODE.POSITION), dofs_idx, envs_idx, n, dtype=torch.int32)
+        self._set("ctrl_pos", position, dofs_idx, envs_idx, n)
+        self._set("ctrl_vel", 0.0, dofs_idx, envs_idx, n)
+
+    def control_dofs_position_velocity(self, position, velocity, dofs_idx=None, envs_idx=None):
+        n = self.model.n_dofs
+        self._set("ctrl_mode", int(CTRL_MODE.POSITION), dofs_idx, envs_idx, n, dtype=torch.int32)
+        self._set("ctrl_pos", position, dofs_idx, envs_idx, n)
+        self._set("ctrl_vel", velocity, dofs_idx, envs_idx, n)
+
+    def control_dofs_velocity(self, velocity, dofs_idx=None, envs_idx=None):
+        n = self.model.n_dofs
+        self._set("ctrl_mode", int(CTRL_MODE.VELOCITY), dofs_idx, envs_idx, n, dtype=torch.int32)
+        self._set("ctrl_vel", velocity, dofs_idx, envs_idx, n)
+
+    def control_dofs_force(self, force, dofs_idx=None, envs_idx=None):
+        n = self.model.n_dofs
+        self._set("ctrl_mode", int(CTRL_MODE.FORCE), dofs_idx, envs_idx, n, dtype=torch.int32)
+        self._set("ctrl_force", force, dofs_idx, envs_idx, n)
+
+    def apply_links_external_force(self, force, links_idx=None, envs_idx=None):
+        """World-frame force at each link's COM -> c-frame wrench (rigid_solver.py:1110-1193, abd/accessor.py)."""
+        m = self.model
+        links = self._idx(links_idx, m.n_links)
+        envs = self._envs(envs_idx)
+        nb = self._B if envs is None else len(envs)
+        force = torch.broadcast_to(torch.as_tensor(force, dtype=torch.float32, device=self.device), (nb, len(links), 3))
+        # c-frame wrench about root_COM: ang += (com_link - root_COM) x F ; vel += F  (sign follows cfrc_applied = -f_ext)
+        pos = self._get_links_com(links, envs)  # (nb, nl, 3)
+        root = self._fields["root_COM"].view(-1, 3, self._B)[links].permute(2, 0, 1)
+        root = root if envs is None else root[envs]
+        torque = torch.cross(pos - root, force, dim=-1)
+        fv = self._fields["cfrc_applied_vel"].view(-1, 3, self._B)
+        fa = self._fields["cfrc_applied_ang"].view(-1, 3, self._B)
+        e = slice(None) if envs is None else envs
+        fv[links[:, None], :, (torch.arange(self._B, device=self.device) if envs is None else envs)[None, :]] -= force.permute(1, 0, 2)
+        fa[links[:, None], :, (torch.arange(self._B, device=self.device) if envs is None else envs)[None, :]] -= torque.permute(1, 0, 2)
+
+    def _get_links_com(self, links, envs):
+        m = self.model
+        pos = self._fields["links_pos"].view(-1, 3, self._B)[links].permute(2, 0, 1)
+        quat = self._fields["links_quat"].view(-1, 4, self._B)[links].permute(2, 0, 1)
+        if envs is not None:
+            pos, quat = pos[envs], quat[envs]
+        ipos = torch.tensor(m.links_inertial_pos, dtype=torch.float32, device=self.device)[links]
+        return pos + _rotate_torch(ipos[None].expand(pos.shape[0], -1, -1), quat)
+
+    # per-dof model parameters (not batched): refresh the constant-memory model
+    def _set_model_array(self, name, values, dofs_idx, width=None):
+        m = self.model
+        arr = getattr(m, name)
+        idx = self._idx(dofs_idx, m.n_dofs).cpu().numpy()
+        vals = np.asarray(torch.as_tensor(values).detach().cpu().numpy(), dtype=np.float64)
+        if vals.ndim >= 1 and self.n_envs > 0 and vals.ndim == (2 if width is None else 3):
+            vals = vals[0]  # unbatched parameters: envs must agree
+        if width is None:
+            arr[idx] = vals
+        else:
+            arr[idx, width] = vals
+        a = np.ascontiguousarray(arr, dtype=np.float32)
+        L = _lib.lib()
+        L.gsr_model_set_f32(self._handle, name.encode(), a.ctypes.data, a.size)
+        _lib.check(self._handle, L.gsr_model_refresh(self._handle))
+
+    def set_dofs_kp(self, kp, dofs_idx=None, envs_idx=None):
+        """abd/accessor.py:566-583: act_gain = kp, act_bias[1] = -kp."""
+        self._set_model_array("dofs_kp", kp, dofs_idx)
+        self._set_model_array("dofs_act_bias", -np.asarray(torch.as_tensor(kp).cpu().numpy()), dofs_idx, width=1)
+
+    def set_dofs_kv(self, kv, dofs_idx=None, envs_idx=None):
+        self._set_model_array("dofs_act_bias", -np.asarray(torch.as_tensor(kv).cpu().numpy()), dofs_idx, width=2)
+
+    def set_dofs_force_range(self, lower, upper, dofs_idx=None, envs_idx=None):
+        self._set_model_array("dofs_force_range", lower, dofs_idx, width=0)
+        self._set_model_array("dofs_force_range", upper, dofs_idx, width=1)
+
+    def set_dofs_armature(self, armature, dofs_idx=None, envs_idx=None):
+        self._set_model_array("dofs_armature", armature, dofs_idx)
+
+    def set_dofs_damping(self, damping, dofs_idx=None, envs_idx=None):
+        self._set_model_array("dofs_damping", damping, dofs_idx)
+
+    def set_dofs_stiffness(self, stiffness, dofs_idx=None, envs_idx=None):
+        self._set_model_array("dofs_stiffness", stiffness, dofs_idx)
+
+    # ------------------------------------------------------------------ getters (kinematic_solver.py:940-1003, rigid_solver.py:2323-2580)
+    def get_qpos(self, qs_idx=None, envs_idx=None):
+        return self._get("qpos", qs_idx, envs_idx, self.model.n_qs)
+
+    def get_dofs_position(self, dofs_idx=None, envs_idx=None):
+        return self._get("dofs_pos", dofs_idx, envs_idx, self.model.n_dofs)
+
+    def get_dofs_velocity(self, dofs_idx=None, envs_idx=None):
+        return self._get("vel", dofs_idx, envs_idx, self.model.n_dofs)
+
+    def get_dofs_force(self, dofs_idx=None, envs_idx=None):
+        return self._get("force", dofs_idx, envs_idx, self.model.n_dofs)
+
+    def get_dofs_control_force(self, dofs_idx=None, envs_idx=None):
+        return self._get("qf_applied", dofs_idx, envs_idx, self.model.n_dofs)
+
+    def get_dofs_limit(self, dofs_idx=None, envs_idx=None):
+        idx = self._idx(dofs_idx, self.model.n_dofs)
+        return self._dofs_limit[idx, 0].clone(), self._dofs_limit[idx, 1].clone()
+
+    def get_dofs_kp(self, dofs_idx=None, envs_idx=None):
+        return torch.tensor(self.model.dofs_kp, dtype=torch.float32, device=self.device)[self._idx(dofs_idx, self.model.n_dofs)]
+
+    def get_dofs_kv(self, dofs_idx=None, envs_idx=None):
+        return -torch.tensor(self.model.dofs_act_bias[:, 2], dtype=torch.float32, device=self.device)[self._idx(dofs_idx, self.model.n_dofs)]
+
+    def get_links_pos(self, links_idx=None, envs_idx=None):
+        return self._get("links_pos", links_idx, envs_idx, self.model.n_links, comps=3)
+
+    def get_links_quat(self, links_idx=None, envs_idx=None):
+        return self._get("links_quat", links_idx, envs_idx, self.model.n_links, comps=4)
+
+    def get_links_ang(self, links_idx=None, envs_idx=None):
+        return self._get("cd_ang", links_idx, envs_idx, self.model.n_links, comps=3)
+
+    def get_links_vel(self, links_idx=None, envs_idx=None):
+        """Velocity of the link frame origin: cd_vel + cd_ang x (pos - root_COM) (forward_dynamics.py:281-288)."""
+        n = self.model.n_links
+        vel = self._get("cd_vel", links_idx, envs_idx, n, comps=3)
+        ang = self._get("cd_ang", links_idx, envs_idx, n, comps=3)
+        pos = self._get("links_pos", links_idx, envs_idx, n, comps=3)
+        com = self._get("root_COM", links_idx, envs_idx, n, comps=3)
+        return vel + torch.cross(ang, pos - com, dim=-1)
+
+    def get_links_net_contact_force(self, links_idx=None, envs_idx=None):
+        return self._get("links_contact_force", links_idx, envs_idx, self.model.n_links, comps=3)
+
+    def get_mass_mat(self, dofs_idx=None, envs_idx=None):
+        nD = self.model.n_dofs
+        M = self._fields["mass_mat"].view(nD, nD, self._B).permute(2, 0, 1)
+        envs = self._envs(envs_idx)
+        M = M if envs is None else M[envs]
+        idx = self._idx(dofs_idx, nD)
+        out = M[:, idx][:, :, idx].clone()
+        return out[0] if self.n_envs == 0 else out
+
+    def get_AABB(self, geoms_idx=None, envs_idx=None):
+        n = self.model.n_geoms
+        lo = self._get("aabb_min", geoms_idx, envs_idx, n, comps=3)
+        hi = self._get("aabb_max", geoms_idx, envs_idx, n, comps=3)
+        return torch.stack([lo, hi], dim=-2)
+
+    def get_contacts(self, as_tensor=True, to_torch=True, keep_batch_dim=False):
+        """collider.py:810-913 (tensor form): dict of (B, n_contacts_max[, 3]) tensors, cleared slots hold -1 / 0."""
+        n_max = int(self._fields["n_contacts"][0].max().item())
+        f = self._fields
+
+        def cut(name, comps=1):
+            t = f[name]
+            if comps > 1:
+                t = t.view(-1, comps, self._B)[:n_max].permute(2, 0, 1)
+            else:
+                t = t[:n_max].permute(1, 0)
+            t = t.clone()
+            if self.n_envs == 0 and not keep_batch_dim:
+                t = t[0]
+            return t if to_torch else t.cpu().numpy()
+
+        return dict(link_a=cut("contact_link_a"), link_b=cut("contact_link_b"), geom_a=cut("contact_geom_a"),
+                    geom_b=cut("contact_geom_b"), penetration=cut("contact_penetration"), position=cut("contact_pos", 3),
+                    normal=cut("contact_normal", 3), force=cut("contact_force", 3))
+
+    @property
+    def n_contacts(self):
+        return self._fields["n_contacts"][0]
+
+    # ------------------------------------------------------------------ state (rigid_solver.py:1430-1579)
+    def get_state(self):
+        f = self._fields
+        return dict(qpos=f["qpos"].clone(), dofs_vel=f["vel"].clone(), dofs_acc=f["acc"].clone(),
+                    links_pos=f["links_pos"].clone(), links_quat=f["links_quat"].clone())
+
+    def set_state(self, state, envs_idx=None, partial=False):
+        f = self._fields
+        envs = self._envs(envs_idx)
+        cols = slice(None) if envs is None else envs
+        for key, name in (("qpos", "qpos"), ("dofs_vel", "vel"), ("dofs_acc", "acc"), ("links_pos", "links_pos"), ("links_quat", "links_quat")):
+            f[name][:, cols] = state[key][:, cols]
+        f["ctrl_force"][:, cols] = 0.0
+        f["ctrl_mode"][:, cols] = int(CTRL_MODE.FORCE)
+        f["cfrc_applied_vel"][:, cols] = 0.0
+        f["cfrc_applied_ang"][:, cols] = 0.0
+        self._reset_warmstart(envs_idx)
+        self._forward(envs_idx)
+
+    def reset(self, envs_idx=None):
+        f = self._fields
+        envs = self._envs(envs_idx)
+        cols = slice(None) if envs is None else envs
+        f["qpos"][:, cols] = self._init_qpos[:, cols]
+        f["vel"][:, cols] = 0.0
+        f["acc"][:, cols] = 0.0
+        f["ctrl_force"][:, cols] = 0.0
+        f["ctrl_mode"][:, cols] = int(CTRL_MODE.FORCE)
+        f["cfrc_applied_vel"][:, cols] = 0.0
+        f["cfrc_applied_ang"][:, cols] = 0.0
+        self._reset_warmstart(envs_idx)
+        self._forward(envs_idx)
+
+    def destroy(self):
+        if self._handle is not None:
+            _lib.lib().gsr_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def _rotate_torch(v, q):
+    w, x, y, z = q[..., 0:1], q[..., 1:2], q[..., 2:3], q[..., 3:4]
+    u = torch.cat([x, y, z], dim=-1)
+    t = 2.0 * torch.cross(u, v, dim=-1)
+    return v + w * t + torch.cross(u, t, dim=-1)
+
+
+def _xyz_to_quat_torch(xyz):
+    """genesis/utils/geom.py:45-65 (intrinsic x-y-z Euler -> quaternion)."""
+    ai, aj, ak = 0.5 * xyz[..., 2], -0.5 * xyz[..., 1], 0.5 * xyz[..., 0]
+    si, sj, sk = torch.sin(ai), torch.sin(aj), torch.sin(ak)
+    ci, cj, ck = torch.cos(ai), torch.cos(aj), torch.cos(ak)
+    cc, cs, sc, ss = ci * ck, ci * sk, si * ck, si * sk
+    return torch.stack([cj * cc + sj * ss, cj * cs - sj * sc, -cj * ss - sj * cc, cj * sc - sj * cs], dim=-1)
