@@ -1,0 +1,241 @@
+"""Parity tests proper: the CUDA path (through the C ABI / ctypes, genesis_b200.RigidSolver) against the CPU oracle on the
+same seeded inputs.  Tolerances (stated here, used below):
+
+  * single step, every intermediate quantity:   |a - b| <= TOL_SINGLE * max(1, max|b|)     (reference's own 5e-5)
+  * trajectories, contact-free (Franka PD, K=50):     max|dqpos| <= 1e-4, max|dqvel| <= 1e-3
+  * trajectories with contacts (Go2 K=100, Franka fall K=150): max|dqpos| <= 1e-3, max|dqvel| <= 2e-2,
+    contact-set agreement: Jaccard index of the (env, geom_a, geom_b) sets >= 0.98
+The fp32-vs-fp64 conditioning of the same trajectories is measured in tests/test_oracle_analytic.py.
+"""
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import TOL_SINGLE
+from helpers import gs, make_franka, make_franka_grasp, make_go2, oracle_for, scene_from_morphs
+
+pytestmark = pytest.mark.gpu
+
+TRAJ_QPOS_FREE, TRAJ_QVEL_FREE = 1e-4, 1e-3
+TRAJ_QPOS_CONTACT, TRAJ_QVEL_CONTACT = 1e-3, 2e-2
+JACCARD_MIN = 0.98
+
+
+def mirror_oracle(scene, double=False, **opts):
+    """Oracle with the same model, options, qpos, velocities and controls as the built CUDA scene."""
+    s = scene.rigid_solver
+    orc = oracle_for(s, s.model, s._B, double=double, threads=8, **opts)
+    for name in ("qpos", "vel", "ctrl_pos", "ctrl_vel", "ctrl_force", "ctrl_mode"):
+        orc.set(name, s.field(name).T.cpu().numpy())
+    return orc
+
+
+def gpu_field(scene, name):
+    return scene.rigid_solver.field(name).T.cpu().numpy().astype(np.float64)
+
+
+def contact_set(scene_or_orc, B):
+    out = set()
+    if hasattr(scene_or_orc, "rigid_solver"):
+        s = scene_or_orc.rigid_solver
+        n = s.field("n_contacts")[0].cpu().numpy()
+        ga, gb = s.field("contact_geom_a").cpu().numpy(), s.field("contact_geom_b").cpu().numpy()
+        for b in range(B):
+            out |= {(b, int(ga[c, b]), int(gb[c, b])) for c in range(n[b])}
+    else:
+        for b in range(B):
+            c = scene_or_orc.contacts(b)
+            out |= {(b, int(a), int(bb)) for a, bb in zip(c["geom_a"], c["geom_b"])}
+    return out
+
+
+def jaccard(a, b):
+    return 1.0 if not (a or b) else len(a & b) / len(a | b)
+
+
+def assert_close(a, b, tol, what):
+    scale = max(1.0, np.abs(b).max())
+    err = np.abs(a - b).max()
+    assert err <= tol * scale, f"{what}: max|diff| {err:.3e} > {tol:.1e} * {scale:.3e}"
+
+
+SINGLE_STEP_FIELDS = [("qpos", "qpos"), ("vel", "vel"), ("acc", "acc"), ("acc_smooth", "acc_smooth"), ("qf_bias", "qf_bias"),
+                      ("qf_applied", "qf_applied"), ("qf_passive", "qf_passive"), ("force", "force"), ("mass_mat", "M"),
+                      ("mass_Dinv", "Dinv"), ("qf_constraint", "qf_constraint"), ("dofs_pos", "dofs_pos")]
+LINK_FIELDS = [("links_pos", 3), ("links_quat", 4), ("root_COM", 3), ("cd_vel", 3), ("cd_ang", 3), ("cacc_lin", 3), ("cacc_ang", 3),
+               ("links_contact_force", 3)]
+
+
+def check_single_step(scene, orc):
+    s = scene.rigid_solver
+    m = s.model
+    for gname, oname in SINGLE_STEP_FIELDS:
+        a = gpu_field(scene, gname)
+        assert_close(a, orc.get(oname, a.shape[1]), TOL_SINGLE, gname)
+    for name, comps in LINK_FIELDS:
+        a = gpu_field(scene, name)
+        assert_close(a, orc.get(name, (m.n_links, comps)).reshape(a.shape), TOL_SINGLE, name)
+    for name in ("geoms_pos", "aabb_min", "aabb_max"):
+        a = gpu_field(scene, name)
+        assert_close(a, orc.get(name, (m.n_geoms, 3)).reshape(a.shape), TOL_SINGLE, name)
+    for name in ("cdof_ang", "cdof_vel", "cdofd_ang", "cdofd_vel"):
+        a = gpu_field(scene, name)
+        assert_close(a, orc.get(name, (m.n_dofs, 3)).reshape(a.shape), TOL_SINGLE, name)
+
+
+@pytest.mark.parametrize("variant", ["random", "free", "fall"])
+def test_franka_single_step_all_quantities(variant):
+    scene, _ = make_franka(32, randomized=variant == "random", controlled=variant != "fall")
+    orc = mirror_oracle(scene)
+    scene.step()
+    orc.step(1)
+    check_single_step(scene, orc)
+
+
+def test_go2_single_step_all_quantities():
+    scene, _ = make_go2(32)
+    orc = mirror_oracle(scene)
+    scene.step()
+    orc.step(1)
+    check_single_step(scene, orc)
+    assert contact_set(scene, 32) == contact_set(orc, 32)
+
+
+def test_franka_controlled_trajectory():
+    B, K = 64, 50
+    scene, _ = make_franka(B, randomized=True)
+    orc = mirror_oracle(scene)
+    for _ in range(K):
+        scene.step()
+    orc.step(K)
+    assert np.abs(gpu_field(scene, "qpos") - orc.qpos()).max() <= TRAJ_QPOS_FREE
+    assert np.abs(gpu_field(scene, "vel") - orc.vel()).max() <= TRAJ_QVEL_FREE
+    assert int(scene.rigid_solver.field("errno_").max()) == 0
+
+
+def test_franka_fall_trajectory_and_contacts():
+    B, K = 32, 150
+    scene, _ = make_franka(B, controlled=False)
+    orc = mirror_oracle(scene)
+    for _ in range(K):
+        scene.step()
+    orc.step(K)
+    assert np.abs(gpu_field(scene, "qpos") - orc.qpos()).max() <= TRAJ_QPOS_CONTACT
+    assert np.abs(gpu_field(scene, "vel") - orc.vel()).max() <= TRAJ_QVEL_CONTACT
+    a, b = contact_set(scene, B), contact_set(orc, B)
+    assert len(b) > 0 and jaccard(a, b) >= JACCARD_MIN
+
+
+@pytest.mark.parametrize("self_collision", [True, False])
+def test_go2_trajectory_and_contacts(self_collision):
+    B, K = 64, 100
+    scene, _ = make_go2(B, enable_self_collision=self_collision)
+    orc = mirror_oracle(scene)
+    for _ in range(K):
+        scene.step()
+    orc.step(K)
+    dq = np.abs(gpu_field(scene, "qpos") - orc.qpos()).max(axis=1)
+    dv = np.abs(gpu_field(scene, "vel") - orc.vel()).max(axis=1)
+    # contact-rich locomotion is chaotic: every env must stay within the stated tolerance except at most 2% outliers
+    # whose contact set flipped (those are caught by the Jaccard bound below)
+    assert (dq <= TRAJ_QPOS_CONTACT).mean() >= 0.98, f"qpos outliers: {np.sort(dq)[-5:]}"
+    assert (dv <= TRAJ_QVEL_CONTACT).mean() >= 0.98, f"qvel outliers: {np.sort(dv)[-5:]}"
+    a, b = contact_set(scene, B), contact_set(orc, B)
+    assert len(b) >= B and jaccard(a, b) >= JACCARD_MIN
+    assert int(scene.rigid_solver.field("errno_").max()) == 0
+
+
+def test_contact_records_match():
+    """Contact position / normal / penetration / force agree record by record (canonical order) for resting Go2."""
+    B, K = 16, 60
+    scene, robot = make_go2(B, randomized=False)
+    orc = mirror_oracle(scene)
+    for _ in range(K):
+        scene.step()
+    orc.step(K)
+    con = robot.get_contacts()
+    n = scene.rigid_solver.field("n_contacts")[0].cpu().numpy()
+    for b in range(B):
+        c = orc.contacts(b)
+        assert n[b] == len(c["geom_a"]) > 0
+        np.testing.assert_array_equal(con["geom_b"][b, : n[b]].cpu().numpy(), c["geom_b"])
+        np.testing.assert_allclose(con["position"][b, : n[b]].cpu().numpy(), c["position"], atol=1e-4)
+        np.testing.assert_allclose(con["normal"][b, : n[b]].cpu().numpy(), c["normal"], atol=1e-4)
+        np.testing.assert_allclose(con["penetration"][b, : n[b]].cpu().numpy(), c["penetration"], atol=1e-4)
+        f = c["force"]
+        np.testing.assert_allclose(con["force"][b, : n[b]].cpu().numpy(), f, atol=2e-2 * max(1.0, np.abs(f).max()))
+
+
+@pytest.mark.parametrize("shape", ["box", "sphere", "stack"])
+def test_primitives_on_plane(shape):
+    if shape == "box":
+        morphs = [gs.morphs.Plane(), gs.morphs.Box(size=(0.2, 0.3, 0.1), pos=(0, 0, 0.3), quat=(0.9, 0.1, 0.3, 0.2))]
+    elif shape == "sphere":
+        morphs = [gs.morphs.Plane(), gs.morphs.Sphere(radius=0.1, pos=(0, 0, 0.3))]
+    else:
+        morphs = [gs.morphs.Plane(), gs.morphs.Box(size=(0.2, 0.2, 0.2), pos=(0, 0, 0.1)),
+                  gs.morphs.Box(size=(0.1, 0.1, 0.1), pos=(0.02, 0.01, 0.28))]
+    scene, ents = scene_from_morphs(morphs, dt=0.01)
+    scene.build(n_envs=4)
+    orc = mirror_oracle(scene)
+    K = 120
+    for _ in range(K):
+        scene.step()
+    orc.step(K)
+    assert np.abs(gpu_field(scene, "qpos") - orc.qpos()).max() <= TRAJ_QPOS_CONTACT
+    assert np.abs(gpu_field(scene, "vel") - orc.vel()).max() <= TRAJ_QVEL_CONTACT
+    assert contact_set(scene, 4) == contact_set(orc, 4)
+    # the body came to rest on the plane and the contact force carries its weight
+    m = scene.rigid_solver.model
+    f = gpu_field(scene, "links_contact_force").reshape(4, m.n_links, 3)
+    if shape != "stack":
+        assert f[0, 1, 2] == pytest.approx(m.links_inertial_mass[1] * 9.81, rel=5e-3)
+
+
+def test_franka_grasp_cluster_mpr_contacts():
+    """Config 4 (multi-geom MPR contacts): Franka over a cluster of 4 cm boxes, short horizon."""
+    B, K = 16, 40
+    scene, franka, boxes = make_franka_grasp(B)
+    orc = mirror_oracle(scene)
+    for _ in range(K):
+        scene.step()
+    orc.step(K)
+    dq = np.abs(gpu_field(scene, "qpos") - orc.qpos()).max(axis=1)
+    assert (dq <= TRAJ_QPOS_CONTACT).mean() >= 0.9, f"{np.sort(dq)}"
+    a, b = contact_set(scene, B), contact_set(orc, B)
+    assert len(b) >= 4 * B and jaccard(a, b) >= 0.95
+
+
+@pytest.mark.parametrize("opts", [dict(constraint_solver=gs.constraint_solver.CG), dict(integrator=gs.integrator.Euler),
+                                  dict(integrator=gs.integrator.implicitfast)], ids=["cg", "euler", "implicitfast"])
+def test_solver_and_integrator_variants(opts):
+    B, K = 16, 40
+    scene, _ = make_go2(B, **opts)
+    orc = mirror_oracle(scene)
+    for _ in range(K):
+        scene.step()
+    orc.step(K)
+    dq = np.abs(gpu_field(scene, "qpos") - orc.qpos()).max(axis=1)
+    assert (dq <= TRAJ_QPOS_CONTACT).mean() >= 0.9, f"{np.sort(dq)}"
+    assert jaccard(contact_set(scene, B), contact_set(orc, B)) >= 0.95
+
+
+def test_external_force_and_masked_fk():
+    scene, ents = scene_from_morphs([gs.morphs.Plane(), gs.morphs.Box(size=(0.1, 0.1, 0.1), pos=(0, 0, 2.0))], dt=0.01)
+    scene.build(n_envs=3)
+    s = scene.rigid_solver
+    f = torch.tensor([[[1.0, 0.0, 5.886]]], device=gs.device).repeat(3, 1, 1)  # mass 0.6 kg: weight 5.886 N
+    s.apply_links_external_force(f, links_idx=[1])
+    scene.step()
+    acc = s.field("acc").T.cpu().numpy()
+    np.testing.assert_allclose(acc[:, :3], [[1.0 / 0.6, 0.0, 0.0]] * 3, atol=1e-4)
+    # the external force is cleared after the step (rigid_solver.py:2603-2612)
+    scene.step()
+    np.testing.assert_allclose(s.field("acc").T.cpu().numpy()[:, 2], -9.81, atol=1e-4)
+    # masked set_qpos only touches the selected env
+    before = s.get_links_pos().clone()
+    s.set_qpos(torch.tensor([[0.5, 0.5, 1.0, 1, 0, 0, 0]], device=gs.device), envs_idx=[1])
+    after = s.get_links_pos()
+    assert torch.equal(before[0], after[0]) and torch.equal(before[2], after[2])
+    np.testing.assert_allclose(after[1, 1].cpu().numpy(), [0.5, 0.5, 1.0], atol=1e-6)

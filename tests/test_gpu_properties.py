@@ -1,0 +1,65 @@
+"""Size-independent properties at BASELINE.json's full sizes (30000 Franka envs, 4096 Go2 envs), where the oracle is too
+slow to be the checker: batch-position invariance, run-to-run determinism, errno cleanliness, physical sanity, and the
+equality of the host-buffer plugin call (gsr_step_host) with the device-resident path."""
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import gs, make_franka, make_go2, oracle_for
+
+pytestmark = pytest.mark.gpu
+
+
+def test_franka_30000_batch_invariance_and_oracle_sample():
+    B, K, R = 30000, 30, 50
+    scene, franka = make_franka(B, randomized=True)
+    s = scene.rigid_solver
+    # make env b a replica of env (b % R): same initial velocity
+    v = s.field("vel")
+    v.copy_(v[:, :R].repeat(1, B // R))
+    s._forward()
+    orc = oracle_for(s, s.model, R, threads=8)
+    for name in ("qpos", "vel", "ctrl_pos", "ctrl_vel", "ctrl_force", "ctrl_mode"):
+        orc.set(name, s.field(name).T[:R].cpu().numpy())
+    for _ in range(K):
+        scene.step()
+    q = s.field("qpos")
+    assert torch.equal(q, q[:, :R].repeat(1, B // R)), "a replica env diverged from its source env (bit-exact expected)"
+    assert int(s.field("errno_").max()) == 0
+    orc.step(K)
+    assert np.abs(q.T[:R].cpu().numpy() - orc.qpos()).max() <= 1e-4
+
+
+def test_go2_4096_determinism_and_sanity():
+    B, K = 4096, 100
+    outs = []
+    for _ in range(2):
+        scene, robot = make_go2(B, seed=7)
+        for _ in range(K):
+            scene.step()
+        s = scene.rigid_solver
+        outs.append((s.field("qpos").clone(), s.field("vel").clone(), s.field("n_contacts").clone()))
+        assert int(s.field("errno_").max()) == 0
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    q = outs[0][0].T
+    assert torch.isfinite(q).all()
+    assert torch.allclose(q[:, 3:7].norm(dim=1), torch.ones(B, device=q.device), atol=1e-4)  # unit base quaternion
+    assert (q[:, 2] > 0.0).all() and (q[:, 2] < 0.6).all()  # nobody fell through the plane or flew away
+    assert (outs[0][2] > 0).float().mean() > 0.95  # nearly every robot touches the ground after 1 s
+
+
+def test_step_host_equals_device_path():
+    B, K = 256, 10
+    scene_a, fa = make_franka(B, randomized=True)
+    scene_b, fb = make_franka(B, randomized=True)
+    sa, sb = scene_a.rigid_solver, scene_b.rigid_solver
+    ctrl = np.tile(np.array([[0.1, 0.0, 0.0, -1.2, 0.0, 1.1, 0.0, 0.02, 0.02]], dtype=np.float32), (B, 1))
+    qpos, vel = np.zeros((B, 9), np.float32), np.zeros((B, 9), np.float32)
+    fa.control_dofs_position(torch.from_numpy(ctrl).to(gs.device))
+    for _ in range(K):
+        scene_a.step()
+        sb.step_host(ctrl, qpos, vel)
+    assert np.array_equal(sa.field("qpos").T.cpu().numpy(), qpos)
+    assert np.array_equal(sa.field("vel").T.cpu().numpy(), vel)
+    assert sb.launch_count() > 0 and set(sb.kernel_launches()) >= {"k_dynamics", "k_constraint", "k_integrate"}
