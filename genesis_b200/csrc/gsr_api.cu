@@ -44,6 +44,30 @@ struct gsr_handle_s {
   size_t stage_elems = 0;
   KernelStat stats[6] = {{"k_dynamics", 0}, {"k_collide", 0}, {"k_constraint", 0}, {"k_integrate", 0}, {"k_forward", 0}, {"k_reset", 0}};
   long long total_launches = 0;
+  // optional per-kernel event timing (gsr_set_profiling)
+  bool profiling = false;
+  struct Span { int k; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> event_pool;
+  double time_ms[6] = {0, 0, 0, 0, 0, 0};
+  long long timed[6] = {0, 0, 0, 0, 0, 0};
+  cudaStream_t prof_stream = nullptr;
+};
+
+// event bracket around one kernel launch; no-op unless profiling is enabled
+struct Bracket {
+  gsr_handle_s* h; int k; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
+  static cudaEvent_t get(gsr_handle_s* h) {
+    if (!h->event_pool.empty()) { cudaEvent_t e = h->event_pool.back(); h->event_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+  Bracket(gsr_handle_s* h_, int k_, cudaStream_t st_) : h(h_), k(k_), st(st_) {
+    h->stats[k].launches++; h->total_launches++;
+    if (h->profiling) { a = get(h); b = get(h); cudaEventRecord(a, st); }
+  }
+  ~Bracket() {
+    if (a) { cudaEventRecord(b, st); h->spans.push_back({k, a, b}); h->prof_stream = st; }
+  }
 };
 
 // which handle's model currently sits in __constant__ memory of each device
@@ -277,7 +301,6 @@ static int launch_cfg(gsr_handle_t h, dim3& grid, dim3& block) {
   grid = dim3((h->B + GSR_BLOCK - 1) / GSR_BLOCK);
   return 0;
 }
-#define COUNT(k) { h->stats[k].launches++; h->total_launches++; }
 
 int gsr_init_state(gsr_handle_t h, void* cuda_stream) {
   if (!h || !h->F) return fail(h, GSR_ESTATE, "state not bound");
@@ -311,8 +334,7 @@ int gsr_init_state(gsr_handle_t h, void* cuda_stream) {
   }
   dim3 grid, block;
   launch_cfg(h, grid, block);
-  k_forward<<<grid, block, 0, st>>>(h->F, h->I, h->B, nullptr, 1);
-  COUNT(4)
+  { Bracket br_(h, 4, st); k_forward<<<grid, block, 0, st>>>(h->F, h->I, h->B, nullptr, 1); }
   CUDA_OK(cudaGetLastError());
   return GSR_OK;
 }
@@ -325,16 +347,12 @@ int gsr_step(gsr_handle_t h, int n_substeps, void* cuda_stream) {
   dim3 grid, block;
   launch_cfg(h, grid, block);
   for (int s = 0; s < n_substeps; s++) {
-    k_dynamics<<<grid, block, 0, st>>>(h->F, h->I, h->B);
-    COUNT(0)
+    { Bracket br_(h, 0, st); k_dynamics<<<grid, block, 0, st>>>(h->F, h->I, h->B); }
     if (h->hm.enable_collision && h->hm.nG > 0) {
-      k_collide<<<grid, block, 0, st>>>(h->F, h->I, h->B);
-      COUNT(1)
+      { Bracket br_(h, 1, st); k_collide<<<grid, block, 0, st>>>(h->F, h->I, h->B); }
     }
-    k_constraint<<<grid, block, 0, st>>>(h->F, h->I, h->B);
-    COUNT(2)
-    k_integrate<<<grid, block, 0, st>>>(h->F, h->I, h->B, s == n_substeps - 1);
-    COUNT(3)
+    { Bracket br_(h, 2, st); k_constraint<<<grid, block, 0, st>>>(h->F, h->I, h->B); }
+    { Bracket br_(h, 3, st); k_integrate<<<grid, block, 0, st>>>(h->F, h->I, h->B, s == n_substeps - 1); }
   }
   CUDA_OK(cudaGetLastError());
   return GSR_OK;
@@ -347,8 +365,7 @@ int gsr_forward_kinematics(gsr_handle_t h, const uint8_t* env_mask_dev, void* cu
   if (rc) return rc;
   dim3 grid, block;
   launch_cfg(h, grid, block);
-  k_forward<<<grid, block, 0, st>>>(h->F, h->I, h->B, env_mask_dev, 0);
-  COUNT(4)
+  { Bracket br_(h, 4, st); k_forward<<<grid, block, 0, st>>>(h->F, h->I, h->B, env_mask_dev, 0); }
   CUDA_OK(cudaGetLastError());
   return GSR_OK;
 }
@@ -360,8 +377,7 @@ int gsr_reset_envs(gsr_handle_t h, const uint8_t* env_mask_dev, void* cuda_strea
   if (rc) return rc;
   dim3 grid, block;
   launch_cfg(h, grid, block);
-  k_reset<<<grid, block, 0, st>>>(h->F, h->I, h->B, env_mask_dev);
-  COUNT(5)
+  { Bracket br_(h, 5, st); k_reset<<<grid, block, 0, st>>>(h->F, h->I, h->B, env_mask_dev); }
   CUDA_OK(cudaGetLastError());
   return GSR_OK;
 }
@@ -406,6 +422,30 @@ int gsr_step_host(gsr_handle_t h, int n_substeps, const float* ctrl_pos_host, fl
   return GSR_OK;
 }
 
+int gsr_set_profiling(gsr_handle_t h, int enabled) {
+  if (!h) return GSR_EINVAL;
+  if (enabled) { for (int k = 0; k < 6; k++) { h->time_ms[k] = 0; h->timed[k] = 0; } }
+  h->profiling = enabled != 0;
+  return GSR_OK;
+}
+int gsr_kernel_time_ms(gsr_handle_t h, int index, double* total_ms, long long* timed_launches) {
+  if (!h || index < 0 || index >= 6) return GSR_EINVAL;
+  if (!h->spans.empty()) {
+    CUDA_OK(cudaSetDevice(h->device));
+    CUDA_OK(cudaEventSynchronize(h->spans.back().b));
+    for (auto& sp : h->spans) {
+      float ms = 0.f;
+      CUDA_OK(cudaEventElapsedTime(&ms, sp.a, sp.b));
+      h->time_ms[sp.k] += ms; h->timed[sp.k]++;
+      h->event_pool.push_back(sp.a); h->event_pool.push_back(sp.b);
+    }
+    h->spans.clear();
+  }
+  if (total_ms) *total_ms = h->time_ms[index];
+  if (timed_launches) *timed_launches = h->timed[index];
+  return GSR_OK;
+}
+
 long long gsr_launch_count(gsr_handle_t h) { return h ? h->total_launches : 0; }
 int gsr_kernel_info(gsr_handle_t h, int index, const char** name, long long* launches) {
   if (!h || index < 0 || index >= 6) return GSR_EINVAL;
@@ -422,6 +462,8 @@ void gsr_destroy(gsr_handle_t h) {
     cudaFree(h->d_verts); cudaFree(h->d_support); cudaFree(h->d_pairs); cudaFree(h->d_pair_idx);
     if (h->d_stage) cudaFree(h->d_stage);
     if (h->h_stage) cudaFreeHost(h->h_stage);
+    for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto e : h->event_pool) cudaEventDestroy(e);
   }
   delete h;
 }

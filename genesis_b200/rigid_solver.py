@@ -204,6 +204,20 @@ class RigidSolver:
             i += 1
         return out
 
+    def set_profiling(self, enabled):
+        _lib.check(self._handle, _lib.lib().gsr_set_profiling(self._handle, int(bool(enabled))))
+
+    def kernel_times(self):
+        """{kernel name: (total ms, timed launches)} recorded with CUDA events while profiling was enabled."""
+        out = {}
+        name, cnt, ms, n = ctypes.c_char_p(), ctypes.c_longlong(), ctypes.c_double(), ctypes.c_longlong()
+        i = 0
+        while _lib.lib().gsr_kernel_info(self._handle, i, ctypes.byref(name), ctypes.byref(cnt)) == 0:
+            _lib.check(self._handle, _lib.lib().gsr_kernel_time_ms(self._handle, i, ctypes.byref(ms), ctypes.byref(n)))
+            out[name.value.decode()] = (ms.value, n.value)
+            i += 1
+        return out
+
     def get_error_envs_mask(self):
         return self._fields["errno_"][0] > 0
 
