@@ -216,7 +216,7 @@ def main():
         solver.substep(1)
     ktimes = solver.kernel_times()
     solver.set_profiling(False)
-    mean_contacts = float(solver.field("n_contacts")[0].float().mean())
+    mean_contacts = float(solver.field("n_contacts").float().mean())
     bytes_step = algorithmic_bytes_per_env_step(m, mean_contacts, mean_contacts)
     step_kernels = {k: v for k, v in ktimes.items() if v[1] > 0}
     total_kernel_ms = sum(v[0] / v[1] for v in step_kernels.values())
@@ -242,7 +242,7 @@ def main():
     # ---- end-to-end through the host-buffer plugin call (pinned host control targets in, qpos / qvel out)
     nD, nQ = m.n_dofs, m.n_qs
     ctrl_h = torch.empty((B, nD), dtype=torch.float32).pin_memory()
-    ctrl_h.copy_(solver.field("ctrl_pos").T)
+    ctrl_h.copy_(solver.field("ctrl_pos"))
     qpos_h = torch.empty((B, nQ), dtype=torch.float32).pin_memory()
     vel_h = torch.empty((B, nD), dtype=torch.float32).pin_memory()
     ctrl_np, qpos_np, vel_np = ctrl_h.numpy(), qpos_h.numpy(), vel_h.numpy()
@@ -279,7 +279,7 @@ def main():
             "config": {"workload": f"{args.workload}-{B}", "description": desc, "envs_per_gpu": B, "total_envs": world * B, "dt": 0.01,
                        "solver": "Newton", "integrator": "approximate_implicitfast", "n_dofs": nD, "n_links": m.n_links, "n_geoms": m.n_geoms,
                        "mean_contacts_per_env": mean_contacts, "errno_max": errno,
-                       "l2": f"per-GPU state {(solver._F.numel() + solver._I.numel()) * 4 / 2**20:.0f} MiB > 126 MB L2 (no flush needed)",
+                       "l2": f"per-GPU state {solver._F.numel() * 4 / 2**20:.0f} MiB > 126 MB L2 (no flush needed)",
                        "parallelism": f"env-sharded x{world}, no step-path collective"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
             "launches_per_step": launches / K, "clocks": clocks.summary(),

@@ -11,7 +11,7 @@ _lib = None
 
 EXPORTS = (
     "gsr_model_begin", "gsr_model_set_f32", "gsr_model_set_i32", "gsr_model_set_scalar", "gsr_model_commit", "gsr_model_refresh",
-    "gsr_state_sizes", "gsr_field_count", "gsr_field_info", "gsr_bind", "gsr_init_state", "gsr_step",
+    "gsr_state_words", "gsr_field_count", "gsr_field_info", "gsr_bind", "gsr_launch_info", "gsr_init_state", "gsr_step",
     "gsr_forward_kinematics", "gsr_reset_envs", "gsr_step_host", "gsr_launch_count", "gsr_kernel_info",
     "gsr_set_profiling", "gsr_kernel_time_ms",
     "gsr_last_error", "gsr_version", "gsr_destroy",
@@ -44,10 +44,11 @@ def lib():
         L.gsr_model_set_scalar.argtypes = [vp, cp, ctypes.c_double]
         L.gsr_model_commit.argtypes = [vp, i, i]
         L.gsr_model_refresh.argtypes = [vp]
-        L.gsr_state_sizes.argtypes = [vp, ctypes.POINTER(sz), ctypes.POINTER(sz)]
+        L.gsr_state_words.argtypes = [vp, ctypes.POINTER(sz)]
         L.gsr_field_count.argtypes = [vp]
-        L.gsr_field_info.argtypes = [vp, i, ctypes.POINTER(cp), ctypes.POINTER(i), ctypes.POINTER(sz), ctypes.POINTER(sz)]
-        L.gsr_bind.argtypes = [vp, vp, vp]
+        L.gsr_field_info.argtypes = [vp, i, ctypes.POINTER(cp), ctypes.POINTER(i)] + [ctypes.POINTER(sz)] * 6
+        L.gsr_bind.argtypes = [vp, vp]
+        L.gsr_launch_info.argtypes = [vp] + [ctypes.POINTER(i)] * 4
         L.gsr_init_state.argtypes = [vp, vp]
         L.gsr_step.argtypes = [vp, i, vp]
         L.gsr_forward_kinematics.argtypes = [vp, vp, vp]

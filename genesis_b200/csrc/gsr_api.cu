@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/gsrigid.h"
+#include <cstdint>
 #include "gsr_kernels.cuh"
 
 namespace {
@@ -14,13 +15,15 @@ namespace {
 struct FieldInfo {
   std::string name;
   int is_int;
-  size_t offset, items;
+  size_t seg_base, env_stride, offset, items, comps, item_stride;
 };
 
 struct KernelStat {
   const char* name;
   long long launches;
 };
+
+enum { K_STEP = 0, K_FORWARD = 1, K_RESET = 2, K_INIT = 3, K_SCATTER = 4, K_GATHER = 5, K_COUNT = 6 };
 
 }  // namespace
 
@@ -31,26 +34,28 @@ struct gsr_handle_s {
   std::string err;
   bool committed = false;
   int device = 0, B = 0;
-  DevModel hm;  // host copy of the constant-memory model
-  Layout lay;
+  int group = 32;  // lanes per environment
+  DevModel hm;     // host copy of the model
+  HotLayout lay;
+  SmemLayout sl;
   std::vector<FieldInfo> fields;
-  size_t n_f32 = 0, n_i32 = 0;
-  float* F = nullptr;
-  int* I = nullptr;
+  size_t n_words = 0;
+  float* state = nullptr;
+  DevModel* d_model = nullptr;  // global-memory copy for lane-varying table reads
   float *d_verts = nullptr, *d_support = nullptr;
   int *d_pairs = nullptr, *d_pair_idx = nullptr;
   // staging for gsr_step_host
   float *d_stage = nullptr, *h_stage = nullptr;
   size_t stage_elems = 0;
-  KernelStat stats[6] = {{"k_dynamics", 0}, {"k_collide", 0}, {"k_constraint", 0}, {"k_integrate", 0}, {"k_forward", 0}, {"k_reset", 0}};
+  KernelStat stats[K_COUNT] = {{"k_step", 0}, {"k_forward", 0}, {"k_reset", 0}, {"k_init", 0}, {"k_scatter", 0}, {"k_gather", 0}};
   long long total_launches = 0;
   // optional per-kernel event timing (gsr_set_profiling)
   bool profiling = false;
   struct Span { int k; cudaEvent_t a, b; };
   std::vector<Span> spans;
   std::vector<cudaEvent_t> event_pool;
-  double time_ms[6] = {0, 0, 0, 0, 0, 0};
-  long long timed[6] = {0, 0, 0, 0, 0, 0};
+  double time_ms[K_COUNT] = {0, 0, 0, 0, 0, 0};
+  long long timed[K_COUNT] = {0, 0, 0, 0, 0, 0};
   cudaStream_t prof_stream = nullptr;
 };
 
@@ -88,7 +93,9 @@ static int activate(gsr_handle_t h, cudaStream_t st) {
   if (g_active[h->device] != h) {
     // constant memory is per device: re-upload when another model (e.g. a second scene on this GPU) ran last
     CUDA_OK(cudaMemcpyToSymbolAsync(c_m, &h->hm, sizeof(DevModel), 0, cudaMemcpyHostToDevice, st));
-    CUDA_OK(cudaMemcpyToSymbolAsync(c_lay, &h->lay, sizeof(Layout), 0, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyToSymbolAsync(c_h, &h->lay, sizeof(HotLayout), 0, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyToSymbolAsync(c_s, &h->sl, sizeof(SmemLayout), 0, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(h->d_model, &h->hm, sizeof(DevModel), cudaMemcpyHostToDevice, st));
     g_active[h->device] = h;
   }
   return GSR_OK;
@@ -122,6 +129,7 @@ static int fill_model(gsr_handle_t h) {
   m.gravity[0] = (float)S("gravity_x", 0.0); m.gravity[1] = (float)S("gravity_y", 0.0); m.gravity[2] = (float)S("gravity_z", -9.81);
   m.ccd_eps = 1e-9f; m.ccd_tolerance = 1e-6f; m.ccd_iterations = 50;  // mpr.py:13-19
   m.n_cache_words = (m.nP + 31) / 32 > 0 ? (m.nP + 31) / 32 : 1;
+  m.diagnostics = (int)S("cfg_diagnostics", 1);
 
   bool missing = false;
   std::string missing_name;
@@ -147,12 +155,11 @@ static int fill_model(gsr_handle_t h) {
   { const float* p = FV("links_invweight", 2 * nL); if (!missing) for (int l = 0; l < nL; l++) m.l_invweight[l] = p[2 * l]; }
   CPI(m.j_type, "joints_type", nJ) CPI(m.j_q_start, "joints_q_start", nJ) CPI(m.j_dof_start, "joints_dof_start", nJ)
   CPI(m.j_n_dofs, "joints_n_dofs", nJ) CPF(m.j_pos, "joints_pos", 3 * nJ) CPF(m.j_sol, "joints_sol_params", 7 * nJ)
-  CPI(m.d_link, "dofs_link", nD) CPI(m.d_entity, "dofs_entity", nD)
+  CPI(m.d_link, "dofs_link", nD) CPI(m.d_entity, "dofs_entity", nD) CPI(m.d_joint, "dofs_joint", nD)
   CPF(m.d_motion_ang, "dofs_motion_ang", 3 * nD) CPF(m.d_motion_vel, "dofs_motion_vel", 3 * nD) CPF(m.d_limit, "dofs_limit", 2 * nD)
   CPF(m.d_stiffness, "dofs_stiffness", nD) CPF(m.d_damping, "dofs_damping", nD) CPF(m.d_armature, "dofs_armature", nD)
   CPF(m.d_frictionloss, "dofs_frictionloss", nD) CPF(m.d_kp, "dofs_kp", nD) CPF(m.d_act_bias, "dofs_act_bias", 3 * nD)
   CPF(m.d_force_range, "dofs_force_range", 2 * nD) CPF(m.d_invweight, "dofs_invweight", nD) CPF(m.qpos0, "qpos0", nQ)
-  { const float* p = FV("mass_parent_mask", (size_t)nD * nD); if (!missing) for (int a = 0; a < nD; a++) for (int b = 0; b < nD; b++) m.mass_mask[a][b] = p[a * nD + b] != 0.f; }
   CPI(m.e_link_start, "entities_link_start", nE) CPI(m.e_link_end, "entities_link_end", nE) CPI(m.e_dof_start, "entities_dof_start", nE)
   CPI(m.e_dof_end, "entities_dof_end", nE) CPI(m.e_geom_start, "entities_geom_start", nE) CPI(m.e_geom_end, "entities_geom_end", nE)
   CPF(m.e_gravcomp, "entities_gravity_compensation", nE)
@@ -172,6 +179,23 @@ static int fill_model(gsr_handle_t h) {
 #undef CPI
 #undef CPF
   if (missing) return fail(h, GSR_EINVAL, "missing or short model array: " + missing_name);
+
+  // derived topology tables: ancestor masks (links and dofs), subtree mass per root, tree depth
+  m.max_depth = 1;
+  for (int l = 0; l < nL; l++) {
+    unsigned long long am = 0ull, dm = 0ull;
+    int a = l, depth = 0;
+    while (a != -1) {
+      am |= 1ull << a;
+      for (int d = m.l_dof_start[a]; d < m.l_dof_end[a]; d++) dm |= 1ull << d;
+      a = m.l_parent[a];
+      depth++;
+    }
+    m.l_ancmask[l] = am; m.l_dofmask[l] = dm; m.l_depth[l] = depth;
+    if (depth > m.max_depth) m.max_depth = depth;
+    m.l_root_mass[l] = 0.f;
+  }
+  for (int l = 0; l < nL; l++) m.l_root_mass[m.l_root[l]] += m.l_mass[l];
 
   // has_cc: any valid pair that is not plane-box (collider.py:449-459) -> contacts are x-sorted (collider.py:804-808)
   m.has_cc = 0;
@@ -213,6 +237,8 @@ int gsr_model_set_scalar(gsr_handle_t h, const char* name, double value) {
   return GSR_OK;
 }
 
+static size_t round4(size_t x) { return (x + 3) & ~(size_t)3; }
+
 int gsr_model_commit(gsr_handle_t h, int device, int n_envs) {
   if (!h || n_envs <= 0) return fail(h, GSR_EINVAL, "bad handle or n_envs");
   if (h->committed) return fail(h, GSR_ESTATE, "model already committed (use gsr_model_refresh)");
@@ -220,6 +246,7 @@ int gsr_model_commit(gsr_handle_t h, int device, int n_envs) {
   int rc_fill = fill_model(h);
   if (rc_fill) return rc_fill;
   DevModel& m = h->hm;
+  if (m.nL > 64 || m.nD > 64) return fail(h, GSR_ELIMIT, "ancestor masks hold at most 64 links / dofs");
   h->device = device;
   h->B = n_envs;
   CUDA_OK(cudaSetDevice(device));
@@ -234,30 +261,101 @@ int gsr_model_commit(gsr_handle_t h, int device, int n_envs) {
     auto& sv = h->f["support_v"]; CUDA_OK(upload(sv.empty() ? nullptr : sv.data(), sv.size() * 4, (void**)&h->d_support));
     auto& pr = h->i["pairs"]; CUDA_OK(upload(pr.empty() ? nullptr : pr.data(), pr.size() * 4, (void**)&h->d_pairs));
     auto& pi = h->i["pair_idx"]; CUDA_OK(upload(pi.empty() ? nullptr : pi.data(), pi.size() * 4, (void**)&h->d_pair_idx));
+    CUDA_OK(cudaMalloc((void**)&h->d_model, sizeof(DevModel)));
   }
   m.verts = h->d_verts; m.support_v = h->d_support; m.pairs = h->d_pairs; m.pair_idx = h->d_pair_idx;
 
-  // ---- state layout
-  const int nL = m.nL, nJ = m.nJ, nD = m.nD, nQ = m.nQ, nG = m.nG;
-  const int nC = m.len_constraints > 0 ? m.len_constraints : 1, nCP = m.max_contact_pairs > 0 ? m.max_contact_pairs : 1;
-  const int nP = m.nP > 0 ? m.nP : 1, nW = m.n_cache_words;
-  size_t off_f = 0, off_i = 0;
+  // ---- lanes per environment: a full warp unless the batch is large enough to fill the machine with smaller groups
+  auto S = [&](const char* k, double d) { auto it = h->s.find(k); return it == h->s.end() ? d : it->second; };
+  int G = (int)S("cfg_group_size", 0);
+  if (G != 8 && G != 16 && G != 32) G = 32;
+  h->group = G;
+
+  // ---- HOT record layout
+  const int nL = m.nL, nD = m.nD, nQ = m.nQ, nG = m.nG;
+  HotLayout& L = h->lay;
+  memset(&L, 0, sizeof(L));
   h->fields.clear();
-#define X(name, is_int, rows)                                                     \
-  {                                                                               \
-    size_t r_ = (size_t)(rows);                                                   \
-    if (r_ == 0) r_ = 1;                                                          \
-    size_t& off_ = (is_int) ? off_i : off_f;                                      \
-    h->lay.name = (int)off_;                                                      \
-    h->fields.push_back(FieldInfo{#name, is_int, off_, r_});                      \
-    off_ += r_;                                                                   \
+  size_t off = 0;
+#define X(name, is_int, items, comps)                                                                   \
+  {                                                                                                     \
+    size_t it_ = (size_t)(items), cp_ = (size_t)(comps);                                                \
+    L.name = (int)off;                                                                                  \
+    h->fields.push_back(FieldInfo{#name, is_int, 0, 0, off, it_, cp_, cp_});                            \
+    off += (it_ * cp_ > 0 ? it_ * cp_ : 1);                                                             \
   }
-  GSR_FIELDS(X)
+  GSR_HOT_IN_FIELDS(X)
+  off = round4(off);
+  L.n_in = (int)off;
+  L.kin_dead = L.cinr_I;
+  GSR_HOT_OUT_FIELDS(X)
 #undef X
-  (void)nP;
-  h->n_f32 = off_f * (size_t)n_envs;
-  h->n_i32 = off_i * (size_t)n_envs;
-  if (off_f >= (size_t)1 << 31 || off_i >= (size_t)1 << 31) return fail(h, GSR_ELIMIT, "state layout exceeds int32 row index");
+  L.hot_stride = (int)round4(off);
+  const int nCP = m.max_contact_pairs > 0 ? m.max_contact_pairs : 1;
+  const int lenC = m.len_constraints > 0 ? m.len_constraints : 1;
+  const int MS = nD | 1, JS = nD | 1;
+  L.contact_stride = nCP * GSR_CONTACT_WORDS;
+  L.cache_valid = (int)round4(3 * (size_t)(m.nP > 0 ? m.nP : 1));
+  L.cache_stride = (int)round4(L.cache_valid + m.n_cache_words);
+  size_t spill = (size_t)lenC * JS + 8 * (size_t)lenC;
+  if (spill < (size_t)nCP * GSR_CONTACT_WORDS) spill = (size_t)nCP * GSR_CONTACT_WORDS;
+  L.spill_stride = (int)round4(spill);
+  const size_t B = (size_t)n_envs;
+  L.contact_base = (long long)(B * L.hot_stride);
+  L.cache_base = L.contact_base + (long long)(B * L.contact_stride);
+  L.spill_base = L.cache_base + (long long)(B * L.cache_stride);
+  h->n_words = (size_t)L.spill_base + B * L.spill_stride;
+  for (auto& f : h->fields) { f.seg_base = 0; f.env_stride = L.hot_stride; }
+  {  // contact record fields (AoS) and the warm-start cache
+    auto add = [&](const char* name, int is_int, size_t base, size_t stride, size_t o, size_t items, size_t comps, size_t istride) {
+      h->fields.push_back(FieldInfo{name, is_int, base, stride, o, items, comps, istride});
+    };
+    const size_t cb = (size_t)L.contact_base, cs = L.contact_stride, W = GSR_CONTACT_WORDS;
+    add("contact_geom_a", 1, cb, cs, CT_GA, nCP, 1, W); add("contact_geom_b", 1, cb, cs, CT_GB, nCP, 1, W);
+    add("contact_link_a", 1, cb, cs, CT_LA, nCP, 1, W); add("contact_link_b", 1, cb, cs, CT_LB, nCP, 1, W);
+    add("contact_penetration", 0, cb, cs, CT_PEN, nCP, 1, W); add("contact_friction", 0, cb, cs, CT_MU, nCP, 1, W);
+    add("contact_pos", 0, cb, cs, CT_POS, nCP, 3, W); add("contact_normal", 0, cb, cs, CT_NRM, nCP, 3, W);
+    add("contact_force", 0, cb, cs, CT_FRC, nCP, 3, W);
+    add("cache_normal", 0, (size_t)L.cache_base, L.cache_stride, 0, m.nP > 0 ? m.nP : 1, 3, 3);
+    add("cache_valid", 1, (size_t)L.cache_base, L.cache_stride, L.cache_valid, m.n_cache_words, 1, 1);
+  }
+
+  // ---- shared-memory workspace layout (see gsr_types.h): [IN mirror | overlay pool | always-live block]
+  SmemLayout& s = h->sl;
+  memset(&s, 0, sizeof(s));
+  s.MS = MS; s.JS = JS;
+  int NCS = (int)S("cfg_smem_rows", nD > 12 ? 64 : 32);
+  if (NCS > lenC) NCS = lenC;
+  if (NCS < 4) NCS = 4;
+  s.NCS = NCS;
+  s.NCC = NCS / 4 > 0 ? NCS / 4 : 1;
+  // scratch of the dynamics / collision / integrate+FK phases starts after the IN mirror
+  int x = L.n_in, xmax = x;
+  s.crb = x; x += 10 * nL; s.fdof = x; x += 6 * nD; s.cdd = x; x += 6 * nL; s.cfrc = x; x += 6 * nL;
+  if (x > xmax) xmax = x;
+  x = L.n_in;
+  s.gpos = x; x += 3 * nG; s.gquat = x; x += 4 * nG; s.aabb = x; x += 6 * nG; s.queue = x; x += 2 * 32;
+  if (x > xmax) xmax = x;
+  x = L.n_in;
+  s.xanchor = x; x += 3 * m.nJ; s.xaxis = x; x += 3 * m.nJ; s.cacc = x; x += 6 * nL; s.vel_next = x; x += nD; s.qpos_next = x; x += nQ;
+  s.pose_a = x; x += 8 * nL; s.pose_b = x; x += 8 * nL;
+  if (x > xmax) xmax = x;
+  // solver arrays overlay the dead part of the kinematic cache and the phase scratch
+  x = L.kin_dead;
+  s.contacts = x; x += s.NCC * GSR_CONTACT_WORDS;
+  s.H = x; x += nD * MS;
+  s.qacc = x; x += nD; s.Ma = x; x += nD; s.grad = x; x += nD; s.Mgrad = x; x += nD; s.search = x; x += nD; s.mv = x; x += nD;
+  s.prev_grad = x; x += nD; s.prev_Mgrad = x; x += nD;
+  s.r_aref = x; x += NCS; s.r_D = x; x += NCS; s.r_R = x; x += NCS; s.r_floss = x; x += NCS; s.r_Jaref = x; x += NCS;
+  s.r_jv = x; x += NCS; s.r_force = x; x += NCS; s.r_active = x; x += NCS;
+  s.J = x; x += NCS * JS;
+  if (x > xmax) xmax = x;
+  // always-live block
+  x = (int)round4(xmax);
+  s.M = x; x += nD * MS; s.L = x; x += nD * MS; s.Dinv = x; x += nD; s.force = x; x += nD; s.acc_smooth = x; x += nD;
+  s.acc = x; x += nD; s.qf_applied = x; x += nD; s.qf_passive = x; x += nD; s.qf_bias = x; x += nD; s.qfrc_c = x; x += nD;
+  s.env_words = (int)round4(x);
+
   h->committed = true;
   g_active[device] = nullptr;
   return GSR_OK;
@@ -267,169 +365,171 @@ int gsr_model_refresh(gsr_handle_t h) {
   if (!h || !h->committed) return fail(h, GSR_ESTATE, "model not committed");
   int rc = fill_model(h);
   if (rc) return rc;
-  g_active[h->device] = nullptr;  // forces a constant-memory re-upload on the next call
+  g_active[h->device] = nullptr;  // forces a re-upload on the next call
   return GSR_OK;
 }
 
-int gsr_state_sizes(gsr_handle_t h, size_t* n_float32, size_t* n_int32) {
+int gsr_state_words(gsr_handle_t h, size_t* n_words) {
   if (!h || !h->committed) return fail(h, GSR_ESTATE, "model not committed");
-  if (n_float32) *n_float32 = h->n_f32;
-  if (n_int32) *n_int32 = h->n_i32;
+  if (n_words) *n_words = h->n_words;
   return GSR_OK;
 }
 int gsr_field_count(gsr_handle_t h) { return (h && h->committed) ? (int)h->fields.size() : GSR_ESTATE; }
-int gsr_field_info(gsr_handle_t h, int index, const char** name, int* is_int, size_t* offset, size_t* items) {
+int gsr_field_info(gsr_handle_t h, int index, const char** name, int* is_int, size_t* segment_base, size_t* env_stride,
+                   size_t* offset, size_t* items, size_t* comps, size_t* item_stride) {
   if (!h || !h->committed) return fail(h, GSR_ESTATE, "model not committed");
   if (index < 0 || index >= (int)h->fields.size()) return fail(h, GSR_EINVAL, "field index out of range");
   const FieldInfo& f = h->fields[index];
   if (name) *name = f.name.c_str();
   if (is_int) *is_int = f.is_int;
+  if (segment_base) *segment_base = f.seg_base;
+  if (env_stride) *env_stride = f.env_stride;
   if (offset) *offset = f.offset;
   if (items) *items = f.items;
+  if (comps) *comps = f.comps;
+  if (item_stride) *item_stride = f.item_stride;
   return GSR_OK;
 }
-int gsr_bind(gsr_handle_t h, float* state_f32, int32_t* state_i32) {
+int gsr_bind(gsr_handle_t h, void* state_words) {
   if (!h || !h->committed) return fail(h, GSR_ESTATE, "model not committed");
-  if (!state_f32 || !state_i32) return fail(h, GSR_EINVAL, "null state buffer");
-  h->F = state_f32;
-  h->I = state_i32;
+  if (!state_words) return fail(h, GSR_EINVAL, "null state buffer");
+  if (((uintptr_t)state_words & 15) != 0) return fail(h, GSR_EINVAL, "state buffer must be 16-byte aligned");
+  h->state = (float*)state_words;
+  return GSR_OK;
+}
+int gsr_launch_info(gsr_handle_t h, int* group_size, int* smem_bytes_per_env, int* smem_rows, int* smem_contacts) {
+  if (!h || !h->committed) return fail(h, GSR_ESTATE, "model not committed");
+  if (group_size) *group_size = h->group;
+  if (smem_bytes_per_env) *smem_bytes_per_env = h->sl.env_words * 4;
+  if (smem_rows) *smem_rows = h->sl.NCS;
+  if (smem_contacts) *smem_contacts = h->sl.NCC;
   return GSR_OK;
 }
 
-static int launch_cfg(gsr_handle_t h, dim3& grid, dim3& block) {
-  block = dim3(GSR_BLOCK);
-  grid = dim3((h->B + GSR_BLOCK - 1) / GSR_BLOCK);
-  return 0;
+}  // extern "C"
+
+// ---- launches ---------------------------------------------------------------------------------------------------------
+template <typename K>
+static cudaError_t set_smem(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
+static int group_launch(gsr_handle_t h, int which, cudaStream_t st, const uint8_t* mask, int clear_ext) {
+  const int G = h->group, EPW = 32 / G, envs_per_cta = GSR_WARPS_PER_CTA * EPW;
+  const size_t smem = (size_t)envs_per_cta * h->sl.env_words * sizeof(float);
+  if (smem > 227 * 1024) return fail(h, GSR_ELIMIT, "per-CTA shared-memory workspace exceeds 227 KB (lower cfg_smem_rows)");
+  dim3 grid((h->B + envs_per_cta - 1) / envs_per_cta), block(GSR_WARPS_PER_CTA * 32);
+#define LAUNCH(GG)                                                                                       \
+  if (which == K_STEP) {                                                                                 \
+    CUDA_OK(set_smem(k_step<GG>, smem));                                                                 \
+    Bracket br_(h, K_STEP, st);                                                                          \
+    k_step<GG><<<grid, block, smem, st>>>(h->state, h->B, h->d_model, clear_ext);                        \
+  } else {                                                                                               \
+    CUDA_OK(set_smem(k_forward<GG>, smem));                                                              \
+    Bracket br_(h, K_FORWARD, st);                                                                       \
+    k_forward<GG><<<grid, block, smem, st>>>(h->state, h->B, h->d_model, mask);                          \
+  }
+  if (G == 32) { LAUNCH(32) } else if (G == 16) { LAUNCH(16) } else { LAUNCH(8) }
+#undef LAUNCH
+  CUDA_OK(cudaGetLastError());
+  return GSR_OK;
+}
+
+extern "C" {
 
 int gsr_init_state(gsr_handle_t h, void* cuda_stream) {
-  if (!h || !h->F) return fail(h, GSR_ESTATE, "state not bound");
+  if (!h || !h->state) return fail(h, GSR_ESTATE, "state not bound");
   cudaStream_t st = (cudaStream_t)cuda_stream;
   int rc = activate(h, st);
   if (rc) return rc;
-  const DevModel& m = h->hm;
-  const size_t B = h->B;
-  CUDA_OK(cudaMemsetAsync(h->F, 0, h->n_f32 * sizeof(float), st));
-  CUDA_OK(cudaMemsetAsync(h->I, 0, h->n_i32 * sizeof(int), st));
-  // host-built initial rows: qpos0, FORCE control mode, unit friction ratio, model pose for every link
-  std::vector<float> rows;
-  auto put_f = [&](int off, int n, const float* vals) -> cudaError_t {
-    rows.assign((size_t)n * B, 0.f);
-    for (int r = 0; r < n; r++) for (size_t b = 0; b < B; b++) rows[r * B + b] = vals[r];
-    return cudaMemcpyAsync(h->F + (size_t)off * B, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice, st);
-  };
-  CUDA_OK(put_f(h->lay.qpos, m.nQ, m.qpos0));
-  CUDA_OK(cudaStreamSynchronize(st));
-  std::vector<float> ones(m.nG > 0 ? m.nG : 1, 1.f);
-  CUDA_OK(put_f(h->lay.friction_ratio, m.nG, ones.data()));
-  CUDA_OK(cudaStreamSynchronize(st));
-  CUDA_OK(put_f(h->lay.links_pos, 3 * m.nL, &m.l_pos[0][0]));
-  CUDA_OK(cudaStreamSynchronize(st));
-  CUDA_OK(put_f(h->lay.links_quat, 4 * m.nL, &m.l_quat[0][0]));
-  CUDA_OK(cudaStreamSynchronize(st));
+  CUDA_OK(cudaMemsetAsync(h->state, 0, h->n_words * sizeof(float), st));
   {
-    std::vector<int> modes((size_t)(m.nD > 0 ? m.nD : 1) * B, CTRL_FORCE);  // abd/misc.py:170-173
-    CUDA_OK(cudaMemcpyAsync(h->I + (size_t)h->lay.ctrl_mode * B, modes.data(), (size_t)m.nD * B * 4, cudaMemcpyHostToDevice, st));
-    CUDA_OK(cudaStreamSynchronize(st));
+    Bracket br_(h, K_INIT, st);
+    k_init<<<(h->B + 127) / 128, 128, 0, st>>>(h->state, h->B);
   }
-  dim3 grid, block;
-  launch_cfg(h, grid, block);
-  { Bracket br_(h, 4, st); k_forward<<<grid, block, 0, st>>>(h->F, h->I, h->B, nullptr, 1); }
   CUDA_OK(cudaGetLastError());
-  return GSR_OK;
+  return group_launch(h, K_FORWARD, st, nullptr, 0);
 }
 
 int gsr_step(gsr_handle_t h, int n_substeps, void* cuda_stream) {
-  if (!h || !h->F) return fail(h, GSR_ESTATE, "state not bound");
+  if (!h || !h->state) return fail(h, GSR_ESTATE, "state not bound");
   cudaStream_t st = (cudaStream_t)cuda_stream;
   int rc = activate(h, st);
   if (rc) return rc;
-  dim3 grid, block;
-  launch_cfg(h, grid, block);
   for (int s = 0; s < n_substeps; s++) {
-    { Bracket br_(h, 0, st); k_dynamics<<<grid, block, 0, st>>>(h->F, h->I, h->B); }
-    if (h->hm.enable_collision && h->hm.nG > 0) {
-      { Bracket br_(h, 1, st); k_collide<<<grid, block, 0, st>>>(h->F, h->I, h->B); }
-    }
-    { Bracket br_(h, 2, st); k_constraint<<<grid, block, 0, st>>>(h->F, h->I, h->B); }
-    { Bracket br_(h, 3, st); k_integrate<<<grid, block, 0, st>>>(h->F, h->I, h->B, s == n_substeps - 1); }
+    rc = group_launch(h, K_STEP, st, nullptr, s == n_substeps - 1);
+    if (rc) return rc;
   }
-  CUDA_OK(cudaGetLastError());
   return GSR_OK;
 }
 
 int gsr_forward_kinematics(gsr_handle_t h, const uint8_t* env_mask_dev, void* cuda_stream) {
-  if (!h || !h->F) return fail(h, GSR_ESTATE, "state not bound");
+  if (!h || !h->state) return fail(h, GSR_ESTATE, "state not bound");
   cudaStream_t st = (cudaStream_t)cuda_stream;
   int rc = activate(h, st);
   if (rc) return rc;
-  dim3 grid, block;
-  launch_cfg(h, grid, block);
-  { Bracket br_(h, 4, st); k_forward<<<grid, block, 0, st>>>(h->F, h->I, h->B, env_mask_dev, 0); }
-  CUDA_OK(cudaGetLastError());
-  return GSR_OK;
+  return group_launch(h, K_FORWARD, st, env_mask_dev, 0);
 }
 
 int gsr_reset_envs(gsr_handle_t h, const uint8_t* env_mask_dev, void* cuda_stream) {
-  if (!h || !h->F) return fail(h, GSR_ESTATE, "state not bound");
+  if (!h || !h->state) return fail(h, GSR_ESTATE, "state not bound");
   cudaStream_t st = (cudaStream_t)cuda_stream;
   int rc = activate(h, st);
   if (rc) return rc;
-  dim3 grid, block;
-  launch_cfg(h, grid, block);
-  { Bracket br_(h, 5, st); k_reset<<<grid, block, 0, st>>>(h->F, h->I, h->B, env_mask_dev); }
+  {
+    Bracket br_(h, K_RESET, st);
+    k_reset<<<(h->B + 127) / 128, 128, 0, st>>>(h->state, h->B, env_mask_dev);
+  }
   CUDA_OK(cudaGetLastError());
   return GSR_OK;
 }
 
 int gsr_step_host(gsr_handle_t h, int n_substeps, const float* ctrl_pos_host, float* qpos_host, float* vel_host, void* cuda_stream) {
-  if (!h || !h->F) return fail(h, GSR_ESTATE, "state not bound");
+  if (!h || !h->state) return fail(h, GSR_ESTATE, "state not bound");
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  CUDA_OK(cudaSetDevice(h->device));
+  int rc = activate(h, st);
+  if (rc) return rc;
   const DevModel& m = h->hm;
   const size_t B = h->B;
-  const size_t need = B * (size_t)(m.nQ > m.nD ? m.nQ : m.nD);
+  const size_t need = B * (size_t)(m.nQ + m.nD);
   if (h->stage_elems < need) {
     if (h->d_stage) cudaFree(h->d_stage);
-    if (h->h_stage) cudaFreeHost(h->h_stage);
     CUDA_OK(cudaMalloc((void**)&h->d_stage, need * 4));
-    CUDA_OK(cudaMallocHost((void**)&h->h_stage, need * 4));
     h->stage_elems = need;
   }
-  // The public API is env-major (B, n) like the reference's transposed torch views; the device rows are item-major.
-  // The transposes are done on the host through a pinned staging buffer.
+  // host arrays are (B, n) env-major like the public API; one contiguous DMA each way plus a scatter / gather kernel
   if (ctrl_pos_host) {
-    for (size_t b = 0; b < B; b++)
-      for (int d = 0; d < m.nD; d++) h->h_stage[(size_t)d * B + b] = ctrl_pos_host[b * m.nD + d];
-    CUDA_OK(cudaMemcpyAsync(h->F + (size_t)h->lay.ctrl_pos * B, h->h_stage, (size_t)m.nD * B * 4, cudaMemcpyHostToDevice, st));
-    CUDA_OK(cudaStreamSynchronize(st));
+    const int n = (int)(B * m.nD);
+    CUDA_OK(cudaMemcpyAsync(h->d_stage, ctrl_pos_host, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    Bracket br_(h, K_SCATTER, st);
+    k_scatter<<<(n + 255) / 256, 256, 0, st>>>(h->state, h->B, h->lay.ctrl_pos, m.nD, h->d_stage);
   }
-  int rc = gsr_step(h, n_substeps, cuda_stream);
+  rc = gsr_step(h, n_substeps, cuda_stream);
   if (rc) return rc;
+  float* d_q = h->d_stage;
+  float* d_v = h->d_stage + B * m.nQ;
   if (qpos_host) {
-    CUDA_OK(cudaMemcpyAsync(h->h_stage, h->F + (size_t)h->lay.qpos * B, (size_t)m.nQ * B * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaStreamSynchronize(st));
-    for (size_t b = 0; b < B; b++)
-      for (int q = 0; q < m.nQ; q++) qpos_host[b * m.nQ + q] = h->h_stage[(size_t)q * B + b];
+    const int n = (int)(B * m.nQ);
+    { Bracket br_(h, K_GATHER, st); k_gather<<<(n + 255) / 256, 256, 0, st>>>(h->state, h->B, h->lay.qpos, m.nQ, d_q); }
+    CUDA_OK(cudaMemcpyAsync(qpos_host, d_q, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
   }
   if (vel_host) {
-    CUDA_OK(cudaMemcpyAsync(h->h_stage, h->F + (size_t)h->lay.vel * B, (size_t)m.nD * B * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaStreamSynchronize(st));
-    for (size_t b = 0; b < B; b++)
-      for (int d = 0; d < m.nD; d++) vel_host[b * m.nD + d] = h->h_stage[(size_t)d * B + b];
+    const int n = (int)(B * m.nD);
+    { Bracket br_(h, K_GATHER, st); k_gather<<<(n + 255) / 256, 256, 0, st>>>(h->state, h->B, h->lay.vel, m.nD, d_v); }
+    CUDA_OK(cudaMemcpyAsync(vel_host, d_v, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
   }
+  CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaStreamSynchronize(st));
   return GSR_OK;
 }
 
 int gsr_set_profiling(gsr_handle_t h, int enabled) {
   if (!h) return GSR_EINVAL;
-  if (enabled) { for (int k = 0; k < 6; k++) { h->time_ms[k] = 0; h->timed[k] = 0; } }
+  if (enabled) { for (int k = 0; k < K_COUNT; k++) { h->time_ms[k] = 0; h->timed[k] = 0; } }
   h->profiling = enabled != 0;
   return GSR_OK;
 }
 int gsr_kernel_time_ms(gsr_handle_t h, int index, double* total_ms, long long* timed_launches) {
-  if (!h || index < 0 || index >= 6) return GSR_EINVAL;
+  if (!h || index < 0 || index >= K_COUNT) return GSR_EINVAL;
   if (!h->spans.empty()) {
     CUDA_OK(cudaSetDevice(h->device));
     CUDA_OK(cudaEventSynchronize(h->spans.back().b));
@@ -448,7 +548,7 @@ int gsr_kernel_time_ms(gsr_handle_t h, int index, double* total_ms, long long* t
 
 long long gsr_launch_count(gsr_handle_t h) { return h ? h->total_launches : 0; }
 int gsr_kernel_info(gsr_handle_t h, int index, const char** name, long long* launches) {
-  if (!h || index < 0 || index >= 6) return GSR_EINVAL;
+  if (!h || index < 0 || index >= K_COUNT) return GSR_EINVAL;
   if (name) *name = h->stats[index].name;
   if (launches) *launches = h->stats[index].launches;
   return GSR_OK;
@@ -459,9 +559,8 @@ void gsr_destroy(gsr_handle_t h) {
   if (h->committed) {
     cudaSetDevice(h->device);
     if (g_active[h->device] == h) g_active[h->device] = nullptr;
-    cudaFree(h->d_verts); cudaFree(h->d_support); cudaFree(h->d_pairs); cudaFree(h->d_pair_idx);
+    cudaFree(h->d_verts); cudaFree(h->d_support); cudaFree(h->d_pairs); cudaFree(h->d_pair_idx); cudaFree(h->d_model);
     if (h->d_stage) cudaFree(h->d_stage);
-    if (h->h_stage) cudaFreeHost(h->h_stage);
     for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : h->event_pool) cudaEventDestroy(e);
   }

@@ -1,0 +1,548 @@
+// gsr_dynamics.cuh -- forward kinematics and smooth dynamics, one lane group per environment, all operands in shared memory.
+// Reference citations use the abbreviations of oracle/rigid_oracle.hpp (FK, FD, CS, BP, NP, MPR, SF, CT, BOX, RS).
+//
+// The reference walks the kinematic tree serially (one thread per entity, FK:580-736, FD:306-388, FD:1186-1400).  Here the
+// tree recursions are restated as data-parallel sums: every c-frame quantity is expressed about the same point (the
+// subtree COM) in world axes, so "propagate from the parent" is a plain sum over the ancestor set and "accumulate into the
+// parent" a plain sum over the descendant set -- each lane evaluates its link's (or dof's) sum directly from a 64-bit
+// ancestor mask, in the reference's summation order.  Only the pose composition of FK is a true scan; it is done by pointer
+// jumping in ceil(log2(depth)) rounds.
+#pragma once
+#include "gsr_group.cuh"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// FK:580-736 one link's pose from its parent's world pose (pp, pq); also joint anchors / axes and dofs_pos when `final`.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int G>
+__device__ void fk_link(const Ctx<G>& C, int l, bool has_parent, f3 pp, f4 pq, const float* qpos, f3& pos, f4& quat, bool final) {
+  const float EPS = CM(eps);
+  pos = f3(GM(l_pos[l][0]), GM(l_pos[l][1]), GM(l_pos[l][2]));
+  quat = f4(GM(l_quat[l][0]), GM(l_quat[l][1]), GM(l_quat[l][2]), GM(l_quat[l][3]));
+  if (has_parent) {
+    pos = pp + rotate(pos, pq);
+    quat = quat_compose(quat, pq);
+  }
+  const int js = GM(l_joint_start[l]), je = GM(l_joint_end[l]);
+  for (int j = js; j < je; j++) {
+    const int type = GM(j_type[j]), qs = GM(j_q_start[j]), ds = GM(j_dof_start[j]);
+    const f3 jpos(GM(j_pos[j][0]), GM(j_pos[j][1]), GM(j_pos[j][2]));
+    f3 xanchor, xaxis(0.f, 0.f, 1.f);
+    if (type == JOINT_FREE) {
+      pos = f3(qpos[qs], qpos[qs + 1], qpos[qs + 2]);
+      const f4 q(qpos[qs + 3], qpos[qs + 4], qpos[qs + 5], qpos[qs + 6]);
+      const float n = 1.0f / sqrtf(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+      quat = f4(q.w * n, q.x * n, q.y * n, q.z * n);
+      xanchor = pos;
+      if (final) {
+        const f3 xyz = quat_to_xyz(quat, EPS);
+        float* dp = IN(dofs_pos);
+        dp[ds] = pos.x; dp[ds + 1] = pos.y; dp[ds + 2] = pos.z; dp[ds + 3] = xyz.x; dp[ds + 4] = xyz.y; dp[ds + 5] = xyz.z;
+      }
+    } else if (type == JOINT_REVOLUTE) {
+      const f3 axis(GM(d_motion_ang[ds][0]), GM(d_motion_ang[ds][1]), GM(d_motion_ang[ds][2]));
+      xanchor = rotate(jpos, quat) + pos;
+      xaxis = rotate(axis, quat);
+      const float dq = qpos[qs] - GM(qpos0[qs]);
+      if (final) IN(dofs_pos)[ds] = dq;
+      quat = quat_compose(rotvec_to_quat(axis * dq, EPS), quat);
+      pos = xanchor - rotate(jpos, quat);
+    } else if (type == JOINT_PRISMATIC) {
+      const f3 axis(GM(d_motion_vel[ds][0]), GM(d_motion_vel[ds][1]), GM(d_motion_vel[ds][2]));
+      xanchor = rotate(jpos, quat) + pos;
+      xaxis = rotate(axis, quat);
+      const float dq = qpos[qs] - GM(qpos0[qs]);
+      if (final) IN(dofs_pos)[ds] = dq;
+      pos = pos + xaxis * dq;
+    } else if (type == JOINT_SPHERICAL) {
+      xanchor = rotate(jpos, quat) + pos;
+      const f4 qloc(qpos[qs], qpos[qs + 1], qpos[qs + 2], qpos[qs + 3]);
+      if (final) {
+        const f3 xyz = quat_to_xyz(qloc, EPS);
+        float* dp = IN(dofs_pos);
+        dp[ds] = xyz.x; dp[ds + 1] = xyz.y; dp[ds + 2] = xyz.z;
+      }
+      quat = quat_compose(qloc, quat);
+      pos = xanchor - rotate(jpos, quat);
+    }
+    if (final) {
+      st3(WK(xanchor), j, xanchor);
+      st3(WK(xaxis), j, xaxis);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Kinematics of the whole environment from qpos / vel (FK:580-736, FK:337-576, FK:993-1116): rebuilds the kinematic cache.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int G>
+__device__ void phase_kinematics(const Ctx<G>& C) {
+  const int nL = CM(nL), nD = CM(nD), nJ = CM(nJ);
+  const float EPS = CM(eps);
+  const int lane = C.lane;
+  const float* qpos = IN(qpos);
+  const float* vel = IN(vel);
+  float* lpos = IN(links_pos);
+  float* lquat = IN(links_quat);
+  // ---- 1. local transforms X_l (pose relative to the parent frame; absolute for roots), pointer-jumping scan to world poses
+  float* pa = WK(pose_a);
+  float* pb = WK(pose_b);
+  int* anc_a = reinterpret_cast<int*>(pa) + 7 * nL;
+  int* anc_b = reinterpret_cast<int*>(pb) + 7 * nL;
+  for (int l = lane; l < nL; l += G) {
+    const int p = GM(l_parent[l]);
+    f3 pos; f4 quat;
+    if (p == -1 && GM(l_is_fixed[l])) { pos = ld3(lpos, l); quat = ld4(lquat, l); }  // fixed roots keep the user-set pose (FK:732-736)
+    else fk_link(C, l, false, f3(), f4(), qpos, pos, quat, false);
+    st3(pa, l, pos); st4(pa + 3 * nL, l, quat);
+    anc_a[l] = p;
+  }
+  C.sync();
+  int rounds = 0;
+  for (int d = 1; d < CM(max_depth); d <<= 1) rounds++;
+  for (int r = 0; r < rounds; r++) {
+    for (int l = lane; l < nL; l += G) {
+      const int a = anc_a[l];
+      f3 pos = ld3(pa, l); f4 quat = ld4(pa + 3 * nL, l);
+      int na = a;
+      if (a >= 0) {
+        const f3 ap = ld3(pa, a); const f4 aq = ld4(pa + 3 * nL, a);
+        pos = ap + rotate(pos, aq);
+        quat = quat_compose(quat, aq);
+        na = anc_a[a];
+      }
+      st3(pb, l, pos); st4(pb + 3 * nL, l, quat);
+      anc_b[l] = na;
+    }
+    C.sync();
+    float* t = pa; pa = pb; pb = t;
+    int* ti = anc_a; anc_a = anc_b; anc_b = ti;
+  }
+  // ---- 2. final pose of every link the reference way, from the parent's scanned world pose; anchors, axes, dofs_pos
+  for (int l = lane; l < nL; l += G) {
+    const int p = GM(l_parent[l]);
+    if (p == -1 && GM(l_is_fixed[l])) continue;
+    f3 pp; f4 pq;
+    if (p >= 0) { pp = ld3(pa, p); pq = ld4(pa + 3 * nL, p); }
+    f3 pos; f4 quat;
+    fk_link(C, l, p >= 0, pp, pq, qpos, pos, quat, true);
+    st3(lpos, l, pos); st4(lquat, l, quat);
+  }
+  C.sync();
+  // ---- 3. subtree COM (FK:337-420): mass-weighted mean of the inertial frame origins of every link below the same root
+  float* mi = pb;  // scratch: m_l * ipos_w[l] (3 nL words) in the scan buffer that does not hold the result
+  for (int l = lane; l < nL; l += G) {
+    const f3 ipw = ld3(lpos, l) + rotate(f3(GM(l_ipos[l][0]), GM(l_ipos[l][1]), GM(l_ipos[l][2])), ld4(lquat, l));
+    st3(mi, l, ipw * GM(l_mass[l]));
+  }
+  C.sync();
+  float* rcom = IN(root_COM);
+  for (int l = lane; l < nL; l += G) {
+    const int r = GM(l_root[l]);
+    f3 s;
+    for (int k = 0; k < nL; k++)
+      if (CM(l_root[k]) == r) s += ld3(mi, k);
+    const float ms = GM(l_root_mass[r]);
+    f3 com;
+    if (ms > EPS) com = s / ms;
+    else com = ld3(lpos, r) + rotate(f3(GM(l_ipos[r][0]), GM(l_ipos[r][1]), GM(l_ipos[r][2])), ld4(lquat, r));
+    st3(rcom, l, com);
+  }
+  C.sync();
+  // ---- 4. c-frame inertia (geom.py:320-336) per link, motion subspaces per joint (FK:517-576)
+  for (int l = lane; l < nL; l += G) {
+    const f3 com = ld3(rcom, l);
+    const f4 quat = ld4(lquat, l);
+    const f3 ipos = ld3(lpos, l) + rotate(f3(GM(l_ipos[l][0]), GM(l_ipos[l][1]), GM(l_ipos[l][2])), quat) - com;
+    const f4 iquat = quat_compose(f4(GM(l_iquat[l][0]), GM(l_iquat[l][1]), GM(l_iquat[l][2]), GM(l_iquat[l][3])), quat);
+    const float mass = GM(l_mass[l]);
+    const mat3 R = quat_to_R(iquat, EPS);
+    float Iin[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) Iin[k] = GM(l_inertia[l][k]);
+    float RI[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int b = 0; b < 3; b++) RI[a][b] = R.m[a][0] * Iin[b] + R.m[a][1] * Iin[3 + b] + R.m[a][2] * Iin[6 + b];
+    sym3 I;
+    const float x = ipos.x, y = ipos.y, z = ipos.z;
+    I.xx = RI[0][0] * R.m[0][0] + RI[0][1] * R.m[0][1] + RI[0][2] * R.m[0][2] + (y * y + z * z) * mass;
+    I.xy = RI[0][0] * R.m[1][0] + RI[0][1] * R.m[1][1] + RI[0][2] * R.m[1][2] - x * y * mass;
+    I.xz = RI[0][0] * R.m[2][0] + RI[0][1] * R.m[2][1] + RI[0][2] * R.m[2][2] - x * z * mass;
+    I.yy = RI[1][0] * R.m[1][0] + RI[1][1] * R.m[1][1] + RI[1][2] * R.m[1][2] + (x * x + z * z) * mass;
+    I.yz = RI[1][0] * R.m[2][0] + RI[1][1] * R.m[2][1] + RI[1][2] * R.m[2][2] - y * z * mass;
+    I.zz = RI[2][0] * R.m[2][0] + RI[2][1] * R.m[2][1] + RI[2][2] * R.m[2][2] + (x * x + y * y) * mass;
+    st6(IN(cinr_I), l, I);
+    st3(IN(cinr_pos), l, ipos * mass);
+  }
+  float* cda = IN(cdof_ang);
+  float* cdv = IN(cdof_vel);
+  for (int j = lane; j < nJ; j += G) {
+    const int type = GM(j_type[j]), ds = GM(j_dof_start[j]);
+    if (type == JOINT_FIXED) continue;
+    const int l = GM(d_link[ds]);
+    const f3 off = ld3(rcom, l) - ld3(WK(xanchor), j);
+    const f3 xaxis = ld3(WK(xaxis), j);
+    if (type == JOINT_REVOLUTE) {
+      st3(cda, ds, xaxis); st3(cdv, ds, cross(xaxis, off));
+    } else if (type == JOINT_PRISMATIC) {
+      st3(cda, ds, f3()); st3(cdv, ds, xaxis);
+    } else {
+      const mat3 R = quat_to_R(ld4(lquat, l), EPS);
+      int o = ds;
+      if (type == JOINT_FREE) {
+        for (int k = 0; k < 3; k++) { f3 v; set_comp(v, k, 1.f); st3(cda, ds + k, f3()); st3(cdv, ds + k, v); }
+        o = ds + 3;
+      }
+      for (int k = 0; k < 3; k++) { const f3 a = mat_col(R, k); st3(cda, o + k, a); st3(cdv, o + k, cross(a, off)); }
+    }
+  }
+  C.sync();
+  // ---- 5. c-frame velocities (FK:993-1116): cd[l] = sum over the dofs on the path to the root; cdof_dot[d] = cvel x cdof[d]
+  // with cvel the velocity accumulated before joint(d)'s own dofs (after the translational dofs for a free joint).
+  for (int l = lane; l < nL; l += G) {
+    const unsigned long long mask = GM(l_dofmask[l]);
+    f3 vv, va;
+    for (int d = 0; d < nD; d++)
+      if (bit64(mask, d)) { const float w = vel[d]; vv += ld3(cdv, d) * w; va += ld3(cda, d) * w; }
+    st3(IN(cd_vel), l, vv); st3(IN(cd_ang), l, va);
+  }
+  for (int d = lane; d < nD; d += G) {
+    const int l = GM(d_link[d]), j = GM(d_joint[d]);
+    const int type = GM(j_type[j]), ds = GM(j_dof_start[j]);
+    const unsigned long long mask = GM(l_dofmask[l]);
+    int lim = ds;
+    if (type == JOINT_FREE && d >= ds + 3) lim = ds + 3;
+    f3 vv, va;
+    for (int k = 0; k < lim; k++)
+      if (bit64(mask, k)) { const float w = vel[k]; vv += ld3(cdv, k) * w; va += ld3(cda, k) * w; }
+    f3 da, dv;
+    if (!(type == JOINT_FREE && d < ds + 3)) {  // geom.py:379-383 motion_cross_motion(cvel, cdof)
+      const f3 a = ld3(cda, d), v = ld3(cdv, d);
+      da = cross(va, a);
+      dv = cross(va, v) + cross(vv, a);
+    }
+    st3(IN(cdofd_ang), d, da); st3(IN(cdofd_vel), d, dv);
+  }
+  C.sync();
+}
+
+// geom poses from link poses (FK:828-864) and world AABBs (FK:1297-1319) into the collision scratch
+template <int G>
+__device__ void phase_geoms(const Ctx<G>& C) {
+  const int nG = CM(nG);
+  float* gpos = WK(gpos);
+  float* gquat = WK(gquat);
+  float* aabb = WK(aabb);
+  for (int g = C.lane; g < nG; g += G) {
+    const int l = GM(g_link[g]);
+    const f3 lp = ld3(IN(links_pos), l);
+    const f4 lq = ld4(IN(links_quat), l);
+    const f3 gp = lp + rotate(f3(GM(g_pos[g][0]), GM(g_pos[g][1]), GM(g_pos[g][2])), lq);
+    const f4 gq = quat_compose(f4(GM(g_quat[g][0]), GM(g_quat[g][1]), GM(g_quat[g][2]), GM(g_quat[g][3])), lq);
+    st3(gpos, g, gp); st4(gquat, g, gq);
+    // the reference transforms the 8 corners of the rest-pose box and takes min / max; the identical box is
+    // centre +- |R| * half-extent
+    const mat3 R = quat_to_R(gq, 0.f);
+    const f3 lo(GM(g_aabb_lo[g][0]), GM(g_aabb_lo[g][1]), GM(g_aabb_lo[g][2])), hi(GM(g_aabb_hi[g][0]), GM(g_aabb_hi[g][1]), GM(g_aabb_hi[g][2]));
+    const f3 c = (lo + hi) * 0.5f, h = (hi - lo) * 0.5f;
+    const f3 wc(R.m[0][0] * c.x + R.m[0][1] * c.y + R.m[0][2] * c.z + gp.x, R.m[1][0] * c.x + R.m[1][1] * c.y + R.m[1][2] * c.z + gp.y,
+                R.m[2][0] * c.x + R.m[2][1] * c.y + R.m[2][2] * c.z + gp.z);
+    const f3 wh(fabsf(R.m[0][0]) * h.x + fabsf(R.m[0][1]) * h.y + fabsf(R.m[0][2]) * h.z,
+                fabsf(R.m[1][0]) * h.x + fabsf(R.m[1][1]) * h.y + fabsf(R.m[1][2]) * h.z,
+                fabsf(R.m[2][0]) * h.x + fabsf(R.m[2][1]) * h.y + fabsf(R.m[2][2]) * h.z);
+    st3(aabb, g, wc - wh); st3(aabb + 3 * nG, g, wc + wh);
+  }
+  C.sync();
+  // accessor-visible copies (get_AABB; geom poses are diagnostics): the scratch is recycled by the solver rows
+  float* o_min = C.rec + c_h.aabb_min;
+  float* o_max = C.rec + c_h.aabb_max;
+  for (int i = C.lane; i < 3 * nG; i += G) { o_min[i] = aabb[i]; o_max[i] = aabb[3 * nG + i]; }
+  if (CM(diagnostics)) {
+    float* o_p = C.rec + c_h.geoms_pos;
+    float* o_q = C.rec + c_h.geoms_quat;
+    for (int i = C.lane; i < 3 * nG; i += G) o_p[i] = gpos[i];
+    for (int i = C.lane; i < 4 * nG; i += G) o_q[i] = gquat[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// L^T D L solve (FD:813-894) of the vector x (shared memory, in place): x <- L^-1 D^-1 L^-T x
+// ---------------------------------------------------------------------------------------------------------------------
+template <int G>
+__device__ void mass_solve(const Ctx<G>& C, float* x) {
+  const int nD = CM(nD), MS = c_s.MS;
+  const float* L = WK(L);
+  const float* Dinv = WK(Dinv);
+  for (int j = nD - 1; j > 0; j--) {  // L^T w = y: once w_j is final, eliminate it from every i < j
+    const float xj = x[j];
+    for (int i = C.lane; i < j; i += G) x[i] -= L[j * MS + i] * xj;
+    C.sync();
+  }
+  for (int i = C.lane; i < nD; i += G) x[i] *= Dinv[i];
+  C.sync();
+  for (int j = 0; j < nD - 1; j++) {  // L x = z
+    const float xj = x[j];
+    for (int i = j + 1 + C.lane; i < nD; i += G) x[i] -= L[i * MS + j] * xj;
+    C.sync();
+  }
+}
+
+// FD:545-602 factor of the matrix stored in WK(L) (lower part), in place; D^-1 to WK(Dinv)
+template <int G>
+__device__ void mass_factor(const Ctx<G>& C) {
+  const int nD = CM(nD), MS = c_s.MS;
+  float* L = WK(L);
+  float* Dinv = WK(Dinv);
+  for (int i = nD - 1; i >= 0; i--) {
+    const float dinv = 1.0f / L[i * MS + i];
+    const int ntask = i * (i + 1) / 2;  // all (j, k) with k <= j < i
+    for (int t = C.lane; t < ntask; t += G) {
+      int j, k;
+      tri_decode(t, j, k);
+      L[j * MS + k] -= (L[i * MS + j] * dinv) * L[i * MS + k];
+    }
+    C.sync();
+    for (int j = C.lane; j < i; j += G) L[i * MS + j] *= dinv;
+    if (C.lane == 0) { Dinv[i] = dinv; L[i * MS + i] = 1.0f; }
+    C.sync();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Smooth dynamics (FD:146-227): CRBA, L^T D L, actuation, RNE bias, acc_smooth = M^-1 qf_smooth
+// ---------------------------------------------------------------------------------------------------------------------
+template <int G>
+__device__ void phase_dynamics(const Ctx<G>& C) {
+  const int nL = CM(nL), nD = CM(nD), MS = c_s.MS;
+  const float dt = CM(dt);
+  const int lane = C.lane;
+  const float* vel = IN(vel);
+  const float* cda = IN(cdof_ang);
+  const float* cdv = IN(cdof_vel);
+  // ---- composite rigid body inertia (FD:306-388): crb[l] = sum of cinr over the subtree of l (leaf-to-root order)
+  float* crb = WK(crb);
+  for (int l = lane; l < nL; l += G) {
+    float s[10];
+#pragma unroll
+    for (int k = 0; k < 10; k++) s[k] = 0.f;
+    for (int d = nL - 1; d >= l; d--)
+      if (bit64(CM(l_ancmask[d]), l)) {
+        const float* I = IN(cinr_I) + 6 * d;
+        const float* P = IN(cinr_pos) + 3 * d;
+#pragma unroll
+        for (int k = 0; k < 6; k++) s[k] += I[k];
+#pragma unroll
+        for (int k = 0; k < 3; k++) s[6 + k] += P[k];
+        s[9] += CM(l_mass[d]);
+      }
+#pragma unroll
+    for (int k = 0; k < 10; k++) crb[10 * l + k] = s[k];
+  }
+  C.sync();
+  // ---- f_d = crb[link(d)] * cdof_d (FD:390-430)
+  float* fdof = WK(fdof);
+  for (int d = lane; d < nD; d += G) {
+    const int l = GM(d_link[d]);
+    const float* c = crb + 10 * l;
+    sym3 I; I.xx = c[0]; I.xy = c[1]; I.xz = c[2]; I.yy = c[3]; I.yz = c[4]; I.zz = c[5];
+    f3 fa, fv;
+    inertial_mul(f3(c[6], c[7], c[8]), I, c[9], ld3(cdv, d), ld3(cda, d), fa, fv);
+    st3(fdof, 2 * d, fa); st3(fdof, 2 * d + 1, fv);
+  }
+  C.sync();
+  // ---- mass matrix (FD:432-541): M[i][j] = f_i . cdof_j for dof j on the path of dof i (lower triangle), mirrored
+  float* M = WK(M);
+  float* L = WK(L);
+  const int ntri = nD * (nD + 1) / 2;
+  const int* mode = C.SI() + c_h.ctrl_mode;
+  for (int t = lane; t < ntri; t += G) {
+    int i, j;
+    tri_decode(t, i, j);
+    float v = 0.f;
+    if (bit64(GM(l_dofmask[GM(d_link[i])]), j)) v = dot(ld3(fdof, 2 * i), ld3(cda, j)) + dot(ld3(fdof, 2 * i + 1), ld3(cdv, j));
+    if (i == j) {
+      v += GM(d_armature[i]);
+      if (CM(integrator) == INTEGRATOR_APPROX_IMPLICITFAST) {
+        v += GM(d_damping[i]) * dt;
+        if (mode[i] <= CTRL_VELOCITY) v -= GM(d_act_bias[i][2]) * dt;
+      }
+    }
+    M[i * MS + j] = v; M[j * MS + i] = v; L[i * MS + j] = v;
+  }
+  C.sync();
+  mass_factor(C);
+
+  // ---- actuation + passive forces (FD:956-1182)
+  float* qf_applied = WK(qf_applied);
+  float* qf_passive = WK(qf_passive);
+  const float* dofs_pos = IN(dofs_pos);
+  for (int d = lane; d < nD; d += G) {
+    const int j = GM(d_joint[d]);
+    const int jt = GM(j_type[j]), ds = GM(j_dof_start[j]);
+    const int md = mode[d];
+    const float v = vel[d], dp = dofs_pos[d];
+    const float kp = GM(d_kp[d]), b0 = GM(d_act_bias[d][0]), b1 = GM(d_act_bias[d][1]), b2 = GM(d_act_bias[d][2]);
+    float force = 0.f;
+    if (md == CTRL_FORCE) force = IN(ctrl_force)[d];
+    else if (md == CTRL_VELOCITY) force = -b2 * (IN(ctrl_vel)[d] - v);
+    else if (md == CTRL_POSITION) {
+      if (!(jt == JOINT_FREE && d >= ds + 3)) {
+        force = kp * (IN(ctrl_pos)[d] - dp) + b0 + (kp + b1) * dp + b2 * (v - IN(ctrl_vel)[d]);
+      }
+    }
+    if (jt == JOINT_FREE && d >= ds + 3 && (mode[ds + 3] == CTRL_POSITION || mode[ds + 4] == CTRL_POSITION || mode[ds + 5] == CTRL_POSITION)) {
+      // rotational PD of a free joint acts on the rotation-vector error (FD:1040-1090)
+      const f3 xyz(dofs_pos[ds + 3], dofs_pos[ds + 4], dofs_pos[ds + 5]);
+      const f3 cxyz(IN(ctrl_pos)[ds + 3], IN(ctrl_pos)[ds + 4], IN(ctrl_pos)[ds + 5]);
+      const f3 rv = quat_to_rotvec(quat_compose(xyz_to_quat(cxyz), quat_inv(xyz_to_quat(xyz))), CM(eps));
+      force = kp * comp(rv, d - ds - 3) + b0 + (kp + b1) * dp + b2 * (v - IN(ctrl_vel)[d]);
+    }
+    qf_applied[d] = fminf(fmaxf(force, GM(d_force_range[d][0])), GM(d_force_range[d][1]));
+    float passive = -GM(d_damping[d]) * v;
+    if (jt != JOINT_FREE && jt != JOINT_FIXED) passive += -dp * GM(d_stiffness[d]);
+    qf_passive[d] = passive;
+  }
+  // ---- RNE bias forces (FD:1186-1486)
+  float* cdd = WK(cdd);    // per link: vel3, ang3
+  float* cfrc = WK(cfrc);  // per link: vel3, ang3 (own contribution)
+  const f3 grav(CM(gravity[0]), CM(gravity[1]), CM(gravity[2]));
+  for (int l = lane; l < nL; l += G) {
+    const unsigned long long mask = GM(l_dofmask[l]);
+    f3 cdd_vel = -grav * (1.0f - GM(e_gravcomp[GM(l_entity[l])])), cdd_ang;
+    for (int d = 0; d < nD; d++)
+      if (bit64(mask, d)) { const float w = vel[d]; cdd_vel += ld3(IN(cdofd_vel), d) * w; cdd_ang += ld3(IN(cdofd_ang), d) * w; }
+    const sym3 I = ld6(IN(cinr_I), l);
+    const f3 ip = ld3(IN(cinr_pos), l);
+    const float mass = GM(l_mass[l]);
+    const f3 cv = ld3(IN(cd_vel), l), ca = ld3(IN(cd_ang), l);
+    f3 f1a, f1v, f2a, f2v;
+    inertial_mul(ip, I, mass, cdd_vel, cdd_ang, f1a, f1v);
+    inertial_mul(ip, I, mass, cv, ca, f2a, f2v);
+    const f3 f3v = cross(ca, f2v);  // geom.py:372-376 motion_cross_force
+    const f3 f3a = cross(ca, f2a) + cross(cv, f2v);
+    st3(cfrc, 2 * l, f1v + f3v + ld3(IN(cfrc_applied_vel), l));
+    st3(cfrc, 2 * l + 1, f1a + f3a + ld3(IN(cfrc_applied_ang), l));
+  }
+  C.sync();
+  for (int l = lane; l < nL; l += G) {  // subtree totals, leaf-to-root order (FD:1375-1400)
+    f3 sv, sa;
+    for (int d = nL - 1; d >= l; d--)
+      if (bit64(CM(l_ancmask[d]), l)) { sv += ld3(cfrc, 2 * d); sa += ld3(cfrc, 2 * d + 1); }
+    st3(cdd, 2 * l, sv); st3(cdd, 2 * l + 1, sa);
+  }
+  C.sync();
+  float* force = WK(force);
+  float* qf_bias = WK(qf_bias);
+  float* acc_smooth = WK(acc_smooth);
+  for (int d = lane; d < nD; d += G) {
+    const int l = GM(d_link[d]);
+    const float bias = dot(ld3(cda, d), ld3(cdd, 2 * l + 1)) + dot(ld3(cdv, d), ld3(cdd, 2 * l));
+    qf_bias[d] = bias;
+    const float f = qf_passive[d] - bias + qf_applied[d];
+    force[d] = f;
+    acc_smooth[d] = f;
+  }
+  C.sync();
+  mass_solve(C, acc_smooth);  // FD:1506-1563
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Integration (RS:2783-2891 kernel_step_2): link accelerations, implicit damping, semi-implicit Euler with NaN guard
+// ---------------------------------------------------------------------------------------------------------------------
+template <int G>
+__device__ void phase_integrate(const Ctx<G>& C) {
+  const int nL = CM(nL), nD = CM(nD), nQ = CM(nQ), MS = c_s.MS;
+  const float dt = CM(dt), EPS = CM(eps);
+  const int lane = C.lane;
+  float* vel = IN(vel);
+  float* qpos = IN(qpos);
+  float* acc = WK(acc);
+  // FD:1186-1285 update_acc(update_cacc=True): link accelerations from the constrained acceleration
+  float* cacc = WK(cacc);
+  for (int l = lane; l < nL; l += G) {
+    const unsigned long long mask = GM(l_dofmask[l]);
+    f3 lin, ang;
+    for (int d = 0; d < nD; d++)
+      if (bit64(mask, d)) {
+        const float v = vel[d], a = acc[d];
+        lin += ld3(IN(cdofd_vel), d) * v + ld3(IN(cdof_vel), d) * a;
+        ang += ld3(IN(cdofd_ang), d) * v + ld3(IN(cdof_ang), d) * a;
+      }
+    st3(cacc, 2 * l, lin); st3(cacc, 2 * l + 1, ang);
+  }
+  if (CM(integrator) != INTEGRATOR_APPROX_IMPLICITFAST) {
+    // FD:1787-1859 func_implicit_damping: refactor M + dt (damping - d act / d vel) and re-solve acc = M'^-1 force
+    const int* mode = C.SI() + c_h.ctrl_mode;
+    auto dof_damped = [&](int k) {
+      return CM(d_damping[k]) > EPS || (CM(integrator) != INTEGRATOR_EULER && mode[k] <= CTRL_VELOCITY && fabsf(CM(d_act_bias[k][2])) > EPS);
+    };
+    // the reference refactors entity by entity and skips entities without damping / velocity-dependent actuation (FD:1806-1832)
+    auto ent_active = [&](int e) {
+      bool a = false;
+      for (int k = 0; k < nD; k++)
+        if (CM(d_entity[k]) == e && dof_damped(k)) a = true;
+      return a;
+    };
+    bool need = false;
+    for (int d = 0; d < nD; d++) need |= dof_damped(d);
+    if (need) {
+      float* L = WK(L);
+      const float* M = WK(M);
+      const int ntri = nD * (nD + 1) / 2;
+      C.sync();
+      for (int t = lane; t < ntri; t += G) {
+        int i, j;
+        tri_decode(t, i, j);
+        float v = M[i * MS + j];
+        if (i == j && ent_active(GM(d_entity[i]))) {
+          v += GM(d_damping[i]) * dt;
+          if (CM(integrator) == INTEGRATOR_IMPLICITFAST && mode[i] <= CTRL_VELOCITY) v -= GM(d_act_bias[i][2]) * dt;
+        }
+        L[i * MS + j] = v;
+      }
+      C.sync();
+      mass_factor(C);
+      float* x = WK(vel_next);  // scratch (the next velocity is formed below)
+      const float* force = WK(force);
+      for (int d = lane; d < nD; d += G) x[d] = force[d];
+      C.sync();
+      mass_solve(C, x);
+      for (int d = lane; d < nD; d += G)
+        if (ent_active(GM(d_entity[d]))) acc[d] = x[d];
+    }
+  }
+  C.sync();
+  // FD:1566-1707 func_integrate + diff.py:25-54 (commit only if finite)
+  float* vn = WK(vel_next);
+  float* qn = WK(qpos_next);
+  bool bad = false;
+  for (int d = lane; d < nD; d += G) { const float v = vel[d] + acc[d] * dt; vn[d] = v; bad |= isnan(v); }
+  C.sync();
+  for (int l = lane; l < nL; l += G) {
+    const int ds = GM(l_dof_start[l]), de = GM(l_dof_end[l]), qs = GM(l_q_start[l]), qe = GM(l_q_end[l]);
+    if (de - ds <= 0) continue;
+    const int jt = GM(j_type[GM(l_joint_start[l])]);
+    if (jt == JOINT_FREE)
+      for (int k = 0; k < 3; k++) qn[qs + k] = qpos[qs + k] + vn[ds + k] * dt;
+    if (jt == JOINT_FREE || jt == JOINT_SPHERICAL) {
+      const int ro = jt == JOINT_FREE ? 3 : 0;
+      const f4 rot0(qpos[qs + ro], qpos[qs + ro + 1], qpos[qs + ro + 2], qpos[qs + ro + 3]);
+      const f3 ang = f3(vn[ds + ro], vn[ds + ro + 1], vn[ds + ro + 2]) * dt;
+      const f4 rot = quat_compose(rotvec_to_quat(ang, EPS), rot0);
+      qn[qs + ro] = rot.w; qn[qs + ro + 1] = rot.x; qn[qs + ro + 2] = rot.y; qn[qs + ro + 3] = rot.z;
+    } else {
+      for (int k = 0; k < qe - qs; k++) qn[qs + k] = qpos[qs + k] + vn[ds + k] * dt;
+    }
+  }
+  C.sync();
+  for (int q = lane; q < nQ; q += G) bad |= isnan(qn[q]);
+  const bool invalid = C.any(bad);
+  if (invalid) {
+    if (lane == 0) C.SI()[c_h.errno_] |= ERR_NAN_ACC;
+  } else {
+    for (int d = lane; d < nD; d += G) vel[d] = vn[d];
+    for (int q = lane; q < nQ; q += G) qpos[q] = qn[q];
+  }
+  C.sync();
+}

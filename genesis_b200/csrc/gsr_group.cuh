@@ -1,0 +1,72 @@
+// gsr_group.cuh -- lane-group primitives and shared-memory accessors of the group-per-environment kernels.
+#pragma once
+#include "gsr_types.h"
+#include "gsr_math.cuh"
+
+__constant__ DevModel c_m;     // warp-uniform reads (scalars, loop bounds, tables indexed by a uniform loop variable)
+__constant__ HotLayout c_h;
+__constant__ SmemLayout c_s;
+
+// Lane-varying table reads go to a global-memory copy of the model (read-only path, L1 resident): constant memory
+// serialises divergent addresses.
+#define CM(x) (c_m.x)
+#define GM(x) (__ldg(&(C.gm->x)))
+
+template <int G>
+struct Ctx {
+  float* S;            // this env's shared-memory workspace
+  float* rec;          // this env's HOT record (global)
+  float* contacts;     // this env's CONTACT records (global)
+  float* cache;        // this env's CACHE record (global)
+  float* spill;        // this env's SPILL record (global)
+  const DevModel* gm;  // global-memory copy of the model
+  int lane;            // lane index inside the group
+  unsigned gmask;      // warp lanes that belong to this group
+
+  __device__ __forceinline__ void sync() const { __syncwarp(gmask); }
+  __device__ __forceinline__ float sum(float v) const {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o, G);
+    return v;
+  }
+  __device__ __forceinline__ int isum(int v) const {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o, G);
+    return v;
+  }
+  // ballot restricted to the group, bit i = lane i of the group
+  __device__ __forceinline__ unsigned ballot(bool p) const {
+    const unsigned b = __ballot_sync(gmask, p);
+    if (G == 32) return b;
+    const int shift = (threadIdx.x & 31) - lane;
+    return (b >> shift) & ((1u << (G & 31)) - 1u);
+  }
+  __device__ __forceinline__ bool any(bool p) const { return ballot(p) != 0u; }
+  __device__ __forceinline__ int* SI() const { return reinterpret_cast<int*>(S); }
+};
+
+__device__ __forceinline__ f3 ld3(const float* p, int i) { return f3(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
+__device__ __forceinline__ void st3(float* p, int i, f3 v) { p[3 * i] = v.x; p[3 * i + 1] = v.y; p[3 * i + 2] = v.z; }
+__device__ __forceinline__ f4 ld4(const float* p, int i) { return f4(p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]); }
+__device__ __forceinline__ void st4(float* p, int i, f4 v) { p[4 * i] = v.w; p[4 * i + 1] = v.x; p[4 * i + 2] = v.y; p[4 * i + 3] = v.z; }
+__device__ __forceinline__ sym3 ld6(const float* p, int i) {
+  sym3 r; r.xx = p[6 * i]; r.xy = p[6 * i + 1]; r.xz = p[6 * i + 2]; r.yy = p[6 * i + 3]; r.yz = p[6 * i + 4]; r.zz = p[6 * i + 5];
+  return r;
+}
+__device__ __forceinline__ void st6(float* p, int i, const sym3& v) {
+  p[6 * i] = v.xx; p[6 * i + 1] = v.xy; p[6 * i + 2] = v.xz; p[6 * i + 3] = v.yy; p[6 * i + 4] = v.yz; p[6 * i + 5] = v.zz;
+}
+__device__ __forceinline__ f3 g3(const float* p) { return f3(__ldg(p), __ldg(p + 1), __ldg(p + 2)); }
+__device__ __forceinline__ f4 g4(const float* p) { return f4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3)); }
+__device__ __forceinline__ bool bit64(unsigned long long m, int i) { return (m >> i) & 1ull; }
+
+// lower-triangle task decode: t = i (i + 1) / 2 + j, j <= i
+__device__ __forceinline__ void tri_decode(int t, int& i, int& j) {
+  i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+  while ((i + 1) * (i + 2) / 2 <= t) i++;
+  while (i * (i + 1) / 2 > t) i--;
+  j = t - i * (i + 1) / 2;
+}
+
+#define IN(field) (C.S + c_h.field)   // IN part of the record, mirrored in shared memory
+#define WK(field) (C.S + c_s.field)   // workspace regions

@@ -1,0 +1,618 @@
+// gsr_solver.cuh -- constraint rows and the Newton / CG solver of one environment by one lane group.
+//
+// Rows live in shared memory (J[NCS][JS] plus eight per-row scalars) and never touch HBM; an environment with more rows
+// than the on-chip capacity runs the same code on its SPILL record in global memory (generic pointers).  Lane mapping:
+//   row assembly : one lane per (contact, dof) Jacobian task / per row for the scalar parameters
+//   J v, J^T f   : one lane per row / per dof
+//   H = M + J^T D J : one lane per lower-triangle entry, Cholesky column by column with the rows of a column on the lanes
+//   line search  : one lane per row for the piecewise-quadratic sums, butterfly reductions give every lane the same
+//                  totals so the control flow of the exact line search stays uniform inside the group
+// Semantics follow the reference's monolith solver body (CS:2033-3261), which is what `gs.cpu` runs.
+#pragma once
+#include "gsr_group.cuh"
+#include "gsr_dynamics.cuh"
+
+struct Rows {
+  float* J; int JS;
+  float *aref, *D, *R, *floss, *Jaref, *jv, *force;
+  int* active;
+  const float* ct;  // contact records (16 words each)
+  int n_con, ne, nef;
+};
+
+struct SolverState {
+  float cost, prev_cost, gauss;
+  float qg0, qg1, qg2, es0, es1, es2;
+  int ls_it;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Row assembly (CS:579-1286), row order [equality | frictionloss | 4 x contacts | joint limits]
+// ---------------------------------------------------------------------------------------------------------------------
+template <int G>
+__device__ void build_rows(const Ctx<G>& C, Rows& R) {
+  const int nD = CM(nD), nJ = CM(nJ), lane = C.lane;
+  const float EPS = CM(eps);
+  const float* qpos = IN(qpos);
+  const float* vel = IN(vel);
+  const int n_contacts = CM(enable_collision) ? C.SI()[c_h.n_contacts] : 0;
+  // ---- static counts: equality rows and friction-loss rows
+  int n_eq = 0;
+  for (int i = 0; i < CM(nEq); i++) n_eq += CM(eq_type[i]) == EQ_JOINT ? 1 : (CM(eq_type[i]) == EQ_CONNECT ? 3 : 0);
+  int n_floss = 0;
+  for (int d = 0; d < nD; d++) n_floss += CM(d_frictionloss[d]) > EPS ? 1 : 0;
+  // ---- joint limits that are violated (CS:1176-1233), in joint order
+  int n_lim = 0;
+  const int lim_base = n_eq + n_floss + 4 * n_contacts;
+  // first pass only counts, second pass (below) fills once the storage is chosen
+  if (CM(enable_joint_limit)) {
+    for (int base = 0; base < nJ; base += G) {
+      const int j = base + lane;
+      bool viol = false;
+      if (j < nJ) {
+        const int type = GM(j_type[j]);
+        if (type == JOINT_REVOLUTE || type == JOINT_PRISMATIC) {
+          const int q = GM(j_q_start[j]), d = GM(j_dof_start[j]);
+          const float qv = qpos[q];
+          viol = fminf(qv - GM(d_limit[d][0]), GM(d_limit[d][1]) - qv) < 0.f;
+        }
+      }
+      n_lim += __popc(C.ballot(viol));
+    }
+  }
+  const int n_con = lim_base + n_lim;
+  R.n_con = n_con; R.ne = n_eq; R.nef = n_eq + n_floss;
+  // ---- storage: shared memory when the rows fit, the SPILL record otherwise
+  const int NCS = c_s.NCS, lenC = CM(len_constraints);
+  R.JS = c_s.JS;
+  if (n_con <= NCS) {
+    R.J = WK(J);
+    R.aref = WK(r_aref); R.D = WK(r_D); R.R = WK(r_R); R.floss = WK(r_floss); R.Jaref = WK(r_Jaref); R.jv = WK(r_jv);
+    R.force = WK(r_force); R.active = reinterpret_cast<int*>(WK(r_active));
+  } else {
+    float* sp = C.spill;
+    R.J = sp; sp += (size_t)lenC * R.JS;
+    R.aref = sp; sp += lenC; R.D = sp; sp += lenC; R.R = sp; sp += lenC; R.floss = sp; sp += lenC; R.Jaref = sp; sp += lenC;
+    R.jv = sp; sp += lenC; R.force = sp; sp += lenC; R.active = reinterpret_cast<int*>(sp);
+  }
+  R.ct = (n_contacts <= c_s.NCC) ? WK(contacts) : C.contacts;
+  if (n_con == 0) return;
+  float* J = R.J;
+  const int JS = R.JS;
+  // ---- zero the non-contact rows
+  for (int t = lane; t < (R.nef + n_lim) * nD; t += G) {
+    int r = t / nD;
+    const int d = t - r * nD;
+    if (r >= R.nef) r = lim_base + (r - R.nef);
+    J[r * JS + d] = 0.f;
+  }
+  C.sync();
+  // ---- equalities (CS:880-937)
+  int row = 0;
+  for (int i = 0; i < CM(nEq); i++) {
+    if (CM(eq_type[i]) == EQ_JOINT) {  // CS:800-877
+      if (lane == 0) {
+        const int j1 = CM(eq_obj1[i]), j2 = CM(eq_obj2[i]);
+        const int q1 = CM(j_q_start[j1]), q2 = CM(j_q_start[j2]), d1 = CM(j_dof_start[j1]), d2 = CM(j_dof_start[j2]);
+        const float diff = qpos[q2] - CM(qpos0[q2]);
+        float pos = qpos[q1] - CM(qpos0[q1]), deriv = 0.f, dp = 1.f;
+        for (int k = 0; k < 5; k++) {
+          pos -= dp * CM(eq_data[i][k]);
+          if (k < 4) deriv += CM(eq_data[i][k + 1]) * dp * (float)(k + 1);
+          dp *= diff;
+        }
+        J[row * JS + d1] = 1.0f;
+        J[row * JS + d2] = -deriv;
+        const float jac_qvel = vel[d1] + (-deriv) * vel[d2];
+        const float invweight = CM(d_invweight[d1]) + CM(d_invweight[d2]);
+        float imp, aref;
+        imp_aref(CM(eq_sol[i]), -fabsf(pos), jac_qvel, pos, imp, aref);
+        const float diag = fmaxf(invweight * (1.0f - imp) / imp, EPS);
+        R.R[row] = diag; R.aref[row] = aref; R.D[row] = 1.0f / diag; R.floss[row] = 0.f;
+      }
+      row += 1;
+    } else if (CM(eq_type[i]) == EQ_CONNECT) {  // CS:688-797
+      const int l1 = CM(eq_obj1[i]), l2 = CM(eq_obj2[i]);
+      const f3 g1 = transform(f3(CM(eq_data[i][0]), CM(eq_data[i][1]), CM(eq_data[i][2])), ld3(IN(links_pos), l1), ld4(IN(links_quat), l1));
+      const f3 g2 = transform(f3(CM(eq_data[i][3]), CM(eq_data[i][4]), CM(eq_data[i][5])), ld3(IN(links_pos), l2), ld4(IN(links_quat), l2));
+      const f3 t1 = g1 - ld3(IN(root_COM), l1), t2 = g2 - ld3(IN(root_COM), l2);
+      const unsigned long long m1 = CM(l_dofmask[l1]), m2 = CM(l_dofmask[l2]);
+      for (int d = lane; d < nD; d += G) {
+        f3 v;
+        if (bit64(m1, d)) v += ld3(IN(cdof_vel), d) - cross(t1, ld3(IN(cdof_ang), d));
+        if (bit64(m2, d)) v -= ld3(IN(cdof_vel), d) - cross(t2, ld3(IN(cdof_ang), d));
+        J[row * JS + d] = v.x; J[(row + 1) * JS + d] = v.y; J[(row + 2) * JS + d] = v.z;
+      }
+      C.sync();
+      if (lane < 3) {
+        float jac_qvel = 0.f;
+        for (int d = 0; d < nD; d++) jac_qvel += J[(row + lane) * JS + d] * vel[d];
+        const f3 pd = g1 - g2;
+        const float invweight = CM(l_invweight[l1]) + CM(l_invweight[l2]);
+        float imp, aref;
+        imp_aref(CM(eq_sol[i]), -norm(pd), jac_qvel, comp(pd, lane), imp, aref);
+        const float diag = fmaxf(invweight * (1.0f - imp) / imp, EPS);
+        R.R[row + lane] = diag; R.aref[row + lane] = aref; R.D[row + lane] = 1.0f / diag; R.floss[row + lane] = 0.f;
+      }
+      row += 3;
+    }
+  }
+  // ---- frictionloss (CS:1236-1286), static rows in dof order
+  if (n_floss > 0 && lane == 0) {
+    int r = n_eq;
+    for (int d = 0; d < nD; d++)
+      if (CM(d_frictionloss[d]) > EPS) {
+        float imp, aref;
+        imp_aref(CM(j_sol[CM(d_joint[d])]), 0.f, vel[d], 0.f, imp, aref);
+        const float diag = fmaxf(CM(d_invweight[d]) * (1.0f - imp) / imp, EPS);
+        R.R[r] = diag; R.aref[r] = aref; R.D[r] = 1.0f / diag; R.floss[r] = CM(d_frictionloss[d]);
+        J[r * JS + d] = 1.0f;
+        r++;
+      }
+  }
+  // ---- contacts (CS:579-685): pyramidal friction, 4 rows per contact; one lane per (contact, dof) entry
+  const int c_base = R.nef;
+  for (int t = lane; t < n_contacts * nD; t += G) {
+    const int ic = t / nD, d = t - ic * nD;
+    const float* ct = R.ct + (size_t)ic * GSR_CONTACT_WORDS;
+    const int la = __float_as_int(ct[CT_LA]), lb = __float_as_int(ct[CT_LB]);
+    const f3 cpos(ct[CT_POS], ct[CT_POS + 1], ct[CT_POS + 2]), cn(ct[CT_NRM], ct[CT_NRM + 1], ct[CT_NRM + 2]);
+    const float mu = ct[CT_MU];
+    f3 d1, d2;
+    orthogonals(cn, d1, d2);
+    f3 diff;
+    const f3 cv = ld3(IN(cdof_vel), d), ca = ld3(IN(cdof_ang), d);
+    if (bit64(GM(l_dofmask[la]), d)) diff -= cv - cross(cpos - ld3(IN(root_COM), la), ca);
+    if (lb > -1 && bit64(GM(l_dofmask[lb]), d)) diff += cv - cross(cpos - ld3(IN(root_COM), lb), ca);
+    const int c0 = c_base + 4 * ic;
+    J[c0 * JS + d] = dot(diff, d1 * (-mu) - cn);
+    J[(c0 + 1) * JS + d] = dot(diff, d1 * mu - cn);
+    J[(c0 + 2) * JS + d] = dot(diff, d2 * (-mu) - cn);
+    J[(c0 + 3) * JS + d] = dot(diff, d2 * mu - cn);
+  }
+  C.sync();
+  for (int r = lane; r < 4 * n_contacts; r += G) {
+    const int ic = r >> 2, c = c_base + r;
+    const float* ct = R.ct + (size_t)ic * GSR_CONTACT_WORDS;
+    const int la = __float_as_int(ct[CT_LA]), lb = __float_as_int(ct[CT_LB]);
+    const int ga = __float_as_int(ct[CT_GA]), gb = __float_as_int(ct[CT_GB]);
+    const float mu = ct[CT_MU], pen = ct[CT_PEN];
+    float jac_qvel = 0.f;
+    for (int d = 0; d < nD; d++) jac_qvel += J[c * JS + d] * vel[d];
+    float sol[7];
+#pragma unroll
+    for (int k = 0; k < 7; k++) sol[k] = 0.5f * (GM(g_sol[ga][k]) + GM(g_sol[gb][k]));
+    float invweight = GM(l_invweight[la]);
+    if (lb > -1) invweight += GM(l_invweight[lb]);
+    float imp, aref;
+    imp_aref(sol, -pen, jac_qvel, -pen, imp, aref);
+    float diag = invweight + mu * mu * invweight;
+    diag *= 2.f * mu * mu * (1.0f - imp) / imp;
+    diag = fmaxf(diag, EPS);
+    R.R[c] = diag; R.aref[c] = aref; R.D[c] = 1.0f / diag; R.floss[c] = 0.f;
+  }
+  // ---- joint limits (CS:1176-1233): ordered compaction of the violated joints
+  if (CM(enable_joint_limit) && n_lim > 0) {
+    int r0 = lim_base;
+    for (int base = 0; base < nJ; base += G) {
+      const int j = base + lane;
+      bool viol = false;
+      int d = 0;
+      float pmin = 0.f, pmax = 0.f;
+      if (j < nJ) {
+        const int type = GM(j_type[j]);
+        if (type == JOINT_REVOLUTE || type == JOINT_PRISMATIC) {
+          const int q = GM(j_q_start[j]);
+          d = GM(j_dof_start[j]);
+          const float qv = qpos[q];
+          pmin = qv - GM(d_limit[d][0]); pmax = GM(d_limit[d][1]) - qv;
+          viol = fminf(pmin, pmax) < 0.f;
+        }
+      }
+      const unsigned bal = C.ballot(viol);
+      if (viol) {
+        const int c = r0 + __popc(bal & ((1u << lane) - 1u));
+        const float pd = fminf(pmin, pmax);
+        const float jac = pmin < pmax ? 1.f : -1.f;
+        float sol[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) sol[k] = GM(j_sol[j][k]);
+        float imp, aref;
+        imp_aref(sol, pd, jac * vel[d], pd, imp, aref);
+        const float diag = fmaxf(GM(d_invweight[d]) * (1.0f - imp) / imp, EPS);
+        R.R[c] = diag; R.aref[c] = aref; R.D[c] = 1.0f / diag; R.floss[c] = 0.f;
+        J[c * JS + d] = jac;
+      }
+      r0 += __popc(bal);
+    }
+  }
+  C.sync();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Solver pieces
+// ---------------------------------------------------------------------------------------------------------------------
+// CS:2619-2694 func_update_constraint_batch
+template <int G>
+__device__ void update_constraint(const Ctx<G>& C, const Rows& R, SolverState& X, bool track_prev) {
+  const int nD = CM(nD), lane = C.lane;
+  X.prev_cost = X.cost;
+  float cost = 0.f;
+  for (int c = lane; c < R.n_con; c += G) {
+    const float Ja = R.Jaref[c], D = R.D[c];
+    const int prev = R.active[c] & 1;
+    int act = 1;
+    float floss_force = 0.f;
+    if (R.ne <= c && c < R.nef) {
+      const float f = R.floss[c], rf = R.R[c] * f;
+      const bool ln = Ja <= -rf, lp = Ja >= rf;
+      act = !(ln || lp);
+      floss_force = (ln ? f : 0.f) + (lp ? -f : 0.f);
+      cost += (ln ? f * (-0.5f * rf - Ja) : 0.f) + (lp ? f * (-0.5f * rf + Ja) : 0.f);
+    } else if (R.nef <= c) {
+      act = Ja < 0.f;
+    }
+    R.active[c] = act | (track_prev ? (prev << 1) : (act << 1));
+    R.force[c] = floss_force + (-Ja * D * (float)act);
+    cost += 0.5f * (Ja * Ja * D * (float)act);
+  }
+  C.sync();
+  float gauss = 0.f;
+  float* qfrc = WK(qfrc_c);
+  for (int d = lane; d < nD; d += G) {
+    float q = 0.f;
+    for (int c = 0; c < R.n_con; c++) q += R.J[c * R.JS + d] * R.force[c];
+    qfrc[d] = q;
+    gauss += 0.5f * (WK(Ma)[d] - WK(force)[d]) * (WK(qacc)[d] - WK(acc_smooth)[d]);
+  }
+  X.gauss = C.sum(gauss);
+  X.cost = C.sum(cost) + X.gauss;
+  C.sync();
+}
+
+// CS:1394-1452 + CS:1594-1621: H = M + J^T (D active) J (lower), then in-place Cholesky
+template <int G>
+__device__ void hessian_cholesky(const Ctx<G>& C, const Rows& R) {
+  const int nD = CM(nD), MS = c_s.MS, lane = C.lane;
+  const float EPS = CM(eps);
+  float* H = WK(H);
+  const float* M = WK(M);
+  const int ntri = nD * (nD + 1) / 2;
+  for (int t = lane; t < ntri; t += G) {
+    int i, j;
+    tri_decode(t, i, j);
+    float s = 0.f;
+    for (int c = 0; c < R.n_con; c++)
+      if (R.active[c] & 1) s += R.J[c * R.JS + j] * (R.J[c * R.JS + i] * R.D[c]);
+    H[i * MS + j] = s + M[i * MS + j];
+  }
+  C.sync();
+  for (int i = 0; i < nD; i++) {
+    float part = 0.f;
+    for (int k = lane; k < i; k += G) { const float h = H[i * MS + k]; part += h * h; }
+    const float tmp = H[i * MS + i] - C.sum(part);
+    const float Lii = sqrtf(fmaxf(tmp, EPS));
+    const float inv = 1.0f / Lii;
+    for (int j = i + 1 + lane; j < nD; j += G) {
+      float dt = 0.f;
+      for (int k = 0; k < i; k++) dt += H[j * MS + k] * H[i * MS + k];
+      H[j * MS + i] = (H[j * MS + i] - dt) * inv;
+    }
+    C.sync();
+    if (lane == 0) H[i * MS + i] = Lii;
+    C.sync();
+  }
+}
+
+// CS:1763-1822 rank-1 Cholesky up / down-dates for the rows whose active flag flipped; true when degenerate
+template <int G>
+__device__ bool hessian_incremental(const Ctx<G>& C, const Rows& R) {
+  const int nD = CM(nD), MS = c_s.MS, lane = C.lane;
+  const float EPS = CM(eps);
+  float* H = WK(H);
+  float* vec = WK(prev_grad);  // scratch (the CG history is unused by the Newton solver)
+  for (int base = 0; base < R.n_con; base += G) {
+    const int cl = base + lane;
+    const int a = cl < R.n_con ? R.active[cl] : 0;
+    unsigned bal = C.ballot(((a ^ (a >> 1)) & 1) != 0);
+    while (bal) {
+      const int b = __ffs(bal) - 1;
+      bal &= bal - 1;
+      const int c = base + b;
+      const float sign = (R.active[c] & 1) ? 1.f : -1.f;
+      const float sq = sqrtf(R.D[c]);
+      C.sync();
+      for (int d = lane; d < nD; d += G) vec[d] = R.J[c * R.JS + d] * sq;
+      for (int k = 0; k < nD; k++) {
+        C.sync();
+        const float vk = vec[k];
+        if (fabsf(vk) > EPS) {
+          const float Lkk = H[k * MS + k];
+          const float tmp = Lkk * Lkk + sign * vk * vk;
+          if (tmp < EPS) return true;
+          const float r = sqrtf(tmp), cc = r / Lkk, cinv = 1.0f / cc, s = vk / Lkk;
+          for (int i = k + 1 + lane; i < nD; i += G) {
+            const float Lik = (H[i * MS + k] + s * vec[i] * sign) * cinv;
+            H[i * MS + k] = Lik;
+            vec[i] = vec[i] * cc - s * Lik;
+          }
+          C.sync();
+          if (lane == 0) H[k * MS + k] = r;
+        }
+      }
+    }
+  }
+  C.sync();
+  return false;
+}
+
+// CS:2721-2750 gradient and preconditioned gradient (Newton: Cholesky solve CS:1892-1910; CG: M^-1 via L^T D L)
+template <int G>
+__device__ void update_gradient(const Ctx<G>& C) {
+  const int nD = CM(nD), MS = c_s.MS, lane = C.lane;
+  float* grad = WK(grad);
+  float* Mgrad = WK(Mgrad);
+  for (int d = lane; d < nD; d += G) { const float g = WK(Ma)[d] - WK(force)[d] - WK(qfrc_c)[d]; grad[d] = g; Mgrad[d] = g; }
+  C.sync();
+  if (CM(solver_type) == SOLVER_CG) {
+    mass_solve(C, Mgrad);
+  } else {
+    const float* H = WK(H);
+    for (int i = 0; i < nD; i++) {  // forward substitution, column oriented
+      const float xi = Mgrad[i] / H[i * MS + i];
+      C.sync();
+      if (lane == 0) Mgrad[i] = xi;
+      for (int j = i + 1 + lane; j < nD; j += G) Mgrad[j] -= H[j * MS + i] * xi;
+      C.sync();
+    }
+    for (int i = nD - 1; i >= 0; i--) {  // backward substitution
+      const float xi = Mgrad[i] / H[i * MS + i];
+      C.sync();
+      if (lane == 0) Mgrad[i] = xi;
+      for (int j = lane; j < i; j += G) Mgrad[j] -= H[i * MS + j] * xi;
+      C.sync();
+    }
+  }
+}
+
+struct LsPoint { float alpha, cost, d0, d1; };
+
+// CS:2154-2354 the piecewise-quadratic cost and its derivatives at step `alpha`
+template <int G>
+__device__ LsPoint ls_eval(const Ctx<G>& C, const Rows& R, const SolverState& X, float alpha) {
+  float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+  for (int c = R.ne + C.lane; c < R.n_con; c += G) {
+    const float Ja = R.Jaref[c], jv = R.jv[c], D = R.D[c];
+    const float x = Ja + alpha * jv;
+    if (c < R.nef) {
+      const float f = R.floss[c], rf = R.R[c] * f;
+      const bool ln = x <= -rf, lp = x >= rf;
+      if (ln || lp) {
+        t0 += (ln ? f * (-0.5f * rf - Ja) : 0.f) + (lp ? f * (-0.5f * rf + Ja) : 0.f);
+        t1 += (ln ? -f * jv : 0.f) + (lp ? f * jv : 0.f);
+      } else {
+        t0 += D * (0.5f * Ja * Ja); t1 += D * (jv * Ja); t2 += D * (0.5f * jv * jv);
+      }
+    } else if (x < 0.f) {
+      t0 += D * (0.5f * Ja * Ja); t1 += D * (jv * Ja); t2 += D * (0.5f * jv * jv);
+    }
+  }
+  t0 = C.sum(t0) + X.qg0 + X.es0; t1 = C.sum(t1) + X.qg1 + X.es1; t2 = C.sum(t2) + X.qg2 + X.es2;
+  LsPoint p;
+  p.alpha = alpha;
+  p.cost = alpha * alpha * t2 + alpha * t1 + t0;
+  p.d0 = 2.f * alpha * t2 + t1;
+  p.d1 = 2.f * t2;
+  if (p.d1 <= 0.f) p.d1 = CM(eps);
+  return p;
+}
+// CS:2357-2388
+__device__ __forceinline__ int update_bracket(LsPoint& p, const LsPoint* cand, float& next_alpha) {
+  int flag = 0;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    if (p.d0 < 0.f && cand[i].d0 < 0.f && p.d0 < cand[i].d0) { p = cand[i]; flag = 1; }
+    else if (p.d0 > 0.f && cand[i].d0 > 0.f && p.d0 > cand[i].d0) { p = cand[i]; flag = 2; }
+  }
+  next_alpha = p.alpha;
+  if (flag > 0) next_alpha = p.alpha - p.d0 / p.d1;
+  return flag;
+}
+
+// CS:2426-2597 func_linesearch_batch (includes CS:2033-2151 init + alpha = 0 evaluation)
+template <int G>
+__device__ float linesearch(const Ctx<G>& C, const Rows& R, SolverState& X) {
+  const int nD = CM(nD), MS = c_s.MS, lane = C.lane;
+  const float EPS = CM(eps);
+  const float* search = WK(search);
+  const float* M = WK(M);
+  float* mv = WK(mv);
+  float sn = 0.f, qg1 = 0.f, qg2 = 0.f;
+  for (int i = lane; i < nD; i += G) {
+    const float s = search[i];
+    sn += s * s;
+    float m = 0.f;
+    for (int j = 0; j < nD; j++) m += M[i * MS + j] * search[j];
+    mv[i] = m;
+    qg1 += s * WK(Ma)[i] - s * WK(force)[i];
+    qg2 += 0.5f * s * m;
+  }
+  const float snorm = sqrtf(C.sum(sn));
+  const float gtol = CM(tolerance) * CM(ls_tolerance) * snorm * (CM(meaninertia) * (float)max(1, nD));
+  X.ls_it = 0;
+  if (snorm < EPS) return 0.f;
+  X.qg0 = X.gauss; X.qg1 = C.sum(qg1); X.qg2 = C.sum(qg2);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  for (int c = lane; c < R.n_con; c += G) {
+    float jv = 0.f;
+    for (int d = 0; d < nD; d++) jv += R.J[c * R.JS + d] * search[d];
+    R.jv[c] = jv;
+    if (c < R.ne) {
+      const float Ja = R.Jaref[c], D = R.D[c];
+      s0 += D * (0.5f * Ja * Ja); s1 += D * (jv * Ja); s2 += D * (0.5f * jv * jv);
+    }
+  }
+  X.es0 = C.sum(s0); X.es1 = C.sum(s1); X.es2 = C.sum(s2);
+  C.sync();
+  const int ls_iterations = CM(ls_iterations);
+  const LsPoint p0 = ls_eval(C, R, X, 0.f);
+  X.ls_it = 1;
+  LsPoint p1 = ls_eval(C, R, X, p0.alpha - p0.d0 / p0.d1);
+  X.ls_it++;
+  if (p0.cost < p1.cost) p1 = p0;
+  if (fabsf(p1.d0) < gtol) return p1.alpha;
+  const float direction = p1.d0 < 0.f ? 1.f : -1.f;
+  bool p2update = false;
+  LsPoint p2 = p1;
+  while (p1.d0 * direction <= -gtol && X.ls_it < ls_iterations) {
+    p2 = p1; p2update = true;
+    p1 = ls_eval(C, R, X, p1.alpha - p1.d0 / p1.d1);
+    X.ls_it++;
+    if (fabsf(p1.d0) < gtol) return p1.alpha;
+  }
+  if (X.ls_it >= ls_iterations) return p1.alpha;
+  if (!p2update) return p1.alpha;
+  float a0 = p1.alpha - p1.d0 / p1.d1, a1 = p1.alpha, a2 = (p1.alpha + p2.alpha) * 0.5f;
+  while (X.ls_it < ls_iterations) {
+    LsPoint cand[3];
+    cand[0] = ls_eval(C, R, X, a0); cand[1] = ls_eval(C, R, X, a1); cand[2] = ls_eval(C, R, X, a2);
+    X.ls_it += 3;
+    float best_alpha = 0.f, best_cost = 0.f;
+    bool found = false;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+      if (fabsf(cand[i].d0) < gtol && (!found || cand[i].cost < best_cost)) { best_alpha = cand[i].alpha; best_cost = cand[i].cost; found = true; }
+    if (found) return best_alpha;
+    float p1n, p2n;
+    const int b1 = update_bracket(p1, cand, p1n), b2 = update_bracket(p2, cand, p2n);
+    if (b1 == 0 && b2 == 0) return a2;
+    a0 = p1n; a1 = p2n; a2 = (p1.alpha + p2.alpha) * 0.5f;
+  }
+  if (p1.cost <= p2.cost && p1.cost < p0.cost) return p1.alpha;
+  if (p2.cost <= p1.cost && p2.cost < p0.cost) return p2.alpha;
+  return 0.f;
+}
+
+// CS:210-245 resolve(): init (CS:2935-3059), monolith body (CS:3163-3190), update_qacc (CS:3240-3261),
+// contact forces (CS:3198-3237)
+template <int G>
+__device__ void phase_constraints(const Ctx<G>& C) {
+  const int nD = CM(nD), nL = CM(nL), MS = c_s.MS, lane = C.lane;
+  const float EPS = CM(eps);
+  Rows R;
+  build_rows(C, R);
+  const int n_con = R.n_con;
+  int* SI = C.SI();
+  SolverState X;
+  X.cost = 0.f; X.prev_cost = 0.f; X.gauss = 0.f; X.ls_it = 0;
+  float* qacc = WK(qacc);
+  float* Ma = WK(Ma);
+  float* search = WK(search);
+  const bool warm = n_con > 0 && SI[c_h.is_warmstart];
+  for (int d = lane; d < nD; d += G) qacc[d] = warm ? IN(qacc_ws)[d] : WK(acc_smooth)[d];
+  C.sync();
+  int iters = 0;
+  if (n_con > 0) {
+    const float* M = WK(M);
+    for (int i = lane; i < nD; i += G) {  // CS:2910-2929
+      float s = 0.f;
+      for (int j = 0; j < nD; j++) s += M[i * MS + j] * qacc[j];
+      Ma[i] = s;
+    }
+    for (int c = lane; c < n_con; c += G) {  // CS:2887-2907
+      float s = -R.aref[c];
+      for (int d = 0; d < nD; d++) s += R.J[c * R.JS + d] * qacc[d];
+      R.Jaref[c] = s;
+      R.active[c] = 0;
+    }
+    C.sync();
+    update_constraint(C, R, X, false);
+    if (CM(solver_type) == SOLVER_NEWTON) hessian_cholesky(C, R);
+    update_gradient(C);
+    for (int d = lane; d < nD; d += G) search[d] = -WK(Mgrad)[d];
+    C.sync();
+    const float tol_scaled = (CM(meaninertia) * (float)max(1, nD)) * CM(tolerance);
+    for (int it = 0; it < CM(iterations); it++) {  // CS:3062-3139 func_solve_iter
+      iters++;
+      const float alpha = linesearch(C, R, X);
+      if (fabsf(alpha) < EPS) break;
+      for (int d = lane; d < nD; d += G) {
+        qacc[d] += search[d] * alpha;
+        Ma[d] += WK(mv)[d] * alpha;
+        if (CM(solver_type) == SOLVER_CG) { WK(prev_grad)[d] = WK(grad)[d]; WK(prev_Mgrad)[d] = WK(Mgrad)[d]; }
+      }
+      for (int c = lane; c < n_con; c += G) R.Jaref[c] += R.jv[c] * alpha;
+      C.sync();
+      update_constraint(C, R, X, true);
+      if (CM(solver_type) == SOLVER_NEWTON) {
+        if (hessian_incremental(C, R)) { C.sync(); hessian_cholesky(C, R); }
+      }
+      update_gradient(C);
+      // CS:2841-2884 termination / new search direction
+      float gn = 0.f;
+      for (int d = lane; d < nD; d += G) { const float g = WK(grad)[d]; gn += g * g; }
+      gn = sqrtf(C.sum(gn));
+      const bool improved = gn > tol_scaled && (X.prev_cost - X.cost) > tol_scaled;
+      if (!improved) break;
+      if (CM(solver_type) == SOLVER_NEWTON) {
+        for (int d = lane; d < nD; d += G) search[d] = -WK(Mgrad)[d];
+      } else {
+        float beta = 0.f, pg = 0.f;
+        for (int d = lane; d < nD; d += G) {
+          beta += WK(grad)[d] * (WK(Mgrad)[d] - WK(prev_Mgrad)[d]);
+          pg += WK(prev_Mgrad)[d] * WK(prev_grad)[d];
+        }
+        beta = fmaxf(C.sum(beta) / fmaxf(EPS, C.sum(pg)), 0.f);
+        for (int d = lane; d < nD; d += G) search[d] = -WK(Mgrad)[d] + beta * search[d];
+      }
+      C.sync();
+    }
+  } else {
+    for (int d = lane; d < nD; d += G) WK(qfrc_c)[d] = 0.f;
+  }
+  C.sync();
+  // ---- CS:3240-3261 func_update_qacc
+  bool has_nan = false;
+  float* acc = WK(acc);
+  for (int d = lane; d < nD; d += G) {
+    const float a = qacc[d];
+    acc[d] = a;
+    IN(qacc_ws)[d] = a;
+    has_nan |= isnan(a);
+  }
+  if (C.any(has_nan) && lane == 0) SI[c_h.errno_] |= ERR_NAN_FORCE;
+  if (lane == 0) {
+    SI[c_h.is_warmstart] = 1;
+    int* out = reinterpret_cast<int*>(C.rec);
+    out[c_h.n_constraints] = n_con; out[c_h.n_constraints_equality] = R.ne; out[c_h.n_constraints_frictionloss] = R.nef - R.ne;
+    out[c_h.solver_iters] = iters;
+  }
+  // ---- CS:3198-3237 func_update_contact_force: per-contact force (global record) and per-link totals
+  const int nc = CM(enable_collision) ? SI[c_h.n_contacts] : 0;
+  for (int ic = lane; ic < nc; ic += G) {
+    const float* ct = R.ct + (size_t)ic * GSR_CONTACT_WORDS;
+    const f3 cn(ct[CT_NRM], ct[CT_NRM + 1], ct[CT_NRM + 2]);
+    const float mu = ct[CT_MU];
+    f3 d1, d2;
+    orthogonals(cn, d1, d2);
+    const int r0 = R.nef + 4 * ic;
+    const f3 force = (d1 * (-mu) - cn) * R.force[r0] + (d1 * mu - cn) * R.force[r0 + 1] + (d2 * (-mu) - cn) * R.force[r0 + 2] + (d2 * mu - cn) * R.force[r0 + 3];
+    float* g = C.contacts + (size_t)ic * GSR_CONTACT_WORDS;
+    g[CT_FRC] = force.x; g[CT_FRC + 1] = force.y; g[CT_FRC + 2] = force.z;
+    if (R.ct != C.contacts) { float* s = const_cast<float*>(ct); s[CT_FRC] = force.x; s[CT_FRC + 1] = force.y; s[CT_FRC + 2] = force.z; }
+  }
+  C.sync();
+  float* lcf = C.rec + c_h.links_contact_force;
+  for (int l = lane; l < nL; l += G) {
+    f3 s;
+    for (int ic = 0; ic < nc; ic++) {
+      const float* ct = R.ct + (size_t)ic * GSR_CONTACT_WORDS;
+      const int la = __float_as_int(ct[CT_LA]), lb = __float_as_int(ct[CT_LB]);
+      const f3 f(ct[CT_FRC], ct[CT_FRC + 1], ct[CT_FRC + 2]);
+      if (la == l) s -= f;
+      if (lb == l) s += f;
+    }
+    st3(lcf, l, s);
+  }
+  C.sync();
+}

@@ -1,11 +1,21 @@
-// gsr_types.h -- device-side model (constant memory) and per-env state layout of libgsrigid.
+// gsr_types.h -- device-side model, per-env record layout (HBM) and per-env workspace layout (shared memory) of libgsrigid.
 //
-// Data layout in HBM (see DESIGN.md "Data layout"): every per-environment quantity lives in one of two big
-// buffers (float32 / int32) as rows of B consecutive environments: element (row r, env b) = buf[r * B + b].
-// A warp of 32 consecutive environments therefore touches 128 contiguous bytes per load/store, which is the
-// reference's `[item, env]` field layout (genesis/utils/array_class.py:1400-1435) with vec3/quat components
-// split into scalar rows.  The model (identical for all envs) sits in __constant__ memory so that the uniform
-// per-link / per-dof / per-geom table reads of a thread-per-env kernel are single broadcast transactions.
+// Execution model (DESIGN.md "Kernels"): one *lane group* of G lanes (G = 32: a full warp; smaller power-of-two groups are
+// supported by the same code) owns one environment for a whole step.  The group stages the environment's record from HBM
+// into shared memory with one bulk copy, runs forward dynamics, collision detection, the constraint solver and the
+// integrator + forward kinematics entirely on chip, and writes the record back.  Lanes of a group split links / dofs /
+// geoms / collision pairs / constraint rows / matrix entries between them and communicate through shared memory and warp
+// shuffles.
+//
+// Data layout in HBM: env-major records.  The caller-owned state buffer of 32-bit words is split into segments
+//   HOT     [B][hot_stride]    : IN part (persistent state + kinematic cache, bulk-loaded every step) followed by the
+//                                OUT part (accessor-visible results, written every step)
+//   CONTACT [B][max_contacts][16] : contact records (AoS, 64 B each), only the first n_contacts are touched
+//   CACHE   [B][cache_stride]  : per-pair warm-start normals of the narrow phase (touched for colliding convex pairs only)
+//   SPILL   [B][spill_stride]  : constraint rows of environments whose row count exceeds the shared-memory capacity
+// so that everything one group touches is contiguous (full 128-byte lines, bulk-copy friendly).  The reference keeps
+// `[item, env]` arrays (genesis/utils/array_class.py:1400-1435) because it maps one thread to one env; the public API is
+// `(B, item)` in both (genesis/utils/misc.py:415-536), which here is a plain strided view of the record.
 #pragma once
 #include <stdint.h>
 
@@ -16,6 +26,7 @@
 #define GSR_MAX_GEOMS 80
 #define GSR_MAX_ENTS 16
 #define GSR_MAX_EQ 8
+#define GSR_CONTACT_WORDS 16
 
 enum { GEOM_PLANE = 0, GEOM_SPHERE = 1, GEOM_ELLIPSOID = 2, GEOM_CYLINDER = 3, GEOM_CAPSULE = 4, GEOM_BOX = 5, GEOM_MESH = 6 };
 enum { JOINT_FIXED = 0, JOINT_REVOLUTE = 1, JOINT_PRISMATIC = 2, JOINT_SPHERICAL = 3, JOINT_FREE = 4 };
@@ -24,32 +35,36 @@ enum { CTRL_POSITION = 0, CTRL_VELOCITY = 1, CTRL_FORCE = 2 };
 enum { INTEGRATOR_EULER = 0, INTEGRATOR_IMPLICITFAST = 1, INTEGRATOR_APPROX_IMPLICITFAST = 2 };
 enum { SOLVER_CG = 0, SOLVER_NEWTON = 1 };
 enum { ERR_BROAD_OVERFLOW = 1, ERR_CONTACT_OVERFLOW = 2, ERR_NAN_FORCE = 8, ERR_NAN_ACC = 16 };
+// contact record word offsets (CONTACT segment, AoS)
+enum { CT_GA = 0, CT_GB = 1, CT_LA = 2, CT_LB = 3, CT_PEN = 4, CT_MU = 5, CT_POS = 6, CT_NRM = 9, CT_FRC = 12, CT_KEY = 15 };
 
 struct DevModel {
   int nL, nJ, nD, nQ, nG, nE, nEq, nP, nV;
   int max_contact_pairs, max_broad_pairs, n_contacts_per_pair, len_constraints;
   int iterations, ls_iterations, integrator, solver_type;
-  int enable_collision, enable_joint_limit, enable_multi_contact, sort_contacts, has_cc, n_cache_words;
+  int enable_collision, enable_joint_limit, enable_multi_contact, sort_contacts, has_cc, n_cache_words, diagnostics;
   float meaninertia, dt, eps, tolerance, ls_tolerance, mc_perturbation, mc_tolerance;
   float gravity[3];
   float ccd_eps, ccd_tolerance;
   int ccd_iterations;
+  int max_depth;  // longest root-to-leaf chain (number of links)
   // links
   int l_parent[GSR_MAX_LINKS], l_root[GSR_MAX_LINKS], l_entity[GSR_MAX_LINKS], l_is_fixed[GSR_MAX_LINKS];
   int l_joint_start[GSR_MAX_LINKS], l_joint_end[GSR_MAX_LINKS], l_dof_start[GSR_MAX_LINKS], l_dof_end[GSR_MAX_LINKS];
-  int l_q_start[GSR_MAX_LINKS], l_q_end[GSR_MAX_LINKS];
+  int l_q_start[GSR_MAX_LINKS], l_q_end[GSR_MAX_LINKS], l_depth[GSR_MAX_LINKS];
+  unsigned long long l_dofmask[GSR_MAX_LINKS];   // dofs of the link and of all its ancestors
+  unsigned long long l_ancmask[GSR_MAX_LINKS];   // the link and all its ancestors
   float l_pos[GSR_MAX_LINKS][3], l_quat[GSR_MAX_LINKS][4], l_ipos[GSR_MAX_LINKS][3], l_iquat[GSR_MAX_LINKS][4];
-  float l_inertia[GSR_MAX_LINKS][9], l_mass[GSR_MAX_LINKS], l_invweight[GSR_MAX_LINKS];
+  float l_inertia[GSR_MAX_LINKS][9], l_mass[GSR_MAX_LINKS], l_invweight[GSR_MAX_LINKS], l_root_mass[GSR_MAX_LINKS];
   // joints
   int j_type[GSR_MAX_JOINTS], j_q_start[GSR_MAX_JOINTS], j_dof_start[GSR_MAX_JOINTS], j_n_dofs[GSR_MAX_JOINTS];
   float j_pos[GSR_MAX_JOINTS][3], j_sol[GSR_MAX_JOINTS][7];
   // dofs
-  int d_link[GSR_MAX_DOFS], d_entity[GSR_MAX_DOFS];
+  int d_link[GSR_MAX_DOFS], d_entity[GSR_MAX_DOFS], d_joint[GSR_MAX_DOFS];
   float d_motion_ang[GSR_MAX_DOFS][3], d_motion_vel[GSR_MAX_DOFS][3], d_limit[GSR_MAX_DOFS][2];
   float d_stiffness[GSR_MAX_DOFS], d_damping[GSR_MAX_DOFS], d_armature[GSR_MAX_DOFS], d_frictionloss[GSR_MAX_DOFS];
   float d_kp[GSR_MAX_DOFS], d_act_bias[GSR_MAX_DOFS][3], d_force_range[GSR_MAX_DOFS][2], d_invweight[GSR_MAX_DOFS];
   float qpos0[GSR_MAX_QS];
-  uint8_t mass_mask[GSR_MAX_DOFS][GSR_MAX_DOFS];
   // entities
   int e_link_start[GSR_MAX_ENTS], e_link_end[GSR_MAX_ENTS], e_dof_start[GSR_MAX_ENTS], e_dof_end[GSR_MAX_ENTS];
   int e_geom_start[GSR_MAX_ENTS], e_geom_end[GSR_MAX_ENTS];
@@ -69,39 +84,59 @@ struct DevModel {
   const int* pair_idx;     // [nG][nG]
 };
 
-// ---- per-env state fields: X(name, is_int, rows) with rows expressed in model counts ------------------------
-// nC = len_constraints, nCP = max_contact_pairs, nW = n_cache_words
-#define GSR_FIELDS(X)                                                                                             \
-  /* generalized coordinates (reference: rigid_global_info.qpos, dofs_state.*) */                                 \
-  X(qpos, 0, nQ) X(vel, 0, nD) X(acc, 0, nD) X(acc_smooth, 0, nD) X(force, 0, nD) X(qf_smooth, 0, nD)             \
-  X(qf_constraint, 0, nD) X(qf_applied, 0, nD) X(qf_passive, 0, nD) X(qf_bias, 0, nD) X(dofs_pos, 0, nD)          \
-  X(ctrl_pos, 0, nD) X(ctrl_vel, 0, nD) X(ctrl_force, 0, nD) X(ctrl_mode, 1, nD)                                  \
-  X(cdof_ang, 0, 3 * nD) X(cdof_vel, 0, 3 * nD) X(cdofd_ang, 0, 3 * nD) X(cdofd_vel, 0, 3 * nD)                   \
-  /* links_state */                                                                                               \
-  X(links_pos, 0, 3 * nL) X(links_quat, 0, 4 * nL) X(root_COM, 0, 3 * nL) X(cinr_I, 0, 6 * nL)                    \
-  X(cinr_pos, 0, 3 * nL) X(cd_vel, 0, 3 * nL) X(cd_ang, 0, 3 * nL) X(cacc_lin, 0, 3 * nL) X(cacc_ang, 0, 3 * nL)  \
-  X(cfrc_applied_vel, 0, 3 * nL) X(cfrc_applied_ang, 0, 3 * nL) X(links_contact_force, 0, 3 * nL)                 \
-  X(joints_xanchor, 0, 3 * nJ) X(joints_xaxis, 0, 3 * nJ) X(scratch, 0, 16 * nL)                                  \
-  /* geoms_state */                                                                                               \
-  X(geoms_pos, 0, 3 * nG) X(geoms_quat, 0, 4 * nG) X(aabb_min, 0, 3 * nG) X(aabb_max, 0, 3 * nG)                  \
-  X(friction_ratio, 0, nG)                                                                                        \
-  /* mass matrix and its L^T D L factor (rigid_global_info.mass_mat, mass_mat_L, mass_mat_D_inv) */               \
-  X(mass_mat, 0, nD * nD) X(mass_L, 0, nD * nD) X(mass_Dinv, 0, nD)                                               \
-  /* collider_state */                                                                                            \
-  X(n_contacts, 1, 1) X(contact_geom_a, 1, nCP) X(contact_geom_b, 1, nCP) X(contact_link_a, 1, nCP)               \
-  X(contact_link_b, 1, nCP) X(contact_normal, 0, 3 * nCP) X(contact_pos, 0, 3 * nCP)                              \
-  X(contact_penetration, 0, nCP) X(contact_friction, 0, nCP) X(contact_force, 0, 3 * nCP)                         \
-  X(cache_normal, 0, 3 * nP) X(cache_valid, 1, nW) X(sort_key, 0, nCP) X(sort_idx, 1, nCP)                        \
-  /* constraint_state */                                                                                          \
-  X(n_constraints, 1, 1) X(n_constraints_equality, 1, 1) X(n_constraints_frictionloss, 1, 1)                      \
-  X(jac, 0, nC * nD) X(efc_diag, 0, nC) X(efc_aref, 0, nC) X(efc_D, 0, nC) X(efc_force, 0, nC)                    \
-  X(efc_frictionloss, 0, nC) X(Jaref, 0, nC) X(jv, 0, nC) X(efc_active, 1, nC)                                    \
-  X(qacc, 0, nD) X(qacc_ws, 0, nD) X(Ma, 0, nD) X(grad, 0, nD) X(Mgrad, 0, nD) X(search, 0, nD) X(mv, 0, nD)      \
-  X(nt_H, 0, nD * nD) X(nt_vec, 0, nD) X(cg_prev_grad, 0, nD) X(cg_prev_Mgrad, 0, nD)                             \
-  X(is_warmstart, 1, 1) X(solver_iters, 1, 1) X(errno_, 1, 1)
+// ---- HOT segment fields: X(name, is_int, items, comps).  Everything up to `kin_end` is the IN part (same offsets in the
+// shared-memory workspace); the rest is OUT.
+// nL/nD/... are the model counts; "items x comps" words, item-major.
+#define GSR_HOT_IN_FIELDS(X)                                                                                       \
+  /* persistent state (rigid_global_info.qpos, dofs_state.vel / ctrl_*, constraint_state.qacc_ws) */               \
+  X(qpos, 0, nQ, 1) X(vel, 0, nD, 1) X(ctrl_pos, 0, nD, 1) X(ctrl_vel, 0, nD, 1) X(ctrl_force, 0, nD, 1)           \
+  X(ctrl_mode, 1, nD, 1) X(qacc_ws, 0, nD, 1)                                                                      \
+  X(is_warmstart, 1, 1, 1) X(errno_, 1, 1, 1) X(n_contacts, 1, 1, 1) X(n_broad, 1, 1, 1)                           \
+  X(friction_ratio, 0, nG, 1) X(cfrc_applied_vel, 0, nL, 3) X(cfrc_applied_ang, 0, nL, 3)                          \
+  /* kinematic cache written by the FK at the end of a step and consumed by the next step */                       \
+  X(dofs_pos, 0, nD, 1) X(root_COM, 0, nL, 3) X(cdof_ang, 0, nD, 3) X(cdof_vel, 0, nD, 3) X(cdofd_ang, 0, nD, 3)   \
+  X(cdofd_vel, 0, nD, 3) X(links_pos, 0, nL, 3) X(links_quat, 0, nL, 4) X(cinr_I, 0, nL, 6) X(cinr_pos, 0, nL, 3)  \
+  X(cd_vel, 0, nL, 3) X(cd_ang, 0, nL, 3)
+#define GSR_HOT_OUT_FIELDS(X)                                                                                      \
+  X(acc, 0, nD, 1) X(force, 0, nD, 1) X(qf_applied, 0, nD, 1) X(qf_constraint, 0, nD, 1)                           \
+  X(cacc_lin, 0, nL, 3) X(cacc_ang, 0, nL, 3) X(links_contact_force, 0, nL, 3)                                     \
+  X(aabb_min, 0, nG, 3) X(aabb_max, 0, nG, 3)                                                                      \
+  X(n_constraints, 1, 1, 1) X(n_constraints_equality, 1, 1, 1) X(n_constraints_frictionloss, 1, 1, 1)              \
+  X(solver_iters, 1, 1, 1)                                                                                         \
+  /* diagnostics (cfg_diagnostics): intermediate quantities the parity tests and get_mass_mat read */               \
+  X(acc_smooth, 0, nD, 1) X(qf_smooth, 0, nD, 1) X(qf_passive, 0, nD, 1) X(qf_bias, 0, nD, 1)                      \
+  X(mass_mat, 0, nD * nD, 1) X(mass_Dinv, 0, nD, 1) X(geoms_pos, 0, nG, 3) X(geoms_quat, 0, nG, 4)
 
-struct Layout {
-#define X(name, is_int, rows) int name;
-  GSR_FIELDS(X)
+struct HotLayout {
+#define X(name, is_int, items, comps) int name;
+  GSR_HOT_IN_FIELDS(X)
+  GSR_HOT_OUT_FIELDS(X)
 #undef X
+  int n_in;        // words of the IN part (multiple of 4)
+  int kin_dead;    // first word of the IN part that is dead after collision detection (links_pos ...)
+  int hot_stride;  // words per env in the HOT segment (multiple of 4)
+  int contact_stride, cache_stride, spill_stride;
+  long long contact_base, cache_base, spill_base;  // word offsets of the segments inside the state buffer
+  int cache_valid;                                 // offset of the validity bit words inside a CACHE record
+};
+
+// Shared-memory workspace of one environment (word offsets from the env's base).  Words [0, n_in) mirror the record's IN
+// part.  Regions are overlaid by liveness: the dynamics scratch and the kinematic cache that is dead after collision
+// detection are reused by the collision scratch and then by the solver rows.
+struct SmemLayout {
+  // live for the whole step
+  int M, L, Dinv, force, acc_smooth, acc, qf_applied, qf_passive, qf_bias, qfrc_c;
+  int MS;  // row stride of M / L / H (odd)
+  // dynamics scratch
+  int crb, fdof, cdd, cfrc;
+  // collision scratch
+  int gpos, gquat, aabb, queue;
+  // contacts kept on chip for row assembly (n <= NCC) + solver
+  int contacts, NCC;
+  int H, qacc, Ma, grad, Mgrad, search, mv, prev_grad, prev_Mgrad;
+  int J, JS, NCS;                 // rows: J[NCS][JS]
+  int r_aref, r_D, r_R, r_floss, r_Jaref, r_jv, r_force, r_active;
+  // integrate / FK scratch
+  int xanchor, xaxis, cacc, vel_next, qpos_next, pose_a, pose_b;
+  int env_words;  // total words per env (multiple of 4, ≡ 8 mod 32 is not required)
 };

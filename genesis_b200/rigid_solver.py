@@ -81,6 +81,13 @@ class RigidSolver:
         self._gravity = rigid_options.gravity or sim_options.gravity
         self._handle = None
         self._n_substeps_total = 0
+        # launch tuning of libgsrigid (0 = library default): lanes per environment, constraint rows kept in shared
+        # memory, and whether the diagnostic fields (mass_mat, qf_*, acc_smooth, geom poses) are written every step
+        import os
+
+        self.tuning = dict(group_size=int(os.environ.get("GSR_GROUP_SIZE", 0)), diagnostics=int(os.environ.get("GSR_DIAGNOSTICS", 1)))
+        if os.environ.get("GSR_SMEM_ROWS"):
+            self.tuning["smem_rows"] = int(os.environ["GSR_SMEM_ROWS"])
         self.model = None
 
     # ------------------------------------------------------------------ build
@@ -120,7 +127,7 @@ class RigidSolver:
         return dict(iterations=o.iterations, ls_iterations=o.ls_iterations, tolerance=o.tolerance, ls_tolerance=o.ls_tolerance,
                     integrator=int(o.integrator), solver_type=int(o.constraint_solver), enable_collision=int(o.enable_collision),
                     enable_joint_limit=int(o.enable_joint_limit), enable_multi_contact=int(o.enable_multi_contact),
-                    sort_contacts=1)
+                    sort_contacts=1, **self.tuning)
 
     def build(self, n_envs, device):
         if not torch.cuda.is_available():
@@ -138,21 +145,27 @@ class RigidSolver:
             L.gsr_model_set_scalar(h, f"cfg_{k}".encode(), float(v))
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         _lib.check(h, L.gsr_model_commit(h, dev_index, self._B))
-        nf, ni = ctypes.c_size_t(), ctypes.c_size_t()
-        _lib.check(h, L.gsr_state_sizes(h, ctypes.byref(nf), ctypes.byref(ni)))
+        nw = ctypes.c_size_t()
+        _lib.check(h, L.gsr_state_words(h, ctypes.byref(nw)))
         with torch.cuda.device(self.device):
-            self._F = torch.zeros(nf.value, dtype=torch.float32, device=self.device)
-            self._I = torch.zeros(ni.value, dtype=torch.int32, device=self.device)
-        _lib.check(h, L.gsr_bind(h, self._F.data_ptr(), self._I.data_ptr()))
+            self._F = torch.zeros(nw.value, dtype=torch.float32, device=self.device)
+        self._I = self._F.view(torch.int32)
+        _lib.check(h, L.gsr_bind(h, self._F.data_ptr()))
         self._fields = {}
-        name, is_int, off, items = ctypes.c_char_p(), ctypes.c_int(), ctypes.c_size_t(), ctypes.c_size_t()
+        name, is_int = ctypes.c_char_p(), ctypes.c_int()
+        v = [ctypes.c_size_t() for _ in range(6)]
         for i in range(L.gsr_field_count(h)):
-            _lib.check(h, L.gsr_field_info(h, i, ctypes.byref(name), ctypes.byref(is_int), ctypes.byref(off), ctypes.byref(items)))
+            _lib.check(h, L.gsr_field_info(h, i, ctypes.byref(name), ctypes.byref(is_int), *[ctypes.byref(x) for x in v]))
+            seg, stride, off, items, comps, istride = (x.value for x in v)
             buf = self._I if is_int.value else self._F
-            self._fields[name.value.decode()] = buf[off.value * self._B: (off.value + items.value) * self._B].view(items.value, self._B)
+            shape, strides = ((self._B, items), (stride, istride)) if comps == 1 else ((self._B, items, comps), (stride, istride, 1))
+            self._fields[name.value.decode()] = torch.as_strided(buf, shape, strides, seg + off)
+        gi = [ctypes.c_int() for _ in range(4)]
+        _lib.check(h, L.gsr_launch_info(h, *[ctypes.byref(x) for x in gi]))
+        self.launch_info = dict(group_size=gi[0].value, smem_bytes_per_env=gi[1].value, smem_rows=gi[2].value, smem_contacts=gi[3].value)
         _lib.check(h, L.gsr_init_state(h, self._stream()))
         self._is_built = True
-        self._init_qpos = self._fields["qpos"].clone()
+        self._init_qpos = self._fields["qpos"].clone()  # (B, nQ)
         self._envs_all = torch.arange(self._B, device=self.device)
         m_ = self.model
         self._dofs_limit = torch.tensor(m_.dofs_limit, dtype=torch.float32, device=self.device).reshape(-1, 2)
@@ -178,8 +191,13 @@ class RigidSolver:
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def field(self, name):
-        """Zero-copy (rows, B) torch view of a state field (the reference's zero-copy qd_to_torch views)."""
+        """Zero-copy torch view of a state field, (B, items) or (B, items, comps): the reference's transposed zero-copy
+        qd_to_torch views (genesis/utils/misc.py:415-536) are plain strided views of the env-major records here."""
         return self._fields[name]
+
+    def rows(self, name):
+        """(B, items * comps) copy-free when possible: every scalar of a field, one row per environment."""
+        return self._fields[name].reshape(self._B, -1)
 
     # ------------------------------------------------------------------ stepping
     def substep(self, n=1):
@@ -219,14 +237,14 @@ class RigidSolver:
         return out
 
     def get_error_envs_mask(self):
-        return self._fields["errno_"][0] > 0
+        return self._fields["errno_"][:, 0] > 0
 
     def check_errno(self):
         """rigid_solver.py:985-1009 (polled every RATE_CHECK_ERRNO substeps by Scene.step)."""
-        errno = int(torch.bitwise_or(self._fields["errno_"][0], 0).max().item()) if self._B else 0
+        errno = int(self._fields["errno_"].max().item()) if self._B else 0
         if errno == 0:
             return
-        bits = int(np.bitwise_or.reduce(self._fields["errno_"][0].cpu().numpy()))
+        bits = int(np.bitwise_or.reduce(self._fields["errno_"][:, 0].cpu().numpy()))
         if bits & ErrorCode.OVERFLOW_CANDIDATE_CONTACTS:
             raise GenesisException(f"Exceeding max number of broad phase candidate contact pairs ({self.model.max_broad_pairs}). "
                                    "Please increase the value of RigidSolver's option 'multiplier_collision_broad_phase'.")
@@ -256,17 +274,11 @@ class RigidSolver:
         return torch.as_tensor(idx, device=self.device, dtype=torch.long).reshape(-1)
 
     def _get(self, name, idx, envs_idx, n, comps=1):
-        """(B, len(idx)[, comps]) copy of field rows."""
+        """(B, len(idx)[, comps]) copy of a field."""
         f = self._fields[name]
-        idx = self._idx(idx, n)
-        if comps > 1:
-            f = f.view(-1, comps, self._B)[idx]  # (n, comps, B)
-            out = f.permute(2, 0, 1)
-        else:
-            out = f[idx].permute(1, 0)
+        out = f[:, self._idx(idx, n)]
         envs = self._envs(envs_idx)
-        out = out if envs is None else out[envs]
-        out = out.clone() if out.dtype != torch.int32 or True else out
+        out = out.clone() if envs is None else out[envs]
         if self.n_envs == 0:
             out = out[0]
         return out
@@ -277,13 +289,11 @@ class RigidSolver:
         envs = self._envs(envs_idx)
         nb = self._B if envs is None else len(envs)
         value = torch.as_tensor(value, dtype=dtype, device=self.device)
-        if self.n_envs == 0 and value.ndim <= 1:
-            value = value.reshape(1, -1) if value.ndim == 1 else value
-        value = torch.broadcast_to(value, (nb, len(idx)))
+        value = torch.broadcast_to(value, (nb, len(idx))).to(f.dtype)
         if envs is None:
-            f[idx] = value.T.to(f.dtype)
+            f[:, idx] = value
         else:
-            f[idx[:, None], envs[None, :]] = value.T.to(f.dtype)
+            f[envs[:, None], idx[None, :]] = value
 
     def _env_mask(self, envs_idx):
         envs = self._envs(envs_idx)
@@ -321,10 +331,10 @@ class RigidSolver:
         envs = self._envs(envs_idx)
         nb = self._B if envs is None else len(envs)
         pos = torch.broadcast_to(torch.as_tensor(position, dtype=torch.float32, device=self.device), (nb, len(dofs)))
-        cur = self._fields["dofs_pos"].T.clone()  # (B, nD)
+        cur = self._fields["dofs_pos"].clone()  # (B, nD)
         sel = cur if envs is None else cur[envs]
         sel[:, dofs] = pos
-        qpos = self._fields["qpos"].T.clone()
+        qpos = self._fields["qpos"].clone()
         qsel = qpos if envs is None else qpos[envs]
         for j in range(m.n_joints):
             t, qs, ds = int(m.joints_type[j]), int(m.joints_q_start[j]), int(m.joints_dof_start[j])
@@ -371,19 +381,17 @@ class RigidSolver:
         force = torch.broadcast_to(torch.as_tensor(force, dtype=torch.float32, device=self.device), (nb, len(links), 3))
         # c-frame wrench about root_COM: ang += (com_link - root_COM) x F ; vel += F  (sign follows cfrc_applied = -f_ext)
         pos = self._get_links_com(links, envs)  # (nb, nl, 3)
-        root = self._fields["root_COM"].view(-1, 3, self._B)[links].permute(2, 0, 1)
+        root = self._fields["root_COM"][:, links]
         root = root if envs is None else root[envs]
         torque = torch.cross(pos - root, force, dim=-1)
-        fv = self._fields["cfrc_applied_vel"].view(-1, 3, self._B)
-        fa = self._fields["cfrc_applied_ang"].view(-1, 3, self._B)
-        e = slice(None) if envs is None else envs
-        fv[links[:, None], :, (torch.arange(self._B, device=self.device) if envs is None else envs)[None, :]] -= force.permute(1, 0, 2)
-        fa[links[:, None], :, (torch.arange(self._B, device=self.device) if envs is None else envs)[None, :]] -= torque.permute(1, 0, 2)
+        e = self._envs_all if envs is None else envs
+        self._fields["cfrc_applied_vel"][e[:, None], links[None, :]] -= force
+        self._fields["cfrc_applied_ang"][e[:, None], links[None, :]] -= torque
 
     def _get_links_com(self, links, envs):
         m = self.model
-        pos = self._fields["links_pos"].view(-1, 3, self._B)[links].permute(2, 0, 1)
-        quat = self._fields["links_quat"].view(-1, 4, self._B)[links].permute(2, 0, 1)
+        pos = self._fields["links_pos"][:, links]
+        quat = self._fields["links_quat"][:, links]
         if envs is not None:
             pos, quat = pos[envs], quat[envs]
         ipos = torch.tensor(m.links_inertial_pos, dtype=torch.float32, device=self.device)[links]
@@ -476,7 +484,7 @@ class RigidSolver:
 
     def get_mass_mat(self, dofs_idx=None, envs_idx=None):
         nD = self.model.n_dofs
-        M = self._fields["mass_mat"].view(nD, nD, self._B).permute(2, 0, 1)
+        M = self._fields["mass_mat"].reshape(self._B, nD, nD)
         envs = self._envs(envs_idx)
         M = M if envs is None else M[envs]
         idx = self._idx(dofs_idx, nD)
@@ -491,27 +499,22 @@ class RigidSolver:
 
     def get_contacts(self, as_tensor=True, to_torch=True, keep_batch_dim=False):
         """collider.py:810-913 (tensor form): dict of (B, n_contacts_max[, 3]) tensors, cleared slots hold -1 / 0."""
-        n_max = int(self._fields["n_contacts"][0].max().item())
+        n_max = int(self._fields["n_contacts"].max().item())
         f = self._fields
 
-        def cut(name, comps=1):
-            t = f[name]
-            if comps > 1:
-                t = t.view(-1, comps, self._B)[:n_max].permute(2, 0, 1)
-            else:
-                t = t[:n_max].permute(1, 0)
-            t = t.clone()
+        def cut(name):
+            t = f[name][:, :n_max].clone()
             if self.n_envs == 0 and not keep_batch_dim:
                 t = t[0]
             return t if to_torch else t.cpu().numpy()
 
         return dict(link_a=cut("contact_link_a"), link_b=cut("contact_link_b"), geom_a=cut("contact_geom_a"),
-                    geom_b=cut("contact_geom_b"), penetration=cut("contact_penetration"), position=cut("contact_pos", 3),
-                    normal=cut("contact_normal", 3), force=cut("contact_force", 3))
+                    geom_b=cut("contact_geom_b"), penetration=cut("contact_penetration"), position=cut("contact_pos"),
+                    normal=cut("contact_normal"), force=cut("contact_force"))
 
     @property
     def n_contacts(self):
-        return self._fields["n_contacts"][0]
+        return self._fields["n_contacts"][:, 0]
 
     # ------------------------------------------------------------------ state (rigid_solver.py:1430-1579)
     def get_state(self):
@@ -519,32 +522,26 @@ class RigidSolver:
         return dict(qpos=f["qpos"].clone(), dofs_vel=f["vel"].clone(), dofs_acc=f["acc"].clone(),
                     links_pos=f["links_pos"].clone(), links_quat=f["links_quat"].clone())
 
-    def set_state(self, state, envs_idx=None, partial=False):
+    def _restore(self, values, envs_idx):
         f = self._fields
         envs = self._envs(envs_idx)
-        cols = slice(None) if envs is None else envs
-        for key, name in (("qpos", "qpos"), ("dofs_vel", "vel"), ("dofs_acc", "acc"), ("links_pos", "links_pos"), ("links_quat", "links_quat")):
-            f[name][:, cols] = state[key][:, cols]
-        f["ctrl_force"][:, cols] = 0.0
-        f["ctrl_mode"][:, cols] = int(CTRL_MODE.FORCE)
-        f["cfrc_applied_vel"][:, cols] = 0.0
-        f["cfrc_applied_ang"][:, cols] = 0.0
+        rows = slice(None) if envs is None else envs
+        for name, val in values.items():
+            f[name][rows] = val[rows] if torch.is_tensor(val) else val
+        f["ctrl_force"][rows] = 0.0
+        f["ctrl_mode"][rows] = int(CTRL_MODE.FORCE)
+        f["cfrc_applied_vel"][rows] = 0.0
+        f["cfrc_applied_ang"][rows] = 0.0
         self._reset_warmstart(envs_idx)
         self._forward(envs_idx)
 
+    def set_state(self, state, envs_idx=None, partial=False):
+        """rigid_solver.py:1458-1579."""
+        self._restore(dict(qpos=state["qpos"], vel=state["dofs_vel"], acc=state["dofs_acc"], links_pos=state["links_pos"],
+                           links_quat=state["links_quat"]), envs_idx)
+
     def reset(self, envs_idx=None):
-        f = self._fields
-        envs = self._envs(envs_idx)
-        cols = slice(None) if envs is None else envs
-        f["qpos"][:, cols] = self._init_qpos[:, cols]
-        f["vel"][:, cols] = 0.0
-        f["acc"][:, cols] = 0.0
-        f["ctrl_force"][:, cols] = 0.0
-        f["ctrl_mode"][:, cols] = int(CTRL_MODE.FORCE)
-        f["cfrc_applied_vel"][:, cols] = 0.0
-        f["cfrc_applied_ang"][:, cols] = 0.0
-        self._reset_warmstart(envs_idx)
-        self._forward(envs_idx)
+        self._restore(dict(qpos=self._init_qpos, vel=0.0, acc=0.0), envs_idx)
 
     def destroy(self):
         if self._handle is not None:

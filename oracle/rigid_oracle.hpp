@@ -633,6 +633,14 @@ struct Oracle {
     }
   }
 
+  // float -> int conversion with CUDA semantics (NaN -> 0, saturating): the reference's GPU backend inherits these from
+  // cvt.rzi.s32.f32, and acos() of a |z| one ulp above 1 does produce NaN here (SF:143-150 has no clamp)
+  static int f2i(T x) {
+    if (std::isnan(x)) return 0;
+    if (x >= T(2147483647.0)) return 2147483647;
+    if (x <= T(-2147483648.0)) return (-2147483647 - 1);
+    return (int)x;
+  }
   // SF:138-180 _func_support_mesh
   V support_mesh(const V& d, int g) {
     const T PI = T(3.14159265358979323846);
@@ -643,9 +651,9 @@ struct Oracle {
     V best;
     for (int i4 = 0; i4 < 4; i4++) {
       int i, j;
-      if (i4 % 2) i = ((int)std::ceil(ii)) % res; else i = ((int)std::floor(ii)) % res;
-      if (i4 / 2 > 0) { j = (int)std::min(std::max(std::ceil(jj), T(0)), T(res - 1)); if (j == res - 1) j = res - 2; }
-      else { j = (int)std::min(std::max(std::floor(jj), T(0)), T(res - 1)); if (j == 0) j = 1; }
+      if (i4 % 2) i = f2i(std::ceil(ii)) % res; else i = f2i(std::floor(ii)) % res;
+      if (i4 / 2 > 0) { j = f2i(std::fmin(std::fmax(std::ceil(jj), T(0)), T(res - 1))); if (j == res - 1) j = res - 2; }
+      else { j = f2i(std::fmin(std::fmax(std::floor(jj), T(0)), T(res - 1))); if (j == 0) j = 1; }
       int idx = m.geoms_support_start[g] + i * res + j;
       V p(m.support_v[3 * idx], m.support_v[3 * idx + 1], m.support_v[3 * idx + 2]);
       T dot = p.dot(d);

@@ -33,8 +33,8 @@ def test_version_and_error_paths_without_gpu():
     # call-sequence errors are reported through return codes + gsr_last_error, never by crashing
     assert L.gsr_step(h, 1, None) == -4  # GSR_ESTATE: not bound
     assert b"not bound" in L.gsr_last_error(h)
-    nf, ni = ctypes.c_size_t(), ctypes.c_size_t()
-    assert L.gsr_state_sizes(h, ctypes.byref(nf), ctypes.byref(ni)) == -4
+    nw = ctypes.c_size_t()
+    assert L.gsr_state_words(h, ctypes.byref(nw)) == -4
     assert L.gsr_model_set_f32(h, b"x", None, 3) == -1  # GSR_EINVAL
     assert L.gsr_field_count(h) == -4
     L.gsr_destroy(h)

@@ -27,7 +27,7 @@ def test_batched_accessor_shapes_and_semantics():
     assert not torch.equal(franka.get_qpos(), q)
     # masked control write
     franka.control_dofs_position(torch.full((2, 2), 0.3, device=gs.device), dofs_idx_local=[1, 2], envs_idx=[0, 4])
-    cp = scene.rigid_solver.field("ctrl_pos").T
+    cp = scene.rigid_solver.field("ctrl_pos")
     assert torch.allclose(cp[[0, 4]][:, [1, 2]], torch.full((2, 2), 0.3, device=gs.device))
     assert float(cp[1, 1]) == 0.0
     lo, hi = franka.get_dofs_limit()
@@ -50,7 +50,7 @@ def test_reset_restores_initial_state_and_clears_warmstart():
     for _ in range(30):
         scene.step()
     assert not torch.equal(s.field("qpos"), q0)
-    robot.set_qpos(q0.T.contiguous())
+    robot.set_qpos(q0)
     robot.set_dofs_velocity(torch.zeros(B, 18, device=gs.device))
     assert torch.equal(s.field("qpos"), q0)
     assert int(s.field("is_warmstart").max()) == 0 and float(s.field("qacc_ws").abs().max()) == 0.0
@@ -59,7 +59,7 @@ def test_reset_restores_initial_state_and_clears_warmstart():
     for _ in range(10):
         scene.step()
     ref = s.field("qpos").clone()
-    robot.set_qpos(q0.T.contiguous())
+    robot.set_qpos(q0)
     robot.set_dofs_velocity(torch.zeros(B, 18, device=gs.device))
     for _ in range(10):
         scene.step()

@@ -27,22 +27,24 @@ def mirror_oracle(scene, double=False, **opts):
     s = scene.rigid_solver
     orc = oracle_for(s, s.model, s._B, double=double, threads=8, **opts)
     for name in ("qpos", "vel", "ctrl_pos", "ctrl_vel", "ctrl_force", "ctrl_mode"):
-        orc.set(name, s.field(name).T.cpu().numpy())
+        orc.set(name, s.rows(name).cpu().numpy())
     return orc
 
 
 def gpu_field(scene, name):
-    return scene.rigid_solver.field(name).T.cpu().numpy().astype(np.float64)
+    return scene.rigid_solver.rows(name).cpu().numpy().astype(np.float64)
 
 
 def contact_set(scene_or_orc, B):
     out = set()
     if hasattr(scene_or_orc, "rigid_solver"):
         s = scene_or_orc.rigid_solver
-        n = s.field("n_contacts")[0].cpu().numpy()
-        ga, gb = s.field("contact_geom_a").cpu().numpy(), s.field("contact_geom_b").cpu().numpy()
+        n = s.field("n_contacts")[:, 0].cpu().numpy()
+        n_max = int(n.max()) if len(n) else 0
+        ga = s.field("contact_geom_a")[:, :n_max].cpu().numpy()
+        gb = s.field("contact_geom_b")[:, :n_max].cpu().numpy()
         for b in range(B):
-            out |= {(b, int(ga[c, b]), int(gb[c, b])) for c in range(n[b])}
+            out |= {(b, int(ga[b, c]), int(gb[b, c])) for c in range(n[b])}
     else:
         for b in range(B):
             c = scene_or_orc.contacts(b)
@@ -155,7 +157,7 @@ def test_contact_records_match():
         scene.step()
     orc.step(K)
     con = robot.get_contacts()
-    n = scene.rigid_solver.field("n_contacts")[0].cpu().numpy()
+    n = scene.rigid_solver.field("n_contacts")[:, 0].cpu().numpy()
     for b in range(B):
         c = orc.contacts(b)
         assert n[b] == len(c["geom_a"]) > 0
@@ -228,11 +230,11 @@ def test_external_force_and_masked_fk():
     f = torch.tensor([[[1.0, 0.0, 5.886]]], device=gs.device).repeat(3, 1, 1)  # mass 0.6 kg: weight 5.886 N
     s.apply_links_external_force(f, links_idx=[1])
     scene.step()
-    acc = s.field("acc").T.cpu().numpy()
+    acc = s.field("acc").cpu().numpy()
     np.testing.assert_allclose(acc[:, :3], [[1.0 / 0.6, 0.0, 0.0]] * 3, atol=1e-4)
     # the external force is cleared after the step (rigid_solver.py:2603-2612)
     scene.step()
-    np.testing.assert_allclose(s.field("acc").T.cpu().numpy()[:, 2], -9.81, atol=1e-4)
+    np.testing.assert_allclose(s.field("acc").cpu().numpy()[:, 2], -9.81, atol=1e-4)
     # masked set_qpos only touches the selected env
     before = s.get_links_pos().clone()
     s.set_qpos(torch.tensor([[0.5, 0.5, 1.0, 1, 0, 0, 0]], device=gs.device), envs_idx=[1])

@@ -17,18 +17,18 @@ def test_franka_30000_batch_invariance_and_oracle_sample():
     s = scene.rigid_solver
     # make env b a replica of env (b % R): same initial velocity
     v = s.field("vel")
-    v.copy_(v[:, :R].repeat(1, B // R))
+    v.copy_(v[:R].repeat(B // R, 1))
     s._forward()
     orc = oracle_for(s, s.model, R, threads=8)
     for name in ("qpos", "vel", "ctrl_pos", "ctrl_vel", "ctrl_force", "ctrl_mode"):
-        orc.set(name, s.field(name).T[:R].cpu().numpy())
+        orc.set(name, s.rows(name)[:R].cpu().numpy())
     for _ in range(K):
         scene.step()
     q = s.field("qpos")
-    assert torch.equal(q, q[:, :R].repeat(1, B // R)), "a replica env diverged from its source env (bit-exact expected)"
+    assert torch.equal(q, q[:R].repeat(B // R, 1)), "a replica env diverged from its source env (bit-exact expected)"
     assert int(s.field("errno_").max()) == 0
     orc.step(K)
-    assert np.abs(q.T[:R].cpu().numpy() - orc.qpos()).max() <= 1e-4
+    assert np.abs(q[:R].cpu().numpy() - orc.qpos()).max() <= 1e-4
 
 
 def test_go2_4096_determinism_and_sanity():
@@ -42,7 +42,7 @@ def test_go2_4096_determinism_and_sanity():
         outs.append((s.field("qpos").clone(), s.field("vel").clone(), s.field("n_contacts").clone()))
         assert int(s.field("errno_").max()) == 0
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
-    q = outs[0][0].T
+    q = outs[0][0]
     assert torch.isfinite(q).all()
     assert torch.allclose(q[:, 3:7].norm(dim=1), torch.ones(B, device=q.device), atol=1e-4)  # unit base quaternion
     assert (q[:, 2] > 0.0).all() and (q[:, 2] < 0.6).all()  # nobody fell through the plane or flew away
@@ -60,6 +60,6 @@ def test_step_host_equals_device_path():
     for _ in range(K):
         scene_a.step()
         sb.step_host(ctrl, qpos, vel)
-    assert np.array_equal(sa.field("qpos").T.cpu().numpy(), qpos)
-    assert np.array_equal(sa.field("vel").T.cpu().numpy(), vel)
-    assert sb.launch_count() > 0 and set(sb.kernel_launches()) >= {"k_dynamics", "k_constraint", "k_integrate"}
+    assert np.array_equal(sa.field("qpos").cpu().numpy(), qpos)
+    assert np.array_equal(sa.field("vel").cpu().numpy(), vel)
+    assert sb.launch_count() > 0 and sb.kernel_launches()["k_step"] >= K

@@ -13,7 +13,7 @@ gs.init(backend=gs.gpu)
 def compare(name, scene, orc, fields):
     s = scene.rigid_solver
     for fname, oname, shape in fields:
-        a = s.field(fname).T.cpu().numpy().astype(np.float64)  # (B, rows)
+        a = s.rows(fname).cpu().numpy().astype(np.float64)  # (B, rows)
         o = orc.get(oname, shape).reshape(a.shape[0], -1)
         if o.shape != a.shape:
             print(f"  {name}:{fname} shape mismatch {a.shape} vs {o.shape}")
@@ -31,10 +31,10 @@ def run(name, make, n_envs, steps):
     s = scene.rigid_solver
     m = s.model
     orc = Oracle(m, n_envs, double=False, options=s.model_options())
-    orc.set("qpos", s.field("qpos").T.cpu().numpy())
-    orc.set("vel", s.field("vel").T.cpu().numpy())
-    orc.set("ctrl_pos", s.field("ctrl_pos").T.cpu().numpy())
-    orc.set("ctrl_mode", s.field("ctrl_mode").T.cpu().numpy())
+    orc.set("qpos", s.rows("qpos").cpu().numpy())
+    orc.set("vel", s.rows("vel").cpu().numpy())
+    orc.set("ctrl_pos", s.rows("ctrl_pos").cpu().numpy())
+    orc.set("ctrl_mode", s.rows("ctrl_mode").cpu().numpy())
     nD, nL, nG, nQ = m.n_dofs, m.n_links, m.n_geoms, m.n_qs
     fields0 = [("links_pos", "links_pos", (nL, 3)), ("links_quat", "links_quat", (nL, 4)), ("root_COM", "root_COM", (nL, 3)),
                ("cdof_ang", "cdof_ang", (nD, 3)), ("cdof_vel", "cdof_vel", (nD, 3)), ("geoms_pos", "geoms_pos", (nG, 3)),
@@ -53,15 +53,15 @@ def run(name, make, n_envs, steps):
             torch.cuda.synchronize()
             print(f"== {name}: after step {k + 1}")
             compare(name, scene, orc, fields)
-            nc_g = s.field("n_contacts")[0].cpu().numpy()
+            nc_g = s.field("n_contacts")[:, 0].cpu().numpy()
             nc_o = orc.get("n_contacts", 1)[:, 0]
-            ncon_g = s.field("n_constraints")[0].cpu().numpy()
+            ncon_g = s.field("n_constraints")[:, 0].cpu().numpy()
             ncon_o = orc.get("n_constraints", 3)[:, 0]
-            it_g = s.field("solver_iters")[0].cpu().numpy()
+            it_g = s.field("solver_iters")[:, 0].cpu().numpy()
             it_o = orc.get("n_iter", 1)[:, 0]
             print(f"  n_contacts gpu={nc_g[:8]} orc={nc_o[:8].astype(int)}  mismatch envs={int((nc_g != nc_o).sum())}")
             print(f"  n_constraints gpu={ncon_g[:8]} orc={ncon_o[:8].astype(int)} mismatch envs={int((ncon_g != ncon_o).sum())}")
-            print(f"  solver iters gpu={it_g[:8]} orc={it_o[:8].astype(int)}  errno={s.field('errno_')[0].cpu().numpy()[:8]}")
+            print(f"  solver iters gpu={it_g[:8]} orc={it_o[:8].astype(int)}  errno={s.field('errno_')[:, 0].cpu().numpy()[:8]}")
     return scene
 
 
