@@ -414,10 +414,14 @@ static cudaError_t set_smem(K kernel, size_t bytes) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 static int group_launch(gsr_handle_t h, int which, cudaStream_t st, const uint8_t* mask, int clear_ext) {
-  const int G = h->group, EPW = 32 / G, envs_per_cta = GSR_WARPS_PER_CTA * EPW;
-  const size_t smem = (size_t)envs_per_cta * h->sl.env_words * sizeof(float);
-  if (smem > 227 * 1024) return fail(h, GSR_ELIMIT, "per-CTA shared-memory workspace exceeds 227 KB (lower cfg_smem_rows)");
-  dim3 grid((h->B + envs_per_cta - 1) / envs_per_cta), block(GSR_WARPS_PER_CTA * 32);
+  const int G = h->group, EPW = 32 / G;
+  const size_t warp_bytes = (size_t)EPW * h->sl.env_words * sizeof(float);
+  int warps = GSR_WARPS_PER_CTA;
+  while (warps > 1 && warps * warp_bytes > 100 * 1024) warps--;  // keep at least two CTAs per SM when possible
+  const int envs_per_cta = warps * EPW;
+  const size_t smem = (size_t)warps * warp_bytes;
+  if (smem > 227 * 1024) return fail(h, GSR_ELIMIT, "per-warp shared-memory workspace exceeds 227 KB (lower cfg_smem_rows or raise cfg_group_size)");
+  dim3 grid((h->B + envs_per_cta - 1) / envs_per_cta), block(warps * 32);
 #define LAUNCH(GG)                                                                                       \
   if (which == K_STEP) {                                                                                 \
     CUDA_OK(set_smem(k_step<GG>, smem));                                                                 \

@@ -254,16 +254,10 @@ __device__ void phase_geoms(const Ctx<G>& C) {
     st3(aabb, g, wc - wh); st3(aabb + 3 * nG, g, wc + wh);
   }
   C.sync();
-  // accessor-visible copies (get_AABB; geom poses are diagnostics): the scratch is recycled by the solver rows
+  // accessor-visible copy (get_AABB): the scratch is recycled by the solver rows
   float* o_min = C.rec + c_h.aabb_min;
   float* o_max = C.rec + c_h.aabb_max;
   for (int i = C.lane; i < 3 * nG; i += G) { o_min[i] = aabb[i]; o_max[i] = aabb[3 * nG + i]; }
-  if (CM(diagnostics)) {
-    float* o_p = C.rec + c_h.geoms_pos;
-    float* o_q = C.rec + c_h.geoms_quat;
-    for (int i = C.lane; i < 3 * nG; i += G) o_p[i] = gpos[i];
-    for (int i = C.lane; i < 4 * nG; i += G) o_q[i] = gquat[i];
-  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -504,8 +498,7 @@ __device__ void phase_integrate(const Ctx<G>& C) {
       C.sync();
       mass_factor(C);
       float* x = WK(vel_next);  // scratch (the next velocity is formed below)
-      const float* force = WK(force);
-      for (int d = lane; d < nD; d += G) x[d] = force[d];
+      for (int d = lane; d < nD; d += G) x[d] = WK(force)[d] + WK(qfrc_c)[d];  // dofs_state.force = qf_smooth + qf_constraint
       C.sync();
       mass_solve(C, x);
       for (int d = lane; d < nD; d += G)

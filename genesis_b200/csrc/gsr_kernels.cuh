@@ -22,7 +22,7 @@ __device__ __forceinline__ bool make_ctx(Ctx<G>& C, float* state, int B, const D
   const int warp = threadIdx.x >> 5, lane32 = threadIdx.x & 31;
   const int sub = lane32 / G;
   const int slot = warp * EPW + sub;
-  const int env = blockIdx.x * (GSR_WARPS_PER_CTA * EPW) + slot;
+  const int env = blockIdx.x * ((blockDim.x >> 5) * EPW) + slot;
   if (env >= B) return false;
   C.lane = lane32 % G;
   C.gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (sub * G));
@@ -52,7 +52,7 @@ __device__ __forceinline__ void store_in(const Ctx<G>& C) {
 }
 
 template <int G>
-__global__ void __launch_bounds__(GSR_WARPS_PER_CTA * 32) k_step(float* state, int B, const DevModel* gm, int clear_ext) {
+__global__ void __launch_bounds__(GSR_WARPS_PER_CTA * 32, 4) k_step(float* state, int B, const DevModel* gm, int clear_ext) {
   extern __shared__ __align__(16) float smem[];
   Ctx<G> C;
   if (!make_ctx(C, state, B, gm, smem)) return;
@@ -86,6 +86,16 @@ __global__ void __launch_bounds__(GSR_WARPS_PER_CTA * 32) k_step(float* state, i
   }
   C.sync();
   phase_kinematics(C);
+  if (CM(diagnostics)) {  // geoms_state.pos / quat of the post-integration configuration (FK:828-864)
+    const int nG = CM(nG);
+    for (int g = lane; g < nG; g += G) {
+      const int l = GM(g_link[g]);
+      const f3 lp = ld3(IN(links_pos), l);
+      const f4 lq = ld4(IN(links_quat), l);
+      st3(rec + c_h.geoms_pos, g, lp + rotate(f3(GM(g_pos[g][0]), GM(g_pos[g][1]), GM(g_pos[g][2])), lq));
+      st4(rec + c_h.geoms_quat, g, quat_compose(f4(GM(g_quat[g][0]), GM(g_quat[g][1]), GM(g_quat[g][2]), GM(g_quat[g][3])), lq));
+    }
+  }
   if (clear_ext) {  // RS:2603-2612 clear_external_force
     for (int i = lane; i < 3 * nL; i += G) { IN(cfrc_applied_vel)[i] = 0.f; IN(cfrc_applied_ang)[i] = 0.f; }
   }
@@ -98,7 +108,7 @@ __global__ void __launch_bounds__(GSR_WARPS_PER_CTA * 32) k_forward(float* state
   Ctx<G> C;
   if (!make_ctx(C, state, B, gm, smem)) return;
   constexpr int EPW = 32 / G;
-  const int env = blockIdx.x * (GSR_WARPS_PER_CTA * EPW) + (threadIdx.x >> 5) * EPW + (threadIdx.x & 31) / G;
+  const int env = blockIdx.x * ((blockDim.x >> 5) * EPW) + (threadIdx.x >> 5) * EPW + (threadIdx.x & 31) / G;
   if (mask && !mask[env]) return;
   load_in(C);
   phase_kinematics(C);

@@ -83,7 +83,11 @@ def test_get_contacts_dictionary():
 
 
 def test_errno_contact_overflow_is_reported():
-    scene, robot = make_go2(4, randomized=False, max_collision_pairs=1)
+    from helpers import scene_from_morphs
+
+    morphs = [gs.morphs.Plane(), gs.morphs.Box(size=(0.2, 0.2, 0.2), pos=(0, 0, 0.1)), gs.morphs.Box(size=(0.2, 0.2, 0.2), pos=(0.5, 0, 0.1))]
+    scene, _ = scene_from_morphs(morphs, dt=0.01, max_collision_pairs=1)  # 5 contact slots, two resting boxes need 8
+    scene.build(n_envs=4)
     with pytest.raises(gs.GenesisException, match="contact pairs|candidate"):
-        for _ in range(60):
+        for _ in range(30):
             scene.step()

@@ -30,6 +30,7 @@ def run(name, make, n_envs, steps):
     scene, robot = make(n_envs)
     s = scene.rigid_solver
     m = s.model
+    print("launch_info", s.launch_info, "state MiB", s._F.numel() * 4 / 2**20)
     orc = Oracle(m, n_envs, double=False, options=s.model_options())
     orc.set("qpos", s.rows("qpos").cpu().numpy())
     orc.set("vel", s.rows("vel").cpu().numpy())
