@@ -180,6 +180,8 @@ static int fill_model(gsr_handle_t h) {
 #undef CPF
   if (missing) return fail(h, GSR_EINVAL, "missing or short model array: " + missing_name);
 
+  for (int i = 0, t = 0; i < GSR_MAX_DOFS; i++)
+    for (int j = 0; j <= i; j++) m.tri[t++] = (unsigned short)((i << 8) | j);
   // derived topology tables: ancestor masks (links and dofs), subtree mass per root, tree depth
   m.max_depth = 1;
   for (int l = 0; l < nL; l++) {
@@ -324,7 +326,7 @@ int gsr_model_commit(gsr_handle_t h, int device, int n_envs) {
   SmemLayout& s = h->sl;
   memset(&s, 0, sizeof(s));
   s.MS = MS; s.JS = JS;
-  int NCS = (int)S("cfg_smem_rows", nD > 12 ? 64 : 32);
+  int NCS = (int)S("cfg_smem_rows", nD > 12 ? 64 : 24);
   if (NCS > lenC) NCS = lenC;
   if (NCS < 4) NCS = 4;
   s.NCS = NCS;
@@ -343,7 +345,9 @@ int gsr_model_commit(gsr_handle_t h, int device, int n_envs) {
   // solver arrays overlay the dead part of the kinematic cache and the phase scratch
   x = L.kin_dead;
   s.contacts = x; x += s.NCC * GSR_CONTACT_WORDS;
-  s.H = x; x += nD * MS;
+  const bool newton = m.solver_type == SOLVER_NEWTON;
+  if (!newton) { s.H = x; x += nD * MS; }  // Newton: H overlays the L^T D L factor, which is dead once acc_smooth is known
+  s.Hinv = x; x += nD; s.tmpv = x; x += nD;
   s.qacc = x; x += nD; s.Ma = x; x += nD; s.grad = x; x += nD; s.Mgrad = x; x += nD; s.search = x; x += nD; s.mv = x; x += nD;
   s.prev_grad = x; x += nD; s.prev_Mgrad = x; x += nD;
   s.r_aref = x; x += NCS; s.r_D = x; x += NCS; s.r_R = x; x += NCS; s.r_floss = x; x += NCS; s.r_Jaref = x; x += NCS;
@@ -352,7 +356,8 @@ int gsr_model_commit(gsr_handle_t h, int device, int n_envs) {
   if (x > xmax) xmax = x;
   // always-live block
   x = (int)round4(xmax);
-  s.M = x; x += nD * MS; s.L = x; x += nD * MS; s.Dinv = x; x += nD; s.force = x; x += nD; s.acc_smooth = x; x += nD;
+  s.M = x; x += nD * MS; s.L = x; x += nD * MS; s.Dinv = x; x += nD;
+  if (newton) s.H = s.L; s.force = x; x += nD; s.acc_smooth = x; x += nD;
   s.acc = x; x += nD; s.qf_applied = x; x += nD; s.qf_passive = x; x += nD; s.qf_bias = x; x += nD; s.qfrc_c = x; x += nD;
   s.env_words = (int)round4(x);
 

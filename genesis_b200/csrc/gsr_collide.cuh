@@ -15,7 +15,7 @@
 
 // SF:138-180 support point of a mesh-backed geom from its 180x180 direction table (L2 resident, read-only path)
 template <int G>
-__device__ f3 dev_support_mesh(const Ctx<G>& C, f3 d, int g) {
+__device__ __noinline__ f3 dev_support_mesh(const Ctx<G>& C, f3 d, int g) {
   const float PI = 3.14159265358979323846f;
   const float theta = atan2f(d.y, d.x), phi = acosf(d.z);
   const int res = 180;
@@ -38,7 +38,7 @@ __device__ f3 dev_support_mesh(const Ctx<G>& C, f3 d, int g) {
 
 // MPR:146-176 support_driver
 template <int G>
-__device__ f3 dev_support(const Ctx<G>& C, f3 d, int g, f3 pos, f4 quat) {
+__device__ __noinline__ f3 dev_support(const Ctx<G>& C, f3 d, int g, f3 pos, f4 quat) {
   const int type = GM(g_type[g]);
   if (type == GEOM_SPHERE) return pos + d * GM(g_data[g][0]);
   if (type == GEOM_BOX) {
@@ -138,7 +138,7 @@ __device__ int discover_portal(const Ctx<G>& C, Simplex& s, const PairPose& P, f
 }
 // MPR:601-819 func_mpr_contact (centre guess + portal discovery/refinement + penetration)
 template <int G>
-__device__ void dev_mpr_contact(const Ctx<G>& C, const PairPose& P, f3 normal_ws, bool& is_col, f3& normal, float& pen, f3& pos) {
+__device__ __noinline__ void dev_mpr_contact(const Ctx<G>& C, const PairPose& P, f3 normal_ws, bool& is_col, f3& normal, float& pen, f3& pos) {
   const float CE = c_m.ccd_eps;
   f3 ca = transform(f3(GM(g_center[P.ga][0]), GM(g_center[P.ga][1]), GM(g_center[P.ga][2])), P.pa, P.qa);
   f3 cb = transform(f3(GM(g_center[P.gb][0]), GM(g_center[P.gb][1]), GM(g_center[P.gb][2])), P.pb, P.qb);
@@ -228,7 +228,7 @@ __device__ __forceinline__ void rotate_frame(f3 pos, f4 quat, f3 cpos, f4 qrot, 
 
 // NP:519-970 func_convex_convex_contact for one broad-phase pair (type[ga] <= type[gb], not plane-box)
 template <int G>
-__device__ void dev_convex_convex(const Ctx<G>& C, LaneContacts& out, int ga, int gb, int i_pair) {
+__device__ __noinline__ void dev_convex_convex(const Ctx<G>& C, LaneContacts& out, int ga, int gb, int i_pair) {
   const float EPS = c_m.eps;
   const int ta = GM(g_type[ga]), tb = GM(g_type[gb]);
   const bool multi = c_m.enable_multi_contact && ta != GEOM_SPHERE && ta != GEOM_ELLIPSOID && tb != GEOM_SPHERE && tb != GEOM_ELLIPSOID;
@@ -313,7 +313,7 @@ __device__ void dev_convex_convex(const Ctx<G>& C, LaneContacts& out, int ga, in
 
 // BOX:24-96 func_plane_box_contact
 template <int G>
-__device__ void dev_plane_box(const Ctx<G>& C, LaneContacts& out, int ga, int gb) {
+__device__ __noinline__ void dev_plane_box(const Ctx<G>& C, LaneContacts& out, int ga, int gb) {
   const f3 pa = ld3(WK(gpos), ga), pb = ld3(WK(gpos), gb);
   const f4 qa = ld4(WK(gquat), ga), qb = ld4(WK(gquat), gb);
   const f3 normal = -normalized(rotate(f3(GM(g_data[ga][0]), GM(g_data[ga][1]), GM(g_data[ga][2])), qa));
@@ -368,7 +368,7 @@ __device__ int narrow_batch(const Ctx<G>& C, const int* queue, int n_batch, int 
   const int base = n_staged + incl - out.n;
   const int cap = CM(max_contact_pairs);
   if (out.n > 0) {
-    const float mu = fmaxf(fmaxf(GM(g_friction[ga]) * IN(friction_ratio)[ga], GM(g_friction[gb]) * IN(friction_ratio)[gb]), 1e-2f);
+    const float mu = fmaxf(fmaxf(GM(g_friction[ga]) * C.rec[c_h.friction_ratio + ga], GM(g_friction[gb]) * C.rec[c_h.friction_ratio + gb]), 1e-2f);
     const int la = GM(g_link[ga]), lb = GM(g_link[gb]);
     for (int k = 0; k < 5; k++) {
       if (k < out.n && base + k < cap) {

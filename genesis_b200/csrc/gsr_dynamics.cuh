@@ -14,7 +14,7 @@
 // FK:580-736 one link's pose from its parent's world pose (pp, pq); also joint anchors / axes and dofs_pos when `final`.
 // ---------------------------------------------------------------------------------------------------------------------
 template <int G>
-__device__ void fk_link(const Ctx<G>& C, int l, bool has_parent, f3 pp, f4 pq, const float* qpos, f3& pos, f4& quat, bool final) {
+__device__ __noinline__ void fk_link(const Ctx<G>& C, int l, bool has_parent, f3 pp, f4 pq, const float* qpos, f3& pos, f4& quat, bool final) {
   const float EPS = CM(eps);
   pos = f3(GM(l_pos[l][0]), GM(l_pos[l][1]), GM(l_pos[l][2]));
   quat = f4(GM(l_quat[l][0]), GM(l_quat[l][1]), GM(l_quat[l][2]), GM(l_quat[l][3]));
@@ -264,7 +264,7 @@ __device__ void phase_geoms(const Ctx<G>& C) {
 // L^T D L solve (FD:813-894) of the vector x (shared memory, in place): x <- L^-1 D^-1 L^-T x
 // ---------------------------------------------------------------------------------------------------------------------
 template <int G>
-__device__ void mass_solve(const Ctx<G>& C, float* x) {
+__device__ __noinline__ void mass_solve(const Ctx<G>& C, float* x) {
   const int nD = CM(nD), MS = c_s.MS;
   const float* L = WK(L);
   const float* Dinv = WK(Dinv);
@@ -284,7 +284,7 @@ __device__ void mass_solve(const Ctx<G>& C, float* x) {
 
 // FD:545-602 factor of the matrix stored in WK(L) (lower part), in place; D^-1 to WK(Dinv)
 template <int G>
-__device__ void mass_factor(const Ctx<G>& C) {
+__device__ __noinline__ void mass_factor(const Ctx<G>& C) {
   const int nD = CM(nD), MS = c_s.MS;
   float* L = WK(L);
   float* Dinv = WK(Dinv);
@@ -401,6 +401,7 @@ __device__ void phase_dynamics(const Ctx<G>& C) {
   float* cdd = WK(cdd);    // per link: vel3, ang3
   float* cfrc = WK(cfrc);  // per link: vel3, ang3 (own contribution)
   const f3 grav(CM(gravity[0]), CM(gravity[1]), CM(gravity[2]));
+  const bool has_ext = C.SI()[c_h.has_ext_force] != 0;
   for (int l = lane; l < nL; l += G) {
     const unsigned long long mask = GM(l_dofmask[l]);
     f3 cdd_vel = -grav * (1.0f - GM(e_gravcomp[GM(l_entity[l])])), cdd_ang;
@@ -415,8 +416,10 @@ __device__ void phase_dynamics(const Ctx<G>& C) {
     inertial_mul(ip, I, mass, cv, ca, f2a, f2v);
     const f3 f3v = cross(ca, f2v);  // geom.py:372-376 motion_cross_force
     const f3 f3a = cross(ca, f2a) + cross(cv, f2v);
-    st3(cfrc, 2 * l, f1v + f3v + ld3(IN(cfrc_applied_vel), l));
-    st3(cfrc, 2 * l + 1, f1a + f3a + ld3(IN(cfrc_applied_ang), l));
+    f3 ev, ea;
+    if (has_ext) { ev = ld3(C.rec + c_h.cfrc_applied_vel, l); ea = ld3(C.rec + c_h.cfrc_applied_ang, l); }
+    st3(cfrc, 2 * l, f1v + f3v + ev);
+    st3(cfrc, 2 * l + 1, f1a + f3a + ea);
   }
   C.sync();
   for (int l = lane; l < nL; l += G) {  // subtree totals, leaf-to-root order (FD:1375-1400)

@@ -60,13 +60,8 @@ __device__ __forceinline__ f3 g3(const float* p) { return f3(__ldg(p), __ldg(p +
 __device__ __forceinline__ f4 g4(const float* p) { return f4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3)); }
 __device__ __forceinline__ bool bit64(unsigned long long m, int i) { return (m >> i) & 1ull; }
 
-// lower-triangle task decode: t = i (i + 1) / 2 + j, j <= i
-__device__ __forceinline__ void tri_decode(int t, int& i, int& j) {
-  i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-  while ((i + 1) * (i + 2) / 2 <= t) i++;
-  while (i * (i + 1) / 2 > t) i--;
-  j = t - i * (i + 1) / 2;
-}
+// lower-triangle task decode: t = i (i + 1) / 2 + j, j <= i (table built on the host, read through the L1 read-only path)
+#define tri_decode(t, i, j) { const unsigned tr_ = GM(tri[t]); i = (int)(tr_ >> 8); j = (int)(tr_ & 255u); }
 
 #define IN(field) (C.S + c_h.field)   // IN part of the record, mirrored in shared memory
 #define WK(field) (C.S + c_s.field)   // workspace regions

@@ -82,7 +82,8 @@ __global__ void __launch_bounds__(GSR_WARPS_PER_CTA * 32, 4) k_step(float* state
       rec[c_h.qf_bias + d] = WK(qf_bias)[d];
       rec[c_h.mass_Dinv + d] = WK(Dinv)[d];
     }
-    for (int t = lane; t < nD * nD; t += G) { const int i = t / nD, j = t - i * nD; rec[c_h.mass_mat + t] = WK(M)[i * MS + j]; }
+    for (int i = 0; i < nD; i++)
+      for (int j = lane; j < nD; j += G) rec[c_h.mass_mat + i * nD + j] = WK(M)[i * MS + j];
   }
   C.sync();
   phase_kinematics(C);
@@ -96,8 +97,10 @@ __global__ void __launch_bounds__(GSR_WARPS_PER_CTA * 32, 4) k_step(float* state
       st4(rec + c_h.geoms_quat, g, quat_compose(f4(GM(g_quat[g][0]), GM(g_quat[g][1]), GM(g_quat[g][2]), GM(g_quat[g][3])), lq));
     }
   }
-  if (clear_ext) {  // RS:2603-2612 clear_external_force
-    for (int i = lane; i < 3 * nL; i += G) { IN(cfrc_applied_vel)[i] = 0.f; IN(cfrc_applied_ang)[i] = 0.f; }
+  if (clear_ext && C.SI()[c_h.has_ext_force]) {  // RS:2603-2612 clear_external_force
+    for (int i = lane; i < 3 * nL; i += G) { rec[c_h.cfrc_applied_vel + i] = 0.f; rec[c_h.cfrc_applied_ang + i] = 0.f; }
+    C.sync();
+    if (lane == 0) C.SI()[c_h.has_ext_force] = 0;
   }
   store_in(C);
 }

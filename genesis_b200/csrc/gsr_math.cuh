@@ -161,7 +161,7 @@ __device__ __forceinline__ void orthogonals(f3 a, f3& d1, f3& d2) {
   d2 = b;
 }
 // geom.py:406-424
-__device__ __forceinline__ void imp_aref(const float* p, float neg_penetration, float vel, float pos, float& imp, float& aref) {
+__device__ __noinline__ void imp_aref(const float* p, float neg_penetration, float vel, float pos, float& imp, float& aref) {
   float timeconst = p[0], dampratio = p[1], dmin = p[2], dmax = p[3], width = p[4], mid = p[5], power = p[6];
   float imp_x = fabsf(neg_penetration) / width;
   float imp_a = (1.0f / powf(mid, power - 1.f)) * powf(imp_x, power);

@@ -30,7 +30,7 @@ struct SolverState {
 // Row assembly (CS:579-1286), row order [equality | frictionloss | 4 x contacts | joint limits]
 // ---------------------------------------------------------------------------------------------------------------------
 template <int G>
-__device__ void build_rows(const Ctx<G>& C, Rows& R) {
+__device__ __noinline__ void build_rows(const Ctx<G>& C, Rows& R) {
   const int nD = CM(nD), nJ = CM(nJ), lane = C.lane;
   const float EPS = CM(eps);
   const float* qpos = IN(qpos);
@@ -80,11 +80,9 @@ __device__ void build_rows(const Ctx<G>& C, Rows& R) {
   float* J = R.J;
   const int JS = R.JS;
   // ---- zero the non-contact rows
-  for (int t = lane; t < (R.nef + n_lim) * nD; t += G) {
-    int r = t / nD;
-    const int d = t - r * nD;
-    if (r >= R.nef) r = lim_base + (r - R.nef);
-    J[r * JS + d] = 0.f;
+  for (int r0 = 0; r0 < R.nef + n_lim; r0++) {
+    const int r = r0 < R.nef ? r0 : lim_base + (r0 - R.nef);
+    for (int d = lane; d < nD; d += G) J[r * JS + d] = 0.f;
   }
   C.sync();
   // ---- equalities (CS:880-937)
@@ -152,8 +150,11 @@ __device__ void build_rows(const Ctx<G>& C, Rows& R) {
   }
   // ---- contacts (CS:579-685): pyramidal friction, 4 rows per contact; one lane per (contact, dof) entry
   const int c_base = R.nef;
-  for (int t = lane; t < n_contacts * nD; t += G) {
-    const int ic = t / nD, d = t - ic * nD;
+  // task t = ic * nD + d, walked without integer division
+  const int ntask = n_contacts * nD;
+  int ic = 0, d = lane;
+  while (d >= nD && ic < n_contacts) { d -= nD; ic++; }
+  for (int t = lane; t < ntask; t += G) {
     const float* ct = R.ct + (size_t)ic * GSR_CONTACT_WORDS;
     const int la = __float_as_int(ct[CT_LA]), lb = __float_as_int(ct[CT_LB]);
     const f3 cpos(ct[CT_POS], ct[CT_POS + 1], ct[CT_POS + 2]), cn(ct[CT_NRM], ct[CT_NRM + 1], ct[CT_NRM + 2]);
@@ -169,6 +170,8 @@ __device__ void build_rows(const Ctx<G>& C, Rows& R) {
     J[(c0 + 1) * JS + d] = dot(diff, d1 * mu - cn);
     J[(c0 + 2) * JS + d] = dot(diff, d2 * (-mu) - cn);
     J[(c0 + 3) * JS + d] = dot(diff, d2 * mu - cn);
+    d += G;
+    while (d >= nD) { d -= nD; ic++; }
   }
   C.sync();
   for (int r = lane; r < 4 * n_contacts; r += G) {
@@ -234,7 +237,7 @@ __device__ void build_rows(const Ctx<G>& C, Rows& R) {
 // ---------------------------------------------------------------------------------------------------------------------
 // CS:2619-2694 func_update_constraint_batch
 template <int G>
-__device__ void update_constraint(const Ctx<G>& C, const Rows& R, SolverState& X, bool track_prev) {
+__device__ __noinline__ void update_constraint(const Ctx<G>& C, const Rows& R, SolverState& X, bool track_prev) {
   const int nD = CM(nD), lane = C.lane;
   X.prev_cost = X.cost;
   float cost = 0.f;
@@ -270,12 +273,13 @@ __device__ void update_constraint(const Ctx<G>& C, const Rows& R, SolverState& X
   C.sync();
 }
 
-// CS:1394-1452 + CS:1594-1621: H = M + J^T (D active) J (lower), then in-place Cholesky
+// CS:1394-1452 + CS:1594-1621: H = M + J^T (D active) J (lower), then in-place Cholesky (1 / L_ii kept in WK(Hinv))
 template <int G>
-__device__ void hessian_cholesky(const Ctx<G>& C, const Rows& R) {
+__device__ __noinline__ void hessian_cholesky(const Ctx<G>& C, const Rows& R) {
   const int nD = CM(nD), MS = c_s.MS, lane = C.lane;
   const float EPS = CM(eps);
   float* H = WK(H);
+  float* Hinv = WK(Hinv);
   const float* M = WK(M);
   const int ntri = nD * (nD + 1) / 2;
   for (int t = lane; t < ntri; t += G) {
@@ -288,25 +292,28 @@ __device__ void hessian_cholesky(const Ctx<G>& C, const Rows& R) {
   }
   C.sync();
   for (int i = 0; i < nD; i++) {
-    float part = 0.f;
-    for (int k = lane; k < i; k += G) { const float h = H[i * MS + k]; part += h * h; }
-    const float tmp = H[i * MS + i] - C.sum(part);
-    const float Lii = sqrtf(fmaxf(tmp, EPS));
-    const float inv = 1.0f / Lii;
-    for (int j = i + 1 + lane; j < nD; j += G) {
+    // every lane owning a row j >= i forms dot_j = sum_{k<i} H[j][k] H[i][k]; the owner of row i turns its dot into L_ii
+    const int owner = i & (G - 1);
+    float Lii = 0.f;
+    for (int j = i + ((lane - i) & (G - 1)); j < nD; j += G) {
       float dt = 0.f;
       for (int k = 0; k < i; k++) dt += H[j * MS + k] * H[i * MS + k];
-      H[j * MS + i] = (H[j * MS + i] - dt) * inv;
+      if (j == i) Lii = sqrtf(fmaxf(H[i * MS + i] - dt, EPS));
+      else H[j * MS + i] = H[j * MS + i] - dt;  // scaled below once L_ii is known
     }
-    C.sync();
-    if (lane == 0) H[i * MS + i] = Lii;
+    Lii = __shfl_sync(C.gmask, Lii, owner, G);
+    const float inv = 1.0f / Lii;
+    for (int j = i + ((lane - i) & (G - 1)); j < nD; j += G) {
+      if (j == i) { H[i * MS + i] = Lii; Hinv[i] = inv; }
+      else H[j * MS + i] *= inv;
+    }
     C.sync();
   }
 }
 
 // CS:1763-1822 rank-1 Cholesky up / down-dates for the rows whose active flag flipped; true when degenerate
 template <int G>
-__device__ bool hessian_incremental(const Ctx<G>& C, const Rows& R) {
+__device__ __noinline__ bool hessian_incremental(const Ctx<G>& C, const Rows& R) {
   const int nD = CM(nD), MS = c_s.MS, lane = C.lane;
   const float EPS = CM(eps);
   float* H = WK(H);
@@ -337,7 +344,7 @@ __device__ bool hessian_incremental(const Ctx<G>& C, const Rows& R) {
             vec[i] = vec[i] * cc - s * Lik;
           }
           C.sync();
-          if (lane == 0) H[k * MS + k] = r;
+          if (lane == 0) { H[k * MS + k] = r; WK(Hinv)[k] = 1.0f / r; }
         }
       }
     }
@@ -348,7 +355,7 @@ __device__ bool hessian_incremental(const Ctx<G>& C, const Rows& R) {
 
 // CS:2721-2750 gradient and preconditioned gradient (Newton: Cholesky solve CS:1892-1910; CG: M^-1 via L^T D L)
 template <int G>
-__device__ void update_gradient(const Ctx<G>& C) {
+__device__ __noinline__ void update_gradient(const Ctx<G>& C) {
   const int nD = CM(nD), MS = c_s.MS, lane = C.lane;
   float* grad = WK(grad);
   float* Mgrad = WK(Mgrad);
@@ -358,18 +365,18 @@ __device__ void update_gradient(const Ctx<G>& C) {
     mass_solve(C, Mgrad);
   } else {
     const float* H = WK(H);
-    for (int i = 0; i < nD; i++) {  // forward substitution, column oriented
-      const float xi = Mgrad[i] / H[i * MS + i];
-      C.sync();
-      if (lane == 0) Mgrad[i] = xi;
-      for (int j = i + 1 + lane; j < nD; j += G) Mgrad[j] -= H[j * MS + i] * xi;
+    const float* Hinv = WK(Hinv);
+    float* y = WK(tmpv);
+    for (int i = 0; i < nD; i++) {  // forward substitution, column oriented: y_i final once columns < i are eliminated
+      const float yi = Mgrad[i] * Hinv[i];
+      if (lane == 0) y[i] = yi;
+      for (int j = i + 1 + lane; j < nD; j += G) Mgrad[j] -= H[j * MS + i] * yi;
       C.sync();
     }
-    for (int i = nD - 1; i >= 0; i--) {  // backward substitution
-      const float xi = Mgrad[i] / H[i * MS + i];
-      C.sync();
+    for (int i = nD - 1; i >= 0; i--) {  // backward substitution on y, result back into Mgrad
+      const float xi = y[i] * Hinv[i];
       if (lane == 0) Mgrad[i] = xi;
-      for (int j = lane; j < i; j += G) Mgrad[j] -= H[i * MS + j] * xi;
+      for (int j = lane; j < i; j += G) y[j] -= H[i * MS + j] * xi;
       C.sync();
     }
   }
@@ -379,7 +386,7 @@ struct LsPoint { float alpha, cost, d0, d1; };
 
 // CS:2154-2354 the piecewise-quadratic cost and its derivatives at step `alpha`
 template <int G>
-__device__ LsPoint ls_eval(const Ctx<G>& C, const Rows& R, const SolverState& X, float alpha) {
+__device__ __noinline__ LsPoint ls_eval(const Ctx<G>& C, const Rows& R, const SolverState& X, float alpha) {
   float t0 = 0.f, t1 = 0.f, t2 = 0.f;
   for (int c = R.ne + C.lane; c < R.n_con; c += G) {
     const float Ja = R.Jaref[c], jv = R.jv[c], D = R.D[c];

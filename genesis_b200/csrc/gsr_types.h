@@ -65,6 +65,7 @@ struct DevModel {
   float d_stiffness[GSR_MAX_DOFS], d_damping[GSR_MAX_DOFS], d_armature[GSR_MAX_DOFS], d_frictionloss[GSR_MAX_DOFS];
   float d_kp[GSR_MAX_DOFS], d_act_bias[GSR_MAX_DOFS][3], d_force_range[GSR_MAX_DOFS][2], d_invweight[GSR_MAX_DOFS];
   float qpos0[GSR_MAX_QS];
+  unsigned short tri[GSR_MAX_DOFS * (GSR_MAX_DOFS + 1) / 2];  // lower-triangle task t -> (row << 8) | col
   // entities
   int e_link_start[GSR_MAX_ENTS], e_link_end[GSR_MAX_ENTS], e_dof_start[GSR_MAX_ENTS], e_dof_end[GSR_MAX_ENTS];
   int e_geom_start[GSR_MAX_ENTS], e_geom_end[GSR_MAX_ENTS];
@@ -92,12 +93,15 @@ struct DevModel {
   X(qpos, 0, nQ, 1) X(vel, 0, nD, 1) X(ctrl_pos, 0, nD, 1) X(ctrl_vel, 0, nD, 1) X(ctrl_force, 0, nD, 1)           \
   X(ctrl_mode, 1, nD, 1) X(qacc_ws, 0, nD, 1)                                                                      \
   X(is_warmstart, 1, 1, 1) X(errno_, 1, 1, 1) X(n_contacts, 1, 1, 1) X(n_broad, 1, 1, 1)                           \
-  X(friction_ratio, 0, nG, 1) X(cfrc_applied_vel, 0, nL, 3) X(cfrc_applied_ang, 0, nL, 3)                          \
+  X(has_ext_force, 1, 1, 1)                                                                                        \
   /* kinematic cache written by the FK at the end of a step and consumed by the next step */                       \
   X(dofs_pos, 0, nD, 1) X(root_COM, 0, nL, 3) X(cdof_ang, 0, nD, 3) X(cdof_vel, 0, nD, 3) X(cdofd_ang, 0, nD, 3)   \
   X(cdofd_vel, 0, nD, 3) X(links_pos, 0, nL, 3) X(links_quat, 0, nL, 4) X(cinr_I, 0, nL, 6) X(cinr_pos, 0, nL, 3)  \
   X(cd_vel, 0, nL, 3) X(cd_ang, 0, nL, 3)
 #define GSR_HOT_OUT_FIELDS(X)                                                                                      \
+  /* rarely used inputs, read from the record on demand: per-geom friction scale (set_friction_ratio) and the external  \
+     wrenches of apply_links_external_force (only read and cleared when has_ext_force is set) */                       \
+  X(friction_ratio, 0, nG, 1) X(cfrc_applied_vel, 0, nL, 3) X(cfrc_applied_ang, 0, nL, 3)                          \
   X(acc, 0, nD, 1) X(force, 0, nD, 1) X(qf_applied, 0, nD, 1) X(qf_constraint, 0, nD, 1)                           \
   X(cacc_lin, 0, nL, 3) X(cacc_ang, 0, nL, 3) X(links_contact_force, 0, nL, 3)                                     \
   X(aabb_min, 0, nG, 3) X(aabb_max, 0, nG, 3)                                                                      \
@@ -125,7 +129,7 @@ struct HotLayout {
 // detection are reused by the collision scratch and then by the solver rows.
 struct SmemLayout {
   // live for the whole step
-  int M, L, Dinv, force, acc_smooth, acc, qf_applied, qf_passive, qf_bias, qfrc_c;
+  int M, L, Dinv, Hinv, force, acc_smooth, acc, qf_applied, qf_passive, qf_bias, qfrc_c;
   int MS;  // row stride of M / L / H (odd)
   // dynamics scratch
   int crb, fdof, cdd, cfrc;
@@ -133,7 +137,7 @@ struct SmemLayout {
   int gpos, gquat, aabb, queue;
   // contacts kept on chip for row assembly (n <= NCC) + solver
   int contacts, NCC;
-  int H, qacc, Ma, grad, Mgrad, search, mv, prev_grad, prev_Mgrad;
+  int H, qacc, Ma, grad, Mgrad, search, mv, prev_grad, prev_Mgrad, tmpv;
   int J, JS, NCS;                 // rows: J[NCS][JS]
   int r_aref, r_D, r_R, r_floss, r_Jaref, r_jv, r_force, r_active;
   // integrate / FK scratch

@@ -387,6 +387,7 @@ class RigidSolver:
         e = self._envs_all if envs is None else envs
         self._fields["cfrc_applied_vel"][e[:, None], links[None, :]] -= force
         self._fields["cfrc_applied_ang"][e[:, None], links[None, :]] -= torque
+        self._fields["has_ext_force"][e] = 1
 
     def _get_links_com(self, links, envs):
         m = self.model
@@ -532,6 +533,7 @@ class RigidSolver:
         f["ctrl_mode"][rows] = int(CTRL_MODE.FORCE)
         f["cfrc_applied_vel"][rows] = 0.0
         f["cfrc_applied_ang"][rows] = 0.0
+        f["has_ext_force"][rows] = 0
         self._reset_warmstart(envs_idx)
         self._forward(envs_idx)
 
