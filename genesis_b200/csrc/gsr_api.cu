@@ -35,6 +35,7 @@ struct gsr_handle_s {
   bool committed = false;
   int device = 0, B = 0;
   int group = 32;  // lanes per environment
+  int warps_per_cta = 0;
   DevModel hm;     // host copy of the model
   HotLayout lay;
   SmemLayout sl;
@@ -198,6 +199,11 @@ static int fill_model(gsr_handle_t h) {
     m.l_root_mass[l] = 0.f;
   }
   for (int l = 0; l < nL; l++) m.l_root_mass[m.l_root[l]] += m.l_mass[l];
+  for (int l = 0; l < nL; l++) {
+    m.l_descmask[l] = 0ull;
+    for (int d = 0; d < nL; d++)
+      if ((m.l_ancmask[d] >> l) & 1ull) m.l_descmask[l] |= 1ull << d;
+  }
 
   // has_cc: any valid pair that is not plane-box (collider.py:449-459) -> contacts are x-sorted (collider.py:804-808)
   m.has_cc = 0;
@@ -270,8 +276,9 @@ int gsr_model_commit(gsr_handle_t h, int device, int n_envs) {
   // ---- lanes per environment: a full warp unless the batch is large enough to fill the machine with smaller groups
   auto S = [&](const char* k, double d) { auto it = h->s.find(k); return it == h->s.end() ? d : it->second; };
   int G = (int)S("cfg_group_size", 0);
-  if (G != 8 && G != 16 && G != 32) G = 32;
+  if (G != 8 && G != 16 && G != 32) G = (m.nD <= 12 && m.nL <= 16) ? 8 : 32;  // measured on B200: profiles/README.md
   h->group = G;
+  h->warps_per_cta = (int)S("cfg_warps_per_cta", 0);
 
   // ---- HOT record layout
   const int nL = m.nL, nD = m.nD, nQ = m.nQ, nG = m.nG;
@@ -421,8 +428,9 @@ static cudaError_t set_smem(K kernel, size_t bytes) {
 static int group_launch(gsr_handle_t h, int which, cudaStream_t st, const uint8_t* mask, int clear_ext) {
   const int G = h->group, EPW = 32 / G;
   const size_t warp_bytes = (size_t)EPW * h->sl.env_words * sizeof(float);
-  int warps = GSR_WARPS_PER_CTA;
-  while (warps > 1 && warps * warp_bytes > 100 * 1024) warps--;  // keep at least two CTAs per SM when possible
+  int warps = h->warps_per_cta > 0 ? h->warps_per_cta : (G == 32 ? 8 : 4);  // measured on B200 (profiles/README.md)
+  if (warps > GSR_MAX_WARPS_PER_CTA) warps = GSR_MAX_WARPS_PER_CTA;
+  while (warps > 1 && warps * warp_bytes > 224 * 1024) warps--;  // one big CTA per SM, its warps in phase lockstep
   const int envs_per_cta = warps * EPW;
   const size_t smem = (size_t)warps * warp_bytes;
   if (smem > 227 * 1024) return fail(h, GSR_ELIMIT, "per-warp shared-memory workspace exceeds 227 KB (lower cfg_smem_rows or raise cfg_group_size)");

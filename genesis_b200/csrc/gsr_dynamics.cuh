@@ -203,8 +203,7 @@ __device__ void phase_kinematics(const Ctx<G>& C) {
   for (int l = lane; l < nL; l += G) {
     const unsigned long long mask = GM(l_dofmask[l]);
     f3 vv, va;
-    for (int d = 0; d < nD; d++)
-      if (bit64(mask, d)) { const float w = vel[d]; vv += ld3(cdv, d) * w; va += ld3(cda, d) * w; }
+    FOR_BITS_UP(mask, d) { const float w = vel[d]; vv += ld3(cdv, d) * w; va += ld3(cda, d) * w; } END_BITS
     st3(IN(cd_vel), l, vv); st3(IN(cd_ang), l, va);
   }
   for (int d = lane; d < nD; d += G) {
@@ -214,8 +213,7 @@ __device__ void phase_kinematics(const Ctx<G>& C) {
     int lim = ds;
     if (type == JOINT_FREE && d >= ds + 3) lim = ds + 3;
     f3 vv, va;
-    for (int k = 0; k < lim; k++)
-      if (bit64(mask, k)) { const float w = vel[k]; vv += ld3(cdv, k) * w; va += ld3(cda, k) * w; }
+    FOR_BITS_UP(mask & ((1ull << lim) - 1ull), k) { const float w = vel[k]; vv += ld3(cdv, k) * w; va += ld3(cda, k) * w; } END_BITS
     f3 da, dv;
     if (!(type == JOINT_FREE && d < ds + 3)) {  // geom.py:379-383 motion_cross_motion(cvel, cdof)
       const f3 a = ld3(cda, d), v = ld3(cdv, d);
@@ -320,16 +318,15 @@ __device__ void phase_dynamics(const Ctx<G>& C) {
     float s[10];
 #pragma unroll
     for (int k = 0; k < 10; k++) s[k] = 0.f;
-    for (int d = nL - 1; d >= l; d--)
-      if (bit64(CM(l_ancmask[d]), l)) {
-        const float* I = IN(cinr_I) + 6 * d;
-        const float* P = IN(cinr_pos) + 3 * d;
+    FOR_BITS_DOWN(GM(l_descmask[l]), d) {
+      const float* I = IN(cinr_I) + 6 * d;
+      const float* P = IN(cinr_pos) + 3 * d;
 #pragma unroll
-        for (int k = 0; k < 6; k++) s[k] += I[k];
+      for (int k = 0; k < 6; k++) s[k] += I[k];
 #pragma unroll
-        for (int k = 0; k < 3; k++) s[6 + k] += P[k];
-        s[9] += CM(l_mass[d]);
-      }
+      for (int k = 0; k < 3; k++) s[6 + k] += P[k];
+      s[9] += GM(l_mass[d]);
+    } END_BITS
 #pragma unroll
     for (int k = 0; k < 10; k++) crb[10 * l + k] = s[k];
   }
@@ -405,8 +402,7 @@ __device__ void phase_dynamics(const Ctx<G>& C) {
   for (int l = lane; l < nL; l += G) {
     const unsigned long long mask = GM(l_dofmask[l]);
     f3 cdd_vel = -grav * (1.0f - GM(e_gravcomp[GM(l_entity[l])])), cdd_ang;
-    for (int d = 0; d < nD; d++)
-      if (bit64(mask, d)) { const float w = vel[d]; cdd_vel += ld3(IN(cdofd_vel), d) * w; cdd_ang += ld3(IN(cdofd_ang), d) * w; }
+    FOR_BITS_UP(mask, d) { const float w = vel[d]; cdd_vel += ld3(IN(cdofd_vel), d) * w; cdd_ang += ld3(IN(cdofd_ang), d) * w; } END_BITS
     const sym3 I = ld6(IN(cinr_I), l);
     const f3 ip = ld3(IN(cinr_pos), l);
     const float mass = GM(l_mass[l]);
@@ -424,8 +420,7 @@ __device__ void phase_dynamics(const Ctx<G>& C) {
   C.sync();
   for (int l = lane; l < nL; l += G) {  // subtree totals, leaf-to-root order (FD:1375-1400)
     f3 sv, sa;
-    for (int d = nL - 1; d >= l; d--)
-      if (bit64(CM(l_ancmask[d]), l)) { sv += ld3(cfrc, 2 * d); sa += ld3(cfrc, 2 * d + 1); }
+    FOR_BITS_DOWN(GM(l_descmask[l]), d) { sv += ld3(cfrc, 2 * d); sa += ld3(cfrc, 2 * d + 1); } END_BITS
     st3(cdd, 2 * l, sv); st3(cdd, 2 * l + 1, sa);
   }
   C.sync();
@@ -460,12 +455,11 @@ __device__ void phase_integrate(const Ctx<G>& C) {
   for (int l = lane; l < nL; l += G) {
     const unsigned long long mask = GM(l_dofmask[l]);
     f3 lin, ang;
-    for (int d = 0; d < nD; d++)
-      if (bit64(mask, d)) {
-        const float v = vel[d], a = acc[d];
-        lin += ld3(IN(cdofd_vel), d) * v + ld3(IN(cdof_vel), d) * a;
-        ang += ld3(IN(cdofd_ang), d) * v + ld3(IN(cdof_ang), d) * a;
-      }
+    FOR_BITS_UP(mask, d) {
+      const float v = vel[d], a = acc[d];
+      lin += ld3(IN(cdofd_vel), d) * v + ld3(IN(cdof_vel), d) * a;
+      ang += ld3(IN(cdofd_ang), d) * v + ld3(IN(cdof_ang), d) * a;
+    } END_BITS
     st3(cacc, 2 * l, lin); st3(cacc, 2 * l + 1, ang);
   }
   if (CM(integrator) != INTEGRATOR_APPROX_IMPLICITFAST) {

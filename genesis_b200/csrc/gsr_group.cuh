@@ -59,6 +59,10 @@ __device__ __forceinline__ void st6(float* p, int i, const sym3& v) {
 __device__ __forceinline__ f3 g3(const float* p) { return f3(__ldg(p), __ldg(p + 1), __ldg(p + 2)); }
 __device__ __forceinline__ f4 g4(const float* p) { return f4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3)); }
 __device__ __forceinline__ bool bit64(unsigned long long m, int i) { return (m >> i) & 1ull; }
+// iterate the set bits of a 64-bit mask in ascending / descending order
+#define FOR_BITS_UP(m_, i_) for (unsigned long long mm_ = (m_); mm_ != 0ull; mm_ &= mm_ - 1ull) { const int i_ = __ffsll((long long)mm_) - 1;
+#define FOR_BITS_DOWN(m_, i_) for (unsigned long long mm_ = (m_); mm_ != 0ull; ) { const int i_ = 63 - __clzll((long long)mm_); mm_ &= ~(1ull << i_);
+#define END_BITS }
 
 // lower-triangle task decode: t = i (i + 1) / 2 + j, j <= i (table built on the host, read through the L1 read-only path)
 #define tri_decode(t, i, j) { const unsigned tr_ = GM(tri[t]); i = (int)(tr_ >> 8); j = (int)(tr_ & 255u); }

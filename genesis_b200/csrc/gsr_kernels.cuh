@@ -14,7 +14,11 @@
 #include "gsr_collide.cuh"
 #include "gsr_solver.cuh"
 
-#define GSR_WARPS_PER_CTA 4
+#define GSR_MAX_WARPS_PER_CTA 16
+// All warps of a CTA walk the phases of the step together (CTA barriers between phases): the step is ~20k instructions of
+// mostly straight-line code per environment, far more than the instruction cache holds, so warps that drift apart each
+// stream the whole kernel from L2 on their own (ncu: stall_no_instruction dominated before this was added).
+#define PHASE_BARRIER() __syncthreads()
 
 template <int G>
 __device__ __forceinline__ bool make_ctx(Ctx<G>& C, float* state, int B, const DevModel* gm, float* smem) {
@@ -52,15 +56,21 @@ __device__ __forceinline__ void store_in(const Ctx<G>& C) {
 }
 
 template <int G>
-__global__ void __launch_bounds__(GSR_WARPS_PER_CTA * 32, 4) k_step(float* state, int B, const DevModel* gm, int clear_ext) {
+__global__ void __launch_bounds__(GSR_MAX_WARPS_PER_CTA * 32, 1) k_step(float* state, int B, const DevModel* gm, int clear_ext) {
   extern __shared__ __align__(16) float smem[];
   Ctx<G> C;
-  if (!make_ctx(C, state, B, gm, smem)) return;
-  load_in(C);
-  phase_dynamics(C);
-  if (CM(enable_collision) && CM(nG) > 0) phase_collide(C);
-  phase_constraints(C);
-  phase_integrate(C);
+  const bool live = make_ctx(C, state, B, gm, smem);
+  if (live) load_in(C);
+  PHASE_BARRIER();
+  if (live) phase_dynamics(C);
+  PHASE_BARRIER();
+  if (live && CM(enable_collision) && CM(nG) > 0) phase_collide(C);
+  PHASE_BARRIER();
+  if (live) phase_constraints(C);
+  PHASE_BARRIER();
+  if (live) phase_integrate(C);
+  PHASE_BARRIER();
+  if (!live) return;
   // ---- outputs that live in scratch recycled by the kinematics
   const int nD = CM(nD), nL = CM(nL), MS = c_s.MS, lane = C.lane;
   float* rec = C.rec;
@@ -106,7 +116,7 @@ __global__ void __launch_bounds__(GSR_WARPS_PER_CTA * 32, 4) k_step(float* state
 }
 
 template <int G>
-__global__ void __launch_bounds__(GSR_WARPS_PER_CTA * 32) k_forward(float* state, int B, const DevModel* gm, const uint8_t* mask) {
+__global__ void __launch_bounds__(GSR_MAX_WARPS_PER_CTA * 32) k_forward(float* state, int B, const DevModel* gm, const uint8_t* mask) {
   extern __shared__ __align__(16) float smem[];
   Ctx<G> C;
   if (!make_ctx(C, state, B, gm, smem)) return;

@@ -43,13 +43,13 @@ __device__ __forceinline__ f4 quat_mul(f4 u, f4 v) {
             u.w * v.y - u.x * v.z + u.y * v.w + u.z * v.x, u.w * v.z + u.x * v.y - u.y * v.x + u.z * v.w);
 }
 // geom.py:245-252: transform_quat_by_quat(v, u) = normalize(u * v)
-__device__ __forceinline__ f4 quat_compose(f4 v, f4 u) {
+__device__ __noinline__ f4 quat_compose(f4 v, f4 u) {
   f4 r = quat_mul(u, v);
   float n = 1.0f / sqrtf(r.w * r.w + r.x * r.x + r.y * r.y + r.z * r.z);
   return f4(r.w * n, r.x * n, r.y * n, r.z * n);
 }
 // geom.py:255-270
-__device__ __forceinline__ f3 rotate(f3 v, f4 q) {
+__device__ __noinline__ f3 rotate(f3 v, f4 q) {
   float xx = q.x * q.x, xy = q.x * q.y, xz = q.x * q.z, wx = q.x * q.w;
   float yy = q.y * q.y, yz = q.y * q.z, wy = q.y * q.w;
   float zz = q.z * q.z, wz = q.z * q.w, ww = q.w * q.w;
@@ -65,7 +65,7 @@ struct mat3 {
   float m[3][3];
 };
 // geom.py:136-161
-__device__ __forceinline__ mat3 quat_to_R(f4 q, float eps) {
+__device__ __noinline__ mat3 quat_to_R(f4 q, float eps) {
   mat3 R;
   R.m[0][0] = 1.f; R.m[0][1] = 0.f; R.m[0][2] = 0.f; R.m[1][0] = 0.f; R.m[1][1] = 1.f; R.m[1][2] = 0.f;
   R.m[2][0] = 0.f; R.m[2][1] = 0.f; R.m[2][2] = 1.f;
@@ -85,7 +85,7 @@ __device__ __forceinline__ mat3 quat_to_R(f4 q, float eps) {
 __device__ __forceinline__ f3 mat_col(const mat3& R, int j) { return f3(R.m[0][j], R.m[1][j], R.m[2][j]); }
 
 // geom.py:110-133
-__device__ __forceinline__ f4 rotvec_to_quat(f3 rv, float eps) {
+__device__ __noinline__ f4 rotvec_to_quat(f3 rv, float eps) {
   f4 q(0.f, 0.f, 0.f, 0.f);
   float thetasq = norm_sqr(rv);
   if (thetasq > eps * eps) {
@@ -102,7 +102,7 @@ __device__ __forceinline__ f4 rotvec_to_quat(f3 rv, float eps) {
   return q;
 }
 // geom.py:164-193
-__device__ __forceinline__ f3 quat_to_xyz(f4 q, float eps) {
+__device__ __noinline__ f3 quat_to_xyz(f4 q, float eps) {
   float roll = 0.f, pitch = 0.f, yaw = 0.f;
   float n2 = q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z;
   if (n2 > eps) {
@@ -124,7 +124,7 @@ __device__ __forceinline__ f3 quat_to_xyz(f4 q, float eps) {
   return f3(roll, pitch, yaw);
 }
 // geom.py:45-65
-__device__ __forceinline__ f4 xyz_to_quat(f3 xyz) {
+__device__ __noinline__ f4 xyz_to_quat(f3 xyz) {
   float si, ci, sj, cj, sk, ck;
   sincosf(0.5f * xyz.z, &si, &ci);
   sincosf(-0.5f * xyz.y, &sj, &cj);
@@ -133,7 +133,7 @@ __device__ __forceinline__ f4 xyz_to_quat(f3 xyz) {
   return f4(cj * cc + sj * ss, cj * cs - sj * sc, -cj * ss - sj * cc, cj * sc - sj * cs);
 }
 // geom.py:196-207
-__device__ __forceinline__ f3 quat_to_rotvec(f4 q, float eps) {
+__device__ __noinline__ f3 quat_to_rotvec(f4 q, float eps) {
   f3 rv(q.x, q.y, q.z);
   float s2 = norm(rv);
   if (s2 > eps) {
@@ -152,7 +152,7 @@ __device__ __forceinline__ void inertial_mul(f3 pos, const sym3& I, float mass, 
   o_vel = vel * mass - cross(pos, ang);
 }
 // geom.py:386-403
-__device__ __forceinline__ void orthogonals(f3 a, f3& d1, f3& d2) {
+__device__ __noinline__ void orthogonals(f3 a, f3& d1, f3& d2) {
   f3 b;
   if (fabsf(a.y) < 0.5f) b = f3(-a.x * a.y, 1.f - a.y * a.y, -a.z * a.y);
   else b = f3(-a.x * a.z, -a.y * a.z, 1.f - a.z * a.z);

@@ -54,6 +54,7 @@ struct DevModel {
   int l_q_start[GSR_MAX_LINKS], l_q_end[GSR_MAX_LINKS], l_depth[GSR_MAX_LINKS];
   unsigned long long l_dofmask[GSR_MAX_LINKS];   // dofs of the link and of all its ancestors
   unsigned long long l_ancmask[GSR_MAX_LINKS];   // the link and all its ancestors
+  unsigned long long l_descmask[GSR_MAX_LINKS];  // the link and all its descendants
   float l_pos[GSR_MAX_LINKS][3], l_quat[GSR_MAX_LINKS][4], l_ipos[GSR_MAX_LINKS][3], l_iquat[GSR_MAX_LINKS][4];
   float l_inertia[GSR_MAX_LINKS][9], l_mass[GSR_MAX_LINKS], l_invweight[GSR_MAX_LINKS], l_root_mass[GSR_MAX_LINKS];
   // joints
