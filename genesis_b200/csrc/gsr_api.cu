@@ -430,9 +430,9 @@ static int group_launch(gsr_handle_t h, int which, cudaStream_t st, const uint8_
   const size_t warp_bytes = (size_t)EPW * h->sl.env_words * sizeof(float);
   int warps = h->warps_per_cta > 0 ? h->warps_per_cta : (G == 32 ? 8 : 4);  // measured on B200 (profiles/README.md)
   if (warps > GSR_MAX_WARPS_PER_CTA) warps = GSR_MAX_WARPS_PER_CTA;
-  while (warps > 1 && warps * warp_bytes > 224 * 1024) warps--;  // one big CTA per SM, its warps in phase lockstep
+  while (warps > 1 && warps * (warp_bytes + 8) > 224 * 1024) warps--;  // one big CTA per SM, its warps in phase lockstep
   const int envs_per_cta = warps * EPW;
-  const size_t smem = (size_t)warps * warp_bytes;
+  const size_t smem = (size_t)warps * warp_bytes + (size_t)warps * 8;  // + one mbarrier per warp (TMA staging)
   if (smem > 227 * 1024) return fail(h, GSR_ELIMIT, "per-warp shared-memory workspace exceeds 227 KB (lower cfg_smem_rows or raise cfg_group_size)");
   dim3 grid((h->B + envs_per_cta - 1) / envs_per_cta), block(warps * 32);
 #define LAUNCH(GG)                                                                                       \

@@ -39,28 +39,69 @@ __device__ __forceinline__ bool make_ctx(Ctx<G>& C, float* state, int B, const D
   return true;
 }
 
-// record IN part <-> shared memory (16-byte vectors; both sides are 16-byte aligned by construction)
+// ---- record IN part <-> shared memory by the TMA (bulk async copies, one per environment, issued by one lane per warp).
+// Both sides are 16-byte aligned and n_in is a multiple of 4 words by construction (gsr_model_commit).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Loads the IN parts of the (up to 32 / G) live environments of this warp; `bar` is this warp's mbarrier (one phase per launch).
 template <int G>
-__device__ __forceinline__ void load_in(const Ctx<G>& C) {
-  const float4* src = reinterpret_cast<const float4*>(C.rec);
-  float4* dst = reinterpret_cast<float4*>(C.S);
-  for (int i = C.lane; i < c_h.n_in / 4; i += G) dst[i] = src[i];
-  C.sync();
+__device__ __forceinline__ void bulk_load_in(float* state, int B, float* smem, uint64_t* bar) {
+  constexpr int EPW = 32 / G;
+  const int warp = threadIdx.x >> 5, lane32 = threadIdx.x & 31;
+  const int env0 = (blockIdx.x * (blockDim.x >> 5) + warp) * EPW;
+  const int n_live = min(EPW, B - env0);  // > 0 for a live warp
+  const uint32_t bytes = (uint32_t)c_h.n_in * 4u;
+  const uint32_t b = smem_u32(bar);
+  if (lane32 == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes * (uint32_t)n_live) : "memory");
+    for (int e = 0; e < n_live; e++) {
+      const float* src = state + (size_t)(env0 + e) * c_h.hot_stride;
+      const uint32_t dst = smem_u32(smem + (size_t)(warp * EPW + e) * c_s.env_words);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dst), "l"(src), "r"(bytes), "r"(b) : "memory");
+    }
+  }
+  __syncwarp();
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra WAIT_%=;\n\t}"
+      ::"r"(b), "r"(0) : "memory");
 }
+// Stores the IN parts back (smem -> global bulk copies); returns after the TMA has finished reading shared memory.
 template <int G>
-__device__ __forceinline__ void store_in(const Ctx<G>& C) {
-  C.sync();
-  float4* dst = reinterpret_cast<float4*>(C.rec);
-  const float4* src = reinterpret_cast<const float4*>(C.S);
-  for (int i = C.lane; i < c_h.n_in / 4; i += G) dst[i] = src[i];
+__device__ __forceinline__ void bulk_store_in(float* state, int B, float* smem) {
+  constexpr int EPW = 32 / G;
+  const int warp = threadIdx.x >> 5, lane32 = threadIdx.x & 31;
+  const int env0 = (blockIdx.x * (blockDim.x >> 5) + warp) * EPW;
+  const int n_live = min(EPW, B - env0);
+  const uint32_t bytes = (uint32_t)c_h.n_in * 4u;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the async proxy
+  __syncwarp();
+  if (lane32 == 0) {
+    for (int e = 0; e < n_live; e++) {
+      float* dst = state + (size_t)(env0 + e) * c_h.hot_stride;
+      const uint32_t src = smem_u32(smem + (size_t)(warp * EPW + e) * c_s.env_words);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+  __syncwarp();
 }
+
+template <int G>
+__device__ __forceinline__ void step_epilogue(const Ctx<G>& C, int clear_ext);
 
 template <int G>
 __global__ void __launch_bounds__(GSR_MAX_WARPS_PER_CTA * 32, 1) k_step(float* state, int B, const DevModel* gm, int clear_ext) {
   extern __shared__ __align__(16) float smem[];
   Ctx<G> C;
   const bool live = make_ctx(C, state, B, gm, smem);
-  if (live) load_in(C);
+  // a warp is live when its first environment exists; its mbarrier sits after the workspaces
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)(blockDim.x >> 5) * (32 / G) * c_s.env_words);
+  const bool warp_live = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (32 / G) < B;
+  if (warp_live) bulk_load_in<G>(state, B, smem, bars + (threadIdx.x >> 5));
   PHASE_BARRIER();
   if (live) phase_dynamics(C);
   PHASE_BARRIER();
@@ -70,7 +111,13 @@ __global__ void __launch_bounds__(GSR_MAX_WARPS_PER_CTA * 32, 1) k_step(float* s
   PHASE_BARRIER();
   if (live) phase_integrate(C);
   PHASE_BARRIER();
-  if (!live) return;
+  if (live) step_epilogue(C, clear_ext);
+  __syncwarp();
+  if (warp_live) bulk_store_in<G>(state, B, smem);
+}
+
+template <int G>
+__device__ __forceinline__ void step_epilogue(const Ctx<G>& C, int clear_ext) {
   // ---- outputs that live in scratch recycled by the kinematics
   const int nD = CM(nD), nL = CM(nL), MS = c_s.MS, lane = C.lane;
   float* rec = C.rec;
@@ -112,7 +159,7 @@ __global__ void __launch_bounds__(GSR_MAX_WARPS_PER_CTA * 32, 1) k_step(float* s
     C.sync();
     if (lane == 0) C.SI()[c_h.has_ext_force] = 0;
   }
-  store_in(C);
+  C.sync();
 }
 
 template <int G>
@@ -123,10 +170,20 @@ __global__ void __launch_bounds__(GSR_MAX_WARPS_PER_CTA * 32) k_forward(float* s
   constexpr int EPW = 32 / G;
   const int env = blockIdx.x * ((blockDim.x >> 5) * EPW) + (threadIdx.x >> 5) * EPW + (threadIdx.x & 31) / G;
   if (mask && !mask[env]) return;
-  load_in(C);
+  {  // masked environments are few: plain vector copies
+    const float4* src = reinterpret_cast<const float4*>(C.rec);
+    float4* dst = reinterpret_cast<float4*>(C.S);
+    for (int i = C.lane; i < c_h.n_in / 4; i += G) dst[i] = src[i];
+    C.sync();
+  }
   phase_kinematics(C);
   phase_geoms(C);
-  store_in(C);
+  C.sync();
+  {
+    float4* dst = reinterpret_cast<float4*>(C.rec);
+    const float4* src = reinterpret_cast<const float4*>(C.S);
+    for (int i = C.lane; i < c_h.n_in / 4; i += G) dst[i] = src[i];
+  }
 }
 
 // collider.clear + constraint_solver.reset for masked envs (collider.py:563-607, solver.py:114-179)
