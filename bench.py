@@ -118,8 +118,11 @@ def oracle_throughput(workload, n_envs, steps, warmup, threads):
         mode = np.full((n_envs, 18), int(gs.CTRL_MODE.FORCE)); mode[:, 6:] = int(gs.CTRL_MODE.POSITION)
         orc.set("qpos", q); orc.set("ctrl_pos", ctrl); orc.set("ctrl_mode", mode)
     orc.step(warmup)
+    if steps <= 0:  # calibrate to about `-steps` seconds of CPU work (bounded sample)
+        probe = orc.step_timed(10)
+        steps = int(max(10, min(5000, round(-steps * 10 / max(probe, 1e-6)))))
     sec = orc.step_timed(steps)
-    return n_envs * steps / sec, sec
+    return n_envs * steps / sec, sec, steps
 
 
 def run_reference(args, rank):
@@ -130,8 +133,8 @@ def run_reference(args, rank):
     name, n_envs_gpu, desc = WORKLOADS[args.workload]
     sample_envs = 64 * cores if args.workload == "franka" else 16 * cores
     t0 = time.time()
-    value, sec = oracle_throughput(args.workload, sample_envs, args.steps, args.warmup, cores)
-    sample = f"{sample_envs} envs x {args.steps} steps of the same scene on {cores} host threads ({sec:.2f} s)"
+    value, sec, steps = oracle_throughput(args.workload, sample_envs, args.steps, args.warmup, cores)
+    sample = f"{sample_envs} envs x {steps} steps of the same scene on {cores} host threads ({sec:.2f} s)"
     print(json.dumps({
         "impl": "reference", "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -147,8 +150,8 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=500)
-    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="franka")
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's BASELINE size)")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
@@ -227,8 +230,7 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    # the dominant kernel's algorithmic bytes: the whole step's compulsory traffic is charged to it (the other kernels of
-    # the step only move on-chip-able intermediates; DESIGN.md "Roofline accounting")
+    # the step IS one kernel (k_step): its algorithmic bytes are the whole step's compulsory traffic (DESIGN.md "Roofline")
     achieved = B * bytes_step / (dom_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": peak_src, "algorithmic_bytes_per_env_step": bytes_step, "kernel_ms": dom_ms,
@@ -267,8 +269,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         n_s = 64 * cores if args.workload == "franka" else 16 * cores
-        k_s = 200
-        v, sec = oracle_throughput(args.workload, n_s, k_s, 10, cores)
+        v, sec, k_s = oracle_throughput(args.workload, n_s, -12, 10, cores)  # ~12 s of CPU work
         cpu_baseline = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
                         "sample": f"{n_s} envs x {k_s} steps of the same scene, {cores} threads, {sec:.2f} s (oracle/: C++ restatement; the reference is not installable offline)"}
 
@@ -280,7 +281,7 @@ def main():
                        "solver": "Newton", "integrator": "approximate_implicitfast", "n_dofs": nD, "n_links": m.n_links, "n_geoms": m.n_geoms,
                        "mean_contacts_per_env": mean_contacts, "errno_max": errno,
                        "l2": f"per-GPU state {solver._F.numel() * 4 / 2**20:.0f} MiB > 126 MB L2 (no flush needed)",
-                       "parallelism": f"env-sharded x{world}, no step-path collective"},
+                       "launch": solver.launch_info, "parallelism": f"env-sharded x{world}, no step-path collective"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
             "launches_per_step": launches / K, "clocks": clocks.summary(),
         }), flush=True)
