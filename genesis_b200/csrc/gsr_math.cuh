@@ -20,36 +20,36 @@ struct sym3 {
   float xx, xy, xz, yy, yz, zz;
 };
 
-__device__ __forceinline__ f3 operator+(f3 a, f3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
-__device__ __forceinline__ f3 operator-(f3 a, f3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
-__device__ __forceinline__ f3 operator-(f3 a) { return f3(-a.x, -a.y, -a.z); }
-__device__ __forceinline__ f3 operator*(f3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
-__device__ __forceinline__ f3 operator*(float s, f3 a) { return f3(a.x * s, a.y * s, a.z * s); }
-__device__ __forceinline__ f3 operator/(f3 a, float s) { return f3(a.x / s, a.y / s, a.z / s); }
-__device__ __forceinline__ void operator+=(f3& a, f3 b) { a.x += b.x; a.y += b.y; a.z += b.z; }
-__device__ __forceinline__ void operator-=(f3& a, f3 b) { a.x -= b.x; a.y -= b.y; a.z -= b.z; }
-__device__ __forceinline__ float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-__device__ __forceinline__ f3 cross(f3 a, f3 b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
-__device__ __forceinline__ float norm_sqr(f3 a) { return dot(a, a); }
-__device__ __forceinline__ float norm(f3 a) { return sqrtf(dot(a, a)); }
-__device__ __forceinline__ f3 normalized(f3 a) { float n = norm(a); return f3(a.x / n, a.y / n, a.z / n); }
-__device__ __forceinline__ float comp(f3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
-__device__ __forceinline__ void set_comp(f3& a, int i, float v) { if (i == 0) a.x = v; else if (i == 1) a.y = v; else a.z = v; }
+__host__ __device__ __forceinline__ f3 operator+(f3 a, f3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__host__ __device__ __forceinline__ f3 operator-(f3 a, f3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__host__ __device__ __forceinline__ f3 operator-(f3 a) { return f3(-a.x, -a.y, -a.z); }
+__host__ __device__ __forceinline__ f3 operator*(f3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+__host__ __device__ __forceinline__ f3 operator*(float s, f3 a) { return f3(a.x * s, a.y * s, a.z * s); }
+__host__ __device__ __forceinline__ f3 operator/(f3 a, float s) { return f3(a.x / s, a.y / s, a.z / s); }
+__host__ __device__ __forceinline__ void operator+=(f3& a, f3 b) { a.x += b.x; a.y += b.y; a.z += b.z; }
+__host__ __device__ __forceinline__ void operator-=(f3& a, f3 b) { a.x -= b.x; a.y -= b.y; a.z -= b.z; }
+__host__ __device__ __forceinline__ float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__host__ __device__ __forceinline__ f3 cross(f3 a, f3 b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__host__ __device__ __forceinline__ float norm_sqr(f3 a) { return dot(a, a); }
+__host__ __device__ __forceinline__ float norm(f3 a) { return sqrtf(dot(a, a)); }
+__host__ __device__ __forceinline__ f3 normalized(f3 a) { float n = norm(a); return f3(a.x / n, a.y / n, a.z / n); }
+__host__ __device__ __forceinline__ float comp(f3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+__host__ __device__ __forceinline__ void set_comp(f3& a, int i, float v) { if (i == 0) a.x = v; else if (i == 1) a.y = v; else a.z = v; }
 
-__device__ __forceinline__ f4 quat_inv(f4 q) { return f4(q.w, -q.x, -q.y, -q.z); }
+__host__ __device__ __forceinline__ f4 quat_inv(f4 q) { return f4(q.w, -q.x, -q.y, -q.z); }
 // geom.py:235-242
-__device__ __forceinline__ f4 quat_mul(f4 u, f4 v) {
+__host__ __device__ __forceinline__ f4 quat_mul(f4 u, f4 v) {
   return f4(u.w * v.w - u.x * v.x - u.y * v.y - u.z * v.z, u.w * v.x + u.x * v.w + u.y * v.z - u.z * v.y,
             u.w * v.y - u.x * v.z + u.y * v.w + u.z * v.x, u.w * v.z + u.x * v.y - u.y * v.x + u.z * v.w);
 }
 // geom.py:245-252: transform_quat_by_quat(v, u) = normalize(u * v)
-__device__ __noinline__ f4 quat_compose(f4 v, f4 u) {
+__host__ __device__ __noinline__ f4 quat_compose(f4 v, f4 u) {
   f4 r = quat_mul(u, v);
   float n = 1.0f / sqrtf(r.w * r.w + r.x * r.x + r.y * r.y + r.z * r.z);
   return f4(r.w * n, r.x * n, r.y * n, r.z * n);
 }
 // geom.py:255-270
-__device__ __noinline__ f3 rotate(f3 v, f4 q) {
+__host__ __device__ __noinline__ f3 rotate(f3 v, f4 q) {
   float xx = q.x * q.x, xy = q.x * q.y, xz = q.x * q.z, wx = q.x * q.w;
   float yy = q.y * q.y, yz = q.y * q.z, wy = q.y * q.w;
   float zz = q.z * q.z, wz = q.z * q.w, ww = q.w * q.w;
@@ -58,14 +58,14 @@ __device__ __noinline__ f3 rotate(f3 v, f4 q) {
             (v.x * (2.f * wz + 2.f * xy) + v.y * (ww - xx + yy - zz) + v.z * (-2.f * wx + 2.f * yz)) * inv,
             (v.x * (-2.f * wy + 2.f * xz) + v.y * (2.f * wx + 2.f * yz) + v.z * (ww - xx - yy + zz)) * inv);
 }
-__device__ __forceinline__ f3 rotate_inv(f3 v, f4 q) { return rotate(v, quat_inv(q)); }
-__device__ __forceinline__ f3 transform(f3 p, f3 t, f4 q) { return rotate(p, q) + t; }
+__host__ __device__ __forceinline__ f3 rotate_inv(f3 v, f4 q) { return rotate(v, quat_inv(q)); }
+__host__ __device__ __forceinline__ f3 transform(f3 p, f3 t, f4 q) { return rotate(p, q) + t; }
 
 struct mat3 {
   float m[3][3];
 };
 // geom.py:136-161
-__device__ __noinline__ mat3 quat_to_R(f4 q, float eps) {
+__host__ __device__ __noinline__ mat3 quat_to_R(f4 q, float eps) {
   mat3 R;
   R.m[0][0] = 1.f; R.m[0][1] = 0.f; R.m[0][2] = 0.f; R.m[1][0] = 0.f; R.m[1][1] = 1.f; R.m[1][2] = 0.f;
   R.m[2][0] = 0.f; R.m[2][1] = 0.f; R.m[2][2] = 1.f;
@@ -82,10 +82,10 @@ __device__ __noinline__ mat3 quat_to_R(f4 q, float eps) {
   }
   return R;
 }
-__device__ __forceinline__ f3 mat_col(const mat3& R, int j) { return f3(R.m[0][j], R.m[1][j], R.m[2][j]); }
+__host__ __device__ __forceinline__ f3 mat_col(const mat3& R, int j) { return f3(R.m[0][j], R.m[1][j], R.m[2][j]); }
 
 // geom.py:110-133
-__device__ __noinline__ f4 rotvec_to_quat(f3 rv, float eps) {
+__host__ __device__ __noinline__ f4 rotvec_to_quat(f3 rv, float eps) {
   f4 q(0.f, 0.f, 0.f, 0.f);
   float thetasq = norm_sqr(rv);
   if (thetasq > eps * eps) {
@@ -102,7 +102,7 @@ __device__ __noinline__ f4 rotvec_to_quat(f3 rv, float eps) {
   return q;
 }
 // geom.py:164-193
-__device__ __noinline__ f3 quat_to_xyz(f4 q, float eps) {
+__host__ __device__ __noinline__ f3 quat_to_xyz(f4 q, float eps) {
   float roll = 0.f, pitch = 0.f, yaw = 0.f;
   float n2 = q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z;
   if (n2 > eps) {
@@ -124,7 +124,7 @@ __device__ __noinline__ f3 quat_to_xyz(f4 q, float eps) {
   return f3(roll, pitch, yaw);
 }
 // geom.py:45-65
-__device__ __noinline__ f4 xyz_to_quat(f3 xyz) {
+__host__ __device__ __noinline__ f4 xyz_to_quat(f3 xyz) {
   float si, ci, sj, cj, sk, ck;
   sincosf(0.5f * xyz.z, &si, &ci);
   sincosf(-0.5f * xyz.y, &sj, &cj);
@@ -133,7 +133,7 @@ __device__ __noinline__ f4 xyz_to_quat(f3 xyz) {
   return f4(cj * cc + sj * ss, cj * cs - sj * sc, -cj * ss - sj * cc, cj * sc - sj * cs);
 }
 // geom.py:196-207
-__device__ __noinline__ f3 quat_to_rotvec(f4 q, float eps) {
+__host__ __device__ __noinline__ f3 quat_to_rotvec(f4 q, float eps) {
   f3 rv(q.x, q.y, q.z);
   float s2 = norm(rv);
   if (s2 > eps) {
@@ -143,16 +143,16 @@ __device__ __noinline__ f3 quat_to_rotvec(f4 q, float eps) {
   return rv;
 }
 
-__device__ __forceinline__ f3 sym_mul(const sym3& I, f3 v) {
+__host__ __device__ __forceinline__ f3 sym_mul(const sym3& I, f3 v) {
   return f3(I.xx * v.x + I.xy * v.y + I.xz * v.z, I.xy * v.x + I.yy * v.y + I.yz * v.z, I.xz * v.x + I.yz * v.y + I.zz * v.z);
 }
 // geom.py:365-369 inertial_mul: (ang, vel) -> (I ang + pos x vel, m vel - pos x ang)
-__device__ __forceinline__ void inertial_mul(f3 pos, const sym3& I, float mass, f3 vel, f3 ang, f3& o_ang, f3& o_vel) {
+__host__ __device__ __forceinline__ void inertial_mul(f3 pos, const sym3& I, float mass, f3 vel, f3 ang, f3& o_ang, f3& o_vel) {
   o_ang = sym_mul(I, ang) + cross(pos, vel);
   o_vel = vel * mass - cross(pos, ang);
 }
 // geom.py:386-403
-__device__ __noinline__ void orthogonals(f3 a, f3& d1, f3& d2) {
+__host__ __device__ __noinline__ void orthogonals(f3 a, f3& d1, f3& d2) {
   f3 b;
   if (fabsf(a.y) < 0.5f) b = f3(-a.x * a.y, 1.f - a.y * a.y, -a.z * a.y);
   else b = f3(-a.x * a.z, -a.y * a.z, 1.f - a.z * a.z);
@@ -161,7 +161,7 @@ __device__ __noinline__ void orthogonals(f3 a, f3& d1, f3& d2) {
   d2 = b;
 }
 // geom.py:406-424
-__device__ __noinline__ void imp_aref(const float* p, float neg_penetration, float vel, float pos, float& imp, float& aref) {
+__host__ __device__ __noinline__ void imp_aref(const float* p, float neg_penetration, float vel, float pos, float& imp, float& aref) {
   float timeconst = p[0], dampratio = p[1], dmin = p[2], dmax = p[3], width = p[4], mid = p[5], power = p[6];
   float imp_x = fabsf(neg_penetration) / width;
   float imp_a = (1.0f / powf(mid, power - 1.f)) * powf(imp_x, power);

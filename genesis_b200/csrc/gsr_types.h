@@ -57,6 +57,8 @@ struct DevModel {
   unsigned long long l_descmask[GSR_MAX_LINKS];  // the link and all its descendants
   float l_pos[GSR_MAX_LINKS][3], l_quat[GSR_MAX_LINKS][4], l_ipos[GSR_MAX_LINKS][3], l_iquat[GSR_MAX_LINKS][4];
   float l_inertia[GSR_MAX_LINKS][9], l_mass[GSR_MAX_LINKS], l_invweight[GSR_MAX_LINKS], l_root_mass[GSR_MAX_LINKS];
+  int n_roots, l_rootslot[GSR_MAX_LINKS];  // compact index of the link's tree root
+  float l_submass[GSR_MAX_LINKS];          // mass of the subtree rooted at the link
   // joints
   int j_type[GSR_MAX_JOINTS], j_q_start[GSR_MAX_JOINTS], j_dof_start[GSR_MAX_JOINTS], j_n_dofs[GSR_MAX_JOINTS];
   float j_pos[GSR_MAX_JOINTS][3], j_sol[GSR_MAX_JOINTS][7];
@@ -144,4 +146,22 @@ struct SmemLayout {
   // integrate / FK scratch
   int xanchor, xaxis, cacc, vel_next, qpos_next, pose_a, pose_b;
   int env_words;  // total words per env (multiple of 4, ≡ 8 mod 32 is not required)
+};
+
+// Workspace of the lane-per-environment kernel (gsr_lane.cuh), word offsets per environment.  Words [0, n_head) mirror the
+// head of the record (qpos .. dofs_pos, same offsets as HotLayout).  The pool is overlaid phase by phase.
+struct LaneLayout {
+  int n_head;
+  int lpos, lquat, rcom, cdof;
+  int M, L, Dinv, Hinv, H;
+  int force, acc_smooth, acc, qf_applied, qfrc_c;
+  int pool;
+  int crb, cfrc, cvel, cdd;                    // dynamics
+  int ct, lcf, aabb, queue, nqueue;            // collision (ct, lcf live through the constraint phase)
+  int qacc, Ma, grad, Mgrad, search, mv, prev_grad, prev_Mgrad, tmpv;
+  int r_aref, r_D, r_R, r_floss, r_Jaref, r_jv, r_force, r_active, J;
+  int NCS, NCC;
+  int cacc, out4, cnt, vn, qn;                 // outputs + integration
+  int fcvel, rcom_out, cinr;                   // final kinematics
+  int env_words;
 };

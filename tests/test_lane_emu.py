@@ -1,0 +1,177 @@
+"""CPU tier: arithmetic of the lane-per-environment step kernel (genesis_b200/csrc/gsr_lane.cuh) against the oracle.
+
+The lane kernel maps one thread to one environment and uses no warp intrinsics inside a phase, so its device functions
+compile verbatim for the host (tests/lane_emu, test infrastructure).  These tests run that host build environment by
+environment on the same seeded inputs as the oracle, with the tolerances of tests/test_gpu_parity.py.  What they do NOT
+cover is the device-only part (interleaved shared-memory addressing, cooperative record copies, launch geometry): that is
+the job of the `-m gpu` suite run with GSR_GROUP_SIZE=1.
+"""
+
+import numpy as np
+import pytest
+
+from conftest import TOL_SINGLE
+from emu import LaneEmu
+from helpers import gs, host_model, make_franka, make_franka_grasp, make_go2, oracle_for
+from genesis_b200.bench_scenes import FRANKA_Q0, GO2_CTRL, GO2_Q0
+
+TOL_SOLVER = 5e-4
+
+
+def pair(make, B, sets, **kw):
+    scene, solver, m = host_model(make, **kw)
+    orc = oracle_for(solver, m, B, threads=4)
+    emu = LaneEmu(m, B, solver.model_options())
+    for name, val in sets(m, B).items():
+        orc.set(name, val)
+        emu.set(name, val)
+    return m, orc, emu
+
+
+def franka_sets(controlled=True, randomized=True):
+    def f(m, B):
+        rng = np.random.default_rng(0)
+        q = np.tile(np.array(FRANKA_Q0), (B, 1))
+        out = {"qpos": q}
+        if randomized:
+            v = 0.2 * np.clip(rng.normal(size=(B, 9)), -1, 1)
+            v[:, 7:] = 0
+            out["vel"] = v
+        if controlled:
+            out["ctrl_pos"] = q.copy()
+            out["ctrl_mode"] = np.full((B, 9), int(gs.CTRL_MODE.POSITION))
+        return out
+    return f
+
+
+def go2_sets(m, B):
+    rng = np.random.default_rng(0)
+    lim = np.asarray(m.dofs_limit).reshape(-1, 2)[6:]
+    q = np.tile(np.array(GO2_Q0), (B, 1))
+    q[:, 7:] = lim[:, 0] + (lim[:, 1] - lim[:, 0]) * rng.random((B, 12))
+    ctrl = np.zeros((B, 18))
+    ctrl[:, 6:] = GO2_CTRL
+    mode = np.full((B, 18), int(gs.CTRL_MODE.FORCE))
+    mode[:, 6:] = int(gs.CTRL_MODE.POSITION)
+    return {"qpos": q, "ctrl_pos": ctrl, "ctrl_mode": mode}
+
+
+def close(a, b, tol, what):
+    scale = max(1.0, np.abs(b).max())
+    err = np.abs(a - b).max()
+    assert err <= tol * scale, f"{what}: max|diff| {err:.3e} > {tol:.1e} * {scale:.3e}"
+
+
+def check_all_quantities(m, orc, emu):
+    pre = {"acc_smooth", "qf_bias", "qf_applied", "qf_passive", "mass_mat", "mass_Dinv"}
+    for gname, oname in [("qpos", "qpos"), ("vel", "vel"), ("acc", "acc"), ("acc_smooth", "acc_smooth"), ("qf_bias", "qf_bias"),
+                         ("qf_applied", "qf_applied"), ("qf_passive", "qf_passive"), ("force", "force"), ("mass_mat", "M"),
+                         ("mass_Dinv", "Dinv"), ("qf_constraint", "qf_constraint"), ("dofs_pos", "dofs_pos")]:
+        a = emu.rows(gname)
+        close(a, orc.get(oname, a.shape[1]), TOL_SINGLE if gname in pre else TOL_SOLVER, gname)
+    for name, comps in [("links_pos", 3), ("links_quat", 4), ("root_COM", 3), ("cd_vel", 3), ("cd_ang", 3), ("cacc_lin", 3),
+                        ("cacc_ang", 3), ("links_contact_force", 3)]:
+        a = emu.rows(name)
+        close(a, orc.get(name, (m.n_links, comps)).reshape(a.shape), TOL_SOLVER, name)
+    for name in ("geoms_pos", "aabb_min", "aabb_max"):
+        a = emu.rows(name)
+        close(a, orc.get(name, (m.n_geoms, 3)).reshape(a.shape), TOL_SOLVER if name == "geoms_pos" else TOL_SINGLE, name)
+    for name in ("cdof_ang", "cdof_vel", "cdofd_ang", "cdofd_vel"):
+        a = emu.rows(name)
+        close(a, orc.get(name, (m.n_dofs, 3)).reshape(a.shape), TOL_SOLVER, name)
+
+
+def contacts_equal(orc, emu, B):
+    n_e = emu.field("n_contacts")[:, 0]
+    n_o = orc.get("n_contacts", 1)[:, 0].astype(int)
+    assert (n_e == n_o).all()
+    for b in range(B):
+        c = orc.contacts(b)
+        n = int(n_o[b])
+        assert (emu.field("contact_geom_a")[b, :n] == c["geom_a"]).all() and (emu.field("contact_geom_b")[b, :n] == c["geom_b"]).all()
+        if n:
+            assert np.abs(emu.field("contact_pos")[b, :n] - c["position"]).max() <= 1e-4
+            assert np.abs(emu.field("contact_normal")[b, :n] - c["normal"]).max() <= 1e-4
+            assert np.abs(emu.field("contact_penetration")[b, :n] - c["penetration"]).max() <= 1e-4
+
+
+@pytest.mark.parametrize("variant", ["random", "fall"])
+def test_lane_franka_single_step_all_quantities(variant):
+    m, orc, emu = pair(make_franka, 4, franka_sets(controlled=variant != "fall", randomized=variant == "random"))
+    orc.step(1)
+    emu.step(1)
+    check_all_quantities(m, orc, emu)
+
+
+def test_lane_go2_single_step_and_trajectory():
+    B = 6
+    m, orc, emu = pair(make_go2, B, go2_sets)
+    orc.step(1)
+    emu.step(1)
+    check_all_quantities(m, orc, emu)
+    contacts_equal(orc, emu, B)
+    orc.step(39)
+    emu.step(39)
+    assert np.abs(emu.rows("qpos") - orc.qpos()).max() <= 1e-3 and np.abs(emu.rows("vel") - orc.vel()).max() <= 2e-2
+    assert int(emu.field("errno_").max()) == 0
+    # rows of a Go2 on its feet exceed the lane kernel's on-chip capacity: the SPILL path is what ran
+    assert int(emu.field("n_constraints").max()) > 8
+
+
+def test_lane_franka_controlled_trajectory():
+    m, orc, emu = pair(make_franka, 4, franka_sets())
+    orc.step(50)
+    emu.step(50)
+    assert np.abs(emu.rows("qpos") - orc.qpos()).max() <= 1e-4 and np.abs(emu.rows("vel") - orc.vel()).max() <= 1e-3
+
+
+def test_lane_franka_fall_self_collision_contacts():
+    B = 3
+
+    def sets(m, B):
+        rng = np.random.default_rng(1)
+        q = np.tile(np.array(FRANKA_Q0), (B, 1)) + 0.05 * rng.normal(size=(B, 9))
+        q[:, 7:] = 0.02
+        return {"qpos": q}
+
+    m, orc, emu = pair(make_franka, B, sets, self_collision=True)
+    orc.step(80)
+    emu.step(80)
+    assert np.abs(emu.rows("qpos") - orc.qpos()).max() <= 1e-3 and np.abs(emu.rows("vel") - orc.vel()).max() <= 2e-2
+    assert int(orc.get("n_contacts", 1).sum()) > 0
+    contacts_equal(orc, emu, B)
+
+
+def test_lane_grasp_cluster_box_mesh_contacts():
+    B = 2
+
+    def sets(m, B):
+        q = np.tile(np.asarray(m.qpos0, dtype=float), (B, 1))
+        q[:, :9] = [-0.0, 0.45, 0.0, -2.2, 0.0, 2.65, 0.78, 0.04, 0.04]
+        ctrl = np.zeros((B, m.n_dofs))
+        ctrl[:, :9] = q[:, :9]
+        ctrl[:, 7:9] = 0.0
+        mode = np.full((B, m.n_dofs), int(gs.CTRL_MODE.FORCE))
+        mode[:, :9] = int(gs.CTRL_MODE.POSITION)
+        return {"qpos": q, "ctrl_pos": ctrl, "ctrl_mode": mode}
+
+    m, orc, emu = pair(make_franka_grasp, B, sets)
+    orc.step(30)
+    emu.step(30)
+    assert np.abs(emu.rows("qpos") - orc.qpos()).max() <= 1e-3 and np.abs(emu.rows("vel") - orc.vel()).max() <= 2e-2
+    assert int(orc.get("n_contacts", 1).sum()) >= 16 * B
+    contacts_equal(orc, emu, B)
+
+
+@pytest.mark.parametrize("opts", [dict(constraint_solver="CG"), dict(integrator="Euler"), dict(integrator="implicitfast")])
+def test_lane_solver_and_integrator_options(opts):
+    kw = {}
+    if "constraint_solver" in opts:
+        kw["constraint_solver"] = gs.constraint_solver.CG
+    if "integrator" in opts:
+        kw["integrator"] = getattr(gs.integrator, opts["integrator"])
+    B = 3
+    m, orc, emu = pair(make_go2, B, go2_sets, **kw)
+    orc.step(20)
+    emu.step(20)
+    assert np.abs(emu.rows("qpos") - orc.qpos()).max() <= 1e-3 and np.abs(emu.rows("vel") - orc.vel()).max() <= 2e-2

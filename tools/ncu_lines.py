@@ -36,6 +36,8 @@ tot = stot = 0
 for r in rows[hi + 1:]:
     if len(r) < len(hdr):
         continue
+    if r[ca] == "Address":  # a second captured launch follows: one launch is enough
+        break
     a = int(r[ca], 16)
     base = a if base is None else base
     n, s = int(r[ci] or 0), int(r[cs] or 0)
