@@ -253,7 +253,12 @@ __device__ __noinline__ void dev_convex_convex(const Ctx<G>& C, LaneContacts& ou
       rotate_frame(ga_pos0, ga_quat0, cpos_0, qrot, P.pa, P.qa);
       rotate_frame(gb_pos0, gb_quat0, cpos_0, quat_inv(qrot), P.pb, P.qb);
     }
-    if (ta == GEOM_PLANE) {
+    if (ta == GEOM_CAPSULE && tb == GEOM_CAPSULE) {  // NP:637-648 analytic capsule pairs
+      capsule_capsule_contact(P.pa, P.qa, GM(g_data[ga][0]), 0.5f * GM(g_data[ga][1]), P.pb, P.qb, GM(g_data[gb][0]), 0.5f * GM(g_data[gb][1]), EPS,
+                              is_col, normal, cpos, pen);
+    } else if (ta == GEOM_SPHERE && tb == GEOM_CAPSULE) {  // NP:649-661 (types are sorted: A is the sphere)
+      sphere_capsule_contact(P.pa, GM(g_data[ga][0]), P.pb, P.qb, GM(g_data[gb][0]), 0.5f * GM(g_data[gb][1]), EPS, is_col, normal, cpos, pen);
+    } else if (ta == GEOM_PLANE) {
       normal = -normalized(rotate(f3(GM(g_data[ga][0]), GM(g_data[ga][1]), GM(g_data[ga][2])), P.qa));
       const f3 v1 = dev_support(C, normal, gb, P.pb, P.qb);
       pen = dot(normal, v1 - P.pa);

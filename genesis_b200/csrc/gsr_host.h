@@ -313,6 +313,8 @@ static inline int gsr_compute_layouts(GsrSpec* h, int n_envs) {
     q.fcvel = y; y += 6 * nL; q.rcom_out = y; y += 3 * nL; q.cinr = y; y += 9 * nL;
     if (y > ymax) ymax = y;
     q.env_words = ymax;
+    // a warp's interleaved workspace must fit one SM's shared memory; larger models run the lane-group kernel
+    if (h->group == 1 && (size_t)q.env_words * 33 * sizeof(float) > 227 * 1024) h->group = (m.nD <= 12 && m.nL <= 16) ? 8 : 32;
   }
   return GSR_OK;
 }

@@ -713,7 +713,12 @@ LHD __noinline__ void lane_convex_convex(const LaneCtx& C, LContacts& out, int g
       lane_rotate_frame(ga_pos0, ga_quat0, cpos_0, qrot, P.pa, P.qa);
       lane_rotate_frame(gb_pos0, gb_quat0, cpos_0, quat_inv(qrot), P.pb, P.qb);
     }
-    if (ta == GEOM_PLANE) {
+    if (ta == GEOM_CAPSULE && tb == GEOM_CAPSULE) {  // NP:637-648 analytic capsule pairs
+      capsule_capsule_contact(P.pa, P.qa, LG(g_data[ga][0]), 0.5f * LG(g_data[ga][1]), P.pb, P.qb, LG(g_data[gb][0]), 0.5f * LG(g_data[gb][1]), EPS,
+                              is_col, normal, cpos, pen);
+    } else if (ta == GEOM_SPHERE && tb == GEOM_CAPSULE) {  // NP:649-661 (types are sorted: A is the sphere)
+      sphere_capsule_contact(P.pa, LG(g_data[ga][0]), P.pb, P.qb, LG(g_data[gb][0]), 0.5f * LG(g_data[gb][1]), EPS, is_col, normal, cpos, pen);
+    } else if (ta == GEOM_PLANE) {
       normal = -normalized(rotate(f3(LG(g_data[ga][0]), LG(g_data[ga][1]), LG(g_data[ga][2])), P.qa));
       const f3 v1 = lane_support(C, normal, gb, P.pb, P.qb);
       pen = dot(normal, v1 - P.pa);

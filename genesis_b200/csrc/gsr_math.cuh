@@ -174,3 +174,65 @@ __host__ __device__ __noinline__ void imp_aref(const float* p, float neg_penetra
   float k = 1.0f / (dmax * dmax * timeconst * timeconst * dampratio * dampratio);
   aref = -b * vel - k * imp * pos;
 }
+
+// ---- analytic capsule contacts (collider/capsule_contact.py, collider/utils.py:9-65) ----------------------------------------
+// closest points of two segments (Ericson, Real-Time Collision Detection 5.1.9)
+__host__ __device__ __noinline__ void closest_points_on_segments(f3 p1, f3 p2, f3 q1, f3 q2, float eps, f3& ca, f3& cb) {
+  const f3 da = p2 - p1, db = q2 - q1, r = p1 - q1;
+  const float a = dot(da, da), b = dot(da, db), c = dot(db, db), d = dot(da, r), f = dot(db, r);
+  const float denom = a * c - b * b;
+  float sp = 0.f, tp = 0.f;
+  if (denom < eps) {
+    tp = c > eps ? fminf(fmaxf(f / c, 0.f), 1.f) : 0.f;
+  } else {
+    sp = fminf(fmaxf((b * f - c * d) / denom, 0.f), 1.f);
+    tp = fminf(fmaxf(c > eps ? (b * sp + f) / c : 0.f, 0.f), 1.f);
+    const float s_new = fminf(fmaxf(a > eps ? (b * tp - d) / a : 0.f, 0.f), 1.f);
+    if (a > eps) sp = s_new;
+  }
+  ca = p1 + da * sp;
+  cb = q1 + db * tp;
+}
+// capsule_contact.py:10-98: capsules along their local z, data = (radius, half length); normal points from B to A
+__host__ __device__ __noinline__ void capsule_capsule_contact(f3 pa, f4 qa, float ra, float hla, f3 pb, f4 qb, float rb, float hlb, float eps,
+                                                              bool& is_col, f3& normal, f3& cpos, float& pen) {
+  const f3 axa = rotate(f3(0.f, 0.f, 1.f), qa), axb = rotate(f3(0.f, 0.f, 1.f), qb);
+  f3 Pa, Pb;
+  closest_points_on_segments(pa - axa * hla, pa + axa * hla, pb - axb * hlb, pb + axb * hlb, eps, Pa, Pb);
+  const f3 diff = Pa - Pb;
+  const float dist_sq = dot(diff, diff), cr = ra + rb;
+  is_col = false; normal = f3(1.f, 0.f, 0.f); cpos = f3(); pen = 0.f;
+  if (dist_sq < cr * cr) {
+    is_col = true;
+    const float dist = sqrtf(dist_sq);
+    if (dist > eps) normal = diff / dist;
+    else {
+      const f3 nd = cross(axa, axb);
+      const float ndl = dot(nd, nd);
+      if (ndl > eps) normal = nd / ndl;  // (sic) the reference divides by the squared length
+      else normal = fabsf(axa.x) < 0.9f ? f3(0.f, -axa.z, axa.y) : f3(axa.z, 0.f, -axa.x);
+    }
+    pen = cr - dist;
+    cpos = Pa - normal * ra + normal * (0.5f * pen);
+  }
+}
+// capsule_contact.py:102-196 with A the sphere and B the capsule (the geoms of a pair are sorted by type)
+__host__ __device__ __noinline__ void sphere_capsule_contact(f3 sc, float rs, f3 cc, f4 cq, float rc, float hl, float eps,
+                                                             bool& is_col, f3& normal, f3& cpos, float& pen) {
+  const f3 ax = rotate(f3(0.f, 0.f, 1.f), cq);
+  const f3 P1 = cc - ax * hl, seg = (cc + ax * hl) - P1;
+  const float l2 = dot(seg, seg);
+  float t = 0.5f;
+  if (l2 > eps) t = fminf(fmaxf(dot(sc - P1, seg) / l2, 0.f), 1.f);
+  const f3 diff = sc - (P1 + seg * t);
+  const float dist_sq = dot(diff, diff), cr = rs + rc;
+  is_col = false; normal = f3(1.f, 0.f, 0.f); cpos = f3(); pen = 0.f;
+  if (dist_sq < cr * cr) {
+    is_col = true;
+    const float dist = sqrtf(dist_sq);
+    if (dist > eps) normal = diff / dist;
+    else normal = fabsf(ax.x) < 0.9f ? f3(0.f, -ax.z, ax.y) : f3(ax.z, 0.f, -ax.x);
+    pen = cr - dist;
+    cpos = sc - normal * (rs - 0.5f * pen);
+  }
+}

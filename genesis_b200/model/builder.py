@@ -90,6 +90,12 @@ def _geom_inertial(g, rho):
         m = rho * np.pi * r * r * h
         ixy = m * (3 * r * r + h * h) / 12.0
         return m, np.zeros(3), np.diag([ixy, ixy, 0.5 * m * r * r])
+    if t == GEOM_TYPE.CAPSULE:  # cylinder + two hemispheres (MuJoCo's closed form)
+        r, h = g["data"][:2]
+        mc, ms = rho * np.pi * r * r * h, rho * 4.0 / 3.0 * np.pi * r**3
+        izz = 0.5 * mc * r * r + 0.4 * ms * r * r
+        ixy = mc * (3 * r * r + h * h) / 12.0 + ms * (0.4 * r * r + 0.25 * h * h + 0.375 * h * r)
+        return mc + ms, np.zeros(3), np.diag([ixy, ixy, izz])
     vol, com, I = meshio.mesh_mass_properties(g["verts"], g["faces"])
     return rho * vol, com, rho * I
 

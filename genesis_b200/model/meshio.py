@@ -138,3 +138,19 @@ def cylinder_mesh(radius, height, sections=32):
          np.concatenate([ring, np.full((sections, 1), 0.5 * height)], axis=1)]
     )
     return convex_hull(verts)
+
+
+def capsule_mesh(radius, height, count=(8, 12)):
+    """Capsule along z (cylinder of ``height`` plus hemispherical caps): ``count`` = (latitude, longitude) sections like
+    trimesh.creation.capsule, which the reference uses for collision capsules (genesis/utils/mjcf.py:517-526).  The
+    longitude angles contain 0 / 90 / 180 / 270 degrees and the poles are vertices, so the rest-pose AABB is exact."""
+    n_lat, n_lon = count
+    phi = np.linspace(0.0, 2.0 * np.pi, n_lon, endpoint=False)
+    verts = [[0.0, 0.0, 0.5 * height + radius], [0.0, 0.0, -0.5 * height - radius]]
+    for k in range(1, n_lat // 2 + 1):
+        th = 0.5 * np.pi * k / (n_lat // 2)  # pole -> equator
+        rr, zz = radius * np.sin(th), radius * np.cos(th)
+        for p in phi:
+            verts.append([rr * np.cos(p), rr * np.sin(p), 0.5 * height + zz])
+            verts.append([rr * np.cos(p), rr * np.sin(p), -0.5 * height - zz])
+    return convex_hull(np.asarray(verts))

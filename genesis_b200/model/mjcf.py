@@ -222,6 +222,22 @@ def parse_mjcf(path, default_armature=0.1, scale=1.0):
             elif gtype == "sphere":
                 verts, faces = meshio.icosphere(size[0] * scale, 2)
                 g_info.update(type=GEOM_TYPE.SPHERE, data=np.concatenate([[size[0] * scale], np.zeros(6)]), verts=verts, faces=faces)
+            elif gtype == "capsule":
+                if "fromto" in attrs:  # segment end points instead of pos / quat / half length
+                    ft = _floats(attrs["fromto"], 6) * scale
+                    a, b = ft[:3], ft[3:]
+                    axis = b - a
+                    half = 0.5 * np.linalg.norm(axis)
+                    g_info["pos"] = 0.5 * (a + b)
+                    z = axis / max(2 * half, 1e-12)
+                    c = np.cross([0.0, 0.0, 1.0], z)
+                    w = 1.0 + z[2]
+                    g_info["quat"] = gn.quat_normalize(np.array([w, *c])) if w > 1e-9 else np.array([0.0, 1.0, 0.0, 0.0])
+                    radius = size[0] * scale
+                else:
+                    radius, half = size[0] * scale, size[1] * scale
+                verts, faces = meshio.capsule_mesh(radius, 2 * half)
+                g_info.update(type=GEOM_TYPE.CAPSULE, data=np.concatenate([[radius, 2 * half], np.zeros(5)]), verts=verts, faces=faces)
             elif gtype == "cylinder":
                 verts, faces = meshio.cylinder_mesh(size[0] * scale, 2 * size[1] * scale)
                 g_info.update(type=GEOM_TYPE.CYLINDER, data=np.concatenate([[size[0] * scale, 2 * size[1] * scale], np.zeros(5)]), verts=verts, faces=faces)

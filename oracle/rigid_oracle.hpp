@@ -893,6 +893,75 @@ struct Oracle {
     npos = pos - vec;
   }
 
+  // collider/utils.py:9-65 func_closest_points_on_segments (Ericson, Real-Time Collision Detection 5.1.9)
+  void closest_points_on_segments(const V& p1, const V& p2, const V& q1, const V& q2, V& ca, V& cb) {
+    V da = p2 - p1, db = q2 - q1, r = p1 - q1;
+    T a = da.dot(da), b = da.dot(db), c = db.dot(db), d = da.dot(r), f = db.dot(r);
+    T denom = a * c - b * b;
+    T sp = 0, tp = 0;
+    if (denom < EPS) {
+      sp = 0;
+      tp = c > EPS ? std::min(std::max(f / c, T(0)), T(1)) : T(0);
+    } else {
+      sp = (b * f - c * d) / denom;
+      tp = (a * f - b * d) / denom;
+      sp = std::min(std::max(sp, T(0)), T(1));
+      tp = std::min(std::max(c > EPS ? (b * sp + f) / c : T(0), T(0)), T(1));
+      T s_new = std::min(std::max(a > EPS ? (b * tp - d) / a : T(0), T(0)), T(1));
+      if (a > EPS) sp = s_new;
+    }
+    ca = p1 + da * sp;
+    cb = q1 + db * tp;
+  }
+  // collider/capsule_contact.py:10-98 func_capsule_capsule_contact
+  void capsule_capsule_contact(int ga, int gb, const V& pa, const Q& qa, const V& pb, const Q& qb, bool& is_col, V& normal, V& cpos, T& pen) {
+    T ra = m.geoms_data[7 * ga], hla = T(0.5) * m.geoms_data[7 * ga + 1];
+    T rb = m.geoms_data[7 * gb], hlb = T(0.5) * m.geoms_data[7 * gb + 1];
+    V axa = transform_by_quat(V(0, 0, 1), qa), axb = transform_by_quat(V(0, 0, 1), qb);
+    V P1 = pa - axa * hla, P2 = pa + axa * hla, Q1 = pb - axb * hlb, Q2 = pb + axb * hlb;
+    V Pa, Pb;
+    closest_points_on_segments(P1, P2, Q1, Q2, Pa, Pb);
+    V diff = Pa - Pb;
+    T dist_sq = diff.dot(diff), cr = ra + rb;
+    is_col = false; normal = V(1, 0, 0); cpos = V(); pen = 0;
+    if (dist_sq < cr * cr) {
+      is_col = true;
+      T dist = std::sqrt(dist_sq);
+      if (dist > EPS) normal = diff / dist;
+      else {
+        V nd = axa.cross(axb);
+        T ndl = nd.dot(nd);
+        if (ndl > EPS) normal = nd / ndl;
+        else normal = std::abs(axa.x) < T(0.9) ? V(0, -axa.z, axa.y) : V(axa.z, 0, -axa.x);
+      }
+      pen = cr - dist;
+      cpos = Pa - normal * ra + normal * (T(0.5) * pen);
+    }
+  }
+  // collider/capsule_contact.py:102-196 func_sphere_capsule_contact (ga = sphere, gb = capsule after the type sort)
+  void sphere_capsule_contact(int ga, int gb, const V& pa, const Q& qa, const V& pb, const Q& qb, bool& is_col, V& normal, V& cpos, T& pen) {
+    T dir = 1;
+    V sc = pa, cc = pb;
+    Q cq = qb;
+    if (m.geoms_type[gb] == GEOM_SPHERE) { std::swap(ga, gb); sc = pb; cc = pa; cq = qa; dir = -1; }
+    T rs = m.geoms_data[7 * ga], rc = m.geoms_data[7 * gb], hl = T(0.5) * m.geoms_data[7 * gb + 1];
+    V ax = transform_by_quat(V(0, 0, 1), cq);
+    V P1 = cc - ax * hl, P2 = cc + ax * hl, seg = P2 - P1;
+    T l2 = seg.dot(seg), t = T(0.5);
+    if (l2 > EPS) t = std::min(std::max((sc - P1).dot(seg) / l2, T(0)), T(1));
+    V closest = P1 + seg * t, diff = sc - closest;
+    T dist_sq = diff.dot(diff), cr = rs + rc;
+    is_col = false; normal = V(1, 0, 0); cpos = V(); pen = 0;
+    if (dist_sq < cr * cr) {
+      is_col = true;
+      T dist = std::sqrt(dist_sq);
+      if (dist > EPS) normal = diff / dist;
+      else normal = std::abs(ax.x) < T(0.9) ? V(0, -ax.z, ax.y) : V(ax.z, 0, -ax.x);
+      pen = cr - dist;
+      cpos = sc - normal * (rs - T(0.5) * pen);
+    }
+    normal = normal * dir;
+  }
   // NP:519-970 func_convex_convex_contact (MPR ccd, no GJK fallback -- see DESIGN.md "gaps")
   void convex_convex_contact(Env<T>& e, int ga, int gb) {
     if (m.geoms_type[ga] == GEOM_PLANE && m.geoms_type[gb] == GEOM_BOX) return;
@@ -917,7 +986,12 @@ struct Oracle {
         rotate_frame(gb_pos0, gb_quat0, cpos_0, inv_quat(qrot), gb_pos, gb_quat);
       }
       if ((multi_contact && is_col_0) || i_det == 0) {
-        if (m.geoms_type[ga] == GEOM_PLANE) {
+        const int ta = m.geoms_type[ga], tb = m.geoms_type[gb];
+        if (ta == GEOM_CAPSULE && tb == GEOM_CAPSULE) {  // NP:637-648
+          capsule_capsule_contact(ga, gb, ga_pos, ga_quat, gb_pos, gb_quat, is_col, normal, cpos, pen);
+        } else if ((ta == GEOM_SPHERE && tb == GEOM_CAPSULE) || (ta == GEOM_CAPSULE && tb == GEOM_SPHERE)) {  // NP:649-661
+          sphere_capsule_contact(ga, gb, ga_pos, ga_quat, gb_pos, gb_quat, is_col, normal, cpos, pen);
+        } else if (m.geoms_type[ga] == GEOM_PLANE) {
           V pdir(m.geoms_data[7 * ga], m.geoms_data[7 * ga + 1], m.geoms_data[7 * ga + 2]);
           pdir = transform_by_quat(pdir, ga_quat);
           normal = -pdir.normalized();

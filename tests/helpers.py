@@ -50,3 +50,33 @@ PENDULUM_XML = """
   </worldbody>
 </mujoco>
 """
+
+# two free capsules crossing over each other and a sphere on top: analytic capsule-capsule / sphere-capsule pairs
+# (collider/capsule_contact.py) plus plane-capsule support contacts
+CAPSULES_XML = """
+<mujoco model="capsules">
+  <worldbody>
+    <geom name="floor" type="plane" size="5 5 0.1"/>
+    <body name="ca" pos="0 0 0.06" euler="0 90 0">
+      <freejoint/>
+      <geom type="capsule" size="0.05 0.15"/>
+    </body>
+    <body name="cb" pos="0.02 0 0.17" euler="90 0 0">
+      <freejoint/>
+      <geom type="capsule" size="0.04 0.12"/>
+    </body>
+    <body name="sp" pos="0.1 0.01 0.15">
+      <freejoint/>
+      <geom type="sphere" size="0.04"/>
+    </body>
+  </worldbody>
+</mujoco>
+"""
+
+
+def make_capsules(n_envs, build=True, **rigid_kwargs):
+    scene = gs.Scene(rigid_options=gs.options.RigidOptions(dt=0.01, **rigid_kwargs))
+    ent = scene.add_entity(gs.morphs.MJCF(file=write_tmp(CAPSULES_XML, ".xml")))
+    if build:
+        scene.build(n_envs=n_envs)
+    return scene, ent

@@ -15,7 +15,7 @@ import pytest
 import torch
 
 from conftest import TOL_SINGLE
-from helpers import gs, make_franka, make_franka_grasp, make_go2, oracle_for, scene_from_morphs
+from helpers import gs, make_capsules, make_franka, make_franka_grasp, make_go2, oracle_for, scene_from_morphs
 
 pytestmark = pytest.mark.gpu
 
@@ -213,6 +213,20 @@ def test_franka_grasp_cluster_mpr_contacts():
     assert (dq <= TRAJ_QPOS_CONTACT).mean() >= 0.9, f"{np.sort(dq)}"
     a, b = contact_set(scene, B), contact_set(orc, B)
     assert len(b) >= 4 * B and jaccard(a, b) >= 0.95
+
+
+def test_capsule_analytic_pairs():
+    """Analytic capsule-capsule / sphere-capsule contacts (collider/capsule_contact.py) and plane-capsule support contacts."""
+    B, K = 8, 60
+    scene, _ = make_capsules(B)
+    orc = mirror_oracle(scene)
+    for _ in range(K):
+        scene.step()
+    orc.step(K)
+    assert np.abs(gpu_field(scene, "qpos") - orc.qpos()).max() <= TRAJ_QPOS_CONTACT
+    assert np.abs(gpu_field(scene, "vel") - orc.vel()).max() <= TRAJ_QVEL_CONTACT
+    a, b = contact_set(scene, B), contact_set(orc, B)
+    assert a == b and len(b) >= 3 * B
 
 
 @pytest.mark.parametrize("opts", [dict(constraint_solver=gs.constraint_solver.CG), dict(integrator=gs.integrator.Euler),

@@ -175,3 +175,17 @@ def test_lane_solver_and_integrator_options(opts):
     orc.step(20)
     emu.step(20)
     assert np.abs(emu.rows("qpos") - orc.qpos()).max() <= 1e-3 and np.abs(emu.rows("vel") - orc.vel()).max() <= 2e-2
+
+
+def test_lane_capsule_analytic_pairs():
+    """capsule-capsule / sphere-capsule closed forms (collider/capsule_contact.py) and plane-capsule support contacts."""
+    from helpers import make_capsules
+
+    B = 2
+    m, orc, emu = pair(make_capsules, B, lambda m, B: {})
+    orc.step(40)
+    emu.step(40)
+    assert np.abs(emu.rows("qpos") - orc.qpos()).max() <= 1e-3 and np.abs(emu.rows("vel") - orc.vel()).max() <= 2e-2
+    types = {(int(m.geoms_type[a]), int(m.geoms_type[b])) for a, b in zip(orc.contacts(0)["geom_a"], orc.contacts(0)["geom_b"])}
+    assert (4, 4) in types and ((1, 4) in types or (0, 1) in types)
+    contacts_equal(orc, emu, B)

@@ -235,3 +235,33 @@ def test_f32_oracle_tracks_f64_oracle():
         outs.append((orc.qpos()[0], orc.vel()[0]))
     assert np.abs(outs[0][0] - outs[1][0]).max() < 1e-4
     assert np.abs(outs[0][1] - outs[1][1]).max() < 1e-3
+
+
+def test_capsule_analytic_contacts_reference_expectations():
+    """tests/test_rigid_physics_analytical_vs_gjk.py:587-615 (test_capsule_analytical_accuracy): two vertical capsules
+    (r = 0.1, half length 0.25) 0.15 apart -> penetration 0.05, normal (-1, 0, 0); plus the sphere-capsule closed form."""
+    from helpers import scene_from_morphs, write_tmp
+
+    xml = """
+    <mujoco><worldbody>
+      <body name="a" pos="0 0 0"><freejoint/><geom type="capsule" size="0.1 0.25"/></body>
+      <body name="b" pos="0.15 0 0"><freejoint/><geom type="capsule" size="0.1 0.25"/></body>
+      <body name="s" pos="-0.17 0 0.1"><freejoint/><geom type="sphere" size="0.1"/></body>
+    </worldbody></mujoco>"""
+    scene, _ = scene_from_morphs([gs.morphs.MJCF(file=write_tmp(xml, ".xml"))], gravity=(0.0, 0.0, 0.0))
+    solver = scene.rigid_solver
+    m = solver.build_model()
+    orc = oracle_for(solver, m, 1)
+    orc.step(1)
+    c = orc.contacts(0)
+    pairs = {}
+    for i, (a, b) in enumerate(zip(c["geom_a"], c["geom_b"])):
+        pairs.setdefault((int(a), int(b)), i)  # first contact of the pair = the unperturbed detection
+    i_cc = pairs[(0, 1)]
+    assert abs(c["penetration"][i_cc] - 0.05) < 1e-5
+    np.testing.assert_allclose(c["normal"][i_cc], (-1.0, 0.0, 0.0), atol=1e-6)
+    np.testing.assert_allclose(c["position"][i_cc][:2], (0.075, 0.0), atol=1e-6)
+    i_sc = pairs[(2, 0)]  # geoms of a pair are ordered by type: the sphere is geom A
+    assert abs(c["penetration"][i_sc] - 0.03) < 1e-5
+    np.testing.assert_allclose(c["normal"][i_sc], (-1.0, 0.0, 0.0), atol=1e-6)
+    np.testing.assert_allclose(c["position"][i_sc], (-0.085, 0.0, 0.1), atol=1e-6)
