@@ -91,7 +91,7 @@ static inline int gsr_fill_model(GsrSpec* h) {
   CPI(m.l_q_end, "links_q_end", nL)
   CPF(m.l_pos, "links_pos", 3 * nL) CPF(m.l_quat, "links_quat", 4 * nL) CPF(m.l_ipos, "links_inertial_pos", 3 * nL)
   CPF(m.l_iquat, "links_inertial_quat", 4 * nL) CPF(m.l_inertia, "links_inertial_i", 9 * nL) CPF(m.l_mass, "links_inertial_mass", nL)
-  { const float* p = FV("links_invweight", 2 * nL); if (!missing) for (int l = 0; l < nL; l++) m.l_invweight[l] = p[2 * l]; }
+  { const float* p = FV("links_invweight", 2 * nL); if (!missing) for (int l = 0; l < nL; l++) { m.l_invweight[l] = p[2 * l]; m.l_invweight_rot[l] = p[2 * l + 1]; } }
   CPI(m.j_type, "joints_type", nJ) CPI(m.j_q_start, "joints_q_start", nJ) CPI(m.j_dof_start, "joints_dof_start", nJ)
   CPI(m.j_n_dofs, "joints_n_dofs", nJ) CPF(m.j_pos, "joints_pos", 3 * nJ) CPF(m.j_sol, "joints_sol_params", 7 * nJ)
   CPI(m.d_link, "dofs_link", nD) CPI(m.d_entity, "dofs_entity", nD) CPI(m.d_joint, "dofs_joint", nD)

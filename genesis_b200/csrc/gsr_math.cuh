@@ -42,6 +42,10 @@ __host__ __device__ __forceinline__ f4 quat_mul(f4 u, f4 v) {
   return f4(u.w * v.w - u.x * v.x - u.y * v.y - u.z * v.z, u.w * v.x + u.x * v.w + u.y * v.z - u.z * v.y,
             u.w * v.y - u.x * v.z + u.y * v.w + u.z * v.x, u.w * v.z + u.x * v.y - u.y * v.x + u.z * v.w);
 }
+// geom.py:224-232 quat_mul_axis: q * (0, axis)
+__host__ __device__ __forceinline__ f4 quat_mul_axis(f4 q, f3 a) {
+  return f4(-q.x * a.x - q.y * a.y - q.z * a.z, q.w * a.x + q.y * a.z - q.z * a.y, q.w * a.y + q.z * a.x - q.x * a.z, q.w * a.z + q.x * a.y - q.y * a.x);
+}
 // geom.py:245-252: transform_quat_by_quat(v, u) = normalize(u * v)
 __host__ __device__ __noinline__ f4 quat_compose(f4 v, f4 u) {
   f4 r = quat_mul(u, v);

@@ -59,6 +59,7 @@ struct DevModel {
   float l_inertia[GSR_MAX_LINKS][9], l_mass[GSR_MAX_LINKS], l_invweight[GSR_MAX_LINKS], l_root_mass[GSR_MAX_LINKS];
   int n_roots, l_rootslot[GSR_MAX_LINKS];  // compact index of the link's tree root
   float l_submass[GSR_MAX_LINKS];          // mass of the subtree rooted at the link
+  float l_invweight_rot[GSR_MAX_LINKS];    // rotational component of links_info.invweight (weld equalities)
   // joints
   int j_type[GSR_MAX_JOINTS], j_q_start[GSR_MAX_JOINTS], j_dof_start[GSR_MAX_JOINTS], j_n_dofs[GSR_MAX_JOINTS];
   float j_pos[GSR_MAX_JOINTS][3], j_sol[GSR_MAX_JOINTS][7];

@@ -344,6 +344,34 @@ def parse_mjcf(path, default_armature=0.1, scale=1.0):
                 data = np.zeros(11)
                 data[:3] = _floats(attrs["anchor"]) * scale
                 eqs_info.append(dict(type=EQUALITY_TYPE.CONNECT, objs_name=(attrs["body1"], attrs.get("body2", "world")), data=data, sol_params=sol_params))
-            # weld equalities are not on the configs' path (out of scope)
+            elif eq.tag == "weld":
+                # MuJoCo's compiled eq_data (the layout func_equality_weld reads, constraint/solver.py:1007-1030): [0:3] anchor
+                # in body 2, [3:6] the same point in body 1, [6:10] orientation of body 2 relative to body 1, [10] torquescale.
+                # Unless `relpose` is given, the relative pose is the one of the reference configuration qpos0.
+                names = [li["name"] for li in l_infos]
+                b1, b2 = attrs["body1"], attrs.get("body2", "world")
+
+                def world_pose(name):
+                    chain, i = [], names.index(name)
+                    while i >= 0:
+                        chain.append(l_infos[i])
+                        i = l_infos[i]["parent_idx"]
+                    pos, quat = np.zeros(3), np.array([1.0, 0.0, 0.0, 0.0])
+                    for li in reversed(chain):
+                        pos, quat = gn.transform_pos_quat(li["pos"], li["quat"], pos, quat)
+                    return pos, quat
+
+                anchor2 = _floats(attrs.get("anchor", "0 0 0"), 3) * scale
+                relpose = _floats(attrs.get("relpose", "0 1 0 0 0 0 0"), 7)
+                if np.abs(relpose[3:]).max() > 0:
+                    relquat = gn.quat_normalize(relpose[3:])
+                    anchor1 = relpose[:3] * scale + gn.quat_to_R(relquat) @ anchor2
+                else:
+                    (p1, q1), (p2, q2) = world_pose(b1), world_pose(b2)
+                    R1, R2 = gn.quat_to_R(q1), gn.quat_to_R(q2)
+                    anchor1 = R1.T @ (p2 + R2 @ anchor2 - p1)
+                    relquat = gn.quat_normalize(gn.quat_mul(gn.quat_inv(q1), q2))
+                data = np.concatenate([anchor2, anchor1, relquat, [float(attrs.get("torquescale", 1.0))]])
+                eqs_info.append(dict(type=EQUALITY_TYPE.WELD, objs_name=(b1, b2), data=data, sol_params=sol_params))
 
     return l_infos, eqs_info

@@ -1182,12 +1182,90 @@ struct Oracle {
     }
   }
 
+  // CS:984-1173 func_equality_weld: 3 position rows (anchor1 = data[3:6] in body 1, anchor2 = data[0:3] in body 2) and
+  // 3 orientation rows (relpose = data[6:10], torquescale = data[10]); translational / rotational invweight components
+  void equality_weld(Env<T>& e, int i_e) {
+    const T* sp = &m.eq_sol_params[7 * i_e];
+    const T* dat = &m.eq_data[11 * i_e];
+    int l1 = m.eq_obj1[i_e], l2 = m.eq_obj2[i_e];
+    V a1(dat[3], dat[4], dat[5]), a2(dat[0], dat[1], dat[2]);
+    Q relpose(dat[6], dat[7], dat[8], dat[9]);
+    T torquescale = dat[10];
+    V g1 = transform_by_trans_quat(a1, e.l_pos[l1], e.l_quat[l1]), g2 = transform_by_trans_quat(a2, e.l_pos[l2], e.l_quat[l2]);
+    V pos_error = g1 - g2;
+    Q q = quat_mul(e.l_quat[l1], relpose);
+    Q inv_q2 = inv_quat(e.l_quat[l2]);
+    Q eq = quat_mul(inv_q2, q);
+    V rot_error = V(eq.x, eq.y, eq.z) * torquescale;
+    T pos_imp = std::sqrt(pos_error.dot(pos_error) + rot_error.dot(rot_error));
+    T iw0 = m.links_invweight[2 * l1] + m.links_invweight[2 * l2], iw1 = m.links_invweight[2 * l1 + 1] + m.links_invweight[2 * l2 + 1];
+    for (int i3 = 0; i3 < 3; i3++) {
+      int c = e.n_con++;
+      e.n_eq++;
+      T* J = jrow(e, c);
+      for (int d = 0; d < m.nD; d++) J[d] = 0;
+      T jac_qvel = 0;
+      for (int ab = 0; ab < 2; ab++) {
+        T sign = ab == 0 ? T(1) : T(-1);
+        int link = ab == 0 ? l1 : l2;
+        V pos = ab == 0 ? g1 : g2;
+        while (link > -1) {
+          for (int d = m.links_dof_end[link] - 1; d >= m.links_dof_start[link]; d--) {
+            V tpos = pos - e.root_COM[link];
+            V vel = e.cdof_vel[d] - tpos.cross(e.cdof_ang[d]);
+            T jac = sign * vel[i3];
+            jac_qvel += jac * e.vel[d];
+            J[d] += jac;
+          }
+          link = m.links_parent[link];
+        }
+      }
+      T imp, aref;
+      imp_aref(sp, -pos_imp, jac_qvel, pos_error[i3], imp, aref);
+      T diag = std::max(iw0 * (T(1) - imp) / imp, EPS);
+      e.diag[c] = diag; e.aref[c] = aref; e.efc_D[c] = T(1) / diag;
+    }
+    int c0 = e.n_con;
+    e.n_con += 3; e.n_eq += 3;
+    for (int k = 0; k < 3; k++) { T* J = jrow(e, c0 + k); for (int d = 0; d < m.nD; d++) J[d] = 0; }
+    for (int ab = 0; ab < 2; ab++) {
+      T sign = ab == 0 ? T(1) : T(-1);
+      int link = ab == 0 ? l1 : l2;
+      while (link > -1) {
+        for (int d = m.links_dof_end[link] - 1; d >= m.links_dof_start[link]; d--)
+          for (int k = 0; k < 3; k++) jrow(e, c0 + k)[d] += sign * e.cdof_ang[d][k];
+        link = m.links_parent[link];
+      }
+    }
+    T jac_qvel[3] = {0, 0, 0};
+    for (int d = 0; d < m.nD; d++) {
+      V jd(jrow(e, c0)[d], jrow(e, c0 + 1)[d], jrow(e, c0 + 2)[d]);
+      // geom.py:224-232 quat_mul_axis(inv_q2, jd), then * q
+      Q quat2(-inv_q2.x * jd.x - inv_q2.y * jd.y - inv_q2.z * jd.z, inv_q2.w * jd.x + inv_q2.y * jd.z - inv_q2.z * jd.y,
+              inv_q2.w * jd.y + inv_q2.z * jd.x - inv_q2.x * jd.z, inv_q2.w * jd.z + inv_q2.x * jd.y - inv_q2.y * jd.x);
+      Q quat3 = quat_mul(quat2, q);
+      T v3[3] = {quat3.x, quat3.y, quat3.z};
+      for (int k = 0; k < 3; k++) {
+        T j = T(0.5) * v3[k] * torquescale;
+        jrow(e, c0 + k)[d] = j;
+        jac_qvel[k] += j * e.vel[d];
+      }
+    }
+    for (int k = 0; k < 3; k++) {
+      T imp, aref;
+      imp_aref(sp, -pos_imp, jac_qvel[k], rot_error[k], imp, aref);
+      T diag = std::max(iw1 * (T(1) - imp) / imp, EPS);
+      e.diag[c0 + k] = diag; e.aref[c0 + k] = aref; e.efc_D[c0 + k] = T(1) / diag;
+    }
+  }
+
   // CS:880-937 add_equality_constraints
   void add_equality_constraints(Env<T>& e) {
     e.n_con = 0; e.n_eq = 0;
     for (int i = 0; i < m.nEq; i++) {
       if (m.eq_type[i] == EQ_JOINT) equality_joint(e, i);
       else if (m.eq_type[i] == EQ_CONNECT) equality_connect(e, i);
+      else if (m.eq_type[i] == EQ_WELD) equality_weld(e, i);
     }
   }
 

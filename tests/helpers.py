@@ -80,3 +80,41 @@ def make_capsules(n_envs, build=True, **rigid_kwargs):
     if build:
         scene.build(n_envs=n_envs)
     return scene, ent
+
+# a free box welded (pose-locked) to the last link of a two-link arm, plus a box welded to the world:
+# func_equality_weld (constraint/solver.py:984-1173), 6 rows per weld
+WELD_XML = """
+<mujoco model="weld">
+  <option gravity="0 0 -9.81"/>
+  <worldbody>
+    <body name="l1" pos="0 0 1.0">
+      <joint name="j1" type="hinge" axis="0 1 0" damping="0.5"/>
+      <inertial pos="0.25 0 0" mass="1.0" diaginertia="0.01 0.02 0.02"/>
+      <body name="l2" pos="0.5 0 0">
+        <joint name="j2" type="hinge" axis="0 1 0" damping="0.5"/>
+        <inertial pos="0.2 0 0" mass="0.5" diaginertia="0.005 0.01 0.01"/>
+      </body>
+    </body>
+    <body name="payload" pos="0.95 0.05 1.0" euler="0 0 30">
+      <freejoint/>
+      <inertial pos="0 0 0" mass="0.3" diaginertia="0.002 0.002 0.002"/>
+    </body>
+    <body name="anchored" pos="0 0.5 0.5">
+      <freejoint/>
+      <inertial pos="0 0 0" mass="0.4" diaginertia="0.003 0.003 0.003"/>
+    </body>
+  </worldbody>
+  <equality>
+    <weld body1="l2" body2="payload" anchor="0.02 0 0"/>
+    <weld body1="anchored"/>
+  </equality>
+</mujoco>
+"""
+
+
+def make_weld(n_envs, build=True, **rigid_kwargs):
+    scene = gs.Scene(rigid_options=gs.options.RigidOptions(dt=0.01, **rigid_kwargs))
+    ent = scene.add_entity(gs.morphs.MJCF(file=write_tmp(WELD_XML, ".xml")))
+    if build:
+        scene.build(n_envs=n_envs)
+    return scene, ent

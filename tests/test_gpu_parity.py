@@ -15,7 +15,7 @@ import pytest
 import torch
 
 from conftest import TOL_SINGLE
-from helpers import gs, make_capsules, make_franka, make_franka_grasp, make_go2, oracle_for, scene_from_morphs
+from helpers import gs, make_capsules, make_weld, make_franka, make_franka_grasp, make_go2, oracle_for, scene_from_morphs
 
 pytestmark = pytest.mark.gpu
 
@@ -84,7 +84,7 @@ def check_single_step(scene, orc):
     for name, comps in LINK_FIELDS:
         a = gpu_field(scene, name)
         assert_close(a, orc.get(name, (m.n_links, comps)).reshape(a.shape), TOL_SOLVER, name)
-    for name in ("geoms_pos", "aabb_min", "aabb_max"):
+    for name in ("geoms_pos", "aabb_min", "aabb_max") if m.n_geoms else ():
         a = gpu_field(scene, name)
         assert_close(a, orc.get(name, (m.n_geoms, 3)).reshape(a.shape), TOL_SOLVER if name == "geoms_pos" else TOL_SINGLE, name)
     for name in ("cdof_ang", "cdof_vel", "cdofd_ang", "cdofd_vel"):
@@ -213,6 +213,22 @@ def test_franka_grasp_cluster_mpr_contacts():
     assert (dq <= TRAJ_QPOS_CONTACT).mean() >= 0.9, f"{np.sort(dq)}"
     a, b = contact_set(scene, B), contact_set(orc, B)
     assert len(b) >= 4 * B and jaccard(a, b) >= 0.95
+
+
+def test_weld_equality():
+    """func_equality_weld (constraint/solver.py:984-1173): arm + welded payload, body welded to the world."""
+    B, K = 8, 100
+    scene, _ = make_weld(B)
+    orc = mirror_oracle(scene)
+    scene.step()
+    orc.step(1)
+    check_single_step(scene, orc)
+    for _ in range(K - 1):
+        scene.step()
+    orc.step(K - 1)
+    assert np.abs(gpu_field(scene, "qpos") - orc.qpos()).max() <= TRAJ_QPOS_FREE
+    assert np.abs(gpu_field(scene, "vel") - orc.vel()).max() <= TRAJ_QVEL_FREE
+    assert (scene.rigid_solver.field("n_constraints_equality")[:, 0] == 12).all()
 
 
 def test_capsule_analytic_pairs():

@@ -73,7 +73,7 @@ def check_all_quantities(m, orc, emu):
                         ("cacc_ang", 3), ("links_contact_force", 3)]:
         a = emu.rows(name)
         close(a, orc.get(name, (m.n_links, comps)).reshape(a.shape), TOL_SOLVER, name)
-    for name in ("geoms_pos", "aabb_min", "aabb_max"):
+    for name in ("geoms_pos", "aabb_min", "aabb_max") if m.n_geoms else ():
         a = emu.rows(name)
         close(a, orc.get(name, (m.n_geoms, 3)).reshape(a.shape), TOL_SOLVER if name == "geoms_pos" else TOL_SINGLE, name)
     for name in ("cdof_ang", "cdof_vel", "cdofd_ang", "cdofd_vel"):
@@ -189,3 +189,17 @@ def test_lane_capsule_analytic_pairs():
     types = {(int(m.geoms_type[a]), int(m.geoms_type[b])) for a, b in zip(orc.contacts(0)["geom_a"], orc.contacts(0)["geom_b"])}
     assert (4, 4) in types and ((1, 4) in types or (0, 1) in types)
     contacts_equal(orc, emu, B)
+
+
+def test_lane_weld_equality():
+    from helpers import make_weld
+
+    B = 2
+    m, orc, emu = pair(make_weld, B, lambda m, B: {})
+    orc.step(1)
+    emu.step(1)
+    check_all_quantities(m, orc, emu)
+    orc.step(99)
+    emu.step(99)
+    assert np.abs(emu.rows("qpos") - orc.qpos()).max() <= 1e-4 and np.abs(emu.rows("vel") - orc.vel()).max() <= 1e-3
+    assert (emu.field("n_constraints_equality")[:, 0] == 12).all()

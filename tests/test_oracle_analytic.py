@@ -265,3 +265,35 @@ def test_capsule_analytic_contacts_reference_expectations():
     assert abs(c["penetration"][i_sc] - 0.03) < 1e-5
     np.testing.assert_allclose(c["normal"][i_sc], (-1.0, 0.0, 0.0), atol=1e-6)
     np.testing.assert_allclose(c["position"][i_sc], (-0.085, 0.0, 0.1), atol=1e-6)
+
+
+def test_weld_equality_static_balance():
+    """func_equality_weld (constraint/solver.py:984-1173): a free body welded to the world settles (soft constraint), its six
+    weld rows carry exactly its weight, and a payload welded to an arm link keeps the anchor offset of the reference pose."""
+    from helpers import make_weld
+
+    scene, solver, m = host_model(make_weld)
+    assert list(m.eq_type) == [int(gs.EQUALITY_TYPE.WELD)] * 2 and m.n_dofs == 14
+    orc = oracle_for(solver, m, 1, double=True)
+    orc.step(400)
+    assert int(orc.get("n_constraints", 1, 0)[0]) == 12
+    acc = orc.get("acc", m.n_dofs, 0)
+    qfc = orc.get("qf_constraint", m.n_dofs, 0)
+    # dofs 8..13: the body welded to the world (0.4 kg): at rest, constraint force = weight on the z translation
+    assert np.abs(acc[8:]).max() < 1e-4  # the solver's own stopping tolerance
+    assert qfc[10] == pytest.approx(0.4 * 9.81, rel=1e-5) and np.abs(qfc[8:10]).max() < 1e-5
+    # the arm swings with the welded payload; the weld keeps the payload at its anchor
+    lp = orc.get("links_pos", (m.n_links, 3), 0)
+    lq = orc.get("links_quat", (m.n_links, 4), 0)
+
+    def rot(q, v):
+        w, x, y, z = q
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                      [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                      [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+        return R @ v
+
+    d = m.eq_data.reshape(-1, 11)[0]
+    g1 = lp[2] + rot(lq[2], d[3:6])
+    g2 = lp[3] + rot(lq[3], d[0:3])
+    assert np.abs(g1 - g2).max() < 5e-3  # soft constraint: millimetres of give while the arm is still swinging
