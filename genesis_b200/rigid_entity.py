@@ -293,3 +293,57 @@ class RigidEntity:
 
     def get_dofs_damping(self, dofs_idx_local=None, envs_idx=None):
         return torch.tensor(self._solver.model.dofs_damping, dtype=torch.float32)[self._dofs(dofs_idx_local)]
+
+    def set_dofs_frictionloss(self, frictionloss, dofs_idx_local=None, envs_idx=None):
+        self._solver.set_dofs_frictionloss(frictionloss, self._dofs(dofs_idx_local), envs_idx)
+
+    def set_dofs_limit(self, lower, upper, dofs_idx_local=None, envs_idx=None):
+        self._solver.set_dofs_limit(lower, upper, self._dofs(dofs_idx_local), envs_idx)
+
+    def get_dofs_armature(self, dofs_idx_local=None, envs_idx=None):
+        return self._solver.get_dofs_armature(self._dofs(dofs_idx_local))
+
+    def get_dofs_frictionloss(self, dofs_idx_local=None, envs_idx=None):
+        return self._solver.get_dofs_frictionloss(self._dofs(dofs_idx_local))
+
+    def get_dofs_force_range(self, dofs_idx_local=None, envs_idx=None):
+        return self._solver.get_dofs_force_range(self._dofs(dofs_idx_local))
+
+    def get_dofs_invweight(self, dofs_idx_local=None, envs_idx=None):
+        return self._solver.get_dofs_invweight(self._dofs(dofs_idx_local))
+
+    def get_links_acc(self, links_idx_local=None, envs_idx=None):
+        return self._solver.get_links_acc(self._links_idx(links_idx_local), envs_idx)
+
+    def get_links_acc_ang(self, links_idx_local=None, envs_idx=None):
+        return self._solver.get_links_acc_ang(self._links_idx(links_idx_local), envs_idx)
+
+    def get_links_root_COM(self, links_idx_local=None, envs_idx=None):
+        return self._solver.get_links_root_COM(self._links_idx(links_idx_local), envs_idx)
+
+    def get_links_invweight(self, links_idx_local=None, envs_idx=None):
+        return self._solver.get_links_invweight(self._links_idx(links_idx_local))
+
+    def get_links_inertial_mass(self, links_idx_local=None, envs_idx=None):
+        return self._solver.get_links_inertial_mass(self._links_idx(links_idx_local))
+
+    def apply_links_external_force(self, force, links_idx_local=None, envs_idx=None):
+        self._solver.apply_links_external_force(force, self._links_idx(links_idx_local), envs_idx)
+
+    def apply_links_external_torque(self, torque, links_idx_local=None, envs_idx=None, *, ref="link_origin", local=False):
+        self._solver.apply_links_external_torque(torque, self._links_idx(links_idx_local), envs_idx, ref=ref, local=local)
+
+    def set_friction_ratio(self, friction_ratio, links_idx_local=None, envs_idx=None):
+        """rigid_entity.py: per-environment friction scale, one value per link, applied to all the link's geoms."""
+        m = self._solver.model
+        links = self._links_idx(links_idx_local)
+        links = torch.as_tensor(links).reshape(-1).tolist()
+        ratio = torch.as_tensor(friction_ratio, dtype=torch.float32)
+        geoms, cols = [], []
+        for k, l in enumerate(links):
+            for g in range(m.n_geoms):
+                if int(m.geoms_link[g]) == int(l):
+                    geoms.append(g)
+                    cols.append(k)
+        if geoms:
+            self._solver.set_geoms_friction_ratio(ratio[..., cols], geoms, envs_idx)

@@ -391,6 +391,26 @@ class RigidSolver:
         self._fields["cfrc_applied_ang"][e[:, None], links[None, :]] -= torque
         self._fields["has_ext_force"][e] = 1
 
+    def apply_links_external_torque(self, torque, links_idx=None, envs_idx=None, *, ref="link_origin", local=False):
+        """World-frame (or, with local=True, link-frame) torque on each link (rigid_solver.py:1152-1193, abd/misc.py:720-734):
+        cfrc_applied_ang -= torque."""
+        m = self.model
+        links = self._idx(links_idx, m.n_links)
+        envs = self._envs(envs_idx)
+        nb = self._B if envs is None else len(envs)
+        torque = torch.broadcast_to(torch.as_tensor(torque, dtype=torch.float32, device=self.device), (nb, len(links), 3))
+        if local:
+            quat = self._fields["links_quat"][:, links]
+            quat = quat if envs is None else quat[envs]
+            if ref == "link_com":  # inertial frame: link quat (x) inertial quat
+                iq = torch.tensor(m.links_inertial_quat, dtype=torch.float32, device=self.device)[links]
+                quat = _quat_mul_torch(quat, iq[None].expand(quat.shape[0], -1, -1))
+            if ref in ("link_origin", "link_com"):
+                torque = _rotate_torch(torque, quat)
+        e = self._envs_all if envs is None else envs
+        self._fields["cfrc_applied_ang"][e[:, None], links[None, :]] -= torque
+        self._fields["has_ext_force"][e] = 1
+
     def _get_links_com(self, links, envs):
         m = self.model
         pos = self._fields["links_pos"][:, links]
@@ -428,6 +448,15 @@ class RigidSolver:
     def set_dofs_force_range(self, lower, upper, dofs_idx=None, envs_idx=None):
         self._set_model_array("dofs_force_range", lower, dofs_idx, width=0)
         self._set_model_array("dofs_force_range", upper, dofs_idx, width=1)
+
+    def set_dofs_frictionloss(self, frictionloss, dofs_idx=None, envs_idx=None):
+        """rigid_solver.py:2100-2120: dofs with a positive friction loss get one constraint row each (solver.py:1236-1286)."""
+        self._set_model_array("dofs_frictionloss", frictionloss, dofs_idx)
+
+    def set_dofs_limit(self, lower, upper, dofs_idx=None, envs_idx=None):
+        self._set_model_array("dofs_limit", lower, dofs_idx, width=0)
+        self._set_model_array("dofs_limit", upper, dofs_idx, width=1)
+        self._dofs_limit = torch.tensor(self.model.dofs_limit, dtype=torch.float32, device=self.device).reshape(-1, 2)
 
     def set_dofs_armature(self, armature, dofs_idx=None, envs_idx=None):
         self._set_model_array("dofs_armature", armature, dofs_idx)
@@ -481,6 +510,49 @@ class RigidSolver:
         pos = self._get("links_pos", links_idx, envs_idx, n, comps=3)
         com = self._get("root_COM", links_idx, envs_idx, n, comps=3)
         return vel + torch.cross(ang, pos - com, dim=-1)
+
+    def get_links_acc(self, links_idx=None, envs_idx=None):
+        """Classical linear acceleration of the link frame origin in world axes (abd/accessor.py:960-983): spatial acceleration
+        moved from the subtree COM to the origin, plus the centripetal term ang x vel."""
+        n = self.model.n_links
+        cpos = self._get("links_pos", links_idx, envs_idx, n, comps=3) - self._get("root_COM", links_idx, envs_idx, n, comps=3)
+        acc_ang = self._get("cacc_ang", links_idx, envs_idx, n, comps=3)
+        acc_lin = self._get("cacc_lin", links_idx, envs_idx, n, comps=3) + torch.cross(acc_ang, cpos, dim=-1)
+        ang = self._get("cd_ang", links_idx, envs_idx, n, comps=3)
+        vel = self._get("cd_vel", links_idx, envs_idx, n, comps=3) + torch.cross(ang, cpos, dim=-1)
+        return acc_lin + torch.cross(ang, vel, dim=-1)
+
+    def get_links_acc_ang(self, links_idx=None, envs_idx=None):
+        return self._get("cacc_ang", links_idx, envs_idx, self.model.n_links, comps=3)
+
+    def get_links_root_COM(self, links_idx=None, envs_idx=None):
+        return self._get("root_COM", links_idx, envs_idx, self.model.n_links, comps=3)
+
+    def get_dofs_armature(self, dofs_idx=None):
+        return torch.tensor(self.model.dofs_armature, dtype=torch.float32, device=self.device)[self._idx(dofs_idx, self.model.n_dofs)]
+
+    def get_dofs_frictionloss(self, dofs_idx=None):
+        return torch.tensor(self.model.dofs_frictionloss, dtype=torch.float32, device=self.device)[self._idx(dofs_idx, self.model.n_dofs)]
+
+    def get_dofs_force_range(self, dofs_idx=None):
+        fr = torch.tensor(self.model.dofs_force_range, dtype=torch.float32, device=self.device).reshape(-1, 2)[self._idx(dofs_idx, self.model.n_dofs)]
+        return fr[:, 0], fr[:, 1]
+
+    def get_dofs_invweight(self, dofs_idx=None):
+        return torch.tensor(self.model.dofs_invweight, dtype=torch.float32, device=self.device)[self._idx(dofs_idx, self.model.n_dofs)]
+
+    def get_links_invweight(self, links_idx=None):
+        return torch.tensor(self.model.links_invweight, dtype=torch.float32, device=self.device).reshape(-1, 2)[self._idx(links_idx, self.model.n_links)]
+
+    def get_links_inertial_mass(self, links_idx=None):
+        return torch.tensor(self.model.links_inertial_mass, dtype=torch.float32, device=self.device)[self._idx(links_idx, self.model.n_links)]
+
+    def get_geoms_friction_ratio(self, geoms_idx=None, envs_idx=None):
+        return self._get("friction_ratio", geoms_idx, envs_idx, self.model.n_geoms)
+
+    def set_geoms_friction_ratio(self, friction_ratio, geoms_idx=None, envs_idx=None):
+        """Per-environment friction scale of each geom (contact friction = max(mu_a ratio_a, mu_b ratio_b, 1e-2), contact.py:202-211)."""
+        self._set("friction_ratio", friction_ratio, geoms_idx, envs_idx, self.model.n_geoms)
 
     def get_links_net_contact_force(self, links_idx=None, envs_idx=None):
         return self._get("links_contact_force", links_idx, envs_idx, self.model.n_links, comps=3)
@@ -564,6 +636,14 @@ def _rotate_torch(v, q):
     u = torch.cat([x, y, z], dim=-1)
     t = 2.0 * torch.cross(u, v, dim=-1)
     return v + w * t + torch.cross(u, t, dim=-1)
+
+
+def _quat_mul_torch(u, v):
+    """Hamilton product u (x) v of (w, x, y, z) quaternions (genesis/utils/geom.py:235-242)."""
+    uw, ux, uy, uz = u.unbind(-1)
+    vw, vx, vy, vz = v.unbind(-1)
+    return torch.stack([uw * vw - ux * vx - uy * vy - uz * vz, uw * vx + ux * vw + uy * vz - uz * vy,
+                        uw * vy - ux * vz + uy * vw + uz * vx, uw * vz + ux * vy - uy * vx + uz * vw], dim=-1)
 
 
 def _xyz_to_quat_torch(xyz):

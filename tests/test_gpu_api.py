@@ -91,3 +91,55 @@ def test_errno_contact_overflow_is_reported():
     with pytest.raises(gs.GenesisException, match="contact pairs|candidate"):
         for _ in range(30):
             scene.step()
+
+
+def test_links_acc_pendulum_closed_form():
+    """tests/test_rigid_physics.py:903-958 (test_pendulum_links_acc): a pendulum released horizontally; get_links_acc returns
+    the classical acceleration of the link frame origin (zero at the hinge) and get_links_acc_ang the angular one."""
+    from helpers import PENDULUM_XML, scene_from_morphs, write_tmp
+
+    scene, (pend,) = scene_from_morphs([gs.morphs.MJCF(file=write_tmp(PENDULUM_XML, ".xml"))], dt=0.01)
+    scene.build(n_envs=2)
+    pend.set_dofs_position(torch.full((2, 1), np.pi / 2, device=gs.device))
+    scene.step()
+    s = scene.rigid_solver
+    # point mass-like rod: I = 0.01 + m l^2 about the hinge (+ armature), torque = m g l at horizontal
+    m_, l_, I_ = 1.0, 0.5, 0.01
+    arm = float(s.model.dofs_armature[0])
+    alpha = m_ * 9.81 * l_ / (I_ + m_ * l_ * l_ + arm)
+    acc_ang = pend.get_links_acc_ang()
+    assert acc_ang.shape == (2, s.model.n_links, 3)
+    assert abs(abs(float(acc_ang[0, -1, 1])) - alpha) < 2e-2 * alpha
+    acc = pend.get_links_acc()
+    assert acc.shape == (2, s.model.n_links, 3)
+    # the link frame origin sits on the hinge axis; like the reference, the getter mixes the pre-integration spatial
+    # acceleration with the post-integration pose / velocity, which leaves an O(dt) residual
+    assert float(acc[0, -1].norm()) < 2e-2
+
+
+def test_external_torque_frictionloss_and_friction_ratio():
+    from helpers import scene_from_morphs
+
+    scene, ents = scene_from_morphs([gs.morphs.Plane(), gs.morphs.Box(size=(0.1, 0.1, 0.1), pos=(0, 0, 1.0))], dt=0.01)
+    scene.build(n_envs=3)
+    s, box = scene.rigid_solver, ents[1]
+    inertia = 0.6 * (0.1**2 + 0.1**2) / 12.0
+    box.apply_links_external_torque(torch.tensor([[[0.0, 0.0, 1e-3]]], device=gs.device).repeat(3, 1, 1))
+    scene.step()
+    acc = s.field("acc").cpu().numpy()
+    np.testing.assert_allclose(acc[:, 5], 1e-3 / inertia, rtol=1e-3)
+    np.testing.assert_allclose(acc[:, 2], -9.81, atol=1e-4)
+    # friction ratio scales the contact friction of the env it is set for (contact.py:202-211)
+    # (the contact takes the larger of the two scaled coefficients, so both geoms of the pair are scaled)
+    box.set_friction_ratio(torch.tensor([[0.5]], device=gs.device), envs_idx=[1])
+    ents[0].set_friction_ratio(torch.tensor([[0.5]], device=gs.device), envs_idx=[1])
+    for _ in range(80):
+        scene.step()
+    mu = s.field("contact_friction")[:, 0].cpu().numpy()
+    assert mu[1] == pytest.approx(0.5 * mu[0]) and mu[2] == pytest.approx(mu[0])
+    # friction loss adds one row per dof with a positive value (solver.py:1236-1286)
+    assert int(s.field("n_constraints_frictionloss").max()) == 0
+    box.set_dofs_frictionloss(torch.full((6,), 0.01, device=gs.device))
+    scene.step()
+    assert (s.field("n_constraints_frictionloss")[:, 0] == 6).all()
+    assert torch.allclose(box.get_dofs_frictionloss(), torch.full((6,), 0.01, device=gs.device))
