@@ -60,6 +60,7 @@ static inline int gsr_fill_model(GsrSpec* h) {
   m.n_contacts_per_pair = (int)S("n_contacts_per_pair", 5); m.len_constraints = (int)S("len_constraints", 0);
   m.iterations = (int)S("cfg_iterations", 50); m.ls_iterations = (int)S("cfg_ls_iterations", 50);
   m.integrator = (int)S("cfg_integrator", INTEGRATOR_APPROX_IMPLICITFAST); m.solver_type = (int)S("cfg_solver_type", SOLVER_NEWTON);
+  m.noslip_iterations = (int)S("cfg_noslip_iterations", 0); m.noslip_tolerance = (float)S("cfg_noslip_tolerance", 1e-6);
   m.enable_collision = (int)S("cfg_enable_collision", 1); m.enable_joint_limit = (int)S("cfg_enable_joint_limit", 1);
   m.enable_multi_contact = (int)S("cfg_enable_multi_contact", 1); m.sort_contacts = (int)S("cfg_sort_contacts", 1);
   m.meaninertia = (float)S("meaninertia", 1.0); m.dt = (float)S("dt", 0.01); m.eps = (float)S("cfg_eps", 1.1920929e-07);
@@ -202,6 +203,8 @@ static inline int gsr_compute_layouts(GsrSpec* h, int n_envs) {
   L.cache_valid = (int)gsr_round4(3 * (size_t)(m.nP > 0 ? m.nP : 1));
   L.cache_stride = (int)gsr_round4(L.cache_valid + m.n_cache_words);
   size_t spill = (size_t)lenC * JS + 8 * (size_t)lenC;
+  L.spill_minvjt = (int)spill;
+  if (m.noslip_iterations > 0) spill += (size_t)lenC * JS;  // M^-1 J^T rows of the noslip post-solver
   if (spill < (size_t)nCP * GSR_CONTACT_WORDS) spill = (size_t)nCP * GSR_CONTACT_WORDS;
   L.spill_stride = (int)gsr_round4(spill);
   const size_t B = (size_t)n_envs;
@@ -248,7 +251,8 @@ static inline int gsr_compute_layouts(GsrSpec* h, int n_envs) {
   x = L.kin_dead;
   s.contacts = x; x += s.NCC * GSR_CONTACT_WORDS;
   const bool newton = m.solver_type == SOLVER_NEWTON;
-  if (!newton) { s.H = x; x += nD * MS; }  // Newton: H overlays the L^T D L factor, which is dead once acc_smooth is known
+  const bool h_own = !newton || m.noslip_iterations > 0;  // noslip solves with the L^T D L factor after the Newton solve
+  if (h_own) { s.H = x; x += nD * MS; }  // otherwise H overlays the L^T D L factor, which is dead once acc_smooth is known
   s.Hinv = x; x += nD; s.tmpv = x; x += nD;
   s.qacc = x; x += nD; s.Ma = x; x += nD; s.grad = x; x += nD; s.Mgrad = x; x += nD; s.search = x; x += nD; s.mv = x; x += nD;
   s.prev_grad = x; x += nD; s.prev_Mgrad = x; x += nD;
@@ -259,7 +263,8 @@ static inline int gsr_compute_layouts(GsrSpec* h, int n_envs) {
   // always-live block
   x = (int)gsr_round4(xmax);
   s.M = x; x += nD * MS; s.L = x; x += nD * MS; s.Dinv = x; x += nD;
-  if (newton) s.H = s.L; s.force = x; x += nD; s.acc_smooth = x; x += nD;
+  if (!h_own) s.H = s.L;
+  s.force = x; x += nD; s.acc_smooth = x; x += nD;
   s.acc = x; x += nD; s.qf_applied = x; x += nD; s.qf_passive = x; x += nD; s.qf_bias = x; x += nD; s.qfrc_c = x; x += nD;
   s.env_words = (int)gsr_round4(x);
 
@@ -300,7 +305,7 @@ static inline int gsr_compute_layouts(GsrSpec* h, int n_envs) {
     y = after_lcf;
     q.qacc = y; y += nD; q.Ma = y; y += nD; q.grad = y; y += nD; q.Mgrad = y; y += nD; q.search = y; y += nD; q.mv = y; y += nD;
     q.prev_grad = y; y += nD; q.prev_Mgrad = y; y += nD; q.tmpv = y; y += nD;
-    if (m.solver_type != SOLVER_NEWTON) { q.H = y; y += ntri; } else q.H = q.L;  // Newton: H overlays the dead L^T D L factor
+    if (m.solver_type != SOLVER_NEWTON || m.noslip_iterations > 0) { q.H = y; y += ntri; } else q.H = q.L;  // Newton: H overlays the dead L^T D L factor
     q.r_aref = y; y += NCSl; q.r_D = y; y += NCSl; q.r_R = y; y += NCSl; q.r_floss = y; y += NCSl; q.r_Jaref = y; y += NCSl;
     q.r_jv = y; y += NCSl; q.r_force = y; y += NCSl; q.r_active = y; y += NCSl;
     q.J = y; y += NCSl * nD;

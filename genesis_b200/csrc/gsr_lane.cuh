@@ -1354,6 +1354,89 @@ LHD __noinline__ float lane_linesearch(const LaneCtx& C, const LRows& R, LSolver
   return 0.f;
 }
 
+// constraint/noslip.py: projected Gauss-Seidel on the friction-loss rows and the opposing pyramid edges with A = J M^-1 J^T.
+// Only the rows M^-1 J^T are stored (SPILL record, global) and q = J^T f is updated incrementally (see gsr_solver.cuh).
+LHD __noinline__ void lane_noslip(const LaneCtx& C, const LRows& R, int n_contacts) {
+  const int nD = CM(nD), JS = R.JS, n_con = R.n_con;
+  const float EPS = CM(eps);
+  float* MJ = C.spill + c_h.spill_minvjt;  // [n_con][nD]
+  const GArr b = R.jv;                     // dead after the primal solve
+  const LArr q = C.A(c_l.grad), acc_smooth = C.A(c_l.acc_smooth), qfrc = C.A(c_l.qfrc_c);
+  const LArr L = C.A(c_l.L), Dinv = C.A(c_l.Dinv);
+  for (int r = 0; r < n_con; r++) {  // noslip.py:9-58
+    float* x = MJ + (size_t)r * nD;
+    for (int d = 0; d < nD; d++) x[d] = R.J[r * JS + d];
+    for (int j = nD - 1; j > 0; j--) {
+      const float xj = x[j];
+      const int rj = tri_idx(j, 0);
+      for (int i = 0; i < j; i++) x[i] -= L[rj + i] * xj;
+    }
+    for (int i = 0; i < nD; i++) x[i] *= Dinv[i];
+    for (int i = 1; i < nD; i++) {
+      const int ri = tri_idx(i, 0);
+      float s = x[i];
+      for (int j = 0; j < i; j++) s -= L[ri + j] * x[j];
+      x[i] = s;
+    }
+    float v = -R.aref[r];
+    for (int d = 0; d < nD; d++) v += R.J[r * JS + d] * acc_smooth[d];
+    b[r] = v;
+  }
+  for (int d = 0; d < nD; d++) q[d] = qfrc[d];
+  const float scale = 1.0f / (CM(meaninertia) * (float)(nD > 1 ? nD : 1));
+  const int const_start = R.nef;
+  for (int it = 0; it < CM(noslip_iterations); it++) {  // noslip.py:166-283
+    float improvement = 0.f;
+    if (it == 0)
+      for (int c = 0; c < n_con; c++) improvement += 0.5f * R.force[c] * R.force[c] * R.R[c];
+    for (int c = R.ne; c < R.nef; c++) {
+      float res = b[c], Acc = 0.f;
+      for (int d = 0; d < nD; d++) { const float mj = MJ[(size_t)c * nD + d]; res += mj * q[d]; Acc += R.J[c * JS + d] * mj; }
+      const float old = R.force[c], fl = R.floss[c];
+      float f = old - res / Acc;
+      f = f < -fl ? -fl : (f > fl ? fl : f);
+      const float delta = f - old;
+      improvement -= 0.5f * delta * delta / Acc + delta * res;
+      R.force[c] = f;
+      for (int d = 0; d < nD; d++) q[d] += R.J[c * JS + d] * delta;
+    }
+    for (int ic = 0; ic < n_contacts; ic++) {
+      for (int j2 = 0; j2 < 2; j2++) {
+        const int j = const_start + 4 * ic + 2 * j2;
+        float res0 = b[j], res1 = b[j + 1], a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
+        for (int d = 0; d < nD; d++) {
+          const float m0 = MJ[(size_t)j * nD + d], m1 = MJ[(size_t)(j + 1) * nD + d], j0 = R.J[j * JS + d], j1 = R.J[(j + 1) * JS + d], qd = q[d];
+          res0 += m0 * qd; res1 += m1 * qd; a00 += j0 * m0; a01 += j1 * m0; a10 += j0 * m1; a11 += j1 * m1;
+        }
+        const float o0 = R.force[j], o1 = R.force[j + 1];
+        const float bc0 = res0 - (a00 * o0 + a01 * o1), bc1 = res1 - (a10 * o0 + a11 * o1);
+        const float mid = 0.5f * (o0 + o1);
+        const float K1 = a00 + a11 - a01 - a10, K0 = mid * (a00 - a11) + bc0 - bc1;
+        float f0 = mid, f1 = mid;
+        if (!(K1 < EPS)) {
+          const float y = -K0 / K1;
+          if (y < -mid) { f0 = 0.f; f1 = 2.f * mid; }
+          else if (y > mid) { f0 = 2.f * mid; f1 = 0.f; }
+          else { f0 = mid + y; f1 = mid - y; }
+        }
+        float d0 = f0 - o0, d1 = f1 - o1;  // noslip.py:358-385 func_cost_change
+        float change = 0.5f * (a00 * d0 * d0 + a01 * d0 * d1 + a10 * d1 * d0 + a11 * d1 * d1) + d0 * res0 + d1 * res1;
+        if (change > EPS) { f0 = o0; f1 = o1; d0 = 0.f; d1 = 0.f; change = 0.f; }
+        improvement -= change;
+        R.force[j] = f0; R.force[j + 1] = f1;
+        for (int d = 0; d < nD; d++) q[d] += R.J[j * JS + d] * d0 + R.J[(j + 1) * JS + d] * d1;
+      }
+    }
+    improvement *= scale;
+    if (improvement < CM(noslip_tolerance)) break;
+  }
+  // noslip.py:286-323 kernel_dual_finish
+  const LArr x = C.A(c_l.tmpv), qacc = C.A(c_l.qacc), acc = C.A(c_l.acc);
+  for (int d = 0; d < nD; d++) { qfrc[d] = q[d]; x[d] = q[d]; }
+  lane_mass_solve(C, x);
+  for (int d = 0; d < nD; d++) { const float a = x[d] + acc_smooth[d]; qacc[d] = a; acc[d] = a; }
+}
+
 // CS:210-245 resolve(): init (CS:2935-3059), monolith body (CS:3163-3190), update_qacc (CS:3240-3261), contact forces
 LHD __noinline__ void lane_constraints(const LaneCtx& C) {
   const int nD = CM(nD), nL = CM(nL);
@@ -1429,8 +1512,9 @@ LHD __noinline__ void lane_constraints(const LaneCtx& C) {
   }
   if (has_nan) C.I(c_h.errno_)[0] |= ERR_NAN_FORCE;
   C.I(c_h.is_warmstart)[0] = 1;
-  // ---- CS:3198-3237 func_update_contact_force: per-contact force (global record) and per-link totals
   const int nc = CM(enable_collision) ? C.I(c_h.n_contacts)[0] : 0;
+  if (CM(noslip_iterations) > 0 && n_con > 0) lane_noslip(C, R, nc);  // CS:237-238
+  // ---- CS:3198-3237 func_update_contact_force: per-contact force (global record) and per-link totals
   const LArr lcf = C.A(c_l.lcf);
   for (int i = 0; i < 3 * nL; i++) lcf[i] = 0.f;
   for (int ic = 0; ic < nc; ic++) {

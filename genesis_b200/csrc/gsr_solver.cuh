@@ -533,6 +533,109 @@ __device__ float linesearch(const Ctx<G>& C, const Rows& R, SolverState& X) {
   return 0.f;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// constraint/noslip.py: post-solver that removes residual slip.  Projected Gauss-Seidel over the friction-loss rows and over
+// the two opposing pyramid edges of each tangent direction with the regulariser dropped (A = J M^-1 J^T).  The reference
+// materialises A (n_con^2 words per env); here only the rows M^-1 J^T are kept (SPILL record) and q = J^T f is updated
+// incrementally, so A f = (M^-1 J^T)^T q and a 2x2 block of A is four dot products.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int G>
+__device__ __noinline__ void phase_noslip(const Ctx<G>& C, const Rows& R, int n_contacts) {
+  const int nD = CM(nD), MS = c_s.MS, JS = R.JS, n_con = R.n_con, lane = C.lane;
+  const float EPS = CM(eps);
+  float* MJ = C.spill + c_h.spill_minvjt;
+  float* b = R.jv;         // dead after the primal solve
+  float* q = WK(grad);     // J^T f
+  const float* L = WK(L);
+  const float* Dinv = WK(Dinv);
+  const float* J = R.J;
+  // noslip.py:9-58: rows of M^-1 J^T (one lane per row: serial L^T D L substitution on its own row) and b = J acc_smooth - aref
+  for (int r = lane; r < n_con; r += G) {
+    float* x = MJ + (size_t)r * JS;
+    for (int d = 0; d < nD; d++) x[d] = J[r * JS + d];
+    for (int j = nD - 1; j > 0; j--) {
+      const float xj = x[j];
+      for (int i = 0; i < j; i++) x[i] -= L[j * MS + i] * xj;
+    }
+    for (int i = 0; i < nD; i++) x[i] *= Dinv[i];
+    for (int j = 0; j < nD - 1; j++) {
+      const float xj = x[j];
+      for (int i = j + 1; i < nD; i++) x[i] -= L[i * MS + j] * xj;
+    }
+    float v = -R.aref[r];
+    for (int d = 0; d < nD; d++) v += J[r * JS + d] * WK(acc_smooth)[d];
+    b[r] = v;
+  }
+  for (int d = lane; d < nD; d += G) q[d] = WK(qfrc_c)[d];
+  __threadfence_block();
+  C.sync();
+  const float scale = 1.0f / (CM(meaninertia) * (float)max(1, nD));
+  const int const_start = R.nef;
+  for (int it = 0; it < CM(noslip_iterations); it++) {  // noslip.py:166-283
+    float improvement = 0.f;
+    if (it == 0) {
+      float s = 0.f;
+      for (int c = lane; c < n_con; c += G) s += 0.5f * R.force[c] * R.force[c] * R.R[c];
+      improvement = C.sum(s);
+    }
+    for (int c = R.ne; c < R.nef; c++) {
+      float r0 = 0.f, a0 = 0.f;
+      for (int d = lane; d < nD; d += G) { const float mj = MJ[(size_t)c * JS + d]; r0 += mj * q[d]; a0 += J[c * JS + d] * mj; }
+      const float res = b[c] + C.sum(r0), Acc = C.sum(a0);
+      const float old = R.force[c], fl = R.floss[c];
+      float f = old - res / Acc;
+      f = f < -fl ? -fl : (f > fl ? fl : f);
+      const float delta = f - old;
+      improvement -= 0.5f * delta * delta / Acc + delta * res;
+      C.sync();
+      if (lane == 0) R.force[c] = f;
+      for (int d = lane; d < nD; d += G) q[d] += J[c * JS + d] * delta;
+      C.sync();
+    }
+    for (int ic = 0; ic < n_contacts; ic++) {
+      for (int j2 = 0; j2 < 2; j2++) {
+        const int j = const_start + 4 * ic + 2 * j2;
+        float r0 = 0.f, r1 = 0.f, a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
+        for (int d = lane; d < nD; d += G) {
+          const float m0 = MJ[(size_t)j * JS + d], m1 = MJ[(size_t)(j + 1) * JS + d], j0 = J[j * JS + d], j1 = J[(j + 1) * JS + d], qd = q[d];
+          r0 += m0 * qd; r1 += m1 * qd; a00 += j0 * m0; a01 += j1 * m0; a10 += j0 * m1; a11 += j1 * m1;
+        }
+        const float res0 = b[j] + C.sum(r0), res1 = b[j + 1] + C.sum(r1);
+        a00 = C.sum(a00); a01 = C.sum(a01); a10 = C.sum(a10); a11 = C.sum(a11);
+        const float o0 = R.force[j], o1 = R.force[j + 1];
+        const float bc0 = res0 - (a00 * o0 + a01 * o1), bc1 = res1 - (a10 * o0 + a11 * o1);
+        const float mid = 0.5f * (o0 + o1);
+        const float K1 = a00 + a11 - a01 - a10, K0 = mid * (a00 - a11) + bc0 - bc1;
+        float f0 = mid, f1 = mid;
+        if (!(K1 < EPS)) {
+          const float y = -K0 / K1;
+          if (y < -mid) { f0 = 0.f; f1 = 2.f * mid; }
+          else if (y > mid) { f0 = 2.f * mid; f1 = 0.f; }
+          else { f0 = mid + y; f1 = mid - y; }
+        }
+        // noslip.py:358-385 func_cost_change: keep the update only if it does not raise the cost
+        float d0 = f0 - o0, d1 = f1 - o1;
+        float change = 0.5f * (a00 * d0 * d0 + a01 * d0 * d1 + a10 * d1 * d0 + a11 * d1 * d1) + d0 * res0 + d1 * res1;
+        if (change > EPS) { f0 = o0; f1 = o1; d0 = 0.f; d1 = 0.f; change = 0.f; }
+        improvement -= change;
+        C.sync();
+        if (lane == 0) { R.force[j] = f0; R.force[j + 1] = f1; }
+        for (int d = lane; d < nD; d += G) q[d] += J[j * JS + d] * d0 + J[(j + 1) * JS + d] * d1;
+        C.sync();
+      }
+    }
+    improvement *= scale;
+    if (improvement < CM(noslip_tolerance)) break;
+  }
+  // noslip.py:286-323 kernel_dual_finish: qacc = acc_smooth + M^-1 J^T f
+  float* x = WK(tmpv);
+  for (int d = lane; d < nD; d += G) { const float v = q[d]; WK(qfrc_c)[d] = v; x[d] = v; }
+  C.sync();
+  mass_solve(C, x);
+  for (int d = lane; d < nD; d += G) { const float a = x[d] + WK(acc_smooth)[d]; WK(qacc)[d] = a; WK(acc)[d] = a; }
+  C.sync();
+}
+
 // CS:210-245 resolve(): init (CS:2935-3059), monolith body (CS:3163-3190), update_qacc (CS:3240-3261),
 // contact forces (CS:3198-3237)
 template <int G>
@@ -627,8 +730,9 @@ __device__ void phase_constraints(const Ctx<G>& C) {
     out[c_h.n_constraints] = n_con; out[c_h.n_constraints_equality] = R.ne; out[c_h.n_constraints_frictionloss] = R.nef - R.ne;
     out[c_h.solver_iters] = iters;
   }
-  // ---- CS:3198-3237 func_update_contact_force: per-contact force (global record) and per-link totals
   const int nc = CM(enable_collision) ? SI[c_h.n_contacts] : 0;
+  if (CM(noslip_iterations) > 0 && n_con > 0) { C.sync(); phase_noslip(C, R, nc); }  // CS:237-238
+  // ---- CS:3198-3237 func_update_contact_force: per-contact force (global record) and per-link totals
   for (int ic = lane; ic < nc; ic += G) {
     const float* ct = R.ct + (size_t)ic * GSR_CONTACT_WORDS;
     const f3 cn(ct[CT_NRM], ct[CT_NRM + 1], ct[CT_NRM + 2]);

@@ -42,6 +42,8 @@ struct DevModel {
   int nL, nJ, nD, nQ, nG, nE, nEq, nP, nV;
   int max_contact_pairs, max_broad_pairs, n_contacts_per_pair, len_constraints;
   int iterations, ls_iterations, integrator, solver_type;
+  int noslip_iterations;  // constraint/noslip.py post-solver (0 = off)
+  float noslip_tolerance;
   int enable_collision, enable_joint_limit, enable_multi_contact, sort_contacts, has_cc, n_cache_words, diagnostics;
   float meaninertia, dt, eps, tolerance, ls_tolerance, mc_perturbation, mc_tolerance;
   float gravity[3];
@@ -126,6 +128,7 @@ struct HotLayout {
   int contact_stride, cache_stride, spill_stride;
   long long contact_base, cache_base, spill_base;  // word offsets of the segments inside the state buffer
   int cache_valid;                                 // offset of the validity bit words inside a CACHE record
+  int spill_minvjt;                                // noslip: offset of the M^-1 J^T rows inside a SPILL record
 };
 
 // Shared-memory workspace of one environment (word offsets from the env's base).  Words [0, n_in) mirror the record's IN

@@ -45,6 +45,7 @@ class RigidOptions(_Options):
     ls_iterations: int = 50
     ls_tolerance: float = 1e-2
     noslip_iterations: int = 0
+    noslip_tolerance: float = 1e-6
     sparse_solve: bool = False
     constraint_timeconst: float = 0.01
     use_contact_island: bool = False

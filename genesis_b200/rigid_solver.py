@@ -102,9 +102,9 @@ class RigidSolver:
 
     def build_model(self):
         o = self._options
-        if o.use_contact_island or o.use_hibernation or o.noslip_iterations or o.enable_mujoco_compatibility or o.use_gjk_collision:
+        if o.use_contact_island or o.use_hibernation or o.enable_mujoco_compatibility or o.use_gjk_collision:
             raise GenesisException(
-                "contact islands, hibernation, noslip, mujoco-compatibility and GJK-first collision are outside the "
+                "contact islands, hibernation, mujoco-compatibility and GJK-first collision are outside the "
                 "hot-path scope of this build (DESIGN.md 'Out of scope')."
             )
         b = ModelBuilder(
@@ -129,6 +129,7 @@ class RigidSolver:
         return dict(iterations=o.iterations, ls_iterations=o.ls_iterations, tolerance=o.tolerance, ls_tolerance=o.ls_tolerance,
                     integrator=int(o.integrator), solver_type=int(o.constraint_solver), enable_collision=int(o.enable_collision),
                     enable_joint_limit=int(o.enable_joint_limit), enable_multi_contact=int(o.enable_multi_contact),
+                    noslip_iterations=int(o.noslip_iterations), noslip_tolerance=float(o.noslip_tolerance),
                     sort_contacts=1, **self.tuning)
 
     def build(self, n_envs, device):

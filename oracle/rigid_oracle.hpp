@@ -113,6 +113,8 @@ struct Config {
   double mc_perturbation = 1e-2, mc_tolerance = 1e-2, mpr_to_gjk_overlap_ratio = 0.25;  // collider.py:85-87
   double ccd_eps = 1e-9, ccd_tolerance = 1e-6;  // mpr.py:13-19
   int ccd_iterations = 50;
+  int noslip_iterations = 0;  // options/solvers.py:506-507
+  double noslip_tolerance = 1e-6;
 };
 
 template <typename T>
@@ -1659,6 +1661,115 @@ struct Oracle {
   }
 
   // CS:210-245 resolve()
+  // constraint/noslip.py: post-solver that removes residual slip -- projected Gauss-Seidel on the friction-loss rows and on
+  // the two opposing pyramid edges of every tangent direction, with the regulariser R dropped (AR = J M^-1 J^T)
+  T noslip_cost_change(const T* Ac, T* force, const T* old_force, const T* res, int dim) {  // noslip.py:358-385
+    T change = 0;
+    if (dim == 1) {
+      T delta = force[0] - old_force[0];
+      change = T(0.5) * Ac[0] * delta * delta + delta * res[0];
+    } else {
+      T delta[2];
+      for (int i = 0; i < dim; i++) delta[i] = force[i] - old_force[i];
+      for (int i = 0; i < dim; i++) {
+        for (int j = 0; j < dim; j++) change += T(0.5) * Ac[i * dim + j] * delta[i] * delta[j];
+        change += delta[i] * res[i];
+      }
+    }
+    if (change > EPS) {
+      for (int i = 0; i < dim; i++) force[i] = old_force[i];
+      change = 0;
+    }
+    return change;
+  }
+  void noslip(Env<T>& e) {
+    const int nD = m.nD, nefc = e.n_con;
+    if (nefc == 0) return;
+    // noslip.py:9-58 kernel_build_efc_AR_b
+    std::vector<T> AR((size_t)nefc * nefc, 0), b(nefc, 0), tmp(nD), rowv(nD);
+    for (int r = 0; r < nefc; r++) {
+      for (int d = 0; d < nD; d++) rowv[d] = jrow(e, r)[d];
+      tmp = rowv;
+      solve_mass(e, rowv, tmp);
+      for (int c = 0; c < nefc; c++) {
+        T sum = 0;
+        for (int d = 0; d < nD; d++) sum += jrow(e, c)[d] * tmp[d];
+        AR[(size_t)r * nefc + c] = sum;
+      }
+    }
+    for (int c = 0; c < nefc; c++) {
+      T v = -e.aref[c];
+      for (int d = 0; d < nD; d++) v += jrow(e, c)[d] * e.acc_smooth[d];
+      b[c] = v;
+    }
+    auto residual = [&](int i_efc, int dim, T* res) {  // noslip.py:343-355
+      for (int j = 0; j < dim; j++) {
+        res[j] = b[i_efc + j];
+        for (int k = 0; k < nefc; k++) res[j] += AR[(size_t)(i_efc + j) * nefc + k] * e.efc_force[k];
+      }
+    };
+    // noslip.py:166-283 kernel_noslip
+    const int ne = e.n_eq, nf = e.n_floss, const_start = ne + nf;
+    const T scale = T(1) / (m.meaninertia * std::max(T(1), T(nD)));
+    for (int it = 0; it < cfg.noslip_iterations; it++) {
+      T improvement = 0;
+      if (it == 0)
+        for (int c = 0; c < nefc; c++) improvement += T(0.5) * e.efc_force[c] * e.efc_force[c] * e.diag[c];
+      T res[2], old_force[2], Ac[4], bc[2];
+      for (int c = ne; c < ne + nf; c++) {
+        residual(c, 1, res);
+        old_force[0] = e.efc_force[c];
+        T Acc = AR[(size_t)c * nefc + c];
+        e.efc_force[c] -= res[0] / Acc;
+        if (e.efc_force[c] < -e.efc_frictionloss[c]) e.efc_force[c] = -e.efc_frictionloss[c];
+        else if (e.efc_force[c] > e.efc_frictionloss[c]) e.efc_force[c] = e.efc_frictionloss[c];
+        T delta = e.efc_force[c] - old_force[0];
+        improvement -= T(0.5) * delta * delta / Acc + delta * res[0];
+      }
+      for (int ic = 0; ic < e.n_contacts; ic++) {
+        int base = const_start + ic * 4;
+        for (int j2 = 0; j2 < 2; j2++) {
+          int j = base + j2 * 2;
+          residual(j, 2, res);
+          for (int i2 = 0; i2 < 2; i2++) old_force[i2] = e.efc_force[j + i2];
+          for (int a = 0; a < 2; a++)
+            for (int k = 0; k < 2; k++) Ac[a * 2 + k] = AR[(size_t)(j + a) * nefc + (j + k)];
+          for (int a = 0; a < 2; a++) {
+            bc[a] = res[a];
+            for (int k = 0; k < 2; k++) bc[a] -= Ac[a * 2 + k] * old_force[k];
+          }
+          T mid = T(0.5) * (e.efc_force[j] + e.efc_force[j + 1]);
+          T K1 = Ac[0] + Ac[3] - Ac[1] - Ac[2];
+          T K0 = mid * (Ac[0] - Ac[3]) + bc[0] - bc[1];
+          if (K1 < EPS) {
+            e.efc_force[j] = e.efc_force[j + 1] = mid;
+          } else {
+            T y = -K0 / K1;
+            if (y < -mid) { e.efc_force[j] = 0; e.efc_force[j + 1] = 2 * mid; }
+            else if (y > mid) { e.efc_force[j] = 2 * mid; e.efc_force[j + 1] = 0; }
+            else { e.efc_force[j] = mid + y; e.efc_force[j + 1] = mid - y; }
+          }
+          improvement -= noslip_cost_change(Ac, &e.efc_force[j], old_force, res, 2);
+        }
+      }
+      improvement *= scale;
+      if (improvement < (T)cfg.noslip_tolerance) break;
+    }
+    // noslip.py:286-323 kernel_dual_finish
+    for (int d = 0; d < nD; d++) {
+      T q = 0;
+      for (int c = 0; c < nefc; c++) q += jrow(e, c)[d] * e.efc_force[c];
+      e.qf_constraint[d] = q;
+    }
+    std::vector<T> qa(nD, 0);
+    solve_mass(e, e.qf_constraint, qa);
+    for (int d = 0; d < nD; d++) {
+      e.qacc[d] = qa[d] + e.acc_smooth[d];
+      e.acc[d] = e.qacc[d];
+      e.force[d] = e.qf_smooth[d] + e.qf_constraint[d];
+    }
+  }
+
   void resolve(Env<T>& e) {
     int nD = m.nD;
     solve_init(e);
@@ -1679,6 +1790,7 @@ struct Oracle {
       if (std::isnan(e.qacc[d])) e.errno_ |= ERR_NAN_FORCE;
     }
     e.is_warmstart = 1;
+    if (cfg.noslip_iterations > 0) noslip(e);  // CS:237-238
     // CS:3198-3237 func_update_contact_force
     for (int l = 0; l < m.nL; l++) e.contact_force[l] = V();
     int cs = e.n_eq + e.n_floss;

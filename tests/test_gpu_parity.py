@@ -231,6 +231,28 @@ def test_weld_equality():
     assert (scene.rigid_solver.field("n_constraints_equality")[:, 0] == 12).all()
 
 
+def test_noslip_post_solver():
+    """constraint/noslip.py after the Newton solve (noslip_iterations=5): Go2 trajectories and a box on a tilted-gravity plane."""
+    B, K = 16, 50
+    scene, _ = make_go2(B, noslip_iterations=5)
+    orc = mirror_oracle(scene)
+    for _ in range(K):
+        scene.step()
+    orc.step(K)
+    dq = np.abs(gpu_field(scene, "qpos") - orc.qpos()).max(axis=1)
+    assert (dq <= TRAJ_QPOS_CONTACT).mean() >= 0.9, f"{np.sort(dq)}"
+    assert jaccard(contact_set(scene, B), contact_set(orc, B)) >= 0.95
+    scene, _ = scene_from_morphs([gs.morphs.Plane(), gs.morphs.Box(size=(0.1, 0.1, 0.1), pos=(0, 0, 0.05))], dt=0.01,
+                                 gravity=(2.0, 0.0, -9.81), noslip_iterations=5)
+    scene.build(n_envs=4)
+    orc = mirror_oracle(scene)
+    for _ in range(200):
+        scene.step()
+    orc.step(200)
+    assert np.abs(gpu_field(scene, "qpos") - orc.qpos()).max() <= TRAJ_QPOS_CONTACT
+    assert np.abs(gpu_field(scene, "vel")[:, 0]).max() < 5e-5  # creeps at ~1 mm/s without the pass (tests/test_oracle_analytic.py)
+
+
 def test_capsule_analytic_pairs():
     """Analytic capsule-capsule / sphere-capsule contacts (collider/capsule_contact.py) and plane-capsule support contacts."""
     B, K = 8, 60

@@ -203,3 +203,19 @@ def test_lane_weld_equality():
     emu.step(99)
     assert np.abs(emu.rows("qpos") - orc.qpos()).max() <= 1e-4 and np.abs(emu.rows("vel") - orc.vel()).max() <= 1e-3
     assert (emu.field("n_constraints_equality")[:, 0] == 12).all()
+
+
+def test_lane_noslip_post_solver():
+    """constraint/noslip.py: the kernel keeps the rows M^-1 J^T and updates J^T f incrementally, the oracle materialises
+    A = J M^-1 J^T like the reference -- two formulations of the same projected Gauss-Seidel."""
+    B = 3
+    m, orc, emu = pair(make_go2, B, go2_sets, noslip_iterations=5)
+    scene, solver, _ = host_model(make_go2)
+    ref = oracle_for(solver, m, B, threads=3, noslip_iterations=0)
+    for name, val in go2_sets(m, B).items():
+        ref.set(name, val)
+    orc.step(50)
+    emu.step(50)
+    ref.step(50)
+    assert np.abs(emu.rows("qpos") - orc.qpos()).max() <= 1e-3 and np.abs(emu.rows("vel") - orc.vel()).max() <= 2e-2
+    assert np.abs(orc.qpos() - ref.qpos()).max() > 5e-3  # the pass is not a no-op on this scene

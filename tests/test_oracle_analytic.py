@@ -297,3 +297,19 @@ def test_weld_equality_static_balance():
     g1 = lp[2] + rot(lq[2], d[3:6])
     g2 = lp[3] + rot(lq[3], d[0:3])
     assert np.abs(g1 - g2).max() < 5e-3  # soft constraint: millimetres of give while the arm is still swinging
+
+
+def test_noslip_suppresses_creep_on_an_incline():
+    """constraint/noslip.py (options/solvers.py:443-447 "suppress slip/drift"): a box on a plane under gravity tilted well
+    inside the friction cone creeps with the soft pyramidal friction rows (about 1 mm/s) and stops with the noslip pass."""
+    vel = {}
+    for ns in (0, 5):
+        scene, _ = scene_from_morphs([gs.morphs.Plane(), gs.morphs.Box(size=(0.1, 0.1, 0.1), pos=(0, 0, 0.05))], dt=0.01,
+                                     gravity=(2.0, 0.0, -9.81), noslip_iterations=ns)
+        solver = scene.rigid_solver
+        m = solver.build_model()
+        orc = oracle_for(solver, m, 1, double=True)
+        orc.step(200)
+        vel[ns] = abs(orc.vel()[0][0])
+        assert int(orc.get("n_contacts", 1, 0)[0]) == 4
+    assert vel[0] > 5e-4 and vel[5] < 1e-2 * vel[0]
