@@ -13,7 +13,7 @@ EXPORTS = (
     "gsr_model_begin", "gsr_model_set_f32", "gsr_model_set_i32", "gsr_model_set_scalar", "gsr_model_commit", "gsr_model_refresh",
     "gsr_state_words", "gsr_field_count", "gsr_field_info", "gsr_bind", "gsr_launch_info", "gsr_init_state", "gsr_step",
     "gsr_forward_kinematics", "gsr_reset_envs", "gsr_step_host", "gsr_launch_count", "gsr_kernel_info",
-    "gsr_set_profiling", "gsr_kernel_time_ms",
+    "gsr_set_profiling", "gsr_kernel_time_ms", "gsr_debug_trace", "gsr_debug_trace_read",
     "gsr_last_error", "gsr_version", "gsr_destroy",
 )
 
@@ -59,6 +59,8 @@ def lib():
         L.gsr_kernel_info.argtypes = [vp, i, ctypes.POINTER(cp), ctypes.POINTER(ctypes.c_longlong)]
         L.gsr_set_profiling.argtypes = [vp, i]
         L.gsr_kernel_time_ms.argtypes = [vp, i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]
+        L.gsr_debug_trace.argtypes = [vp, i]
+        L.gsr_debug_trace_read.argtypes = [vp, vp]
         L.gsr_last_error.argtypes = [vp]
         L.gsr_last_error.restype = cp
         L.gsr_version.restype = cp

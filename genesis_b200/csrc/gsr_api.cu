@@ -8,6 +8,8 @@
 
 #include "../../include/gsrigid.h"
 #include <cstdint>
+#include <cub/cub.cuh>
+
 #include "gsr_host.h"
 #include "gsr_kernels.cuh"
 #include "gsr_lane.cuh"
@@ -29,6 +31,15 @@ struct gsr_handle_s : GsrSpec {
   float* state = nullptr;
   DevModel* d_model = nullptr;  // global-memory copy for lane-varying table reads
   float *d_verts = nullptr, *d_support = nullptr;
+  unsigned short* d_fac = nullptr;
+  unsigned long long* d_trace = nullptr;  // gsr_debug_trace
+  // cost-ordered scheduling of the lane-group step kernel: every `reorder_period` steps the environments are sorted by the
+  // busy time they measured in their last step (descending), so the expensive ones start first and the tail of a launch
+  // overlaps the bulk of the batch instead of running alone on a few SMs (profiles/README.md "tail")
+  int *d_order = nullptr, *d_iota = nullptr, *d_cost = nullptr, *d_cost_sorted = nullptr;
+  void* d_sort_tmp = nullptr;
+  size_t sort_tmp_bytes = 0;
+  int reorder_period = 16, steps_since_reorder = 0;
   int *d_pairs = nullptr, *d_pair_idx = nullptr;
   // staging for gsr_step_host
   float *d_stage = nullptr, *h_stage = nullptr;
@@ -136,11 +147,14 @@ int gsr_model_commit(gsr_handle_t h, int device, int n_envs) {
     auto& sv = h->f["support_v"]; CUDA_OK(upload(sv.empty() ? nullptr : sv.data(), sv.size() * 4, (void**)&h->d_support));
     auto& pr = h->i["pairs"]; CUDA_OK(upload(pr.empty() ? nullptr : pr.data(), pr.size() * 4, (void**)&h->d_pairs));
     auto& pi = h->i["pair_idx"]; CUDA_OK(upload(pi.empty() ? nullptr : pi.data(), pi.size() * 4, (void**)&h->d_pair_idx));
+    CUDA_OK(upload(h->fac_tasks.empty() ? nullptr : h->fac_tasks.data(), h->fac_tasks.size() * sizeof(unsigned short), (void**)&h->d_fac));
     CUDA_OK(cudaMalloc((void**)&h->d_model, sizeof(DevModel)));
   }
+  m.fac_tasks = h->d_fac;
   m.verts = h->d_verts; m.support_v = h->d_support; m.pairs = h->d_pairs; m.pair_idx = h->d_pair_idx;
 
   { int rc_lay = gsr_compute_layouts(h, n_envs); if (rc_lay) return rc_lay; }
+  h->reorder_period = (int)h->S("cfg_reorder_period", 16);
   h->committed = true;
   g_active[device] = nullptr;
   return GSR_OK;
@@ -218,11 +232,40 @@ static int lane_launch(gsr_handle_t h, cudaStream_t st, int clear_ext) {
   return GSR_OK;
 }
 
+__global__ void k_iota(int* v, int n) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) v[t] = t;
+}
+// order[B] = 1 when the most expensive environment costs at least 1.5x the median one
+__global__ void k_order_flag(const int* cost_sorted, int* order, int B) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) order[B] = (2 * (long long)cost_sorted[0] > 3 * (long long)cost_sorted[B / 2]) ? 1 : 0;
+}
+__global__ void k_gather_cost(const float* state, int B, int field_off, int* dst) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env < B) dst[env] = reinterpret_cast<const int*>(state + (size_t)env * c_h.hot_stride)[field_off];
+}
+// sort the environments by their last measured step cost, most expensive first (two tiny kernels + one radix sort)
+static int reorder_envs(gsr_handle_t h, cudaStream_t st) {
+  const int B = h->B;
+  if (!h->d_order) {
+    CUDA_OK(cudaMalloc((void**)&h->d_order, sizeof(int) * (B + 1))); CUDA_OK(cudaMalloc((void**)&h->d_iota, sizeof(int) * B));
+    CUDA_OK(cudaMalloc((void**)&h->d_cost, sizeof(int) * B)); CUDA_OK(cudaMalloc((void**)&h->d_cost_sorted, sizeof(int) * B));
+    CUDA_OK(cub::DeviceRadixSort::SortPairsDescending(nullptr, h->sort_tmp_bytes, h->d_cost, h->d_cost_sorted, h->d_iota, h->d_order, B, 0, 32, st));
+    CUDA_OK(cudaMalloc(&h->d_sort_tmp, h->sort_tmp_bytes));
+    k_iota<<<(B + 255) / 256, 256, 0, st>>>(h->d_iota, B);
+  }
+  k_gather_cost<<<(B + 255) / 256, 256, 0, st>>>(h->state, B, h->lay.step_cost, h->d_cost);
+  CUDA_OK(cub::DeviceRadixSort::SortPairsDescending(h->d_sort_tmp, h->sort_tmp_bytes, h->d_cost, h->d_cost_sorted, h->d_iota, h->d_order, B, 0, 32, st));
+  k_order_flag<<<1, 32, 0, st>>>(h->d_cost_sorted, h->d_order, B);
+  CUDA_OK(cudaGetLastError());
+  return GSR_OK;
+}
+
 static int group_launch(gsr_handle_t h, int which, cudaStream_t st, const uint8_t* mask, int clear_ext) {
   if (h->group == 1 && which == K_STEP) return lane_launch(h, st, clear_ext);
   const int G = h->group == 1 ? 8 : h->group, EPW = 32 / G;  // the (cold) forward-kinematics paths of a lane model use the group kernel
   const size_t warp_bytes = (size_t)EPW * h->sl.env_words * sizeof(float);
-  int warps = h->warps_per_cta > 0 ? h->warps_per_cta : (G == 32 ? 8 : 4);  // measured on B200 (profiles/README.md)
+  int warps = h->warps_per_cta > 0 ? h->warps_per_cta : (G == 32 ? 8 : 1);  // measured on B200 (profiles/README.md, r1c sweeps)
   if (warps > GSR_MAX_WARPS_PER_CTA) warps = GSR_MAX_WARPS_PER_CTA;
   while (warps > 1 && warps * (warp_bytes + 8) > 224 * 1024) warps--;  // one big CTA per SM, its warps in phase lockstep
   const int envs_per_cta = warps * EPW;
@@ -233,7 +276,7 @@ static int group_launch(gsr_handle_t h, int which, cudaStream_t st, const uint8_
   if (which == K_STEP) {                                                                                 \
     CUDA_OK(set_smem(k_step<GG>, smem));                                                                 \
     Bracket br_(h, K_STEP, st);                                                                          \
-    k_step<GG><<<grid, block, smem, st>>>(h->state, h->B, h->d_model, clear_ext);                        \
+    k_step<GG><<<grid, block, smem, st>>>(h->state, h->B, h->d_model, clear_ext, h->d_order, h->d_trace);                        \
   } else {                                                                                               \
     CUDA_OK(set_smem(k_forward<GG>, smem));                                                              \
     Bracket br_(h, K_FORWARD, st);                                                                       \
@@ -267,6 +310,11 @@ int gsr_step(gsr_handle_t h, int n_substeps, void* cuda_stream) {
   int rc = activate(h, st);
   if (rc) return rc;
   for (int s = 0; s < n_substeps; s++) {
+    if (h->group != 1 && h->reorder_period > 0 && ++h->steps_since_reorder >= h->reorder_period) {
+      h->steps_since_reorder = 0;
+      rc = reorder_envs(h, st);
+      if (rc) return rc;
+    }
     rc = group_launch(h, K_STEP, st, nullptr, s == n_substeps - 1);
     if (rc) return rc;
   }
@@ -357,6 +405,21 @@ int gsr_kernel_time_ms(gsr_handle_t h, int index, double* total_ms, long long* t
   return GSR_OK;
 }
 
+// Developer diagnostics (tools/step_trace.py): while enabled, the lane-group step kernel records for every environment the
+// start / end time (globaltimer, ns) and the SM it ran on; gsr_debug_trace_read copies 8 * n_envs words to the host.
+int gsr_debug_trace(gsr_handle_t h, int enabled) {
+  if (!h || !h->committed) return fail(h, GSR_ESTATE, "model not committed");
+  CUDA_OK(cudaSetDevice(h->device));
+  if (enabled && !h->d_trace) { CUDA_OK(cudaMalloc((void**)&h->d_trace, (size_t)h->B * 8 * sizeof(unsigned long long))); CUDA_OK(cudaMemset(h->d_trace, 0, (size_t)h->B * 8 * sizeof(unsigned long long))); }
+  if (!enabled && h->d_trace) { cudaFree(h->d_trace); h->d_trace = nullptr; }
+  return GSR_OK;
+}
+int gsr_debug_trace_read(gsr_handle_t h, unsigned long long* host_out) {
+  if (!h || !h->d_trace || !host_out) return fail(h, GSR_ESTATE, "tracing is not enabled");
+  CUDA_OK(cudaMemcpy(host_out, h->d_trace, (size_t)h->B * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return GSR_OK;
+}
+
 long long gsr_launch_count(gsr_handle_t h) { return h ? h->total_launches : 0; }
 int gsr_kernel_info(gsr_handle_t h, int index, const char** name, long long* launches) {
   if (!h || index < 0 || index >= K_COUNT) return GSR_EINVAL;
@@ -370,7 +433,8 @@ void gsr_destroy(gsr_handle_t h) {
   if (h->committed) {
     cudaSetDevice(h->device);
     if (g_active[h->device] == h) g_active[h->device] = nullptr;
-    cudaFree(h->d_verts); cudaFree(h->d_support); cudaFree(h->d_pairs); cudaFree(h->d_pair_idx); cudaFree(h->d_model);
+    cudaFree(h->d_verts); cudaFree(h->d_support); cudaFree(h->d_pairs); cudaFree(h->d_pair_idx); cudaFree(h->d_model); cudaFree(h->d_fac); if (h->d_trace) cudaFree(h->d_trace);
+    if (h->d_order) { cudaFree(h->d_order); cudaFree(h->d_iota); cudaFree(h->d_cost); cudaFree(h->d_cost_sorted); cudaFree(h->d_sort_tmp); }
     if (h->d_stage) cudaFree(h->d_stage);
     for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : h->event_pool) cudaEventDestroy(e);

@@ -226,93 +226,110 @@ __device__ __forceinline__ void rotate_frame(f3 pos, f4 quat, f3 cpos, f4 qrot, 
   npos = pos - (rotate(rel, qrot) - rel);
 }
 
-// NP:519-970 func_convex_convex_contact for one broad-phase pair (type[ga] <= type[gb], not plane-box)
+// NP:519-970 func_convex_convex_contact for one broad-phase pair (type[ga] <= type[gb], not plane-box), split in two so that
+// the four perturbed multi-contact detections of a pair -- which depend only on the unperturbed one -- run on four lanes
+// instead of back to back on the pair's lane (the MPR of an unusual pose is the long pole of a launch, profiles/README.md).
+struct PairDet {
+  int ga, gb, ta, tb, p;
+  bool multi, is_col_0;
+  float tolerance;
+  f3 pa0, pb0, normal_0, cpos_0, axis_0, axis_1;
+  f4 qa0, qb0;
+};
+
+// one detection at the (possibly perturbed) poses in P: analytic capsule pairs, plane support query, or MPR with warm start
 template <int G>
-__device__ __noinline__ void dev_convex_convex(const Ctx<G>& C, LaneContacts& out, int ga, int gb, int i_pair) {
+__device__ __forceinline__ void dev_detect(const Ctx<G>& C, const PairDet& D, const PairPose& P, int i_det, bool& is_col, f3& normal, float& pen, f3& cpos) {
   const float EPS = c_m.eps;
-  const int ta = GM(g_type[ga]), tb = GM(g_type[gb]);
-  const bool multi = c_m.enable_multi_contact && ta != GEOM_SPHERE && ta != GEOM_ELLIPSOID && tb != GEOM_SPHERE && tb != GEOM_ELLIPSOID;
-  const float tolerance = dev_tolerance(C, ga, gb);
-  const float* gpos = WK(gpos);
-  const float* gquat = WK(gquat);
-  const f3 ga_pos0 = ld3(gpos, ga), gb_pos0 = ld3(gpos, gb);
-  const f4 ga_quat0 = ld4(gquat, ga), gb_quat0 = ld4(gquat, gb);
+  const int ga = D.ga, gb = D.gb;
+  if (D.ta == GEOM_CAPSULE && D.tb == GEOM_CAPSULE) {  // NP:637-648 analytic capsule pairs
+    capsule_capsule_contact(P.pa, P.qa, GM(g_data[ga][0]), 0.5f * GM(g_data[ga][1]), P.pb, P.qb, GM(g_data[gb][0]), 0.5f * GM(g_data[gb][1]), EPS,
+                            is_col, normal, cpos, pen);
+  } else if (D.ta == GEOM_SPHERE && D.tb == GEOM_CAPSULE) {  // NP:649-661 (types are sorted: A is the sphere)
+    sphere_capsule_contact(P.pa, GM(g_data[ga][0]), P.pb, P.qb, GM(g_data[gb][0]), 0.5f * GM(g_data[gb][1]), EPS, is_col, normal, cpos, pen);
+  } else if (D.ta == GEOM_PLANE) {
+    normal = -normalized(rotate(f3(GM(g_data[ga][0]), GM(g_data[ga][1]), GM(g_data[ga][2])), P.qa));
+    const f3 v1 = dev_support(C, normal, gb, P.pb, P.qb);
+    pen = dot(normal, v1 - P.pa);
+    cpos = v1 - normal * (0.5f * pen);
+    is_col = pen > 0.f;
+  } else {
+    // the perturbed detections read the normal the unperturbed one has just cached (same as the sequential reference flow)
+    int* cvalid = reinterpret_cast<int*>(C.cache) + c_h.cache_valid;
+    f3 normal_ws;
+    const bool valid = (cvalid[D.p >> 5] >> (D.p & 31)) & 1;
+    if (valid) normal_ws = ld3(C.cache, D.p);
+    const bool guess = fabsf(normal_ws.x) > EPS || fabsf(normal_ws.y) > EPS || fabsf(normal_ws.z) > EPS;
+    dev_mpr_contact(C, P, normal_ws, is_col, normal, pen, cpos);
+    if (i_det == 0 && !is_col && guess) dev_mpr_contact(C, P, f3(), is_col, normal, pen, cpos);
+  }
+}
+
+// unperturbed detection of a pair: contact 0, warm-start cache update, perturbation axes
+template <int G>
+__device__ __noinline__ void dev_pair_det0(const Ctx<G>& C, LaneContacts& out, PairDet& D) {
+  const float EPS = c_m.eps;
+  const int ga = D.ga, gb = D.gb;
+  D.ta = GM(g_type[ga]); D.tb = GM(g_type[gb]);
+  D.multi = c_m.enable_multi_contact && D.ta != GEOM_SPHERE && D.ta != GEOM_ELLIPSOID && D.tb != GEOM_SPHERE && D.tb != GEOM_ELLIPSOID;
+  D.tolerance = dev_tolerance(C, ga, gb);
+  D.pa0 = ld3(WK(gpos), ga); D.pb0 = ld3(WK(gpos), gb);
+  D.qa0 = ld4(WK(gquat), ga); D.qb0 = ld4(WK(gquat), gb);
   PairPose P;
-  P.ga = ga; P.gb = gb; P.pa = ga_pos0; P.pb = gb_pos0; P.qa = ga_quat0; P.qb = gb_quat0;
-  bool is_col_0 = false, is_col = false;
+  P.ga = ga; P.gb = gb; P.pa = D.pa0; P.pb = D.pb0; P.qa = D.qa0; P.qb = D.qb0;
+  bool is_col;
+  f3 normal, cpos;
   float pen = 0.f;
-  f3 normal_0, cpos_0, normal, cpos, axis_0, axis_1;
-  f4 qrot(0.f, 0.f, 0.f, 0.f);
-  const bool use_cache = ta != GEOM_PLANE;
-  int* cvalid = reinterpret_cast<int*>(C.cache) + c_h.cache_valid;
-  for (int i_det = 0; i_det < 5; i_det++) {
-    if (i_det > 0 && !(multi && is_col_0)) break;
-    if (i_det > 0) {
-      const f3 axis = axis_0 * (float)(2 * (i_det % 2) - 1) + axis_1 * (float)(1 - 2 * ((i_det / 2) % 2));
-      qrot = rotvec_to_quat(axis * c_m.mc_perturbation, EPS);
-      rotate_frame(ga_pos0, ga_quat0, cpos_0, qrot, P.pa, P.qa);
-      rotate_frame(gb_pos0, gb_quat0, cpos_0, quat_inv(qrot), P.pb, P.qb);
-    }
-    if (ta == GEOM_CAPSULE && tb == GEOM_CAPSULE) {  // NP:637-648 analytic capsule pairs
-      capsule_capsule_contact(P.pa, P.qa, GM(g_data[ga][0]), 0.5f * GM(g_data[ga][1]), P.pb, P.qb, GM(g_data[gb][0]), 0.5f * GM(g_data[gb][1]), EPS,
-                              is_col, normal, cpos, pen);
-    } else if (ta == GEOM_SPHERE && tb == GEOM_CAPSULE) {  // NP:649-661 (types are sorted: A is the sphere)
-      sphere_capsule_contact(P.pa, GM(g_data[ga][0]), P.pb, P.qb, GM(g_data[gb][0]), 0.5f * GM(g_data[gb][1]), EPS, is_col, normal, cpos, pen);
-    } else if (ta == GEOM_PLANE) {
-      normal = -normalized(rotate(f3(GM(g_data[ga][0]), GM(g_data[ga][1]), GM(g_data[ga][2])), P.qa));
-      const f3 v1 = dev_support(C, normal, gb, P.pb, P.qb);
-      pen = dot(normal, v1 - P.pa);
-      cpos = v1 - normal * (0.5f * pen);
-      is_col = pen > 0.f;
-    } else {
-      f3 normal_ws;
-      const bool valid = (cvalid[i_pair >> 5] >> (i_pair & 31)) & 1;
-      if (valid) normal_ws = ld3(C.cache, i_pair);
-      const bool guess = fabsf(normal_ws.x) > EPS || fabsf(normal_ws.y) > EPS || fabsf(normal_ws.z) > EPS;
-      dev_mpr_contact(C, P, normal_ws, is_col, normal, pen, cpos);
-      if (i_det == 0 && !is_col && guess) dev_mpr_contact(C, P, f3(), is_col, normal, pen, cpos);
-    }
-    if (i_det == 0) {
-      is_col_0 = is_col; normal_0 = normal; cpos_0 = cpos;
-      if (is_col_0) {
-        out.add(normal, cpos, pen);
-        if (multi) {
-          // CT:353-412 func_contact_orthogonals: perturbation axes from the principal inertia frame of the smaller geom
-          int g = gb;
-          if (ta != GEOM_PLANE) {
-            const float va = GM(g_aabb_hi[ga][0]) * GM(g_aabb_hi[ga][1]) * GM(g_aabb_hi[ga][2]);
-            const float vb = GM(g_aabb_hi[gb][0]) * GM(g_aabb_hi[gb][1]) * GM(g_aabb_hi[gb][2]);
-            g = (va < vb) ? ga : gb;
-          }
-          const int l = GM(g_link[g]);
-          const mat3 rot = quat_to_R(quat_compose(f4(GM(l_iquat[l][0]), GM(l_iquat[l][1]), GM(l_iquat[l][2]), GM(l_iquat[l][3])), ld4(IN(links_quat), l)), EPS);
-          int axis_idx = 0;
-          float amax = 0.f;
-          for (int i = 0; i < 3; i++) { const float a = fabsf(dot(mat_col(rot, i), normal)); if (a > amax) { amax = a; axis_idx = i; } }
-          axis_idx = (axis_idx + 1) % 3;
-          axis_0 = mat_col(rot, axis_idx);
-          axis_0 = normalized(axis_0 - normal * dot(normal, axis_0));
-          axis_1 = cross(normal, axis_0);
-        }
+  dev_detect(C, D, P, 0, is_col, normal, pen, cpos);
+  D.is_col_0 = is_col; D.normal_0 = normal; D.cpos_0 = cpos;
+  if (is_col) {
+    out.add(normal, cpos, pen);
+    if (D.multi) {
+      // CT:353-412 func_contact_orthogonals: perturbation axes from the principal inertia frame of the smaller geom
+      int g = gb;
+      if (D.ta != GEOM_PLANE) {
+        const float va = GM(g_aabb_hi[ga][0]) * GM(g_aabb_hi[ga][1]) * GM(g_aabb_hi[ga][2]);
+        const float vb = GM(g_aabb_hi[gb][0]) * GM(g_aabb_hi[gb][1]) * GM(g_aabb_hi[gb][2]);
+        g = (va < vb) ? ga : gb;
       }
-      if (use_cache) {
-        if (is_col_0) { st3(C.cache, i_pair, normal); atomicOr(&cvalid[i_pair >> 5], 1 << (i_pair & 31)); }
-        else atomicAnd(&cvalid[i_pair >> 5], ~(1 << (i_pair & 31)));
-      }
-    } else if (is_col) {
-      const f3 cpa = rotate((cpos - normal * (0.5f * pen)) - cpos_0, quat_inv(qrot)) + cpos_0;
-      const f3 cpb = rotate((cpos + normal * (0.5f * pen)) - cpos_0, qrot) + cpos_0;
-      cpos = (cpa + cpb) * 0.5f;
-      f3 twist = cross(normal, normal_0);
-      const float mcp = c_m.mc_perturbation;
-      twist = f3(fminf(fmaxf(twist.x, -mcp), mcp), fminf(fmaxf(twist.y, -mcp), mcp), fminf(fmaxf(twist.z, -mcp), mcp));
-      normal = normal + cross(twist, normal);
-      pen = dot(normal, cpb - cpa);
-      bool repeated = false;
-      for (int c = 0; c < out.n; c++)
-        if (norm(cpos - out.pos[c]) < tolerance) repeated = true;
-      if (!repeated && pen > -tolerance) out.add(normal, cpos, fmaxf(pen, 0.f));
+      const int l = GM(g_link[g]);
+      const mat3 rot = quat_to_R(quat_compose(f4(GM(l_iquat[l][0]), GM(l_iquat[l][1]), GM(l_iquat[l][2]), GM(l_iquat[l][3])), ld4(IN(links_quat), l)), EPS);
+      int axis_idx = 0;
+      float amax = 0.f;
+      for (int i = 0; i < 3; i++) { const float a = fabsf(dot(mat_col(rot, i), normal)); if (a > amax) { amax = a; axis_idx = i; } }
+      axis_idx = (axis_idx + 1) % 3;
+      D.axis_0 = mat_col(rot, axis_idx);
+      D.axis_0 = normalized(D.axis_0 - normal * dot(normal, D.axis_0));
+      D.axis_1 = cross(normal, D.axis_0);
     }
+  }
+  if (D.ta != GEOM_PLANE) {
+    int* cvalid = reinterpret_cast<int*>(C.cache) + c_h.cache_valid;
+    if (is_col) { st3(C.cache, D.p, normal); atomicOr(&cvalid[D.p >> 5], 1 << (D.p & 31)); }
+    else atomicAnd(&cvalid[D.p >> 5], ~(1 << (D.p & 31)));
+  }
+}
+
+// perturbed detection i_det (1..4) of a colliding pair, corrected back to the unperturbed frame (NP:889-936)
+template <int G>
+__device__ __noinline__ void dev_pair_perturbed(const Ctx<G>& C, const PairDet& D, int i_det, bool& is_col, f3& normal, float& pen, f3& cpos) {
+  const float EPS = c_m.eps;
+  const f3 axis = D.axis_0 * (float)(2 * (i_det % 2) - 1) + D.axis_1 * (float)(1 - 2 * ((i_det / 2) % 2));
+  const f4 qrot = rotvec_to_quat(axis * c_m.mc_perturbation, EPS);
+  PairPose P;
+  P.ga = D.ga; P.gb = D.gb;
+  rotate_frame(D.pa0, D.qa0, D.cpos_0, qrot, P.pa, P.qa);
+  rotate_frame(D.pb0, D.qb0, D.cpos_0, quat_inv(qrot), P.pb, P.qb);
+  dev_detect(C, D, P, i_det, is_col, normal, pen, cpos);
+  if (is_col) {
+    const f3 cpa = rotate((cpos - normal * (0.5f * pen)) - D.cpos_0, quat_inv(qrot)) + D.cpos_0;
+    const f3 cpb = rotate((cpos + normal * (0.5f * pen)) - D.cpos_0, qrot) + D.cpos_0;
+    cpos = (cpa + cpb) * 0.5f;
+    f3 twist = cross(normal, D.normal_0);
+    const float mcp = c_m.mc_perturbation;
+    twist = f3(fminf(fmaxf(twist.x, -mcp), mcp), fminf(fmaxf(twist.y, -mcp), mcp), fminf(fmaxf(twist.z, -mcp), mcp));
+    normal = normal + cross(twist, normal);
+    pen = dot(normal, cpb - cpa);
   }
 }
 
@@ -353,6 +370,8 @@ __device__ int narrow_batch(const Ctx<G>& C, const int* queue, int n_batch, int 
   LaneContacts out;
   out.n = 0;
   int ga = 0, gb = 0, p = 0, plane_box = 0;
+  PairDet D;
+  D.multi = false; D.is_col_0 = false;
   if (lane < n_batch) {
     p = queue[lane];
     const int ga0 = __ldg(CM(pairs) + 2 * p), gb0 = __ldg(CM(pairs) + 2 * p + 1);
@@ -360,7 +379,53 @@ __device__ int narrow_batch(const Ctx<G>& C, const int* queue, int n_batch, int 
     if (GM(g_type[ga0]) > GM(g_type[gb0])) { ga = gb0; gb = ga0; }
     plane_box = GM(g_type[ga]) == GEOM_PLANE && GM(g_type[gb]) == GEOM_BOX;
     if (plane_box) dev_plane_box(C, out, ga, gb);
-    else dev_convex_convex(C, out, ga, gb, p);
+    else { D.ga = ga; D.gb = gb; D.p = p; dev_pair_det0(C, out, D); }
+  }
+  // ---- perturbed detections: task (pair k of the colliding multi-contact pairs, i_det) -> lane, results through the
+  // staging area behind the contact staging records, then every pair lane applies the de-duplication in detection order
+  const bool want = lane < n_batch && !plane_box && D.multi && D.is_col_0;
+  const unsigned wm = C.ballot(want);
+  const int n_task = 4 * __popc(wm);
+  float* stage = C.spill + (size_t)CM(max_contact_pairs) * GSR_CONTACT_WORDS;  // [lane][4][8]
+  __threadfence_block();
+  C.sync();
+  for (int base = 0; base < n_task; base += G) {
+    const int tt = base + lane;
+    const bool active = tt < n_task;
+    const int src = active ? (int)__fns(wm, 0, (tt >> 2) + 1) : 0;
+    const int i_det = (tt & 3) + 1;
+    PairDet T;
+#define SHF(v) __shfl_sync(C.gmask, v, src, G)
+#define SHF3(a) f3(SHF(a.x), SHF(a.y), SHF(a.z))
+#define SHF4(a) f4(SHF(a.w), SHF(a.x), SHF(a.y), SHF(a.z))
+    T.ga = SHF(D.ga); T.gb = SHF(D.gb); T.ta = SHF(D.ta); T.tb = SHF(D.tb); T.p = SHF(D.p);
+    T.pa0 = SHF3(D.pa0); T.pb0 = SHF3(D.pb0); T.qa0 = SHF4(D.qa0); T.qb0 = SHF4(D.qb0);
+    T.normal_0 = SHF3(D.normal_0); T.cpos_0 = SHF3(D.cpos_0); T.axis_0 = SHF3(D.axis_0); T.axis_1 = SHF3(D.axis_1);
+#undef SHF4
+#undef SHF3
+#undef SHF
+    if (active) {
+      bool is_col;
+      f3 normal, cpos;
+      float pen = 0.f;
+      dev_pair_perturbed(C, T, i_det, is_col, normal, pen, cpos);
+      float* r = stage + ((size_t)src * 4 + (i_det - 1)) * 8;
+      r[0] = is_col ? 1.f : 0.f; r[1] = normal.x; r[2] = normal.y; r[3] = normal.z; r[4] = cpos.x; r[5] = cpos.y; r[6] = cpos.z; r[7] = pen;
+    }
+  }
+  __threadfence_block();
+  C.sync();
+  if (want) {
+    for (int i_det = 1; i_det < 5; i_det++) {
+      const float* r = stage + ((size_t)lane * 4 + (i_det - 1)) * 8;
+      if (r[0] == 0.f) continue;
+      const f3 normal(r[1], r[2], r[3]), cpos(r[4], r[5], r[6]);
+      const float pen = r[7];
+      bool repeated = false;
+      for (int c = 0; c < out.n; c++)
+        if (norm(cpos - out.pos[c]) < D.tolerance) repeated = true;
+      if (!repeated && pen > -D.tolerance) out.add(normal, cpos, fmaxf(pen, 0.f));
+    }
   }
   // exclusive prefix of the per-lane counts (lane order = pair order)
   int incl = out.n;

@@ -266,6 +266,25 @@ __device__ __noinline__ void mass_solve(const Ctx<G>& C, float* x) {
   const int nD = CM(nD), MS = c_s.MS;
   const float* L = WK(L);
   const float* Dinv = WK(Dinv);
+  if (nD <= G) {
+    // one lane per unknown, the running right-hand side in a register; the pivot value travels by shuffle, so the
+    // 2 (nD - 1) elimination steps need no shared-memory round trip and no barrier (same products, same order)
+    const int lane = C.lane;
+    const bool own = lane < nD;
+    float s = own ? x[lane] : 0.f;
+    for (int j = nD - 1; j > 0; j--) {  // L^T w = y
+      const float xj = __shfl_sync(C.gmask, s, j, G);
+      if (lane < j) s -= L[j * MS + lane] * xj;
+    }
+    if (own) s *= Dinv[lane];
+    for (int j = 0; j < nD - 1; j++) {  // L x = z
+      const float xj = __shfl_sync(C.gmask, s, j, G);
+      if (own && lane > j) s -= L[lane * MS + j] * xj;
+    }
+    if (own) x[lane] = s;
+    C.sync();
+    return;
+  }
   for (int j = nD - 1; j > 0; j--) {  // L^T w = y: once w_j is final, eliminate it from every i < j
     const float xj = x[j];
     for (int i = C.lane; i < j; i += G) x[i] -= L[j * MS + i] * xj;
@@ -288,10 +307,11 @@ __device__ __noinline__ void mass_factor(const Ctx<G>& C) {
   float* Dinv = WK(Dinv);
   for (int i = nD - 1; i >= 0; i--) {
     const float dinv = 1.0f / L[i * MS + i];
-    const int ntask = i * (i + 1) / 2;  // all (j, k) with k <= j < i
-    for (int t = C.lane; t < ntask; t += G) {
-      int j, k;
-      tri_decode(t, j, k);
+    // (j, k), k <= j < i, over the ancestor dofs of i only: entries of other branches are structurally zero and stay zero
+    const int t1 = CM(fac_start[i + 1]);
+    for (int t = CM(fac_start[i]) + C.lane; t < t1; t += G) {
+      const unsigned tr = __ldg(CM(fac_tasks) + t);
+      const int j = (int)(tr >> 8), k = (int)(tr & 255u);
       L[j * MS + k] -= (L[i * MS + j] * dinv) * L[i * MS + k];
     }
     C.sync();

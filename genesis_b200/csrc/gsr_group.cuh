@@ -21,6 +21,7 @@ struct Ctx {
   float* spill;        // this env's SPILL record (global)
   const DevModel* gm;  // global-memory copy of the model
   int lane;            // lane index inside the group
+  int env;             // environment index
   unsigned gmask;      // warp lanes that belong to this group
 
   __device__ __forceinline__ void sync() const { __syncwarp(gmask); }

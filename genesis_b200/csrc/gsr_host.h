@@ -28,6 +28,7 @@ struct GsrSpec {
   SmemLayout sl;
   LaneLayout ll;
   std::vector<GsrFieldInfo> fields;
+  std::vector<unsigned short> fac_tasks;  // DevModel::fac_tasks (host copy)
   size_t n_words = 0;
   int group = 32;  // lanes per environment (1 = lane-per-environment kernel)
   int warps_per_cta = 0;
@@ -43,8 +44,9 @@ static inline size_t gsr_round4(size_t x) { return (x + 3) & ~(size_t)3; }
 static inline int gsr_fill_model(GsrSpec* h) {
   DevModel& m = h->hm;
   const float* keep_verts = m.verts; const float* keep_support = m.support_v; const int* keep_pairs = m.pairs; const int* keep_pidx = m.pair_idx;
+  const unsigned short* keep_fac = m.fac_tasks;
   memset(&m, 0, sizeof(m));
-  m.verts = keep_verts; m.support_v = keep_support; m.pairs = keep_pairs; m.pair_idx = keep_pidx;
+  m.verts = keep_verts; m.support_v = keep_support; m.pairs = keep_pairs; m.pair_idx = keep_pidx; m.fac_tasks = keep_fac;
   auto S = [&](const char* k, double d) { auto it = h->s.find(k); return it == h->s.end() ? d : it->second; };
   m.nL = (int)S("n_links", 0); m.nJ = (int)S("n_joints", 0); m.nD = (int)S("n_dofs", 0); m.nQ = (int)S("n_qs", 0);
   m.nG = (int)S("n_geoms", 0); m.nE = (int)S("n_entities", 0); m.nEq = (int)S("n_equalities", 0); m.nP = (int)S("n_pairs", 0);
@@ -138,6 +140,18 @@ static inline int gsr_fill_model(GsrSpec* h) {
     m.l_root_mass[l] = 0.f;
   }
   for (int l = 0; l < nL; l++) m.l_root_mass[m.l_root[l]] += m.l_mass[l];
+  // sparse L^T D L elimination: for pivot i only the pairs (j, k), k <= j < i, of its ancestor dofs
+  h->fac_tasks.clear();
+  for (int i = 0; i < nD; i++) {
+    m.fac_start[i] = (int)h->fac_tasks.size();
+    const unsigned long long anc = m.l_dofmask[m.d_link[i]];
+    for (int j = 0; j < i; j++) {
+      if (!((anc >> j) & 1ull)) continue;
+      for (int k = 0; k <= j; k++)
+        if ((anc >> k) & 1ull) h->fac_tasks.push_back((unsigned short)((j << 8) | k));
+    }
+  }
+  m.fac_start[nD] = (int)h->fac_tasks.size();
   // lane kernel tables: compact slot of every tree root, composite (subtree) mass accumulated leaf-to-root like FD:382-388
   m.n_roots = 0;
   for (int l = 0; l < nL; l++)
@@ -205,7 +219,8 @@ static inline int gsr_compute_layouts(GsrSpec* h, int n_envs) {
   size_t spill = (size_t)lenC * JS + 8 * (size_t)lenC;
   L.spill_minvjt = (int)spill;
   if (m.noslip_iterations > 0) spill += (size_t)lenC * JS;  // M^-1 J^T rows of the noslip post-solver
-  if (spill < (size_t)nCP * GSR_CONTACT_WORDS) spill = (size_t)nCP * GSR_CONTACT_WORDS;
+  // contact staging records + the results of the perturbed multi-contact detections of one batch (32 lanes x 4 x 8 words)
+  if (spill < (size_t)nCP * GSR_CONTACT_WORDS + 1024) spill = (size_t)nCP * GSR_CONTACT_WORDS + 1024;
   L.spill_stride = (int)gsr_round4(spill);
   const size_t B = (size_t)n_envs;
   L.contact_base = (long long)(B * L.hot_stride);

@@ -21,13 +21,15 @@
 #define PHASE_BARRIER() __syncthreads()
 
 template <int G>
-__device__ __forceinline__ bool make_ctx(Ctx<G>& C, float* state, int B, const DevModel* gm, float* smem) {
+__device__ __forceinline__ bool make_ctx(Ctx<G>& C, float* state, int B, const DevModel* gm, float* smem, const int* order = nullptr) {
   constexpr int EPW = 32 / G;
   const int warp = threadIdx.x >> 5, lane32 = threadIdx.x & 31;
   const int sub = lane32 / G;
   const int slot = warp * EPW + sub;
-  const int env = blockIdx.x * ((blockDim.x >> 5) * EPW) + slot;
-  if (env >= B) return false;
+  const int gslot = blockIdx.x * ((blockDim.x >> 5) * EPW) + slot;  // position in the launch order
+  if (gslot >= B) return false;
+  const int env = order ? __ldg(order + gslot) : gslot;  // cost-ordered scheduling (gsr_api.cu: reorder_envs)
+  C.env = env;
   C.lane = lane32 % G;
   C.gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (sub * G));
   C.S = smem + (size_t)slot * c_s.env_words;
@@ -45,7 +47,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 // Loads the IN parts of the (up to 32 / G) live environments of this warp; `bar` is this warp's mbarrier (one phase per launch).
 template <int G>
-__device__ __forceinline__ void bulk_load_in(float* state, int B, float* smem, uint64_t* bar) {
+__device__ __forceinline__ void bulk_load_in(float* state, int B, float* smem, uint64_t* bar, const int* order) {
   constexpr int EPW = 32 / G;
   const int warp = threadIdx.x >> 5, lane32 = threadIdx.x & 31;
   const int env0 = (blockIdx.x * (blockDim.x >> 5) + warp) * EPW;
@@ -57,7 +59,7 @@ __device__ __forceinline__ void bulk_load_in(float* state, int B, float* smem, u
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes * (uint32_t)n_live) : "memory");
     for (int e = 0; e < n_live; e++) {
-      const float* src = state + (size_t)(env0 + e) * c_h.hot_stride;
+      const float* src = state + (size_t)(order ? __ldg(order + env0 + e) : env0 + e) * c_h.hot_stride;
       const uint32_t dst = smem_u32(smem + (size_t)(warp * EPW + e) * c_s.env_words);
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                    ::"r"(dst), "l"(src), "r"(bytes), "r"(b) : "memory");
@@ -70,7 +72,7 @@ __device__ __forceinline__ void bulk_load_in(float* state, int B, float* smem, u
 }
 // Stores the IN parts back (smem -> global bulk copies); returns after the TMA has finished reading shared memory.
 template <int G>
-__device__ __forceinline__ void bulk_store_in(float* state, int B, float* smem) {
+__device__ __forceinline__ void bulk_store_in(float* state, int B, float* smem, const int* order) {
   constexpr int EPW = 32 / G;
   const int warp = threadIdx.x >> 5, lane32 = threadIdx.x & 31;
   const int env0 = (blockIdx.x * (blockDim.x >> 5) + warp) * EPW;
@@ -80,7 +82,7 @@ __device__ __forceinline__ void bulk_store_in(float* state, int B, float* smem) 
   __syncwarp();
   if (lane32 == 0) {
     for (int e = 0; e < n_live; e++) {
-      float* dst = state + (size_t)(env0 + e) * c_h.hot_stride;
+      float* dst = state + (size_t)(order ? __ldg(order + env0 + e) : env0 + e) * c_h.hot_stride;
       const uint32_t src = smem_u32(smem + (size_t)(warp * EPW + e) * c_s.env_words);
       asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
     }
@@ -94,26 +96,65 @@ template <int G>
 __device__ __forceinline__ void step_epilogue(const Ctx<G>& C, int clear_ext);
 
 template <int G>
-__global__ void __launch_bounds__(GSR_MAX_WARPS_PER_CTA * 32, 1) k_step(float* state, int B, const DevModel* gm, int clear_ext) {
+__global__ void __launch_bounds__(GSR_MAX_WARPS_PER_CTA * 32, 1) k_step(float* state, int B, const DevModel* gm, int clear_ext, const int* order,
+                                                                        unsigned long long* trace) {
   extern __shared__ __align__(16) float smem[];
   Ctx<G> C;
-  const bool live = make_ctx(C, state, B, gm, smem);
+  // order[B] tells whether the measured costs are spread enough for the permutation to pay (uniform batches keep the
+  // identity order and with it the adjacency of the records a CTA touches)
+  if (order && !__ldg(order + B)) order = nullptr;
+  const bool live = make_ctx(C, state, B, gm, smem, order);
+  // gsr_debug_trace: per environment, the time (globaltimer, ns) at the start and after every phase, and the SM
+  unsigned long long tr[6] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
+#define TRACE_MARK(k) if (trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr[k]))
+  // own busy time of the environment (SM cycles between leaving a phase barrier and finishing the phase): the cost the next
+  // launches are ordered by, so that the expensive environments start first and their tail overlaps the bulk of the batch
+  long long busy = 0, t_phase = clock64();
+#define PHASE_END() busy += clock64() - t_phase
+#define PHASE_BEGIN() t_phase = clock64()
+  TRACE_MARK(0);
   // a warp is live when its first environment exists; its mbarrier sits after the workspaces
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)(blockDim.x >> 5) * (32 / G) * c_s.env_words);
   const bool warp_live = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (32 / G) < B;
-  if (warp_live) bulk_load_in<G>(state, B, smem, bars + (threadIdx.x >> 5));
+  if (warp_live) bulk_load_in<G>(state, B, smem, bars + (threadIdx.x >> 5), order);
   PHASE_BARRIER();
+  PHASE_BEGIN();
   if (live) phase_dynamics(C);
+  PHASE_END();
+  TRACE_MARK(1);
   PHASE_BARRIER();
+  PHASE_BEGIN();
   if (live && CM(enable_collision) && CM(nG) > 0) phase_collide(C);
+  PHASE_END();
+  TRACE_MARK(2);
   PHASE_BARRIER();
+  PHASE_BEGIN();
   if (live) phase_constraints(C);
+  PHASE_END();
+  TRACE_MARK(3);
   PHASE_BARRIER();
+  PHASE_BEGIN();
   if (live) phase_integrate(C);
+  PHASE_END();
+  TRACE_MARK(4);
   PHASE_BARRIER();
+  PHASE_BEGIN();
   if (live) step_epilogue(C, clear_ext);
+  PHASE_END();
+  if (live && C.lane == 0) reinterpret_cast<int*>(C.rec)[c_h.step_cost] = (int)min(busy, (long long)0x7fffffff);
   __syncwarp();
-  if (warp_live) bulk_store_in<G>(state, B, smem);
+  if (warp_live) bulk_store_in<G>(state, B, smem, order);
+  if (trace && live && C.lane == 0) {
+    unsigned smid;
+    TRACE_MARK(5);
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+#pragma unroll
+    for (int k = 0; k < 6; k++) trace[8 * C.env + k] = tr[k];
+    trace[8 * C.env + 6] = smid;
+  }
+#undef TRACE_MARK
+#undef PHASE_END
+#undef PHASE_BEGIN
 }
 
 template <int G>
@@ -167,9 +208,7 @@ __global__ void __launch_bounds__(GSR_MAX_WARPS_PER_CTA * 32) k_forward(float* s
   extern __shared__ __align__(16) float smem[];
   Ctx<G> C;
   if (!make_ctx(C, state, B, gm, smem)) return;
-  constexpr int EPW = 32 / G;
-  const int env = blockIdx.x * ((blockDim.x >> 5) * EPW) + (threadIdx.x >> 5) * EPW + (threadIdx.x & 31) / G;
-  if (mask && !mask[env]) return;
+  if (mask && !mask[C.env]) return;
   {  // masked environments are few: plain vector copies
     const float4* src = reinterpret_cast<const float4*>(C.rec);
     float4* dst = reinterpret_cast<float4*>(C.S);

@@ -315,13 +315,34 @@ __device__ __noinline__ void hessian_cholesky(const Ctx<G>& C, const Rows& R) {
   float* Hinv = WK(Hinv);
   const float* M = WK(M);
   const int ntri = nD * (nD + 1) / 2;
-  for (int t = lane; t < ntri; t += G) {
-    int i, j;
-    tri_decode(t, i, j);
-    float s = 0.f;
-    for (int c = 0; c < R.n_con; c++)
-      if (R.active[c] & 1) s += R.J[c * R.JS + j] * (R.J[c * R.JS + i] * R.D[c]);
-    H[i * MS + j] = s + M[i * MS + j];
+  // every lane accumulates up to NE lower-triangle entries at once, so one sweep over the rows (with the row weight
+  // D_c * active_c loaded once, inactive rows skipped by a group-uniform branch) serves NE * G entries
+  constexpr int NE = 6;
+  float* w = R.jv;  // scratch: the line search recomputes jv before it reads it
+  for (int c = lane; c < R.n_con; c += G) w[c] = (R.active[c] & 1) ? R.D[c] : 0.f;
+  C.sync();
+  for (int t0 = 0; t0 < ntri; t0 += NE * G) {
+    int oi[NE], oj[NE];
+    float acc[NE];
+#pragma unroll
+    for (int e = 0; e < NE; e++) {
+      const int t = t0 + e * G + lane;
+      int i = 0, j = 0;
+      if (t < ntri) tri_decode(t, i, j);
+      oi[e] = i; oj[e] = j; acc[e] = 0.f;
+    }
+    for (int c = 0; c < R.n_con; c++) {
+      const float wc = w[c];
+      if (wc == 0.f) continue;
+      const float* Jc = R.J + c * R.JS;
+#pragma unroll
+      for (int e = 0; e < NE; e++) acc[e] += Jc[oj[e]] * (Jc[oi[e]] * wc);
+    }
+#pragma unroll
+    for (int e = 0; e < NE; e++) {
+      const int t = t0 + e * G + lane;
+      if (t < ntri) H[oi[e] * MS + oj[e]] = acc[e] + M[oi[e] * MS + oj[e]];
+    }
   }
   C.sync();
   for (int i = 0; i < nD; i++) {
@@ -399,6 +420,26 @@ __device__ __noinline__ void update_gradient(const Ctx<G>& C) {
   } else {
     const float* H = WK(H);
     const float* Hinv = WK(Hinv);
+    if (nD <= G) {
+      // one lane per unknown with the running right-hand side in a register and the pivot broadcast by shuffle: no
+      // shared-memory round trip or barrier per column (same products in the same order as the column sweeps below)
+      const bool own = lane < nD;
+      float s = own ? Mgrad[lane] : 0.f;
+      const float hinv = own ? Hinv[lane] : 0.f;
+      for (int i = 0; i < nD; i++) {  // L y = g
+        const float yi = __shfl_sync(C.gmask, s * hinv, i, G);
+        if (lane == i) s = yi;
+        if (own && lane > i) s -= H[lane * MS + i] * yi;
+      }
+      for (int i = nD - 1; i >= 0; i--) {  // L^T x = y
+        const float xi = __shfl_sync(C.gmask, s * hinv, i, G);
+        if (lane == i) s = xi;
+        if (lane < i) s -= H[i * MS + lane] * xi;
+      }
+      if (own) Mgrad[lane] = s;
+      C.sync();
+      return;
+    }
     float* y = WK(tmpv);
     for (int i = 0; i < nD; i++) {  // forward substitution, column oriented: y_i final once columns < i are eliminated
       const float yi = Mgrad[i] * Hinv[i];

@@ -89,6 +89,10 @@ struct DevModel {
   const float* support_v;  // [n_support_cells][3]
   const int* pairs;        // [nP][2]
   const int* pair_idx;     // [nG][nG]
+  // L^T D L elimination tasks of pivot i: fac_tasks[fac_start[i] .. fac_start[i + 1]) = (j << 8) | k over the ancestor dofs
+  // k <= j < i of dof i (branches of the tree never fill in, so only ancestor pairs are touched)
+  const unsigned short* fac_tasks;
+  int fac_start[GSR_MAX_DOFS + 1];
 };
 
 // ---- HOT segment fields: X(name, is_int, items, comps).  Everything up to `kin_end` is the IN part (same offsets in the
@@ -112,7 +116,7 @@ struct DevModel {
   X(cacc_lin, 0, nL, 3) X(cacc_ang, 0, nL, 3) X(links_contact_force, 0, nL, 3)                                     \
   X(aabb_min, 0, nG, 3) X(aabb_max, 0, nG, 3)                                                                      \
   X(n_constraints, 1, 1, 1) X(n_constraints_equality, 1, 1, 1) X(n_constraints_frictionloss, 1, 1, 1)              \
-  X(solver_iters, 1, 1, 1)                                                                                         \
+  X(solver_iters, 1, 1, 1) X(step_cost, 1, 1, 1)                                                                   \
   /* diagnostics (cfg_diagnostics): intermediate quantities the parity tests and get_mass_mat read */               \
   X(acc_smooth, 0, nD, 1) X(qf_smooth, 0, nD, 1) X(qf_passive, 0, nD, 1) X(qf_bias, 0, nD, 1)                      \
   X(mass_mat, 0, nD * nD, 1) X(mass_Dinv, 0, nD, 1) X(geoms_pos, 0, nG, 3) X(geoms_quat, 0, nG, 4)

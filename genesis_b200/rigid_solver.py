@@ -88,6 +88,8 @@ class RigidSolver:
         self.tuning = dict(group_size=int(os.environ.get("GSR_GROUP_SIZE", 0)), diagnostics=int(os.environ.get("GSR_DIAGNOSTICS", 1)))
         if os.environ.get("GSR_SMEM_ROWS"):
             self.tuning["smem_rows"] = int(os.environ["GSR_SMEM_ROWS"])
+        if os.environ.get("GSR_REORDER_PERIOD"):
+            self.tuning["reorder_period"] = int(os.environ["GSR_REORDER_PERIOD"])
         if os.environ.get("GSR_WARPS"):
             self.tuning["warps_per_cta"] = int(os.environ["GSR_WARPS"])
         self.model = None

@@ -42,7 +42,7 @@ int gsr_model_commit(gsr_handle_t h, int, int n_envs) {
   if (rc) return rc;
   DevModel& m = h->hm;
   m.verts = h->f["verts"].data(); m.support_v = h->f["support_v"].data();
-  m.pairs = h->i["pairs"].data(); m.pair_idx = h->i["pair_idx"].data();
+  m.pairs = h->i["pairs"].data(); m.pair_idx = h->i["pair_idx"].data(); m.fac_tasks = h->fac_tasks.data();
   h->B = n_envs;
   h->s["cfg_group_size"] = 1;
   rc = gsr_compute_layouts(h, n_envs);
