@@ -20,7 +20,8 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 
 def raw_rows(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # either a report (read through ncu) or the `--page raw --csv` export tools/gpu_round.sh keeps (reports exceed gpurun's 64 MiB)
+    out = open(rep, errors="replace").read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     return [{h: (r[i], units[i]) for i, h in enumerate(hdr)} for r in rows[2:]]
@@ -49,7 +50,7 @@ def main(tag):
             for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
                 md.append(f"| `{k}` | {a[0]} | {a[1] / a[0]:.2f} | {100 * a[1] / tot:.1f} % |")
             md.append("")
-        if f.endswith(".ncu-rep"):
+        if f.endswith(".ncu-rep") or f.endswith(".raw.csv"):
             recs = raw_rows(p)
             md.append(f"## `--set full` capture `{f}`\n")
             traffic = {}
@@ -64,8 +65,15 @@ def main(tag):
                     v, u = r[k]
                     return float(v) * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}[u]
                 traffic.setdefault(name.replace("void ", "").split("<")[0], []).append(b("dram__bytes_read.sum") + b("dram__bytes_write.sum"))
-            wl = f.replace("prof_", "").replace(".ncu-rep", "")
+            wl = f.replace("prof_", "").replace(".ncu-rep", "").replace(".raw.csv", "")
             json.dump({k: sum(v) / len(v) for k, v in traffic.items()}, open(os.path.join(dst, f"traffic_{wl}.json"), "w"))
+        if f.endswith(".funcs.txt") or f.endswith(".lines.txt") or f.startswith("trace_"):
+            txt = open(p, errors="replace").read()
+            open(os.path.join(dst, f"{tag}_{f}"), "w").write(txt)
+            if f.endswith(".funcs.txt"):
+                md.append(f"## per-function attribution `{f}` (tools/ncu_funcs.py)\n\n```\n" + "\n".join(txt.splitlines()[:24]) + "\n```\n")
+            if f.startswith("trace_"):
+                md.append(f"## per-environment phase timeline `{f}` (tools/step_trace.py)\n\n```\n" + txt + "\n```\n")
         if f.startswith("bench_") and f.endswith(".json"):
             lines = [l for l in open(p).read().splitlines() if l.startswith("{")]
             if lines:
