@@ -130,21 +130,22 @@ __device__ void phase_kinematics(const Ctx<G>& C) {
   C.sync();
   // ---- 3. subtree COM (FK:337-420): mass-weighted mean of the inertial frame origins of every link below the same root
   float* mi = pb;  // scratch: m_l * ipos_w[l] (3 nL words) in the scan buffer that does not hold the result
+  const bool shifted = C.SI()[c_h.has_shift] != 0;
   for (int l = lane; l < nL; l += G) {
-    const f3 ipw = ld3(lpos, l) + rotate(f3(GM(l_ipos[l][0]), GM(l_ipos[l][1]), GM(l_ipos[l][2])), ld4(lquat, l));
-    st3(mi, l, ipw * GM(l_mass[l]));
+    const f3 ipw = ld3(lpos, l) + rotate(link_ipos(C, l, shifted), ld4(lquat, l));
+    st3(mi, l, ipw * link_mass(C, l, shifted));
   }
   C.sync();
   float* rcom = IN(root_COM);
   for (int l = lane; l < nL; l += G) {
     const int r = GM(l_root[l]);
     f3 s;
+    float ms = shifted ? 0.f : GM(l_root_mass[r]);
     for (int k = 0; k < nL; k++)
-      if (CM(l_root[k]) == r) s += ld3(mi, k);
-    const float ms = GM(l_root_mass[r]);
+      if (CM(l_root[k]) == r) { s += ld3(mi, k); if (shifted) ms += CM(l_mass[k]) + C.rec[c_h.mass_shift + k]; }
     f3 com;
     if (ms > EPS) com = s / ms;
-    else com = ld3(lpos, r) + rotate(f3(GM(l_ipos[r][0]), GM(l_ipos[r][1]), GM(l_ipos[r][2])), ld4(lquat, r));
+    else com = ld3(lpos, r) + rotate(link_ipos(C, r, shifted), ld4(lquat, r));
     st3(rcom, l, com);
   }
   C.sync();
@@ -152,9 +153,9 @@ __device__ void phase_kinematics(const Ctx<G>& C) {
   for (int l = lane; l < nL; l += G) {
     const f3 com = ld3(rcom, l);
     const f4 quat = ld4(lquat, l);
-    const f3 ipos = ld3(lpos, l) + rotate(f3(GM(l_ipos[l][0]), GM(l_ipos[l][1]), GM(l_ipos[l][2])), quat) - com;
+    const f3 ipos = ld3(lpos, l) + rotate(link_ipos(C, l, shifted), quat) - com;
     const f4 iquat = quat_compose(f4(GM(l_iquat[l][0]), GM(l_iquat[l][1]), GM(l_iquat[l][2]), GM(l_iquat[l][3])), quat);
-    const float mass = GM(l_mass[l]);
+    const float mass = link_mass(C, l, shifted);
     const mat3 R = quat_to_R(iquat, EPS);
     float Iin[9];
 #pragma unroll
@@ -333,6 +334,7 @@ __device__ void phase_dynamics(const Ctx<G>& C) {
   const float* cda = IN(cdof_ang);
   const float* cdv = IN(cdof_vel);
   // ---- composite rigid body inertia (FD:306-388): crb[l] = sum of cinr over the subtree of l (leaf-to-root order)
+  const bool shifted = C.SI()[c_h.has_shift] != 0;
   float* crb = WK(crb);
   for (int l = lane; l < nL; l += G) {
     float s[10];
@@ -345,7 +347,7 @@ __device__ void phase_dynamics(const Ctx<G>& C) {
       for (int k = 0; k < 6; k++) s[k] += I[k];
 #pragma unroll
       for (int k = 0; k < 3; k++) s[6 + k] += P[k];
-      s[9] += GM(l_mass[d]);
+      s[9] += link_mass(C, d, shifted);
     } END_BITS
 #pragma unroll
     for (int k = 0; k < 10; k++) crb[10 * l + k] = s[k];
@@ -425,7 +427,7 @@ __device__ void phase_dynamics(const Ctx<G>& C) {
     FOR_BITS_UP(mask, d) { const float w = vel[d]; cdd_vel += ld3(IN(cdofd_vel), d) * w; cdd_ang += ld3(IN(cdofd_ang), d) * w; } END_BITS
     const sym3 I = ld6(IN(cinr_I), l);
     const f3 ip = ld3(IN(cinr_pos), l);
-    const float mass = GM(l_mass[l]);
+    const float mass = link_mass(C, l, shifted);
     const f3 cv = ld3(IN(cd_vel), l), ca = ld3(IN(cd_ang), l);
     f3 f1a, f1v, f2a, f2v;
     inertial_mul(ip, I, mass, cdd_vel, cdd_ang, f1a, f1v);

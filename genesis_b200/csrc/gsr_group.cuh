@@ -68,5 +68,19 @@ __device__ __forceinline__ bool bit64(unsigned long long m, int i) { return (m >
 // lower-triangle task decode: t = i (i + 1) / 2 + j, j <= i (table built on the host, read through the L1 read-only path)
 #define tri_decode(t, i, j) { const unsigned tr_ = GM(tri[t]); i = (int)(tr_ >> 8); j = (int)(tr_ & 255u); }
 
+// per-environment inertial parameters: model value plus the domain-randomisation shift of the record (FK:377-382, 437)
+template <int G>
+__device__ __forceinline__ float link_mass(const Ctx<G>& C, int l, bool shifted) {
+  float m = GM(l_mass[l]);
+  if (shifted) m += C.rec[c_h.mass_shift + l];
+  return m;
+}
+template <int G>
+__device__ __forceinline__ f3 link_ipos(const Ctx<G>& C, int l, bool shifted) {
+  f3 p(GM(l_ipos[l][0]), GM(l_ipos[l][1]), GM(l_ipos[l][2]));
+  if (shifted) p += ld3(C.rec + c_h.com_shift, l);
+  return p;
+}
+
 #define IN(field) (C.S + c_h.field)   // IN part of the record, mirrored in shared memory
 #define WK(field) (C.S + c_s.field)   // workspace regions

@@ -130,6 +130,18 @@ LHD __forceinline__ void lane_coop_flush(const LaneCtx& C, int w0, int rec_off, 
 #endif
 }
 
+// per-environment inertial parameters: model value plus the domain-randomisation shift of the record (FK:377-382, 437)
+LHD __forceinline__ float lane_link_mass(const LaneCtx& C, int l, bool shifted) {
+  float m = CM(l_mass[l]);
+  if (shifted) m += C.rec[c_h.mass_shift + l];
+  return m;
+}
+LHD __forceinline__ f3 lane_link_ipos(const LaneCtx& C, int l, bool shifted) {
+  f3 p(CM(l_ipos[l][0]), CM(l_ipos[l][1]), CM(l_ipos[l][2]));
+  if (shifted) p += gld3(C.rec + c_h.com_shift, l);
+  return p;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Kinematics (FK:580-736, FK:337-576, FK:993-1116) from qpos / vel: link poses, dofs_pos, subtree COM, motion subspaces,
 // c-frame velocities (to workspace offset `cvel_off`: vel[3 nL] then ang[3 nL]) and cdof_dot.
@@ -195,6 +207,7 @@ LHD __noinline__ void lane_kinematics(const LaneCtx& C, int cvel_off) {
   const LArr vel = C.A(c_h.vel);
   const LArr cda = C.A(c_l.cdof), cdv = C.A(c_l.cdof + 3 * nD), cdda = C.A(c_l.cdof + 6 * nD), cddv = C.A(c_l.cdof + 9 * nD);
   // ---- 1. poses root -> leaf, mass-weighted inertial origins per tree
+  const bool shifted = C.I(c_h.has_shift)[0] != 0;
   for (int r = 0; r < 3 * CM(n_roots); r++) rcom[r] = 0.f;
   for (int l = 0; l < nL; l++) {
     const int p = CM(l_parent[l]);
@@ -209,18 +222,23 @@ LHD __noinline__ void lane_kinematics(const LaneCtx& C, int cvel_off) {
       lane_fk_link(C, l, p >= 0, pp, pq, pos, quat);
     }
     st3(lpos, l, pos); st4(lquat, l, quat);
-    const f3 ipw = pos + rotate(f3(CM(l_ipos[l][0]), CM(l_ipos[l][1]), CM(l_ipos[l][2])), quat);
+    const f3 ipw = pos + rotate(lane_link_ipos(C, l, shifted), quat);
     const int rs = CM(l_rootslot[l]);
-    st3(rcom, rs, ld3(rcom, rs) + ipw * CM(l_mass[l]));
+    st3(rcom, rs, ld3(rcom, rs) + ipw * lane_link_mass(C, l, shifted));
   }
   // ---- 2. subtree COM (FK:337-420)
   for (int l = 0; l < nL; l++) {
     if (CM(l_parent[l]) != -1) continue;
     const int rs = CM(l_rootslot[l]);
-    const float ms = CM(l_root_mass[l]);
+    float ms = CM(l_root_mass[l]);
+    if (shifted) {
+      ms = 0.f;
+      for (int k = 0; k < nL; k++)
+        if (CM(l_root[k]) == l) ms += lane_link_mass(C, k, true);
+    }
     f3 com;
     if (ms > EPS) com = ld3(rcom, rs) / ms;
-    else com = ld3(lpos, l) + rotate(f3(CM(l_ipos[l][0]), CM(l_ipos[l][1]), CM(l_ipos[l][2])), ld4(lquat, l));
+    else com = ld3(lpos, l) + rotate(lane_link_ipos(C, l, shifted), ld4(lquat, l));
     st3(rcom, rs, com);
   }
   // ---- 3. motion subspaces (FK:517-576) from the parked axis / anchor
@@ -279,12 +297,13 @@ LHD __noinline__ void lane_cinr(const LaneCtx& C, int off) {
   const float EPS = CM(eps);
   const LArr lpos = C.A(c_l.lpos), lquat = C.A(c_l.lquat), rcom = C.A(c_l.rcom);
   const LArr cI = C.A(off), cP = C.A(off + 6 * nL);
+  const bool shifted = C.I(c_h.has_shift)[0] != 0;
   for (int l = 0; l < nL; l++) {
     const f3 com = ld3(rcom, CM(l_rootslot[l]));
     const f4 quat = ld4(lquat, l);
-    const f3 ipos = ld3(lpos, l) + rotate(f3(CM(l_ipos[l][0]), CM(l_ipos[l][1]), CM(l_ipos[l][2])), quat) - com;
+    const f3 ipos = ld3(lpos, l) + rotate(lane_link_ipos(C, l, shifted), quat) - com;
     const f4 iquat = quat_compose(f4(CM(l_iquat[l][0]), CM(l_iquat[l][1]), CM(l_iquat[l][2]), CM(l_iquat[l][3])), quat);
-    const float mass = CM(l_mass[l]);
+    const float mass = lane_link_mass(C, l, shifted);
     const mat3 R = quat_to_R(iquat, EPS);
     float RI[3][3];
 #pragma unroll
@@ -354,6 +373,7 @@ LHD __noinline__ void lane_dynamics(const LaneCtx& C) {
   const LArr cv = C.A(c_l.cvel), ca = C.A(c_l.cvel + 3 * nL);
   const LArr cdd_v = C.A(c_l.cdd), cdd_a = C.A(c_l.cdd + 3 * nL);
   lane_cinr(C, c_l.crb);
+  const bool shifted = C.I(c_h.has_shift)[0] != 0;
   // ---- RNE bias forces, root -> leaf (FD:1186-1400): cdd = parent's + cdof_dot * vel; own cfrc = I cdd + cvel x* (I cvel)
   const f3 grav(CM(gravity[0]), CM(gravity[1]), CM(gravity[2]));
   const bool has_ext = C.I(c_h.has_ext_force)[0] != 0;
@@ -367,7 +387,7 @@ LHD __noinline__ void lane_dynamics(const LaneCtx& C) {
     sym3 I;
     I.xx = crbI[6 * l]; I.xy = crbI[6 * l + 1]; I.xz = crbI[6 * l + 2]; I.yy = crbI[6 * l + 3]; I.yz = crbI[6 * l + 4]; I.zz = crbI[6 * l + 5];
     const f3 ip = ld3(crbP, l);
-    const float mass = CM(l_mass[l]);
+    const float mass = lane_link_mass(C, l, shifted);
     const f3 lv = ld3(cv, l), la = ld3(ca, l);
     f3 f1a, f1v, f2a, f2v;
     inertial_mul(ip, I, mass, dv, da, f1a, f1v);
@@ -399,7 +419,13 @@ LHD __noinline__ void lane_dynamics(const LaneCtx& C) {
     sym3 I;
     I.xx = crbI[6 * l]; I.xy = crbI[6 * l + 1]; I.xz = crbI[6 * l + 2]; I.yy = crbI[6 * l + 3]; I.yz = crbI[6 * l + 4]; I.zz = crbI[6 * l + 5];
     f3 fa, fv;
-    inertial_mul(ld3(crbP, l), I, CM(l_submass[l]), ld3(cdv, i), ld3(cda, i), fa, fv);
+    float submass = CM(l_submass[l]);
+    if (shifted) {  // composite mass of the subtree with the per-environment shifts (leaf-to-root sum like FD:382-388)
+      submass = 0.f;
+      for (int k = nL - 1; k >= l; k--)
+        if ((CM(l_descmask[l]) >> k) & 1ull) submass += lane_link_mass(C, k, true);
+    }
+    inertial_mul(ld3(crbP, l), I, submass, ld3(cdv, i), ld3(cda, i), fa, fv);
     const unsigned long long mask = CM(l_dofmask[l]);
     const int ri = tri_idx(i, 0);
     for (int j = 0; j <= i; j++) {

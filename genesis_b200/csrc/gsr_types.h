@@ -103,7 +103,7 @@ struct DevModel {
   X(qpos, 0, nQ, 1) X(vel, 0, nD, 1) X(ctrl_pos, 0, nD, 1) X(ctrl_vel, 0, nD, 1) X(ctrl_force, 0, nD, 1)           \
   X(ctrl_mode, 1, nD, 1) X(qacc_ws, 0, nD, 1)                                                                      \
   X(is_warmstart, 1, 1, 1) X(errno_, 1, 1, 1) X(n_contacts, 1, 1, 1) X(n_broad, 1, 1, 1)                           \
-  X(has_ext_force, 1, 1, 1)                                                                                        \
+  X(has_ext_force, 1, 1, 1) X(has_shift, 1, 1, 1)                                                                  \
   /* kinematic cache written by the FK at the end of a step and consumed by the next step */                       \
   X(dofs_pos, 0, nD, 1) X(root_COM, 0, nL, 3) X(cdof_ang, 0, nD, 3) X(cdof_vel, 0, nD, 3) X(cdofd_ang, 0, nD, 3)   \
   X(cdofd_vel, 0, nD, 3) X(links_pos, 0, nL, 3) X(links_quat, 0, nL, 4) X(cinr_I, 0, nL, 6) X(cinr_pos, 0, nL, 3)  \
@@ -112,6 +112,8 @@ struct DevModel {
   /* rarely used inputs, read from the record on demand: per-geom friction scale (set_friction_ratio) and the external  \
      wrenches of apply_links_external_force (only read and cleared when has_ext_force is set) */                       \
   X(friction_ratio, 0, nG, 1) X(cfrc_applied_vel, 0, nL, 3) X(cfrc_applied_ang, 0, nL, 3)                          \
+  /* domain randomisation (links_state.mass_shift / i_pos_shift), read only when has_shift is set */                  \
+  X(mass_shift, 0, nL, 1) X(com_shift, 0, nL, 3)                                                                   \
   X(acc, 0, nD, 1) X(force, 0, nD, 1) X(qf_applied, 0, nD, 1) X(qf_constraint, 0, nD, 1)                           \
   X(cacc_lin, 0, nL, 3) X(cacc_ang, 0, nL, 3) X(links_contact_force, 0, nL, 3)                                     \
   X(aabb_min, 0, nG, 3) X(aabb_max, 0, nG, 3)                                                                      \

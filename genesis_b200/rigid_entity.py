@@ -347,3 +347,15 @@ class RigidEntity:
                     cols.append(k)
         if geoms:
             self._solver.set_geoms_friction_ratio(ratio[..., cols], geoms, envs_idx)
+
+    def set_mass_shift(self, mass_shift, links_idx_local=None, envs_idx=None):
+        self._solver.set_links_mass_shift(mass_shift, self._links_idx(links_idx_local), envs_idx)
+
+    def set_COM_shift(self, com_shift, links_idx_local=None, envs_idx=None):
+        self._solver.set_links_COM_shift(com_shift, self._links_idx(links_idx_local), envs_idx)
+
+    def get_mass_shift(self, links_idx_local=None, envs_idx=None):
+        return self._solver.get_links_mass_shift(self._links_idx(links_idx_local), envs_idx)
+
+    def get_COM_shift(self, links_idx_local=None, envs_idx=None):
+        return self._solver.get_links_COM_shift(self._links_idx(links_idx_local), envs_idx)

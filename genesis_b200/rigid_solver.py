@@ -557,6 +557,37 @@ class RigidSolver:
         """Per-environment friction scale of each geom (contact friction = max(mu_a ratio_a, mu_b ratio_b, 1e-2), contact.py:202-211)."""
         self._set("friction_ratio", friction_ratio, geoms_idx, envs_idx, self.model.n_geoms)
 
+    # ---- per-environment domain randomisation of the inertial parameters (rigid_solver.py:1825-1860, accessor.py:400-430)
+    def set_links_mass_shift(self, mass_shift, links_idx=None, envs_idx=None):
+        """links_state.mass_shift: added to the link mass in the COM and c-frame inertia (forward_kinematics.py:377, 437)."""
+        self._set("mass_shift", mass_shift, links_idx, envs_idx, self.model.n_links)
+        self._mark_shifted(envs_idx)
+
+    def set_links_COM_shift(self, com_shift, links_idx=None, envs_idx=None):
+        """links_state.i_pos_shift: added to the inertial frame origin of the link (forward_kinematics.py:382)."""
+        f = self._fields["com_shift"]
+        idx = self._idx(links_idx, self.model.n_links)
+        envs = self._envs(envs_idx)
+        nb = self._B if envs is None else len(envs)
+        v = torch.broadcast_to(torch.as_tensor(com_shift, dtype=torch.float32, device=self.device), (nb, len(idx), 3))
+        if envs is None:
+            f[:, idx] = v
+        else:
+            f[envs[:, None], idx[None, :]] = v
+        self._mark_shifted(envs_idx)
+
+    def _mark_shifted(self, envs_idx):
+        envs = self._envs(envs_idx)
+        e = self._envs_all if envs is None else envs
+        self._fields["has_shift"][e] = 1
+        self._forward(envs_idx)  # the kinematic cache (subtree COM, c-frame inertias) depends on the masses
+
+    def get_links_mass_shift(self, links_idx=None, envs_idx=None):
+        return self._get("mass_shift", links_idx, envs_idx, self.model.n_links)
+
+    def get_links_COM_shift(self, links_idx=None, envs_idx=None):
+        return self._get("com_shift", links_idx, envs_idx, self.model.n_links, comps=3)
+
     def get_links_net_contact_force(self, links_idx=None, envs_idx=None):
         return self._get("links_contact_force", links_idx, envs_idx, self.model.n_links, comps=3)
 

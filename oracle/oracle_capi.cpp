@@ -75,6 +75,8 @@ static bool set_field(Oracle<T>& o, int b, const std::string& n, const double* i
   if (n == "ctrl_mode") { for (size_t i = 0; i < e.ctrl_mode.size(); i++) e.ctrl_mode[i] = (int)in[i]; return true; }
   if (n == "cfrc_applied_vel") { for (size_t i = 0; i < e.cfrc_applied_vel.size(); i++) for (int k = 0; k < 3; k++) e.cfrc_applied_vel[i][k] = (T)in[3 * i + k]; return true; }
   if (n == "cfrc_applied_ang") { for (size_t i = 0; i < e.cfrc_applied_ang.size(); i++) for (int k = 0; k < 3; k++) e.cfrc_applied_ang[i][k] = (T)in[3 * i + k]; return true; }
+  if (n == "mass_shift") { cp(e.mass_shift); o.forward_all(e); return true; }
+  if (n == "com_shift") { for (size_t i = 0; i < e.i_pos_shift.size(); i++) for (int k = 0; k < 3; k++) e.i_pos_shift[i][k] = (T)in[3 * i + k]; o.forward_all(e); return true; }
   if (n == "reset") { o.reset_env(e); return true; }
   return false;
 }

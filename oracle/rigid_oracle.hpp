@@ -139,6 +139,8 @@ struct Env {
   std::vector<Q4<T>> l_quat, i_quat, j_quat;
   std::vector<M3<T>> cinr_I, crb_I;
   std::vector<T> mass_sum, cinr_mass, crb_mass;
+  std::vector<T> mass_shift;        // links_state.mass_shift (domain randomisation, accessor.py:415)
+  std::vector<V3<T>> i_pos_shift;   // links_state.i_pos_shift (accessor.py:429)
   std::vector<V> xanchor, xaxis;
   // geoms
   std::vector<V> g_pos, aabb_min, aabb_max;
@@ -202,6 +204,7 @@ struct Oracle {
     for (auto* v : {&e.l_quat, &e.i_quat, &e.j_quat}) v->assign(nL, Q());
     e.cinr_I.assign(nL, M3<T>()); e.crb_I.assign(nL, M3<T>());
     e.mass_sum.assign(nL, 0); e.cinr_mass.assign(nL, 0); e.crb_mass.assign(nL, 0);
+    e.mass_shift.assign(nL, 0); e.i_pos_shift.assign(nL, V());
     e.xanchor.assign(m.nJ, V()); e.xaxis.assign(m.nJ, V());
     e.g_pos.assign(nG, V()); e.aabb_min.assign(nG, V()); e.aabb_max.assign(nG, V()); e.g_quat.assign(nG, Q());
     e.friction_ratio.assign(nG, 1);
@@ -319,8 +322,8 @@ struct Oracle {
     int ls = m.entities_link_start[i_e], le = m.entities_link_end[i_e];
     for (int l = ls; l < le; l++) { e.root_COM_bw[l] = V(); e.mass_sum[l] = 0; }
     for (int l = ls; l < le; l++) {
-      T mass = m.links_inertial_mass[l];
-      e.i_pos_bw[l] = e.l_pos[l] + transform_by_quat(m.v3(m.links_inertial_pos, l), e.l_quat[l]);
+      T mass = m.links_inertial_mass[l] + e.mass_shift[l];  // FK:377
+      e.i_pos_bw[l] = e.l_pos[l] + transform_by_quat(m.v3(m.links_inertial_pos, l) + e.i_pos_shift[l], e.l_quat[l]);  // FK:382
       e.i_quat[l] = transform_quat_by_quat(m.q4(m.links_inertial_quat, l), e.l_quat[l]);
       int r = m.links_root[l];
       e.mass_sum[r] += mass;
@@ -337,8 +340,9 @@ struct Oracle {
       e.i_pos[l] = e.i_pos_bw[l] - e.root_COM[l];
       M3<T> Iin;
       for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) Iin.m[a][b] = m.links_inertial_i[9 * l + 3 * a + b];
-      transform_inertia(Iin, m.links_inertial_mass[l], e.i_pos[l], e.i_quat[l], e.cinr_I[l], e.cinr_pos[l]);
-      e.cinr_mass[l] = m.links_inertial_mass[l];
+      const T i_mass = m.links_inertial_mass[l] + e.mass_shift[l];  // FK:437
+      transform_inertia(Iin, i_mass, e.i_pos[l], e.i_quat[l], e.cinr_I[l], e.cinr_pos[l]);
+      e.cinr_mass[l] = i_mass;
     }
     // j_pos/j_quat (FK:451-515) are only consumed by accessors; omitted.
     for (int l = ls; l < le; l++) {

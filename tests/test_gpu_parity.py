@@ -231,6 +231,37 @@ def test_weld_equality():
     assert (scene.rigid_solver.field("n_constraints_equality")[:, 0] == 12).all()
 
 
+def test_mass_and_com_shift_domain_randomisation():
+    """set_mass_shift / set_COM_shift per environment (links_state.mass_shift / i_pos_shift, forward_kinematics.py:377-437)."""
+    B, K = 16, 40
+    scene, robot = make_go2(B)
+    s = scene.rigid_solver
+    m = s.model
+    g = torch.Generator(device="cpu").manual_seed(3)
+    ms = 0.5 * torch.rand((B, m.n_links - 1), generator=g)
+    cs = 0.02 * torch.randn((B, m.n_links - 1, 3), generator=g)
+    robot.set_mass_shift(ms.to(gs.device))
+    robot.set_COM_shift(cs.to(gs.device))
+    assert torch.allclose(robot.get_mass_shift().cpu(), ms) and torch.allclose(robot.get_COM_shift().cpu(), cs)
+    orc = mirror_oracle(scene)
+    full_ms = np.zeros((B, m.n_links)); full_ms[:, 1:] = ms.numpy()
+    full_cs = np.zeros((B, m.n_links, 3)); full_cs[:, 1:] = cs.numpy()
+    orc.set("mass_shift", full_ms)
+    orc.set("com_shift", full_cs.reshape(B, -1))
+    scene.step()
+    orc.step(1)
+    check_single_step(scene, orc)
+    for _ in range(K - 1):
+        scene.step()
+    orc.step(K - 1)
+    dq = np.abs(gpu_field(scene, "qpos") - orc.qpos()).max(axis=1)
+    assert (dq <= TRAJ_QPOS_CONTACT).mean() >= 0.9, f"{np.sort(dq)}"
+    # mass matrix of env 0: translational block = total mass including the shifts
+    M = s.get_mass_mat()[0].cpu().numpy()
+    total = float(np.asarray(m.links_inertial_mass)[1:].sum() + ms[0].sum())
+    assert M[0, 0] == pytest.approx(total + float(m.dofs_armature[0]), rel=1e-4)
+
+
 def test_noslip_post_solver():
     """constraint/noslip.py after the Newton solve (noslip_iterations=5): Go2 trajectories and a box on a tilted-gravity plane."""
     B, K = 16, 50

@@ -219,3 +219,35 @@ def test_lane_noslip_post_solver():
     ref.step(50)
     assert np.abs(emu.rows("qpos") - orc.qpos()).max() <= 1e-3 and np.abs(emu.rows("vel") - orc.vel()).max() <= 2e-2
     assert np.abs(orc.qpos() - ref.qpos()).max() > 5e-3  # the pass is not a no-op on this scene
+
+
+def test_lane_mass_and_com_shift():
+    """Per-environment mass / COM shifts (domain randomisation): different shifts per environment, Go2 trajectories."""
+    B = 3
+
+    def sets(m, B):
+        out = go2_sets(m, B)
+        rng = np.random.default_rng(3)
+        out["mass_shift"] = np.abs(rng.normal(size=(B, m.n_links))) * 0.5
+        out["mass_shift"][:, 0] = 0.0
+        out["com_shift"] = 0.02 * rng.normal(size=(B, m.n_links * 3))
+        return out
+
+    scene, solver, m = host_model(make_go2)
+    orc = oracle_for(solver, m, B, threads=3)
+    emu = LaneEmu(m, B, solver.model_options())
+    for name, val in sets(m, B).items():
+        orc.set(name, val)
+        emu.set(name, val)
+    emu.field("has_shift")[:] = 1
+    ref = oracle_for(solver, m, B, threads=3)
+    for name, val in go2_sets(m, B).items():
+        ref.set(name, val)
+    orc.step(1)
+    emu.step(1)
+    check_all_quantities(m, orc, emu)
+    orc.step(39)
+    emu.step(39)
+    ref.step(40)
+    assert np.abs(emu.rows("qpos") - orc.qpos()).max() <= 1e-3 and np.abs(emu.rows("vel") - orc.vel()).max() <= 2e-2
+    assert np.abs(orc.qpos() - ref.qpos()).max() > 1e-3  # the shifts matter

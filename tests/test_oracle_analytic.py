@@ -313,3 +313,27 @@ def test_noslip_suppresses_creep_on_an_incline():
         vel[ns] = abs(orc.vel()[0][0])
         assert int(orc.get("n_contacts", 1, 0)[0]) == 4
     assert vel[0] > 5e-4 and vel[5] < 1e-2 * vel[0]
+
+
+def test_mass_shift_changes_free_fall_contact_force_not_acceleration():
+    """links_state.mass_shift (forward_kinematics.py:377, 437): free fall is mass independent, the resting contact force and
+    the mass matrix are not: a 0.6 kg box with a +0.4 kg shift weighs 1.0 kg."""
+    scene, _ = scene_from_morphs([gs.morphs.Plane(), gs.morphs.Box(size=(0.1, 0.1, 0.1), pos=(0, 0, 0.05))], dt=0.01)
+    solver = scene.rigid_solver
+    m = solver.build_model()
+    orc = oracle_for(solver, m, 1, double=True)
+    shift = np.zeros(m.n_links)
+    shift[1] = 0.4
+    orc.set("mass_shift", shift)
+    orc.step(150)
+    M = orc.get("M", m.n_dofs * m.n_dofs, 0).reshape(m.n_dofs, m.n_dofs)
+    assert M[0, 0] == pytest.approx(1.0 + float(m.dofs_armature[0]), rel=1e-9)
+    f = orc.get("links_contact_force", (m.n_links, 3), 0)
+    assert f[1, 2] == pytest.approx(1.0 * 9.81, rel=2e-3)
+    # a COM shift along x tilts nothing for a free box at rest on its face but moves the subtree COM
+    orc2 = oracle_for(solver, m, 1, double=True)
+    cs = np.zeros((m.n_links, 3))
+    cs[1, 0] = 0.02
+    orc2.set("com_shift", cs.reshape(-1))
+    orc2.step(1)
+    assert orc2.get("root_COM", (m.n_links, 3), 0)[1, 0] == pytest.approx(0.02, abs=1e-6)
