@@ -246,7 +246,7 @@ static inline int gsr_compute_layouts(GsrSpec* h, int n_envs) {
   SmemLayout& s = h->sl;
   memset(&s, 0, sizeof(s));
   s.MS = MS; s.JS = JS;
-  int NCS = (int)S("cfg_smem_rows", nD > 12 ? 64 : 24);
+  int NCS = (int)S("cfg_smem_rows", nD > 12 ? 64 : 16);  // rows kept on chip (more => SPILL record); sized so that 13 Franka CTAs fit an SM
   if (NCS > lenC) NCS = lenC;
   if (NCS < 4) NCS = 4;
   s.NCS = NCS;
@@ -256,11 +256,16 @@ static inline int gsr_compute_layouts(GsrSpec* h, int n_envs) {
   s.crb = x; x += 10 * nL; s.fdof = x; x += 6 * nD; s.cdd = x; x += 6 * nL; s.cfrc = x; x += 6 * nL;
   if (x > xmax) xmax = x;
   x = L.n_in;
-  s.gpos = x; x += 3 * nG; s.gquat = x; x += 4 * nG; s.aabb = x; x += 6 * nG; s.queue = x; x += 2 * 32;
+  // the broad-phase work queue holds at most 2 G - 1 candidates (a full batch is flushed as soon as G are queued)
+  s.gpos = x; x += 3 * nG; s.gquat = x; x += 4 * nG; s.aabb = x; x += 6 * nG; s.queue = x; x += 2 * (h->group == 1 ? 32 : h->group);
+  if (x > xmax) xmax = x;
+  // integration scratch (link accelerations, next velocity / position): written out by the epilogue before the kinematics
+  // of the new configuration start, whose scratch (joint anchors / axes, the two scan buffers) therefore overlays it
+  x = L.n_in;
+  s.cacc = x; x += 6 * nL; s.vel_next = x; x += nD; s.qpos_next = x; x += nQ;
   if (x > xmax) xmax = x;
   x = L.n_in;
-  s.xanchor = x; x += 3 * m.nJ; s.xaxis = x; x += 3 * m.nJ; s.cacc = x; x += 6 * nL; s.vel_next = x; x += nD; s.qpos_next = x; x += nQ;
-  s.pose_a = x; x += 8 * nL; s.pose_b = x; x += 8 * nL;
+  s.xanchor = x; x += 3 * m.nJ; s.xaxis = x; x += 3 * m.nJ; s.pose_a = x; x += 8 * nL; s.pose_b = x; x += 8 * nL;
   if (x > xmax) xmax = x;
   // solver arrays overlay the dead part of the kinematic cache and the phase scratch
   x = L.kin_dead;
