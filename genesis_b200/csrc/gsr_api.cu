@@ -265,7 +265,7 @@ static int group_launch(gsr_handle_t h, int which, cudaStream_t st, const uint8_
   if (h->group == 1 && which == K_STEP) return lane_launch(h, st, clear_ext);
   const int G = h->group == 1 ? 8 : h->group, EPW = 32 / G;  // the (cold) forward-kinematics paths of a lane model use the group kernel
   const size_t warp_bytes = (size_t)EPW * h->sl.env_words * sizeof(float);
-  int warps = h->warps_per_cta > 0 ? h->warps_per_cta : (G == 32 ? 8 : 1);  // measured on B200 (profiles/README.md, r1c sweeps)
+  int warps = h->warps_per_cta > 0 ? h->warps_per_cta : (G == 32 ? 7 : 1);  // measured on B200 (profiles/README.md, r1c sweeps)
   if (warps > GSR_MAX_WARPS_PER_CTA) warps = GSR_MAX_WARPS_PER_CTA;
   while (warps > 1 && warps * (warp_bytes + 8) > 224 * 1024) warps--;  // one big CTA per SM, its warps in phase lockstep
   const int envs_per_cta = warps * EPW;

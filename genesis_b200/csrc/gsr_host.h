@@ -246,7 +246,8 @@ static inline int gsr_compute_layouts(GsrSpec* h, int n_envs) {
   SmemLayout& s = h->sl;
   memset(&s, 0, sizeof(s));
   s.MS = MS; s.JS = JS;
-  int NCS = (int)S("cfg_smem_rows", nD > 12 ? 64 : 16);  // rows kept on chip (more => SPILL record); sized so that 13 Franka CTAs fit an SM
+  int NCS = (int)S("cfg_smem_rows", nD > 12 ? 32 : 16);  // rows kept on chip (more => SPILL record): 16 lets 13 Franka CTAs fit an SM,
+  // 32 covers 99.9 % of the Go2 env-steps and leaves twice the L1 for the model tables (profiles/README.md, r1c sweeps)
   if (NCS > lenC) NCS = lenC;
   if (NCS < 4) NCS = 4;
   s.NCS = NCS;
