@@ -21,7 +21,7 @@ struct KernelStat {
   long long launches;
 };
 
-enum { K_STEP = 0, K_FORWARD = 1, K_RESET = 2, K_INIT = 3, K_SCATTER = 4, K_GATHER = 5, K_COUNT = 6 };
+enum { K_STEP = 0, K_FORWARD = 1, K_RESET = 2, K_INIT = 3, K_SCATTER = 4, K_GATHER = 5, K_GATHER_COST = 6, K_ORDER_FLAG = 7, K_COUNT = 8 };
 
 }  // namespace
 
@@ -44,15 +44,16 @@ struct gsr_handle_s : GsrSpec {
   // staging for gsr_step_host
   float *d_stage = nullptr, *h_stage = nullptr;
   size_t stage_elems = 0;
-  KernelStat stats[K_COUNT] = {{"k_step", 0}, {"k_forward", 0}, {"k_reset", 0}, {"k_init", 0}, {"k_scatter", 0}, {"k_gather", 0}};
+  KernelStat stats[K_COUNT] = {{"k_step", 0}, {"k_forward", 0}, {"k_reset", 0}, {"k_init", 0}, {"k_scatter", 0}, {"k_gather", 0},
+                              {"k_gather_cost", 0}, {"k_order_flag", 0}};
   long long total_launches = 0;
   // optional per-kernel event timing (gsr_set_profiling)
   bool profiling = false;
   struct Span { int k; cudaEvent_t a, b; };
   std::vector<Span> spans;
   std::vector<cudaEvent_t> event_pool;
-  double time_ms[K_COUNT] = {0, 0, 0, 0, 0, 0};
-  long long timed[K_COUNT] = {0, 0, 0, 0, 0, 0};
+  double time_ms[K_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long timed[K_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
   cudaStream_t prof_stream = nullptr;
 };
 
@@ -254,9 +255,9 @@ static int reorder_envs(gsr_handle_t h, cudaStream_t st) {
     CUDA_OK(cudaMalloc(&h->d_sort_tmp, h->sort_tmp_bytes));
     k_iota<<<(B + 255) / 256, 256, 0, st>>>(h->d_iota, B);
   }
-  k_gather_cost<<<(B + 255) / 256, 256, 0, st>>>(h->state, B, h->lay.step_cost, h->d_cost);
+  { Bracket br_(h, K_GATHER_COST, st); k_gather_cost<<<(B + 255) / 256, 256, 0, st>>>(h->state, B, h->lay.step_cost, h->d_cost); }
   CUDA_OK(cub::DeviceRadixSort::SortPairsDescending(h->d_sort_tmp, h->sort_tmp_bytes, h->d_cost, h->d_cost_sorted, h->d_iota, h->d_order, B, 0, 32, st));
-  k_order_flag<<<1, 32, 0, st>>>(h->d_cost_sorted, h->d_order, B);
+  { Bracket br_(h, K_ORDER_FLAG, st); k_order_flag<<<1, 32, 0, st>>>(h->d_cost_sorted, h->d_order, B); }
   CUDA_OK(cudaGetLastError());
   return GSR_OK;
 }
