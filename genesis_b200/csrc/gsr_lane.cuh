@@ -940,6 +940,47 @@ struct LSolver {
 };
 LHD __forceinline__ int& gi(GArr a, int i) { return reinterpret_cast<int&>(a[i]); }
 
+// CS:984-1173 func_equality_weld: 3 position rows (anchor1 = data[3:6] in body 1, anchor2 = data[0:3] in body 2) + 3 orientation
+// rows (relpose = data[6:10], torquescale = data[10]); translational / rotational invweight components
+LHD __noinline__ void lane_weld_rows(const LaneCtx& C, const LRows& R, int row, int l1, int l2, const float* dat, const float* sol) {
+  const int nD = CM(nD), JS = R.JS;
+  const float EPS = CM(eps);
+  const GArr J = R.J;
+  const LArr vel = C.A(c_h.vel);
+  const LArr cda = C.A(c_l.cdof), cdv = C.A(c_l.cdof + 3 * nD);
+  const LArr lpos = C.A(c_l.lpos), lquat = C.A(c_l.lquat), rcom = C.A(c_l.rcom);
+  const f4 q1 = ld4(lquat, l1), q2 = ld4(lquat, l2);
+  const f3 g1 = transform(f3(dat[3], dat[4], dat[5]), ld3(lpos, l1), q1);
+  const f3 g2 = transform(f3(dat[0], dat[1], dat[2]), ld3(lpos, l2), q2);
+  const f3 t1 = g1 - ld3(rcom, LG(l_rootslot[l1])), t2 = g2 - ld3(rcom, LG(l_rootslot[l2]));
+  const float ts = dat[10];
+  const f4 q = quat_mul(q1, f4(dat[6], dat[7], dat[8], dat[9]));
+  const f4 iq2 = quat_inv(q2);
+  const f4 eq = quat_mul(iq2, q);
+  const f3 pos_error = g1 - g2, rot_error = f3(eq.x, eq.y, eq.z) * ts;
+  const unsigned long long m1 = LG(l_dofmask[l1]), m2 = LG(l_dofmask[l2]);
+  float jq[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int d = 0; d < nD; d++) {
+    f3 v, jr;
+    const f3 ca = ld3(cda, d);
+    if ((m1 >> d) & 1ull) { v += ld3(cdv, d) - cross(t1, ca); jr += ca; }
+    if ((m2 >> d) & 1ull) { v -= ld3(cdv, d) - cross(t2, ca); jr -= ca; }
+    const f4 q3 = quat_mul(quat_mul_axis(iq2, jr), q);
+    const float jv[6] = {v.x, v.y, v.z, 0.5f * q3.x * ts, 0.5f * q3.y * ts, 0.5f * q3.z * ts};
+    const float w = vel[d];
+#pragma unroll
+    for (int k = 0; k < 6; k++) { J[(row + k) * JS + d] = jv[k]; jq[k] += jv[k] * w; }
+  }
+  const float pos_imp = sqrtf(dot(pos_error, pos_error) + dot(rot_error, rot_error));
+  for (int k = 0; k < 6; k++) {
+    const float invweight = k < 3 ? LG(l_invweight[l1]) + LG(l_invweight[l2]) : LG(l_invweight_rot[l1]) + LG(l_invweight_rot[l2]);
+    float imp, aref;
+    imp_aref(sol, -pos_imp, jq[k], k < 3 ? comp(pos_error, k) : comp(rot_error, k - 3), imp, aref);
+    const float diag = fmaxf(invweight * (1.0f - imp) / imp, EPS);
+    R.R[row + k] = diag; R.aref[row + k] = aref; R.D[row + k] = 1.0f / diag; R.floss[row + k] = 0.f;
+  }
+}
+
 LHD __noinline__ void lane_build_rows(const LaneCtx& C, LRows& R) {
   const int nD = CM(nD), nJ = CM(nJ);
   const float EPS = CM(eps);
@@ -949,6 +990,9 @@ LHD __noinline__ void lane_build_rows(const LaneCtx& C, LRows& R) {
   const int n_contacts = CM(enable_collision) ? C.I(c_h.n_contacts)[0] : 0;
   int n_eq = 0;
   for (int i = 0; i < CM(nEq); i++) n_eq += CM(eq_type[i]) == EQ_JOINT ? 1 : (CM(eq_type[i]) == EQ_CONNECT ? 3 : (CM(eq_type[i]) == EQ_WELD ? 6 : 0));
+  int n_dyn = C.I(c_h.n_dyn_eq)[0];
+  n_dyn = n_dyn < 0 ? 0 : (n_dyn > GSR_MAX_DYN_EQ ? GSR_MAX_DYN_EQ : n_dyn);
+  n_eq += 6 * n_dyn;
   int n_floss = 0;
   for (int d = 0; d < nD; d++) n_floss += CM(d_frictionloss[d]) > EPS ? 1 : 0;
   int n_lim = 0;
@@ -1035,40 +1079,16 @@ LHD __noinline__ void lane_build_rows(const LaneCtx& C, LRows& R) {
         R.R[row + k] = diag; R.aref[row + k] = aref; R.D[row + k] = 1.0f / diag; R.floss[row + k] = 0.f;
       }
       row += 3;
-    } else if (CM(eq_type[i]) == EQ_WELD) {  // CS:984-1173: 3 position rows + 3 orientation rows
-      const int l1 = CM(eq_obj1[i]), l2 = CM(eq_obj2[i]);
-      const f4 q1 = ld4(lquat, l1), q2 = ld4(lquat, l2);
-      const f3 g1 = transform(f3(CM(eq_data[i][3]), CM(eq_data[i][4]), CM(eq_data[i][5])), ld3(lpos, l1), q1);
-      const f3 g2 = transform(f3(CM(eq_data[i][0]), CM(eq_data[i][1]), CM(eq_data[i][2])), ld3(lpos, l2), q2);
-      const f3 t1 = g1 - ld3(rcom, CM(l_rootslot[l1])), t2 = g2 - ld3(rcom, CM(l_rootslot[l2]));
-      const float ts = CM(eq_data[i][10]);
-      const f4 q = quat_mul(q1, f4(CM(eq_data[i][6]), CM(eq_data[i][7]), CM(eq_data[i][8]), CM(eq_data[i][9])));
-      const f4 iq2 = quat_inv(q2);
-      const f4 eq = quat_mul(iq2, q);
-      const f3 pos_error = g1 - g2, rot_error = f3(eq.x, eq.y, eq.z) * ts;
-      const unsigned long long m1 = CM(l_dofmask[l1]), m2 = CM(l_dofmask[l2]);
-      float jq[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int d = 0; d < nD; d++) {
-        f3 v, jr;
-        const f3 ca = ld3(cda, d);
-        if ((m1 >> d) & 1ull) { v += ld3(cdv, d) - cross(t1, ca); jr += ca; }
-        if ((m2 >> d) & 1ull) { v -= ld3(cdv, d) - cross(t2, ca); jr -= ca; }
-        const f4 q3 = quat_mul(quat_mul_axis(iq2, jr), q);
-        const float jv[6] = {v.x, v.y, v.z, 0.5f * q3.x * ts, 0.5f * q3.y * ts, 0.5f * q3.z * ts};
-        const float w = vel[d];
-#pragma unroll
-        for (int k = 0; k < 6; k++) { J[(row + k) * JS + d] = jv[k]; jq[k] += jv[k] * w; }
-      }
-      const float pos_imp = sqrtf(dot(pos_error, pos_error) + dot(rot_error, rot_error));
-      for (int k = 0; k < 6; k++) {
-        const float invweight = k < 3 ? CM(l_invweight[l1]) + CM(l_invweight[l2]) : CM(l_invweight_rot[l1]) + CM(l_invweight_rot[l2]);
-        float imp, aref;
-        imp_aref(CM(eq_sol[i]), -pos_imp, jq[k], k < 3 ? comp(pos_error, k) : comp(rot_error, k - 3), imp, aref);
-        const float diag = fmaxf(invweight * (1.0f - imp) / imp, EPS);
-        R.R[row + k] = diag; R.aref[row + k] = aref; R.D[row + k] = 1.0f / diag; R.floss[row + k] = 0.f;
-      }
+    } else if (CM(eq_type[i]) == EQ_WELD) {
+      lane_weld_rows(C, R, row, CM(eq_obj1[i]), CM(eq_obj2[i]), CM(eq_data[i]), CM(eq_sol[i]));
       row += 6;
     }
+  }
+  // dynamic welds of this environment (add_weld_constraint), after the static equalities like in the reference's table
+  for (int k = 0; k < n_dyn; k++) {
+    const float* rec_eq = C.rec + c_h.dyn_eq + k * GSR_DYN_EQ_WORDS;
+    lane_weld_rows(C, R, row, lane_f2i(rec_eq[0]), lane_f2i(rec_eq[1]), rec_eq + 2, rec_eq + 13);
+    row += 6;
   }
   // ---- frictionloss (CS:1236-1286), static rows in dof order
   if (n_floss > 0) {

@@ -26,6 +26,46 @@ struct SolverState {
   int ls_it;
 };
 
+// CS:984-1173 func_equality_weld: 3 position rows (anchor1 = data[3:6] in body 1, anchor2 = data[0:3] in body 2) + 3 orientation
+// rows (relpose = data[6:10], torquescale = data[10]); translational / rotational invweight components
+template <int G>
+__device__ __noinline__ void weld_rows(const Ctx<G>& C, Rows& R, int row, int l1, int l2, const float* dat, const float* sol) {
+  const int nD = CM(nD), lane = C.lane, JS = R.JS;
+  const float EPS = CM(eps);
+  float* J = R.J;
+  const float* vel = IN(vel);
+  const f4 q1 = ld4(IN(links_quat), l1), q2 = ld4(IN(links_quat), l2);
+  const f3 g1 = transform(f3(dat[3], dat[4], dat[5]), ld3(IN(links_pos), l1), q1);
+  const f3 g2 = transform(f3(dat[0], dat[1], dat[2]), ld3(IN(links_pos), l2), q2);
+  const f3 t1 = g1 - ld3(IN(root_COM), l1), t2 = g2 - ld3(IN(root_COM), l2);
+  const float ts = dat[10];
+  const f4 q = quat_mul(q1, f4(dat[6], dat[7], dat[8], dat[9]));
+  const f4 iq2 = quat_inv(q2);
+  const f4 eq = quat_mul(iq2, q);
+  const f3 pos_error = g1 - g2, rot_error = f3(eq.x, eq.y, eq.z) * ts;
+  const unsigned long long m1 = GM(l_dofmask[l1]), m2 = GM(l_dofmask[l2]);
+  for (int d = lane; d < nD; d += G) {
+    f3 v, jr;
+    const f3 ca = ld3(IN(cdof_ang), d);
+    if (bit64(m1, d)) { v += ld3(IN(cdof_vel), d) - cross(t1, ca); jr += ca; }
+    if (bit64(m2, d)) { v -= ld3(IN(cdof_vel), d) - cross(t2, ca); jr -= ca; }
+    J[row * JS + d] = v.x; J[(row + 1) * JS + d] = v.y; J[(row + 2) * JS + d] = v.z;
+    const f4 q3 = quat_mul(quat_mul_axis(iq2, jr), q);
+    J[(row + 3) * JS + d] = 0.5f * q3.x * ts; J[(row + 4) * JS + d] = 0.5f * q3.y * ts; J[(row + 5) * JS + d] = 0.5f * q3.z * ts;
+  }
+  C.sync();
+  if (lane < 6) {
+    float jac_qvel = 0.f;
+    for (int d = 0; d < nD; d++) jac_qvel += J[(row + lane) * JS + d] * vel[d];
+    const float pos_imp = sqrtf(dot(pos_error, pos_error) + dot(rot_error, rot_error));
+    const float invweight = lane < 3 ? GM(l_invweight[l1]) + GM(l_invweight[l2]) : GM(l_invweight_rot[l1]) + GM(l_invweight_rot[l2]);
+    float imp, aref;
+    imp_aref(sol, -pos_imp, jac_qvel, lane < 3 ? comp(pos_error, lane) : comp(rot_error, lane - 3), imp, aref);
+    const float diag = fmaxf(invweight * (1.0f - imp) / imp, EPS);
+    R.R[row + lane] = diag; R.aref[row + lane] = aref; R.D[row + lane] = 1.0f / diag; R.floss[row + lane] = 0.f;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Row assembly (CS:579-1286), row order [equality | frictionloss | 4 x contacts | joint limits]
 // ---------------------------------------------------------------------------------------------------------------------
@@ -39,6 +79,8 @@ __device__ __noinline__ void build_rows(const Ctx<G>& C, Rows& R) {
   // ---- static counts: equality rows and friction-loss rows
   int n_eq = 0;
   for (int i = 0; i < CM(nEq); i++) n_eq += CM(eq_type[i]) == EQ_JOINT ? 1 : (CM(eq_type[i]) == EQ_CONNECT ? 3 : (CM(eq_type[i]) == EQ_WELD ? 6 : 0));
+  const int n_dyn = min(max(C.SI()[c_h.n_dyn_eq], 0), GSR_MAX_DYN_EQ);
+  n_eq += 6 * n_dyn;
   int n_floss = 0;
   for (int d = 0; d < nD; d++) n_floss += CM(d_frictionloss[d]) > EPS ? 1 : 0;
   // ---- joint limits that are violated (CS:1176-1233), in joint order
@@ -133,40 +175,16 @@ __device__ __noinline__ void build_rows(const Ctx<G>& C, Rows& R) {
         R.R[row + lane] = diag; R.aref[row + lane] = aref; R.D[row + lane] = 1.0f / diag; R.floss[row + lane] = 0.f;
       }
       row += 3;
-    } else if (CM(eq_type[i]) == EQ_WELD) {  // CS:984-1173: 3 position rows + 3 orientation rows
-      const int l1 = CM(eq_obj1[i]), l2 = CM(eq_obj2[i]);
-      const f4 q1 = ld4(IN(links_quat), l1), q2 = ld4(IN(links_quat), l2);
-      const f3 g1 = transform(f3(CM(eq_data[i][3]), CM(eq_data[i][4]), CM(eq_data[i][5])), ld3(IN(links_pos), l1), q1);
-      const f3 g2 = transform(f3(CM(eq_data[i][0]), CM(eq_data[i][1]), CM(eq_data[i][2])), ld3(IN(links_pos), l2), q2);
-      const f3 t1 = g1 - ld3(IN(root_COM), l1), t2 = g2 - ld3(IN(root_COM), l2);
-      const float ts = CM(eq_data[i][10]);
-      const f4 q = quat_mul(q1, f4(CM(eq_data[i][6]), CM(eq_data[i][7]), CM(eq_data[i][8]), CM(eq_data[i][9])));
-      const f4 iq2 = quat_inv(q2);
-      const f4 eq = quat_mul(iq2, q);
-      const f3 pos_error = g1 - g2, rot_error = f3(eq.x, eq.y, eq.z) * ts;
-      const unsigned long long m1 = CM(l_dofmask[l1]), m2 = CM(l_dofmask[l2]);
-      for (int d = lane; d < nD; d += G) {
-        f3 v, jr;
-        const f3 ca = ld3(IN(cdof_ang), d);
-        if (bit64(m1, d)) { v += ld3(IN(cdof_vel), d) - cross(t1, ca); jr += ca; }
-        if (bit64(m2, d)) { v -= ld3(IN(cdof_vel), d) - cross(t2, ca); jr -= ca; }
-        J[row * JS + d] = v.x; J[(row + 1) * JS + d] = v.y; J[(row + 2) * JS + d] = v.z;
-        const f4 q3 = quat_mul(quat_mul_axis(iq2, jr), q);
-        J[(row + 3) * JS + d] = 0.5f * q3.x * ts; J[(row + 4) * JS + d] = 0.5f * q3.y * ts; J[(row + 5) * JS + d] = 0.5f * q3.z * ts;
-      }
-      C.sync();
-      if (lane < 6) {
-        float jac_qvel = 0.f;
-        for (int d = 0; d < nD; d++) jac_qvel += J[(row + lane) * JS + d] * vel[d];
-        const float pos_imp = sqrtf(dot(pos_error, pos_error) + dot(rot_error, rot_error));
-        const float invweight = lane < 3 ? CM(l_invweight[l1]) + CM(l_invweight[l2]) : CM(l_invweight_rot[l1]) + CM(l_invweight_rot[l2]);
-        float imp, aref;
-        imp_aref(CM(eq_sol[i]), -pos_imp, jac_qvel, lane < 3 ? comp(pos_error, lane) : comp(rot_error, lane - 3), imp, aref);
-        const float diag = fmaxf(invweight * (1.0f - imp) / imp, EPS);
-        R.R[row + lane] = diag; R.aref[row + lane] = aref; R.D[row + lane] = 1.0f / diag; R.floss[row + lane] = 0.f;
-      }
+    } else if (CM(eq_type[i]) == EQ_WELD) {
+      weld_rows(C, R, row, CM(eq_obj1[i]), CM(eq_obj2[i]), CM(eq_data[i]), CM(eq_sol[i]));
       row += 6;
     }
+  }
+  // dynamic welds of this environment (add_weld_constraint), after the static equalities like in the reference's table
+  for (int k = 0; k < n_dyn; k++) {
+    const float* rec_eq = C.rec + c_h.dyn_eq + k * GSR_DYN_EQ_WORDS;
+    weld_rows(C, R, row, __float_as_int(rec_eq[0]), __float_as_int(rec_eq[1]), rec_eq + 2, rec_eq + 13);
+    row += 6;
   }
   // ---- frictionloss (CS:1236-1286), static rows in dof order
   if (n_floss > 0 && lane == 0) {

@@ -27,6 +27,8 @@
 #define GSR_MAX_ENTS 16
 #define GSR_MAX_EQ 8
 #define GSR_CONTACT_WORDS 16
+#define GSR_MAX_DYN_EQ 8      /* RigidOptions.max_dynamic_constraints (options/solvers.py) */
+#define GSR_DYN_EQ_WORDS 20
 
 enum { GEOM_PLANE = 0, GEOM_SPHERE = 1, GEOM_ELLIPSOID = 2, GEOM_CYLINDER = 3, GEOM_CAPSULE = 4, GEOM_BOX = 5, GEOM_MESH = 6 };
 enum { JOINT_FIXED = 0, JOINT_REVOLUTE = 1, JOINT_PRISMATIC = 2, JOINT_SPHERICAL = 3, JOINT_FREE = 4 };
@@ -103,7 +105,7 @@ struct DevModel {
   X(qpos, 0, nQ, 1) X(vel, 0, nD, 1) X(ctrl_pos, 0, nD, 1) X(ctrl_vel, 0, nD, 1) X(ctrl_force, 0, nD, 1)           \
   X(ctrl_mode, 1, nD, 1) X(qacc_ws, 0, nD, 1)                                                                      \
   X(is_warmstart, 1, 1, 1) X(errno_, 1, 1, 1) X(n_contacts, 1, 1, 1) X(n_broad, 1, 1, 1)                           \
-  X(has_ext_force, 1, 1, 1) X(has_shift, 1, 1, 1)                                                                  \
+  X(has_ext_force, 1, 1, 1) X(has_shift, 1, 1, 1) X(n_dyn_eq, 1, 1, 1)                                             \
   /* kinematic cache written by the FK at the end of a step and consumed by the next step */                       \
   X(dofs_pos, 0, nD, 1) X(root_COM, 0, nL, 3) X(cdof_ang, 0, nD, 3) X(cdof_vel, 0, nD, 3) X(cdofd_ang, 0, nD, 3)   \
   X(cdofd_vel, 0, nD, 3) X(links_pos, 0, nL, 3) X(links_quat, 0, nL, 4) X(cinr_I, 0, nL, 6) X(cinr_pos, 0, nL, 3)  \
@@ -114,6 +116,9 @@ struct DevModel {
   X(friction_ratio, 0, nG, 1) X(cfrc_applied_vel, 0, nL, 3) X(cfrc_applied_ang, 0, nL, 3)                          \
   /* domain randomisation (links_state.mass_shift / i_pos_shift), read only when has_shift is set */                  \
   X(mass_shift, 0, nL, 1) X(com_shift, 0, nL, 3)                                                                   \
+  /* dynamic weld equalities (add_weld_constraint, solver.py:1293-1340): n_dyn_eq records of GSR_DYN_EQ_WORDS words   \
+     [link1, link2, eq_data[11], sol_params[7]] */                                                                    \
+  X(dyn_eq, 0, GSR_MAX_DYN_EQ, GSR_DYN_EQ_WORDS)                                                                    \
   X(acc, 0, nD, 1) X(force, 0, nD, 1) X(qf_applied, 0, nD, 1) X(qf_constraint, 0, nD, 1)                           \
   X(cacc_lin, 0, nL, 3) X(cacc_ang, 0, nL, 3) X(links_contact_force, 0, nL, 3)                                     \
   X(aabb_min, 0, nG, 3) X(aabb_max, 0, nG, 3)                                                                      \

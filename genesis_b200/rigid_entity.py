@@ -359,3 +359,7 @@ class RigidEntity:
 
     def get_COM_shift(self, links_idx_local=None, envs_idx=None):
         return self._solver.get_links_COM_shift(self._links_idx(links_idx_local), envs_idx)
+
+    def add_weld_constraint(self, link_local, other_entity, other_link_local=0, envs_idx=None):
+        """Convenience forwarder: weld a link of another entity to a link of this one at their current relative pose."""
+        self._solver.add_weld_constraint(self.link_start + link_local, other_entity.link_start + other_link_local, envs_idx)

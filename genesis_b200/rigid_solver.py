@@ -557,6 +557,59 @@ class RigidSolver:
         """Per-environment friction scale of each geom (contact friction = max(mu_a ratio_a, mu_b ratio_b, 1e-2), contact.py:202-211)."""
         self._set("friction_ratio", friction_ratio, geoms_idx, envs_idx, self.model.n_geoms)
 
+    # ---- dynamic weld equalities (rigid_solver.py:2591-2598, constraint/solver.py:1293-1390)
+    MAX_DYN_EQ, DYN_EQ_WORDS = 8, 20
+
+    def add_weld_constraint(self, link1_idx, link2_idx, envs_idx=None):
+        """Welds link2 to link1 at their current relative pose in the selected environments (kernel_add_weld_constraint:
+        anchors = link1's origin expressed in both frames, relpose = inv(q1) (x) q2, torquescale 1, sol_params
+        (2 dt, 1, 0.9, 0.95, 0.001, 0.5, 2))."""
+        envs = self._envs(envs_idx)
+        e = self._envs_all if envs is None else envs
+        n = self._fields["n_dyn_eq"][e, 0]
+        if int(n.max()) >= self.MAX_DYN_EQ:
+            raise GenesisException("Exceeding max number of dynamic equality constraints (max_dynamic_constraints).")
+        p1, q1 = self._fields["links_pos"][e, link1_idx], self._fields["links_quat"][e, link1_idx]
+        p2, q2 = self._fields["links_pos"][e, link2_idx], self._fields["links_quat"][e, link2_idx]
+        q2c = torch.cat([q2[:, :1], -q2[:, 1:]], dim=-1)
+        q1c = torch.cat([q1[:, :1], -q1[:, 1:]], dim=-1)
+        pos1 = torch.zeros_like(p1)                      # the shared point is link1's origin
+        pos2 = _rotate_torch(p1 - p2, q2c)
+        rel = _quat_mul_torch(q1c, q2)
+        rec = torch.zeros((len(e), self.DYN_EQ_WORDS), dtype=torch.float32, device=self.device)
+        rec[:, 0] = torch.tensor([link1_idx], dtype=torch.int32, device=self.device).view(torch.float32)
+        rec[:, 1] = torch.tensor([link2_idx], dtype=torch.int32, device=self.device).view(torch.float32)
+        rec[:, 2:5], rec[:, 5:8], rec[:, 8:12], rec[:, 12] = pos2, pos1, rel, 1.0
+        rec[:, 13:20] = torch.tensor([2 * self._substep_dt, 1.0, 0.9, 0.95, 0.001, 0.5, 2.0], device=self.device)
+        self._fields["dyn_eq"][e, n.long()] = rec
+        self._fields["n_dyn_eq"][e, 0] = n + 1
+
+    def delete_weld_constraint(self, link1_idx, link2_idx, envs_idx=None):
+        """Removes the dynamic weld between the two links where it exists (the last record takes the freed slot)."""
+        envs = self._envs(envs_idx)
+        e = self._envs_all if envs is None else envs
+        recs = self._fields["dyn_eq"]
+        ids = recs[..., :2].contiguous().view(torch.int32)           # (B, MAX, 2)
+        n = self._fields["n_dyn_eq"][:, 0]
+        for k in range(self.MAX_DYN_EQ):
+            hit = (ids[e, k, 0] == link1_idx) & (ids[e, k, 1] == link2_idx) & (k < n[e])
+            he = e[hit]
+            if len(he) == 0:
+                continue
+            last = (n[he] - 1).long()
+            recs[he, k] = recs[he, last]
+            self._fields["n_dyn_eq"][he, 0] = n[he] - 1
+            ids = recs[..., :2].contiguous().view(torch.int32)
+            n = self._fields["n_dyn_eq"][:, 0]
+
+    def get_weld_constraints(self):
+        """{"link_a", "link_b"}: (B, MAX_DYN_EQ) int tensors, -1 where no dynamic weld is stored."""
+        ids = self._fields["dyn_eq"][..., :2].contiguous().view(torch.int32).clone()
+        n = self._fields["n_dyn_eq"][:, :1]
+        valid = torch.arange(self.MAX_DYN_EQ, device=self.device)[None, :] < n
+        ids[~valid] = -1
+        return {"link_a": ids[..., 0], "link_b": ids[..., 1], "n": n[:, 0].clone()}
+
     # ---- per-environment domain randomisation of the inertial parameters (rigid_solver.py:1825-1860, accessor.py:400-430)
     def set_links_mass_shift(self, mass_shift, links_idx=None, envs_idx=None):
         """links_state.mass_shift: added to the link mass in the COM and c-frame inertia (forward_kinematics.py:377, 437)."""

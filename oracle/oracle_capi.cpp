@@ -77,6 +77,21 @@ static bool set_field(Oracle<T>& o, int b, const std::string& n, const double* i
   if (n == "cfrc_applied_ang") { for (size_t i = 0; i < e.cfrc_applied_ang.size(); i++) for (int k = 0; k < 3; k++) e.cfrc_applied_ang[i][k] = (T)in[3 * i + k]; return true; }
   if (n == "mass_shift") { cp(e.mass_shift); o.forward_all(e); return true; }
   if (n == "com_shift") { for (size_t i = 0; i < e.i_pos_shift.size(); i++) for (int k = 0; k < 3; k++) e.i_pos_shift[i][k] = (T)in[3 * i + k]; o.forward_all(e); return true; }
+  if (n == "add_weld") {  // [link1, link2]: the reference's kernel_add_weld_constraint at the current poses
+    typename Env<T>::DynWeld w;
+    w.l1 = (int)in[0]; w.l2 = (int)in[1];
+    auto shared = e.l_pos[w.l1];
+    auto p1 = inv_transform_by_quat(shared - e.l_pos[w.l1], e.l_quat[w.l1]);
+    auto p2 = inv_transform_by_quat(shared - e.l_pos[w.l2], e.l_quat[w.l2]);
+    for (int k = 0; k < 3; k++) { w.data[k] = p2[k]; w.data[3 + k] = p1[k]; }
+    auto rel = quat_mul(inv_quat(e.l_quat[w.l1]), e.l_quat[w.l2]);
+    w.data[6] = rel.w; w.data[7] = rel.x; w.data[8] = rel.y; w.data[9] = rel.z; w.data[10] = 1;
+    const T sol[7] = {T(2) * (T)o.cfg.dt, 1, T(0.9), T(0.95), T(0.001), T(0.5), 2};
+    for (int k = 0; k < 7; k++) w.sol[k] = sol[k];
+    e.dyn_welds.push_back(w);
+    return true;
+  }
+  if (n == "clear_welds") { e.dyn_welds.clear(); return true; }
   if (n == "reset") { o.reset_env(e); return true; }
   return false;
 }

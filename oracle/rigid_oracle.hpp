@@ -139,6 +139,8 @@ struct Env {
   std::vector<Q4<T>> l_quat, i_quat, j_quat;
   std::vector<M3<T>> cinr_I, crb_I;
   std::vector<T> mass_sum, cinr_mass, crb_mass;
+  struct DynWeld { int l1, l2; T data[11]; T sol[7]; };
+  std::vector<DynWeld> dyn_welds;   // add_weld_constraint (solver.py:1293-1340): per-env equalities after the static ones
   std::vector<T> mass_shift;        // links_state.mass_shift (domain randomisation, accessor.py:415)
   std::vector<V3<T>> i_pos_shift;   // links_state.i_pos_shift (accessor.py:429)
   std::vector<V> xanchor, xaxis;
@@ -1190,10 +1192,8 @@ struct Oracle {
 
   // CS:984-1173 func_equality_weld: 3 position rows (anchor1 = data[3:6] in body 1, anchor2 = data[0:3] in body 2) and
   // 3 orientation rows (relpose = data[6:10], torquescale = data[10]); translational / rotational invweight components
-  void equality_weld(Env<T>& e, int i_e) {
-    const T* sp = &m.eq_sol_params[7 * i_e];
-    const T* dat = &m.eq_data[11 * i_e];
-    int l1 = m.eq_obj1[i_e], l2 = m.eq_obj2[i_e];
+  void equality_weld(Env<T>& e, int i_e) { weld_rows(e, m.eq_obj1[i_e], m.eq_obj2[i_e], &m.eq_data[11 * i_e], &m.eq_sol_params[7 * i_e]); }
+  void weld_rows(Env<T>& e, int l1, int l2, const T* dat, const T* sp) {
     V a1(dat[3], dat[4], dat[5]), a2(dat[0], dat[1], dat[2]);
     Q relpose(dat[6], dat[7], dat[8], dat[9]);
     T torquescale = dat[10];
@@ -1273,6 +1273,7 @@ struct Oracle {
       else if (m.eq_type[i] == EQ_CONNECT) equality_connect(e, i);
       else if (m.eq_type[i] == EQ_WELD) equality_weld(e, i);
     }
+    for (auto& w : e.dyn_welds) weld_rows(e, w.l1, w.l2, w.data, w.sol);
   }
 
   // CS:1236-1286 add_frictionloss_constraints

@@ -231,6 +231,46 @@ def test_weld_equality():
     assert (scene.rigid_solver.field("n_constraints_equality")[:, 0] == 12).all()
 
 
+def test_dynamic_weld_constraint_api():
+    """add_weld_constraint / delete_weld_constraint per environment (rigid_solver.py:2591-2598, solver.py:1293-1390)."""
+    B = 6
+    scene, ents = scene_from_morphs([gs.morphs.Plane(), gs.morphs.Box(size=(0.1, 0.1, 0.1), pos=(0, 0, 1.0)),
+                                     gs.morphs.Box(size=(0.08, 0.08, 0.08), pos=(0.2, 0.05, 1.1))], dt=0.01)
+    scene.build(n_envs=B)
+    s = scene.rigid_solver
+    v = torch.zeros((B, s.model.n_dofs), device=gs.device)
+    v[:, 3:6] = torch.tensor([1.0, -2.0, 0.5])
+    v[:, 6] = 0.3
+    s.set_dofs_velocity(v)
+    orc = mirror_oracle(scene)
+    for _ in range(5):
+        scene.step()
+    orc.step(5)
+    welded = [0, 2, 3, 5]
+    s.add_weld_constraint(1, 2, envs_idx=welded)
+    for b in welded:
+        orc.set("add_weld", [1, 2], env=b)
+    w = s.get_weld_constraints()
+    assert w["n"].tolist() == [1, 0, 1, 1, 0, 1] and int(w["link_a"][0, 0]) == 1 and int(w["link_b"][0, 0]) == 2
+    for _ in range(30):
+        scene.step()
+    orc.step(30)
+    assert s.field("n_constraints_equality")[:, 0].tolist() == [6, 0, 6, 6, 0, 6]
+    assert np.abs(gpu_field(scene, "qpos") - orc.qpos()).max() <= TRAJ_QPOS_FREE
+    assert np.abs(gpu_field(scene, "vel") - orc.vel()).max() <= TRAJ_QVEL_FREE
+    s.delete_weld_constraint(1, 2, envs_idx=[2, 3])
+    for b in (2, 3):
+        orc.set("clear_welds", [0.0], env=b)
+    assert s.get_weld_constraints()["n"].tolist() == [1, 0, 0, 0, 0, 1]
+    for _ in range(10):
+        scene.step()
+    orc.step(10)
+    assert np.abs(gpu_field(scene, "qpos") - orc.qpos()).max() <= TRAJ_QPOS_FREE
+    with pytest.raises(gs.GenesisException):
+        for _ in range(9):
+            s.add_weld_constraint(1, 2, envs_idx=[0])
+
+
 def test_mass_and_com_shift_domain_randomisation():
     """set_mass_shift / set_COM_shift per environment (links_state.mass_shift / i_pos_shift, forward_kinematics.py:377-437)."""
     B, K = 16, 40

@@ -251,3 +251,55 @@ def test_lane_mass_and_com_shift():
     ref.step(40)
     assert np.abs(emu.rows("qpos") - orc.qpos()).max() <= 1e-3 and np.abs(emu.rows("vel") - orc.vel()).max() <= 2e-2
     assert np.abs(orc.qpos() - ref.qpos()).max() > 1e-3  # the shifts matter
+
+
+def _np_quat_mul(u, v):
+    return np.array([u[0] * v[0] - u[1] * v[1] - u[2] * v[2] - u[3] * v[3], u[0] * v[1] + u[1] * v[0] + u[2] * v[3] - u[3] * v[2],
+                     u[0] * v[2] - u[1] * v[3] + u[2] * v[0] + u[3] * v[1], u[0] * v[3] + u[1] * v[2] - u[2] * v[1] + u[3] * v[0]])
+
+
+def _np_rotate(v, q):
+    qv = np.array([0.0, *v])
+    qc = np.array([q[0], -q[1], -q[2], -q[3]])
+    return _np_quat_mul(_np_quat_mul(q, qv), qc)[1:]
+
+
+def test_lane_dynamic_weld_constraint():
+    """add_weld_constraint (constraint/solver.py:1293-1340): a box welded in flight to a second, spinning box."""
+    from helpers import scene_from_morphs
+
+    B = 2
+    scene, _ = scene_from_morphs([gs.morphs.Plane(), gs.morphs.Box(size=(0.1, 0.1, 0.1), pos=(0, 0, 1.0)),
+                                  gs.morphs.Box(size=(0.08, 0.08, 0.08), pos=(0.2, 0.05, 1.1))], dt=0.01)
+    solver = scene.rigid_solver
+    m = solver.build_model()
+    orc = oracle_for(solver, m, B, threads=2)
+    emu = LaneEmu(m, B, solver.model_options())
+    v = np.zeros((B, m.n_dofs))
+    v[:, 3:6] = [1.0, -2.0, 0.5]
+    v[:, 6] = 0.3
+    orc.set("vel", v)
+    emu.set("vel", v)
+    orc.step(5)
+    emu.step(5)
+    l1, l2 = 1, 2
+    for b in range(B):
+        orc.set("add_weld", [l1, l2], env=b)
+        p1, q1 = emu.field("links_pos")[b, l1].astype(float), emu.field("links_quat")[b, l1].astype(float)
+        p2, q2 = emu.field("links_pos")[b, l2].astype(float), emu.field("links_quat")[b, l2].astype(float)
+        q1c, q2c = q1 * [1, -1, -1, -1], q2 * [1, -1, -1, -1]
+        rec = np.zeros(20, np.float32)
+        rec[:2] = np.array([l1, l2], np.int32).view(np.float32)
+        rec[2:5] = _np_rotate(p1 - p2, q2c)
+        rec[8:12] = _np_quat_mul(q1c, q2)
+        rec[12] = 1.0
+        rec[13:20] = [2 * 0.01, 1.0, 0.9, 0.95, 0.001, 0.5, 2.0]
+        emu.field("dyn_eq")[b, 0] = rec
+        emu.field("n_dyn_eq")[b, 0] = 1
+    d0 = np.linalg.norm(emu.field("links_pos")[0, l1] - emu.field("links_pos")[0, l2])
+    orc.step(40)
+    emu.step(40)
+    assert (emu.field("n_constraints_equality")[:, 0] == 6).all()
+    assert np.abs(emu.rows("qpos") - orc.qpos()).max() <= 1e-4 and np.abs(emu.rows("vel") - orc.vel()).max() <= 1e-3
+    d1 = np.linalg.norm(emu.field("links_pos")[0, l1] - emu.field("links_pos")[0, l2])
+    assert abs(d1 - d0) < 5e-3  # the welded boxes keep their distance while tumbling (soft constraint: millimetres of give)
