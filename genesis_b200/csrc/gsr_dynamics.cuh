@@ -286,6 +286,28 @@ __device__ __noinline__ void mass_solve(const Ctx<G>& C, float* x) {
     C.sync();
     return;
   }
+  if (nD <= 2 * G) {
+    // same scheme with two unknowns per lane (rows lane and lane + G): Franka's 9 dofs on 8 lanes
+    const int lane = C.lane, r1 = lane + G;
+    const bool own1 = r1 < nD;
+    float s0 = x[lane], s1 = own1 ? x[r1] : 0.f;
+    for (int j = nD - 1; j > 0; j--) {  // L^T w = y
+      const float xj = __shfl_sync(C.gmask, j < G ? s0 : s1, j < G ? j : j - G, G);
+      if (lane < j) s0 -= L[j * MS + lane] * xj;
+      if (r1 < j) s1 -= L[j * MS + r1] * xj;
+    }
+    s0 *= Dinv[lane];
+    if (own1) s1 *= Dinv[r1];
+    for (int j = 0; j < nD - 1; j++) {  // L x = z
+      const float xj = __shfl_sync(C.gmask, j < G ? s0 : s1, j < G ? j : j - G, G);
+      if (lane > j) s0 -= L[lane * MS + j] * xj;
+      if (own1 && r1 > j) s1 -= L[r1 * MS + j] * xj;
+    }
+    x[lane] = s0;
+    if (own1) x[r1] = s1;
+    C.sync();
+    return;
+  }
   for (int j = nD - 1; j > 0; j--) {  // L^T w = y: once w_j is final, eliminate it from every i < j
     const float xj = x[j];
     for (int i = C.lane; i < j; i += G) x[i] -= L[j * MS + i] * xj;

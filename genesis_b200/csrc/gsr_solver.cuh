@@ -458,6 +458,31 @@ __device__ __noinline__ void update_gradient(const Ctx<G>& C) {
       C.sync();
       return;
     }
+    if (nD <= 2 * G) {
+      // two unknowns per lane (rows lane and lane + G), G < nD <= 2 G
+      const int r1 = lane + G;
+      const bool own1 = r1 < nD;
+      float s0 = Mgrad[lane], s1 = own1 ? Mgrad[r1] : 0.f;
+      const float h0 = Hinv[lane], h1 = own1 ? Hinv[r1] : 0.f;
+      for (int i = 0; i < nD; i++) {  // L y = g
+        const float yi = __shfl_sync(C.gmask, i < G ? s0 * h0 : s1 * h1, i < G ? i : i - G, G);
+        if (lane == i) s0 = yi;
+        if (r1 == i) s1 = yi;
+        if (lane > i) s0 -= H[lane * MS + i] * yi;
+        if (own1 && r1 > i) s1 -= H[r1 * MS + i] * yi;
+      }
+      for (int i = nD - 1; i >= 0; i--) {  // L^T x = y
+        const float xi = __shfl_sync(C.gmask, i < G ? s0 * h0 : s1 * h1, i < G ? i : i - G, G);
+        if (lane == i) s0 = xi;
+        if (r1 == i) s1 = xi;
+        if (lane < i) s0 -= H[i * MS + lane] * xi;
+        if (r1 < i) s1 -= H[i * MS + r1] * xi;
+      }
+      Mgrad[lane] = s0;
+      if (own1) Mgrad[r1] = s1;
+      C.sync();
+      return;
+    }
     float* y = WK(tmpv);
     for (int i = 0; i < nD; i++) {  // forward substitution, column oriented: y_i final once columns < i are eliminated
       const float yi = Mgrad[i] * Hinv[i];
