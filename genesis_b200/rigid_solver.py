@@ -660,15 +660,22 @@ class RigidSolver:
         return torch.stack([lo, hi], dim=-2)
 
     def get_contacts(self, as_tensor=True, to_torch=True, keep_batch_dim=False):
-        """collider.py:810-913 (tensor form): dict of (B, n_contacts_max[, 3]) tensors, cleared slots hold -1 / 0."""
-        n_max = int(self._fields["n_contacts"].max().item())
+        """collider.py:810-913: dict of (B, n_contacts_max[, 3]) tensors, cleared slots hold -1 / 0 (`as_tensor=True`), or of
+        per-environment tuples cut to each environment's own contact count (`as_tensor=False`, collider.py:834-838)."""
+        n = self._fields["n_contacts"][:, 0]
+        n_max = int(n.max().item())
         f = self._fields
+        counts = n.tolist() if not as_tensor else None
 
         def cut(name):
             t = f[name][:, :n_max].clone()
-            if self.n_envs == 0 and not keep_batch_dim:
-                t = t[0]
-            return t if to_torch else t.cpu().numpy()
+            if not to_torch:
+                t = t.cpu().numpy()
+            if self.n_envs == 0:
+                return t if keep_batch_dim else t[0]
+            if not as_tensor:
+                return tuple(t[i: i + 1, :j] if keep_batch_dim else t[i, :j] for i, j in enumerate(counts))
+            return t
 
         return dict(link_a=cut("contact_link_a"), link_b=cut("contact_link_b"), geom_a=cut("contact_geom_a"),
                     geom_b=cut("contact_geom_b"), penetration=cut("contact_penetration"), position=cut("contact_pos"),
@@ -677,6 +684,16 @@ class RigidSolver:
     @property
     def n_contacts(self):
         return self._fields["n_contacts"][:, 0]
+
+    @property
+    def collider(self):
+        """`rigid_solver.collider.get_contacts(...)` like in the reference (collider/collider.py:810)."""
+        return _ColliderFacade(self)
+
+    @property
+    def constraint_solver(self):
+        """The attributes of the reference's ConstraintSolver that user code and tests read (constraint/solver.py:27-112)."""
+        return _ConstraintSolverFacade(self)
 
     # ------------------------------------------------------------------ state (rigid_solver.py:1430-1579)
     def get_state(self):
@@ -716,6 +733,38 @@ class RigidSolver:
             self.destroy()
         except Exception:
             pass
+
+
+class _ColliderFacade:
+    def __init__(self, solver):
+        self._solver = solver
+
+    def get_contacts(self, as_tensor=True, to_torch=True, keep_batch_dim=False):
+        return self._solver.get_contacts(as_tensor, to_torch, keep_batch_dim)
+
+    @property
+    def n_contacts(self):
+        return self._solver.n_contacts
+
+
+class _ConstraintSolverFacade:
+    def __init__(self, solver):
+        self._solver = solver
+
+    qacc_ws = property(lambda self: self._solver.field("qacc_ws"))
+    n_constraints = property(lambda self: self._solver.field("n_constraints")[:, 0])
+    n_constraints_equality = property(lambda self: self._solver.field("n_constraints_equality")[:, 0])
+    n_constraints_frictionloss = property(lambda self: self._solver.field("n_constraints_frictionloss")[:, 0])
+    n_iterations = property(lambda self: self._solver.field("solver_iters")[:, 0])
+
+    def add_weld_constraint(self, link1_idx, link2_idx, envs_idx=None):
+        return self._solver.add_weld_constraint(link1_idx, link2_idx, envs_idx)
+
+    def delete_weld_constraint(self, link1_idx, link2_idx, envs_idx=None):
+        return self._solver.delete_weld_constraint(link1_idx, link2_idx, envs_idx)
+
+    def get_weld_constraints(self, as_tensor=True, to_torch=True):
+        return self._solver.get_weld_constraints()
 
 
 def _rotate_torch(v, q):

@@ -143,3 +143,24 @@ def test_external_torque_frictionloss_and_friction_ratio():
     scene.step()
     assert (s.field("n_constraints_frictionloss")[:, 0] == 6).all()
     assert torch.allclose(box.get_dofs_frictionloss(), torch.full((6,), 0.01, device=gs.device))
+
+
+def test_collider_and_constraint_solver_facades():
+    """`scene.rigid_solver.collider.get_contacts(as_tensor, to_torch, keep_batch_dim)` and the ConstraintSolver attributes the
+    reference's tests read (collider.py:810-913, constraint/solver.py:27-112)."""
+    B = 4
+    scene, robot = make_go2(B, randomized=False)
+    for _ in range(60):
+        scene.step()
+    s = scene.rigid_solver
+    c = s.collider.get_contacts(as_tensor=True, to_torch=True)
+    n = s.collider.n_contacts
+    assert c["geom_a"].shape == (B, int(n.max()))
+    ragged = s.collider.get_contacts(as_tensor=False, to_torch=False)
+    assert isinstance(ragged["position"], tuple) and len(ragged["position"]) == B
+    for b in range(B):
+        assert ragged["position"][b].shape == (int(n[b]), 3) and isinstance(ragged["position"][b], np.ndarray)
+    cs = s.constraint_solver
+    assert cs.qacc_ws.shape == (B, 18)
+    assert (cs.n_constraints >= 4 * n).all() and (cs.n_constraints_equality == 0).all()
+    assert (cs.n_iterations >= 1).all()
