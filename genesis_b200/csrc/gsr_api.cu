@@ -40,6 +40,7 @@ struct gsr_handle_s : GsrSpec {
   void* d_sort_tmp = nullptr;
   size_t sort_tmp_bytes = 0;
   int reorder_period = 16, steps_since_reorder = 0;
+  int auto_warps = 0;  // warps per CTA chosen by auto_warps_per_cta (0 = not chosen yet)
   int *d_pairs = nullptr, *d_pair_idx = nullptr;
   // staging for gsr_step_host
   float *d_stage = nullptr, *h_stage = nullptr;
@@ -262,11 +263,39 @@ static int reorder_envs(gsr_handle_t h, cudaStream_t st) {
   return GSR_OK;
 }
 
+// Warps per CTA of the full-warp (G = 32) step kernel when the caller does not fix it.  All warps of a CTA walk the phases
+// together, a CTA needs w x (workspace + mbarrier) + 1 KB of the SM's 228 KB and the 128-register kernel allows 16 warps per
+// SM, so w decides how many environments are resident (r = CTAs x w) and into how many waves the batch falls.  Measured on
+// B200 (profiles/README.md: Go2 w = 7 vs 8, grasp cluster w = 7 vs 11): a wave costs about 1 + 0.35 r / 16 (more resident
+// warps hide more latency but share the issue slots), and partial waves cost a whole one.
+static int auto_warps_per_cta(const gsr_handle_t h, size_t warp_bytes) {
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  int best_w = 1;
+  double best = 1e30;
+  for (int w = 1; w <= GSR_MAX_WARPS_PER_CTA; w++) {
+    const size_t cta = (size_t)w * (warp_bytes + 8);
+    if (cta > 227 * 1024) break;
+    int ctas = (int)((size_t)233472 / (cta + 1024));
+    if (ctas > 16 / w) ctas = 16 / w;
+    if (ctas < 1) continue;
+    const int r = ctas * w;
+    const long long per_wave = (long long)n_sm * r;
+    const double waves = (double)((h->B + per_wave - 1) / per_wave);
+    // ties go to the CTA size closest to 8 warps: 1-2 warp CTAs drift apart in the 20 k-instruction kernel (instruction cache)
+    const double cost = waves * (1.0 + 0.35 * r / 16.0) * (1.0 + 0.002 * (w > 8 ? w - 8 : 8 - w));
+    if (cost < best - 1e-9) { best = cost; best_w = w; }
+  }
+  return best_w;
+}
+
 static int group_launch(gsr_handle_t h, int which, cudaStream_t st, const uint8_t* mask, int clear_ext) {
   if (h->group == 1 && which == K_STEP) return lane_launch(h, st, clear_ext);
   const int G = h->group == 1 ? 8 : h->group, EPW = 32 / G;  // the (cold) forward-kinematics paths of a lane model use the group kernel
   const size_t warp_bytes = (size_t)EPW * h->sl.env_words * sizeof(float);
-  int warps = h->warps_per_cta > 0 ? h->warps_per_cta : (G == 32 ? 7 : 1);  // measured on B200 (profiles/README.md, r1c sweeps)
+  if (h->auto_warps == 0) h->auto_warps = G == 32 ? auto_warps_per_cta(h, warp_bytes) : 1;  // G < 32: 1-warp CTAs measured best
+  int warps = h->warps_per_cta > 0 ? h->warps_per_cta : h->auto_warps;
   if (warps > GSR_MAX_WARPS_PER_CTA) warps = GSR_MAX_WARPS_PER_CTA;
   while (warps > 1 && warps * (warp_bytes + 8) > 224 * 1024) warps--;  // one big CTA per SM, its warps in phase lockstep
   const int envs_per_cta = warps * EPW;

@@ -5,13 +5,13 @@ import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import genesis_b200 as gs
 from genesis_b200 import _lib
-from genesis_b200.bench_scenes import make_go2, make_franka
+from genesis_b200.bench_scenes import make_go2, make_franka, make_franka_grasp
 gs.init(backend=gs.gpu)
 which = sys.argv[1] if len(sys.argv) > 1 else "go2"
-n = int(sys.argv[2]) if len(sys.argv) > 2 else (4096 if which == "go2" else 30000)
-scene, robot = (make_go2(n) if which == "go2" else make_franka(n, randomized=True))
+n = int(sys.argv[2]) if len(sys.argv) > 2 else {"go2": 4096, "grasp": 8192}.get(which, 30000)
+scene = {"go2": lambda: make_go2(n), "grasp": lambda: make_franka_grasp(n)}.get(which, lambda: make_franka(n, randomized=True))()[0]
 s = scene.rigid_solver
-for _ in range(400):
+for _ in range(int(os.environ.get("TRACE_WARMUP", 400))):
     scene.step()
 L = _lib.lib()
 _lib.check(s._handle, L.gsr_debug_trace(s._handle, 1))
