@@ -7,10 +7,15 @@ import os
 import numpy as np
 import pytest
 
-from helpers import gs, make_franka, make_go2, oracle_for, host_model
+from helpers import gs, make_franka, make_go2, make_weld, oracle_for, host_model
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = {"franka_random": (make_franka, 1e-4, 1e-3), "go2_random": (make_go2, 1e-3, 2e-2)}
+# name: (scene factory, factory kwargs, |dqpos| tolerance, |dqvel| tolerance)
+CASES = {"franka_random": (make_franka, {}, 1e-4, 1e-3), "go2_random": (make_go2, {}, 1e-3, 2e-2),
+         # (the capsule scene is left out on purpose: a sphere balanced on a capsule amplifies fp32 rounding to centimetres in
+         # 20 steps, so fp64 vectors cannot pin an fp32 path there; it is covered against the fp32 oracle instead)
+         "weld": (make_weld, {}, 1e-4, 1e-3),
+         "go2_noslip": (make_go2, dict(noslip_iterations=5), 1e-3, 2e-2)}
 
 
 def _load(name):
@@ -20,9 +25,9 @@ def _load(name):
 @pytest.mark.parametrize("name", sorted(CASES))
 @pytest.mark.parametrize("double", [True, False], ids=["f64", "f32"])
 def test_oracle_reproduces_golden(name, double):
-    make, tq, tv = CASES[name]
+    make, kw, tq, tv = CASES[name]
     g = _load(name)
-    scene, solver, model = host_model(make)
+    scene, solver, model = host_model(make, **kw)
     B = g["init_qpos"].shape[0]
     orc = oracle_for(solver, model, B, double=double)
     for k in ("qpos", "vel", "ctrl_pos", "ctrl_mode"):
@@ -44,14 +49,14 @@ def test_oracle_reproduces_golden(name, double):
 def test_cuda_reproduces_golden(name):
     import torch
 
-    make, tq, tv = CASES[name]
+    make, kw, tq, tv = CASES[name]
     g = _load(name)
     B = g["init_qpos"].shape[0]
-    scene, robot = make(B)
+    scene = make(B, **kw)[0]
     s = scene.rigid_solver
     dev = s.device
-    robot.set_qpos(torch.tensor(g["init_qpos"], dtype=torch.float32, device=dev))
-    robot.set_dofs_velocity(torch.tensor(g["init_vel"], dtype=torch.float32, device=dev))
+    s.set_qpos(torch.tensor(g["init_qpos"], dtype=torch.float32, device=dev), skip_forward=True)
+    s.set_dofs_velocity(torch.tensor(g["init_vel"], dtype=torch.float32, device=dev))
     s.field("ctrl_pos")[:] = torch.tensor(g["init_ctrl_pos"], dtype=torch.float32, device=dev)
     s.field("ctrl_mode")[:] = torch.tensor(g["init_ctrl_mode"], dtype=torch.int32, device=dev)
     done = 0

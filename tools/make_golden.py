@@ -36,9 +36,30 @@ def go2_case(B=8, K=80, seed=1):
     return scene, m, dict(qpos=q, vel=np.zeros((B, 18)), ctrl_pos=ctrl, ctrl_mode=mode), K
 
 
+def default_state_case(make, K, **kw):
+    """Scenes that start from the model's own qpos0 with zero velocity and the build-time control state."""
+    def case():
+        scene = make(0, build=False, **kw)[0]
+        m = scene.rigid_solver.build_model()
+        B = 4
+        q = np.tile(np.asarray(m.qpos0, dtype=np.float64), (B, 1))
+        mode = np.full((B, m.n_dofs), int(gs.CTRL_MODE.FORCE))
+        return scene, m, dict(qpos=q, vel=np.zeros((B, m.n_dofs)), ctrl_pos=np.zeros((B, m.n_dofs)), ctrl_mode=mode), K
+    return case
+
+
+def go2_noslip_case():
+    scene, m, init, K = go2_case(B=4, K=60, seed=2)
+    scene, _ = make_go2(0, build=False, noslip_iterations=5)
+    return scene, scene.rigid_solver.build_model(), init, K
+
+
 if __name__ == "__main__":
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    from helpers import make_weld
+
     os.makedirs(OUT, exist_ok=True)
-    for name, case in (("franka_random", franka_case), ("go2_random", go2_case)):
+    for name, case in (("franka_random", franka_case), ("go2_random", go2_case), ("weld", default_state_case(make_weld, 100)), ("go2_noslip", go2_noslip_case)):
         scene, m, init, K = case()
         B = init["qpos"].shape[0]
         orc = Oracle(m, B, double=True, options=scene.rigid_solver.model_options())
