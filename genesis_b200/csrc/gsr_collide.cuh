@@ -12,6 +12,7 @@
 //                 against the others and writes it to its final slot of the CONTACT record (and of the on-chip copy).
 #pragma once
 #include "gsr_group.cuh"
+#include "gsr_epa.cuh"
 
 // SF:138-180 support point of a mesh-backed geom from its 180x180 direction table (L2 resident, read-only path)
 template <int G>
@@ -79,6 +80,12 @@ __device__ __forceinline__ void mpr_support(const Ctx<G>& C, const PairPose& P, 
   v2 = dev_support(C, -d, P.gb, P.pb, P.qb);
   v = v1 - v2;
 }
+template <int G>
+struct GroupSupport {  // support functor of the pair for gsr_epa.cuh
+  const Ctx<G>& C;
+  const PairPose& P;
+  __device__ __forceinline__ void operator()(f3 d, f3& v, f3& v1, f3& v2) const { mpr_support(C, P, d, v, v1, v2); }
+};
 __device__ __forceinline__ f3 portal_dir(const Simplex& s) { return normalized(cross(s.v[2] - s.v[1], s.v[3] - s.v[1])); }
 __device__ __forceinline__ bool reach_tolerance(const Simplex& s, f3 v, f3 dir) {  // MPR:134-143
   const float dv4 = dot(v, dir);
@@ -138,7 +145,8 @@ __device__ int discover_portal(const Ctx<G>& C, Simplex& s, const PairPose& P, f
 }
 // MPR:601-819 func_mpr_contact (centre guess + portal discovery/refinement + penetration)
 template <int G>
-__device__ __noinline__ void dev_mpr_contact(const Ctx<G>& C, const PairPose& P, f3 normal_ws, bool& is_col, f3& normal, float& pen, f3& pos) {
+__device__ __noinline__ void dev_mpr_contact(const Ctx<G>& C, const PairPose& P, f3 normal_ws, bool& is_col, f3& normal, float& pen, f3& pos,
+                                             Simplex& s, bool& tetra) {
   const float CE = c_m.ccd_eps;
   f3 ca = transform(f3(GM(g_center[P.ga][0]), GM(g_center[P.ga][1]), GM(g_center[P.ga][2])), P.pa, P.qa);
   f3 cb = transform(f3(GM(g_center[P.gb][0]), GM(g_center[P.gb][1]), GM(g_center[P.gb][2])), P.pb, P.qb);
@@ -163,9 +171,9 @@ __device__ __noinline__ void dev_mpr_contact(const Ctx<G>& C, const PairPose& P,
       }
     }
   }
-  Simplex s;
   int res = discover_portal(C, s, P, ca, cb);
   is_col = false; pos = f3(); normal = f3(); pen = 0.f;
+  tetra = false;  // true when s ends as the interior point + final portal, a tetrahedron around the origin (EPA seed)
   if (res == 1) { is_col = true; normal = -normalized(s.v[0]); pos = (s.v1[1] + s.v2[1]) * 0.5f; }
   else if (res == 2) { is_col = true; pen = norm(s.v[1]); normal = -normalized(s.v[1]); pos = (s.v1[1] + s.v2[1]) * 0.5f; }
   else if (res == 0) {
@@ -192,6 +200,7 @@ __device__ __noinline__ void dev_mpr_contact(const Ctx<G>& C, const PairPose& P,
           const float sum = b1 + b2 + b3;
           const f3 p1 = s.v1[1] * b1 + s.v1[2] * b2 + s.v1[3] * b3, p2 = s.v2[1] * b1 + s.v2[2] * b2 + s.v2[3] * b3;
           pos = (p1 + p2) * (0.5f / sum);
+          tetra = true;
           break;
         }
         expand_portal(s, v, v1, v2);
@@ -260,8 +269,17 @@ __device__ __forceinline__ void dev_detect(const Ctx<G>& C, const PairDet& D, co
     const bool valid = (cvalid[D.p >> 5] >> (D.p & 31)) & 1;
     if (valid) normal_ws = ld3(C.cache, D.p);
     const bool guess = fabsf(normal_ws.x) > EPS || fabsf(normal_ws.y) > EPS || fabsf(normal_ws.z) > EPS;
-    dev_mpr_contact(C, P, normal_ws, is_col, normal, pen, cpos);
-    if (i_det == 0 && !is_col && guess) dev_mpr_contact(C, P, f3(), is_col, normal, pen, cpos);
+    Simplex sx;
+    bool tetra = false, guess_used = guess;
+    dev_mpr_contact(C, P, normal_ws, is_col, normal, pen, cpos, sx, tetra);
+    if (i_det == 0 && !is_col && guess) { dev_mpr_contact(C, P, f3(), is_col, normal, pen, cpos, sx, tetra); guess_used = false; }
+    // NP:726-733: MPR's answer is replaced by the exact one when the overlap is large or no direction was cached
+    if (c_m.gjk_fallback && is_col && tetra && pen > D.tolerance && (!guess_used || c_m.mc_tolerance * pen >= 0.25f * D.tolerance)) {
+      const GroupSupport<G> sup{C, P};
+      f3 n2, c2;
+      float p2 = 0.f;
+      if (epa_penetration(sx.v, sx.v1, sx.v2, sup, n2, p2, c2)) { normal = n2; pen = p2; cpos = c2; is_col = p2 > 0.f; }
+    }
   }
 }
 
@@ -401,6 +419,7 @@ __device__ int narrow_batch(const Ctx<G>& C, const int* queue, int n_batch, int 
     T.ga = SHF(D.ga); T.gb = SHF(D.gb); T.ta = SHF(D.ta); T.tb = SHF(D.tb); T.p = SHF(D.p);
     T.pa0 = SHF3(D.pa0); T.pb0 = SHF3(D.pb0); T.qa0 = SHF4(D.qa0); T.qb0 = SHF4(D.qb0);
     T.normal_0 = SHF3(D.normal_0); T.cpos_0 = SHF3(D.cpos_0); T.axis_0 = SHF3(D.axis_0); T.axis_1 = SHF3(D.axis_1);
+    T.tolerance = SHF(D.tolerance);
 #undef SHF4
 #undef SHF3
 #undef SHF

@@ -18,6 +18,7 @@
 // infrastructure; libgsrigid.so only contains the device kernel.
 #pragma once
 #include "gsr_group.cuh"
+#include "gsr_epa.cuh"
 
 #ifdef __CUDA_ARCH__
 #define GSR_LS 33
@@ -573,6 +574,11 @@ LHD __forceinline__ void lane_mpr_support(const LaneCtx& C, const LPairPose& P, 
   v2 = lane_support(C, -d, P.gb, P.pb, P.qb);
   v = v1 - v2;
 }
+struct LaneSupport {  // support functor of the pair for gsr_epa.cuh
+  const LaneCtx& C;
+  const LPairPose& P;
+  LHD __forceinline__ void operator()(f3 d, f3& v, f3& v1, f3& v2) const { lane_mpr_support(C, P, d, v, v1, v2); }
+};
 LHD __forceinline__ f3 lportal_dir(const LSimplex& s) { return normalized(cross(s.v[2] - s.v[1], s.v[3] - s.v[1])); }
 LHD __forceinline__ bool lreach_tolerance(const LSimplex& s, f3 v, f3 dir) {  // MPR:134-143
   const float dv4 = dot(v, dir);
@@ -630,7 +636,8 @@ LHD __noinline__ int lane_discover_portal(const LaneCtx& C, LSimplex& s, const L
   }
 }
 // MPR:601-819 func_mpr_contact (centre guess + portal discovery / refinement + penetration)
-LHD __noinline__ void lane_mpr_contact(const LaneCtx& C, const LPairPose& P, f3 normal_ws, bool& is_col, f3& normal, float& pen, f3& pos) {
+LHD __noinline__ void lane_mpr_contact(const LaneCtx& C, const LPairPose& P, f3 normal_ws, bool& is_col, f3& normal, float& pen, f3& pos,
+                                       LSimplex& s, bool& tetra) {
   const float CE = CM(ccd_eps);
   f3 ca = transform(f3(LG(g_center[P.ga][0]), LG(g_center[P.ga][1]), LG(g_center[P.ga][2])), P.pa, P.qa);
   f3 cb = transform(f3(LG(g_center[P.gb][0]), LG(g_center[P.gb][1]), LG(g_center[P.gb][2])), P.pb, P.qb);
@@ -655,9 +662,9 @@ LHD __noinline__ void lane_mpr_contact(const LaneCtx& C, const LPairPose& P, f3 
       }
     }
   }
-  LSimplex s;
   int res = lane_discover_portal(C, s, P, ca, cb);
   is_col = false; pos = f3(); normal = f3(); pen = 0.f;
+  tetra = false;  // true when s ends as the interior point + final portal, a tetrahedron around the origin (EPA seed)
   if (res == 1) { is_col = true; normal = -normalized(s.v[0]); pos = (s.v1[1] + s.v2[1]) * 0.5f; }
   else if (res == 2) { is_col = true; pen = norm(s.v[1]); normal = -normalized(s.v[1]); pos = (s.v1[1] + s.v2[1]) * 0.5f; }
   else if (res == 0) {
@@ -684,6 +691,7 @@ LHD __noinline__ void lane_mpr_contact(const LaneCtx& C, const LPairPose& P, f3 
           const float sum = b1 + b2 + b3;
           const f3 p1 = s.v1[1] * b1 + s.v1[2] * b2 + s.v1[3] * b3, p2 = s.v2[1] * b1 + s.v2[2] * b2 + s.v2[3] * b3;
           pos = (p1 + p2) * (0.5f / sum);
+          tetra = true;
           break;
         }
         lexpand_portal(s, v, v1, v2);
@@ -755,8 +763,17 @@ LHD __noinline__ void lane_convex_convex(const LaneCtx& C, LContacts& out, int g
       const bool valid = (cvalid[i_pair >> 5] >> (i_pair & 31)) & 1;
       if (valid) normal_ws = gld3(C.cache, i_pair);
       const bool guess = fabsf(normal_ws.x) > EPS || fabsf(normal_ws.y) > EPS || fabsf(normal_ws.z) > EPS;
-      lane_mpr_contact(C, P, normal_ws, is_col, normal, pen, cpos);
-      if (i_det == 0 && !is_col && guess) lane_mpr_contact(C, P, f3(), is_col, normal, pen, cpos);
+      LSimplex sx;
+      bool tetra = false, guess_used = guess;
+      lane_mpr_contact(C, P, normal_ws, is_col, normal, pen, cpos, sx, tetra);
+      if (i_det == 0 && !is_col && guess) { lane_mpr_contact(C, P, f3(), is_col, normal, pen, cpos, sx, tetra); guess_used = false; }
+      // NP:726-733: MPR's answer is replaced by the exact one when the overlap is large or no direction was cached
+      if (CM(gjk_fallback) && is_col && tetra && pen > tolerance && (!guess_used || CM(mc_tolerance) * pen >= 0.25f * tolerance)) {
+        const LaneSupport sup{C, P};
+        f3 n2, c2;
+        float p2 = 0.f;
+        if (epa_penetration(sx.v, sx.v1, sx.v2, sup, n2, p2, c2)) { normal = n2; pen = p2; cpos = c2; is_col = p2 > 0.f; }
+      }
     }
     if (i_det == 0) {
       is_col_0 = is_col; normal_0 = normal; cpos_0 = cpos;

@@ -106,6 +106,7 @@ static void load_cfg(const RawModel& r, Config& c) {
   c.enable_collision = (int)S("cfg_enable_collision", 1); c.enable_joint_limit = (int)S("cfg_enable_joint_limit", 1);
   c.enable_multi_contact = (int)S("cfg_enable_multi_contact", 1); c.sort_contacts = (int)S("cfg_sort_contacts", 1);
   c.eps = S("cfg_eps", c.eps);
+  c.gjk_fallback = (int)S("cfg_gjk_fallback", 1);
   c.noslip_iterations = (int)S("cfg_noslip_iterations", 0); c.noslip_tolerance = S("cfg_noslip_tolerance", c.noslip_tolerance);
 }
 

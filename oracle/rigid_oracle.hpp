@@ -113,6 +113,7 @@ struct Config {
   double mc_perturbation = 1e-2, mc_tolerance = 1e-2, mpr_to_gjk_overlap_ratio = 0.25;  // collider.py:85-87
   double ccd_eps = 1e-9, ccd_tolerance = 1e-6;  // mpr.py:13-19
   int ccd_iterations = 50;
+  int gjk_fallback = 1;       // exact-penetration fallback after MPR (NP:726-733); 0 keeps MPR's answer (A/B tests)
   int noslip_iterations = 0;  // options/solvers.py:506-507
   double noslip_tolerance = 1e-6;
 };
@@ -840,18 +841,118 @@ struct Oracle {
     }
   }
   // MPR:686-819 func_mpr_contact
-  void mpr_contact(int ga, int gb, const V& normal_ws, const V& pa, const Q& qa, const V& pb, const Q& qb, bool& is_col, V& normal, T& pen, V& pos) {
+  void mpr_contact(int ga, int gb, const V& normal_ws, const V& pa, const Q& qa, const V& pb, const Q& qb, bool& is_col, V& normal, T& pen, V& pos,
+                   Simplex& last_simplex, bool& last_simplex_valid) {
     V ca, cb;
     guess_centers(ga, gb, pa, qa, pb, qb, normal_ws, ca, cb);
     Simplex s;
     int res = discover_portal(s, ga, gb, ca, cb, pa, qa, pb, qb);
     is_col = false; pos = V(); normal = V(); pen = 0;
+    last_simplex_valid = false;
     if (res == 1) { is_col = true; pen = 0; normal = -s.v[0].normalized(); pos = (s.v1[1] + s.v2[1]) * T(0.5); }
     else if (res == 2) { is_col = true; pen = s.v[1].norm(); normal = -s.v[1].normalized(); pos = (s.v1[1] + s.v2[1]) * T(0.5); }
     else if (res == 0) {
       res = refine_portal(s, ga, gb, pa, qa, pb, qb);
-      if (res >= 0) find_penetration(s, ga, gb, pa, qa, pb, qb, is_col, normal, pen, pos);
+      if (res >= 0) {
+        find_penetration(s, ga, gb, pa, qa, pb, qb, is_col, normal, pen, pos);
+        last_simplex = s; last_simplex_valid = is_col;  // v[0] interior point + final portal: a tetrahedron around the origin
+      }
     }
+  }
+
+  // ---- a17: exact penetration for deep / un-cached convex pairs (NP:726-733 decides when; gjk.py:170-446 func_gjk_contact,
+  // epa.py:970-1183 func_safe_epa define the result: witness points w1, w2 of the minimum-translation face of the Minkowski
+  // difference, pos = (w1 + w2) / 2, normal = (w2 - w1) / |w2 - w1|, penetration = face distance).  The reference seeds EPA
+  // with a GJK tetrahedron; this restatement seeds it with the tetrahedron MPR has just built around the origin (interior
+  // point + final portal), which the expanding polytope algorithm (van den Bergen 2001) accepts as well: the minimum over the
+  // boundary of a convex set does not depend on the seed.  Limits as in gjk.py:53-56, 89-90 (50 iterations, tolerance 1e-6).
+  struct EpaFace { int a, b, c; V n; T d; bool alive; };
+  bool epa_make_face(const std::vector<V>& pv, const V& inside, int a, int b, int c, EpaFace& f) {
+    V n = (pv[b] - pv[a]).cross(pv[c] - pv[a]);
+    T len = n.norm();
+    if (!(len > T(1e-20))) return false;
+    n = n / len;
+    if (n.dot(inside - pv[a]) > 0) { std::swap(b, c); n = -n; }
+    f.a = a; f.b = b; f.c = c; f.n = n; f.d = n.dot(pv[a]); f.alive = true;
+    return true;
+  }
+  bool epa_penetration(const Simplex& s0, int ga, int gb, const V& pa, const Q& qa, const V& pb, const Q& qb, V& normal, T& pen, V& pos) {
+    const int MAXV = 40, MAXF = 128, MAXIT = 50;
+    const T TOL = T(1e-6);
+    std::vector<V> pv, p1, p2;
+    for (int i = 0; i < 4; i++) { pv.push_back(s0.v[i]); p1.push_back(s0.v1[i]); p2.push_back(s0.v2[i]); }
+    V inside = (pv[0] + pv[1] + pv[2] + pv[3]) * T(0.25);
+    std::vector<EpaFace> faces;
+    const int tri[4][3] = {{0, 1, 2}, {0, 2, 3}, {0, 3, 1}, {1, 3, 2}};
+    for (int i = 0; i < 4; i++) {
+      EpaFace f;
+      if (!epa_make_face(pv, inside, tri[i][0], tri[i][1], tri[i][2], f)) return false;
+      if (f.d < -TOL) return false;  // the origin is not inside the seed
+      faces.push_back(f);
+    }
+    int best = -1;
+    for (int it = 0; it < MAXIT; it++) {
+      best = -1;
+      for (int i = 0; i < (int)faces.size(); i++)
+        if (faces[i].alive && (best < 0 || faces[i].d < faces[best].d)) best = i;
+      if (best < 0) return false;
+      const EpaFace fb = faces[best];
+      V w, w1, w2;
+      compute_support(fb.n, ga, gb, pa, qa, pb, qb, w, w1, w2);
+      if (w.dot(fb.n) - fb.d < TOL) break;
+      bool dup = false;
+      for (size_t i = 0; i < pv.size(); i++)
+        if ((pv[i] - w).dot(pv[i] - w) < T(1e-16)) dup = true;
+      if (dup || (int)pv.size() >= MAXV) break;
+      const int iw = (int)pv.size();
+      pv.push_back(w); p1.push_back(w1); p2.push_back(w2);
+      // faces seen from w go away; the boundary of the hole (edges used by exactly one removed face) is the horizon
+      const size_t MAXE = 48;
+      std::vector<std::pair<int, int>> edges;
+      bool overflow = false;
+      for (auto& f : faces) {
+        if (!f.alive || !(f.n.dot(w) - f.d > T(1e-12))) continue;
+        f.alive = false;
+        const int e[3][2] = {{f.a, f.b}, {f.b, f.c}, {f.c, f.a}};
+        for (int k = 0; k < 3; k++) {
+          bool found = false;
+          for (size_t q = 0; q < edges.size(); q++)
+            if (edges[q].first == e[k][1] && edges[q].second == e[k][0]) { edges[q] = edges.back(); edges.pop_back(); found = true; break; }
+          if (!found) {
+            if (edges.size() >= MAXE) { overflow = true; break; }
+            edges.push_back({e[k][0], e[k][1]});
+          }
+        }
+        if (overflow) break;
+      }
+      if (overflow || edges.size() < 3 || (int)faces.size() + (int)edges.size() > MAXF) { faces[best].alive = true; break; }
+      bool ok = true;
+      for (auto& ed : edges) {
+        EpaFace f;
+        if (!epa_make_face(pv, inside, ed.first, ed.second, iw, f)) { ok = false; break; }
+        faces.push_back(f);
+      }
+      if (!ok) return false;
+    }
+    if (best < 0 || !faces[best].alive) {  // the loop ended right after a removal: take the nearest surviving face
+      best = -1;
+      for (int i = 0; i < (int)faces.size(); i++)
+        if (faces[i].alive && (best < 0 || faces[i].d < faces[best].d)) best = i;
+      if (best < 0) return false;
+    }
+    const EpaFace& f = faces[best];
+    const V p = f.n * f.d, e0 = pv[f.b] - pv[f.a], e1 = pv[f.c] - pv[f.a], e2 = p - pv[f.a];
+    const T d00 = e0.dot(e0), d01 = e0.dot(e1), d11 = e1.dot(e1), d20 = e2.dot(e0), d21 = e2.dot(e1);
+    const T den = d00 * d11 - d01 * d01;
+    if (!(std::abs(den) > T(1e-30))) return false;
+    const T lb = (d11 * d20 - d01 * d21) / den, lc = (d00 * d21 - d01 * d20) / den, la = T(1) - lb - lc;
+    const V w1 = p1[f.a] * la + p1[f.b] * lb + p1[f.c] * lc, w2 = p2[f.a] * la + p2[f.b] * lb + p2[f.c] * lc;
+    const V dlt = w2 - w1;
+    const T len = dlt.norm();
+    normal = len > T(1e-10) ? dlt / len : -f.n;
+    pen = f.d;
+    pos = (w1 + w2) * T(0.5);
+    return true;
   }
 
   // CT:181-222 func_add_contact
@@ -970,7 +1071,7 @@ struct Oracle {
     }
     normal = normal * dir;
   }
-  // NP:519-970 func_convex_convex_contact (MPR ccd, no GJK fallback -- see DESIGN.md "gaps")
+  // NP:519-970 func_convex_convex_contact (MPR ccd with the exact-penetration fallback of NP:726-733)
   void convex_convex_contact(Env<T>& e, int ga, int gb) {
     if (m.geoms_type[ga] == GEOM_PLANE && m.geoms_type[gb] == GEOM_BOX) return;
     bool multi_contact = cfg.enable_multi_contact && m.geoms_type[ga] != GEOM_SPHERE && m.geoms_type[ga] != GEOM_ELLIPSOID &&
@@ -1011,9 +1112,20 @@ struct Oracle {
           V normal_ws = e.contact_cache_normal[i_pair];
           bool guess = std::abs(normal_ws.x) > EPS || std::abs(normal_ws.y) > EPS || std::abs(normal_ws.z) > EPS;
           bool updated = false;
+          Simplex last_simplex;
+          bool last_simplex_valid = false;
           for (int i_mpr = 0; i_mpr < 2; i_mpr++) {
             if (i_mpr == 1 && i_det == 0 && !is_col && guess) { normal_ws = V(); guess = false; updated = false; }
-            if (!updated) { mpr_contact(ga, gb, normal_ws, ga_pos, ga_quat, gb_pos, gb_quat, is_col, normal, pen, cpos); updated = true; }
+            if (!updated) { mpr_contact(ga, gb, normal_ws, ga_pos, ga_quat, gb_pos, gb_quat, is_col, normal, pen, cpos, last_simplex, last_simplex_valid); updated = true; }
+          }
+          // NP:726-733: MPR's answer is replaced by the exact one when the overlap is large or no direction was cached
+          if (cfg.gjk_fallback && is_col && pen > tolerance && last_simplex_valid) {
+            const bool prefer_gjk = !guess || (T(cfg.mc_tolerance) * pen >= T(cfg.mpr_to_gjk_overlap_ratio) * tolerance);
+            V n2, c2;
+            T p2 = 0;
+            if (prefer_gjk && epa_penetration(last_simplex, ga, gb, ga_pos, ga_quat, gb_pos, gb_quat, n2, p2, c2)) {
+              normal = n2; pen = p2; cpos = c2; is_col = p2 > 0;
+            }
           }
         }
       }

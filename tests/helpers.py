@@ -118,3 +118,26 @@ def make_weld(n_envs, build=True, **rigid_kwargs):
     if build:
         scene.build(n_envs=n_envs)
     return scene, ent
+
+# deeply interpenetrating convex pairs (box-box, box-capsule, box-cylinder mesh): the exact-penetration fallback after MPR
+# (narrowphase.py:726-733, gjk.py / epa.py) decides the first contacts
+JUMBLE_XML = """
+<mujoco model="jumble">
+  <option gravity="0 0 -9.81"/>
+  <worldbody>
+    <geom name="floor" type="plane" size="5 5 0.1"/>
+    <body name="a" pos="0 0 0.3"><freejoint/><geom type="box" size="0.05 0.05 0.05"/></body>
+    <body name="b" pos="0.03 0.06 0.32" euler="10 25 40"><freejoint/><geom type="box" size="0.03 0.06 0.02"/></body>
+    <body name="c" pos="-0.04 -0.03 0.36" euler="70 -20 15"><freejoint/><geom type="capsule" size="0.03 0.08"/></body>
+    <body name="d" pos="0.02 -0.05 0.24" euler="-35 50 5"><freejoint/><geom type="cylinder" size="0.03 0.05"/></body>
+  </worldbody>
+</mujoco>
+"""
+
+
+def make_jumble(n_envs, build=True, **rigid_kwargs):
+    scene = gs.Scene(rigid_options=gs.options.RigidOptions(dt=0.01, **rigid_kwargs))
+    ent = scene.add_entity(gs.morphs.MJCF(file=write_tmp(JUMBLE_XML, ".xml")))
+    if build:
+        scene.build(n_envs=n_envs)
+    return scene, ent

@@ -15,7 +15,7 @@ import pytest
 import torch
 
 from conftest import TOL_SINGLE
-from helpers import gs, make_capsules, make_weld, make_franka, make_franka_grasp, make_go2, oracle_for, scene_from_morphs
+from helpers import gs, make_capsules, make_jumble, make_weld, make_franka, make_franka_grasp, make_go2, oracle_for, scene_from_morphs
 
 pytestmark = pytest.mark.gpu
 
@@ -229,6 +229,35 @@ def test_weld_equality():
     assert np.abs(gpu_field(scene, "qpos") - orc.qpos()).max() <= TRAJ_QPOS_FREE
     assert np.abs(gpu_field(scene, "vel") - orc.vel()).max() <= TRAJ_QVEL_FREE
     assert (scene.rigid_solver.field("n_constraints_equality")[:, 0] == 12).all()
+
+
+def test_exact_penetration_fallback_epa():
+    """Row a17: deeply interpenetrating box / capsule / cylinder-mesh pairs; the EPA fallback after MPR (gsr_epa.cuh, trigger of
+    narrowphase.py:726-733) decides the first contacts.  Contact records against the oracle's own implementation, and against
+    the oracle with the fallback switched off to show that it is what ran."""
+    B = 8
+    scene, _ = make_jumble(B)
+    orc = mirror_oracle(scene)
+    ref = mirror_oracle(scene, gjk_fallback=0)
+    scene.step()
+    orc.step(1)
+    ref.step(1)
+    s = scene.rigid_solver
+    n = s.field("n_contacts")[:, 0].cpu().numpy()
+    assert (n == orc.get("n_contacts", 1)[:, 0]).all() and n.min() >= 4
+    for b in range(B):
+        c = orc.contacts(b)
+        k = int(n[b])
+        assert (s.field("contact_geom_a")[b, :k].cpu().numpy() == c["geom_a"]).all()
+        np.testing.assert_allclose(s.field("contact_penetration")[b, :k].cpu().numpy(), c["penetration"], atol=1e-4)
+        np.testing.assert_allclose(s.field("contact_normal")[b, :k].cpu().numpy(), c["normal"], atol=1e-3)
+        np.testing.assert_allclose(s.field("contact_pos")[b, :k].cpu().numpy(), c["position"], atol=1e-4)
+    c1, c0 = orc.contacts(0), ref.contacts(0)
+    assert len(c1["penetration"]) != len(c0["penetration"]) or np.abs(c1["penetration"] - c0["penetration"]).max() > 1e-4
+    for _ in range(19):
+        scene.step()
+    orc.step(19)
+    assert np.abs(gpu_field(scene, "qpos") - orc.qpos()).max() <= TRAJ_QPOS_FREE
 
 
 def test_dynamic_weld_constraint_api():

@@ -303,3 +303,25 @@ def test_lane_dynamic_weld_constraint():
     assert np.abs(emu.rows("qpos") - orc.qpos()).max() <= 1e-4 and np.abs(emu.rows("vel") - orc.vel()).max() <= 1e-3
     d1 = np.linalg.norm(emu.field("links_pos")[0, l1] - emu.field("links_pos")[0, l2])
     assert abs(d1 - d0) < 5e-3  # the welded boxes keep their distance while tumbling (soft constraint: millimetres of give)
+
+
+def test_lane_exact_penetration_fallback():
+    """Deeply interpenetrating convex pairs: the EPA fallback after MPR (gsr_epa.cuh) against the oracle's own implementation."""
+    from helpers import make_jumble
+
+    B = 2
+    m, orc, emu = pair(make_jumble, B, lambda m, B: {})
+    scene, solver, _ = host_model(make_jumble)
+    ref = oracle_for(solver, m, B, threads=2, gjk_fallback=0)
+    orc.step(1)
+    emu.step(1)
+    ref.step(1)
+    contacts_equal(orc, emu, B)
+    # the fallback is what decided these contacts: MPR alone reports different ones
+    c1, c0 = orc.contacts(0), ref.contacts(0)
+    assert len(c1["penetration"]) != len(c0["penetration"]) or np.abs(c1["penetration"] - c0["penetration"]).max() > 1e-4
+    # the bodies fly apart at > 10 m/s; compare until they land on each other again (later the fp32 paths bifurcate, as the
+    # fp32 and fp64 oracles do between themselves)
+    orc.step(19)
+    emu.step(19)
+    assert np.abs(emu.rows("qpos") - orc.qpos()).max() <= 1e-4 and np.abs(emu.rows("vel") - orc.vel()).max() <= 2e-2

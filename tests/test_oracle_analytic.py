@@ -337,3 +337,41 @@ def test_mass_shift_changes_free_fall_contact_force_not_acceleration():
     orc2.set("com_shift", cs.reshape(-1))
     orc2.step(1)
     assert orc2.get("root_COM", (m.n_links, 3), 0)[1, 0] == pytest.approx(0.02, abs=1e-6)
+
+
+def test_exact_penetration_fallback_minimum_translation():
+    """Row a17 (narrowphase.py:726-733 + gjk.py:420-446 result convention): for a deep overlap the contact of the pair is the
+    minimum-translation one.  Two axis-aligned 0.1 cubes offset by (0.03, 0.06, 0.02) overlap by 0.07 / 0.04 / 0.08 along
+    x / y / z: penetration 0.04 along y, normal from B to A = (0, -1, 0).  On random deep overlaps the fallback never reports
+    a larger penetration than MPR (it is the minimum over all directions) and reports a smaller one for some."""
+    xml = """
+    <mujoco><option gravity="0 0 0"/><worldbody>
+      <body name="a" pos="0 0 0"><freejoint/><geom type="box" size="0.05 0.05 0.05"/></body>
+      <body name="b" pos="{p}" euler="{e}"><freejoint/><geom type="{t}" size="{s}"/></body>
+    </worldbody></mujoco>"""
+
+    def contact0(p, e, t, s, fallback):
+        scene, _ = scene_from_morphs([gs.morphs.MJCF(file=write_tmp(xml.format(p=p, e=e, t=t, s=s), ".xml"))], dt=0.01)
+        solver = scene.rigid_solver
+        orc = oracle_for(solver, solver.build_model(), 1, double=True, gjk_fallback=fallback)
+        orc.step(1)
+        c = orc.contacts(0)
+        return (c["penetration"][0], c["normal"][0], c["position"][0]) if len(c["penetration"]) else None
+
+    pen, nrm, pos = contact0("0.03 0.06 0.02", "0 0 0", "box", "0.05 0.05 0.05", 1)
+    assert pen == pytest.approx(0.04, abs=1e-6)
+    np.testing.assert_allclose(nrm, (0.0, -1.0, 0.0), atol=1e-6)
+    assert pos[1] == pytest.approx(0.03, abs=1e-6)  # midway between the two overlapping faces (y = 0.05 and y = 0.01)
+    rng = np.random.default_rng(0)
+    smaller = 0
+    for trial in range(12):
+        t, s = [("capsule", "0.03 0.08"), ("box", "0.03 0.06 0.02"), ("cylinder", "0.03 0.05")][trial % 3]
+        p = "%f %f %f" % tuple(rng.uniform(-0.07, 0.07, 3))
+        e = "%f %f %f" % tuple(rng.uniform(-90, 90, 3))
+        a, b = contact0(p, e, t, s, 0), contact0(p, e, t, s, 1)
+        if a is None or b is None:
+            continue
+        assert b[0] <= a[0] + 1e-5, f"trial {trial}: exact {b[0]} > MPR {a[0]}"
+        assert abs(np.linalg.norm(b[1]) - 1.0) < 1e-6
+        smaller += b[0] < a[0] - 1e-4
+    assert smaller >= 3
