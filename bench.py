@@ -262,6 +262,7 @@ def main():
     vel_h = torch.empty((B, nD), dtype=torch.float32).pin_memory()
     ctrl_np, qpos_np, vel_np = ctrl_h.numpy(), qpos_h.numpy(), vel_h.numpy()
     Ke = max(10, min(K, 200))
+    staged0 = solver.kernel_launches().get("k_scatter", 0)
     for _ in range(3):
         solver.step_host(ctrl_np, qpos_np, vel_np)
     barrier()
@@ -274,7 +275,9 @@ def main():
     e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)))
     e2e = {"value": world * B * Ke / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": 4 * B * nD,
            "d2h_bytes_per_step": 4 * B * (nQ + nD), "steps": Ke, "ms_per_step": e2e_ms / Ke,
-           "api": "gsr_step_host (C ABI) via RigidSolver.step_host"}
+           "api": "gsr_step_host (C ABI) via RigidSolver.step_host",
+           "transfer": ("staged cudaMemcpyAsync + k_scatter / k_gather" if solver.kernel_launches().get("k_scatter", 0) > staged0 else
+                        "pinned host buffers read / written in place over PCIe by k_step (no staging launches)")}
     assert np.isfinite(qpos_np).all()
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload on the host cores

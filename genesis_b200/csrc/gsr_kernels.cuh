@@ -95,9 +95,18 @@ __device__ __forceinline__ void bulk_store_in(float* state, int B, float* smem, 
 template <int G>
 __device__ __forceinline__ void step_epilogue(const Ctx<G>& C, int clear_ext);
 
+// gsr_step_host: the step kernel itself reads this step's control targets from a dense (B, nD) device staging buffer and
+// writes the new qpos / vel to dense (B, n) buffers -- device staging, or the device-side aliases of the caller's PAGE-LOCKED
+// host buffers (posted PCIe writes that overlap the compute of the same launch) -- so no scatter / gather launch is left.
+struct HostIO {
+  const float* ctrl_pos;  // (B, nD) or null
+  float* qpos;            // (B, nQ) or null
+  float* vel;             // (B, nD) or null
+};
+
 template <int G>
 __global__ void __launch_bounds__(GSR_MAX_WARPS_PER_CTA * 32, 1) k_step(float* state, int B, const DevModel* gm, int clear_ext, const int* order,
-                                                                        unsigned long long* trace) {
+                                                                        unsigned long long* trace, HostIO io) {
   extern __shared__ __align__(16) float smem[];
   Ctx<G> C;
   // order[B] tells whether the measured costs are spread enough for the permutation to pay (uniform batches keep the
@@ -117,6 +126,11 @@ __global__ void __launch_bounds__(GSR_MAX_WARPS_PER_CTA * 32, 1) k_step(float* s
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)(blockDim.x >> 5) * (32 / G) * c_s.env_words);
   const bool warp_live = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (32 / G) < B;
   if (warp_live) bulk_load_in<G>(state, B, smem, bars + (threadIdx.x >> 5), order);
+  if (io.ctrl_pos && live) {  // this step's control targets from the dense staging buffer
+    const int nD = CM(nD);
+    const float* src = io.ctrl_pos + (size_t)C.env * nD;
+    for (int d = C.lane; d < nD; d += G) IN(ctrl_pos)[d] = __ldcs(src + d);
+  }
   PHASE_BARRIER();
   PHASE_BEGIN();
   if (live) phase_dynamics(C);
@@ -142,6 +156,11 @@ __global__ void __launch_bounds__(GSR_MAX_WARPS_PER_CTA * 32, 1) k_step(float* s
   if (live) step_epilogue(C, clear_ext);
   PHASE_END();
   if (live && C.lane == 0) reinterpret_cast<int*>(C.rec)[c_h.step_cost] = (int)min(busy, (long long)0x7fffffff);
+  if (live && (io.qpos || io.vel)) {  // results into dense staging or straight into the caller's pinned buffers (posted PCIe writes)
+    const int nQ = CM(nQ), nD = CM(nD);
+    if (io.qpos) for (int q = C.lane; q < nQ; q += G) __stcs(io.qpos + (size_t)C.env * nQ + q, IN(qpos)[q]);
+    if (io.vel) for (int d = C.lane; d < nD; d += G) __stcs(io.vel + (size_t)C.env * nD + d, IN(vel)[d]);
+  }
   __syncwarp();
   if (warp_live) bulk_store_in<G>(state, B, smem, order);
   if (trace && live && C.lane == 0) {

@@ -92,6 +92,10 @@ class RigidSolver:
             self.tuning["reorder_period"] = int(os.environ["GSR_REORDER_PERIOD"])
         if os.environ.get("GSR_WARPS"):
             self.tuning["warps_per_cta"] = int(os.environ["GSR_WARPS"])
+        if "GSR_HOST_IO" in os.environ:  # gsr_step_host: 0 staged + scatter / gather kernels, 1 fused device staging, 2 posted writes to pinned buffers
+            self.tuning["host_io"] = int(os.environ["GSR_HOST_IO"])
+        if "GSR_GJK_FALLBACK" in os.environ:  # A/B measurements only: 0 keeps MPR's answer for deep / un-cached pairs
+            self.tuning["gjk_fallback"] = int(os.environ["GSR_GJK_FALLBACK"])
         self.model = None
 
     # ------------------------------------------------------------------ build

@@ -141,3 +141,44 @@ def make_jumble(n_envs, build=True, **rigid_kwargs):
     if build:
         scene.build(n_envs=n_envs)
     return scene, ent
+
+# the reference's `box_box` fixture (tests/test_rigid_physics.py:82-97): two 0.4 m cubes over a plane
+BOX_BOX_XML = """
+<mujoco model="one_box">
+  <option timestep="0.01"/>
+  <default><geom contype="1" conaffinity="1" condim="3" friction="1. 0.5 0.5"/></default>
+  <worldbody>
+    <geom type="plane" name="floor" pos="0. 0. 0." size="40. 40. 40."/>
+    <body name="box1" pos="0. 0. 0.2"><geom type="box" size="0.2 0.2 0.2" pos="0. 0. 0."/><joint name="root1" type="free"/></body>
+    <body name="box2" pos="0. 0. 0.8"><geom type="box" size="0.2 0.2 0.2" pos="0. 0. 0."/><joint name="root2" type="free"/></body>
+  </worldbody>
+</mujoco>
+"""
+
+
+def make_box_box(n_envs, build=True, **rigid_kwargs):
+    scene = gs.Scene(rigid_options=gs.options.RigidOptions(dt=0.01, **rigid_kwargs))
+    ent = scene.add_entity(gs.morphs.MJCF(file=write_tmp(BOX_BOX_XML, ".xml")))
+    if build:
+        scene.build(n_envs=n_envs)
+    return scene, ent
+
+
+def box_box_qpos(n, seed=0):
+    """Initial states of the reference's test_box_box_dynamics (tests/test_rigid_physics.py:1038-1045): the lower cube at
+    rest, the upper one dropped from 0.65-0.75 m with a small tilt and an arbitrary yaw."""
+    rng = np.random.default_rng(seed)
+    q = np.zeros((n, 14))
+    q[:, :7] = (0, 0, 0.2, 1, 0, 0, 0)
+    for b in range(n):
+        rx, ry, rz = 0.15 * rng.random(), 0.15 * rng.random(), np.pi * rng.random()
+        # intrinsic x-y-z Euler angles -> quaternion (w, x, y, z), as gu.xyz_to_quat
+        cx, sx, cy, sy, cz, sz = np.cos(rx / 2), np.sin(rx / 2), np.cos(ry / 2), np.sin(ry / 2), np.cos(rz / 2), np.sin(rz / 2)
+        qx, qy, qz_ = np.array([cx, sx, 0, 0]), np.array([cy, 0, sy, 0]), np.array([cz, 0, 0, sz])
+
+        def mul(a, c):
+            return np.array([a[0] * c[0] - a[1] * c[1] - a[2] * c[2] - a[3] * c[3], a[0] * c[1] + a[1] * c[0] + a[2] * c[3] - a[3] * c[2],
+                             a[0] * c[2] - a[1] * c[3] + a[2] * c[0] + a[3] * c[1], a[0] * c[3] + a[1] * c[2] - a[2] * c[1] + a[3] * c[0]])
+        q[b, 7:10] = (0, 0, 0.65 + 0.1 * rng.random())
+        q[b, 10:14] = mul(mul(qx, qy), qz_)
+    return q

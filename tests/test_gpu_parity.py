@@ -399,3 +399,29 @@ def test_external_force_and_masked_fk():
     after = s.get_links_pos()
     assert torch.equal(before[0], after[0]) and torch.equal(before[2], after[2])
     np.testing.assert_allclose(after[1, 1].cpu().numpy(), [0.5, 0.5, 1.0], atol=1e-6)
+
+
+@pytest.mark.parametrize("solver_name,integrator_name", [("Newton", "approximate_implicitfast"), ("CG", "Euler"), ("Newton", "implicitfast")])
+def test_box_box_dynamics_reference_expectations(solver_name, integrator_name):
+    """The reference's own test_box_box_dynamics (tests/test_rigid_physics.py:1031-1053) on the CUDA path: 64 tilted cubes
+    dropped onto cubes come to rest (|qvel| <= 1e-2 after step 100, upper cube at z = 0.6 +- 2e-3), and the first 30 steps
+    (free fall, first touch with the exact-penetration fallback, multi-contact settling) follow the fp32 oracle."""
+    from helpers import box_box_qpos, make_box_box
+
+    B = 64
+    scene, ent = make_box_box(B, constraint_solver=getattr(gs.constraint_solver, solver_name), integrator=getattr(gs.integrator, integrator_name))
+    ent.set_qpos(torch.tensor(box_box_qpos(B, seed=2), dtype=torch.float32, device=gs.device))
+    orc = mirror_oracle(scene)
+    for _ in range(30):
+        scene.step()
+    orc.step(30)
+    dq = np.abs(gpu_field(scene, "qpos") - orc.qpos()).max(axis=1)
+    assert (dq <= TRAJ_QPOS_CONTACT).mean() >= 0.95, f"qpos outliers: {np.sort(dq)[-5:]}"
+    assert jaccard(contact_set(scene, B), contact_set(orc, B)) >= JACCARD_MIN
+    for i in range(30, 110):
+        scene.step()
+        if i > 100:
+            assert float(ent.get_dofs_velocity().abs().max()) <= 1e-2
+    q = ent.get_qpos().cpu().numpy()
+    np.testing.assert_allclose(q[:, 9], 0.6, atol=2e-3)
+    np.testing.assert_allclose(q[:, 2], 0.2, atol=2e-3)

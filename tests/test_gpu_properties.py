@@ -49,20 +49,40 @@ def test_go2_4096_determinism_and_sanity():
     assert (outs[0][2] > 0).float().mean() > 0.95  # nearly every robot touches the ground after 1 s
 
 
-def test_step_host_equals_device_path():
+@pytest.mark.parametrize("buffers,host_io", [("pinned", 2), ("pinned", 1), ("pageable", 2), ("pinned", 0), ("pageable", 0)])
+def test_step_host_equals_device_path(buffers, host_io):
+    """gsr_step_host equals the device-resident path bit for bit in all its variants: k_step reading the targets from and
+    writing the results to dense staging (cfg_host_io = 1), results posted straight into page-locked caller buffers (2, the
+    default; pageable buffers fall back to 1), and the staged copies with k_scatter / k_gather launches (0)."""
+    import os
+
     B, K = 256, 10
     scene_a, fa = make_franka(B, randomized=True)
-    scene_b, fb = make_franka(B, randomized=True)
+    os.environ["GSR_HOST_IO"] = str(host_io)
+    try:
+        scene_b, fb = make_franka(B, randomized=True)
+    finally:
+        del os.environ["GSR_HOST_IO"]
     sa, sb = scene_a.rigid_solver, scene_b.rigid_solver
-    ctrl = np.tile(np.array([[0.1, 0.0, 0.0, -1.2, 0.0, 1.1, 0.0, 0.02, 0.02]], dtype=np.float32), (B, 1))
-    qpos, vel = np.zeros((B, 9), np.float32), np.zeros((B, 9), np.float32)
-    fa.control_dofs_position(torch.from_numpy(ctrl).to(gs.device))
+    ctrl0 = np.tile(np.array([[0.1, 0.0, 0.0, -1.2, 0.0, 1.1, 0.0, 0.02, 0.02]], dtype=np.float32), (B, 1))
+    if buffers == "pinned":
+        keep = [torch.empty((B, 9), dtype=torch.float32).pin_memory() for _ in range(3)]
+        ctrl, qpos, vel = (t.numpy() for t in keep)
+        ctrl[:] = ctrl0
+        qpos[:] = 0
+        vel[:] = 0
+    else:
+        ctrl, qpos, vel = ctrl0.copy(), np.zeros((B, 9), np.float32), np.zeros((B, 9), np.float32)
+    fa.control_dofs_position(torch.from_numpy(ctrl0).to(gs.device))
     for _ in range(K):
         scene_a.step()
         sb.step_host(ctrl, qpos, vel)
     assert np.array_equal(sa.field("qpos").cpu().numpy(), qpos)
     assert np.array_equal(sa.field("vel").cpu().numpy(), vel)
-    assert sb.launch_count() > 0 and sb.kernel_launches()["k_step"] >= K
+    assert np.array_equal(sb.field("ctrl_pos").cpu().numpy(), ctrl0)  # the targets also landed in the device record
+    launches = sb.kernel_launches()
+    assert sb.launch_count() > 0 and launches["k_step"] >= K
+    assert (launches["k_scatter"] == 0) == (host_io > 0) and (launches["k_gather"] == 0) == (host_io > 0)
 
 
 def test_grasp_8192_determinism_launch_order_and_sanity():

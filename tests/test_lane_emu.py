@@ -325,3 +325,18 @@ def test_lane_exact_penetration_fallback():
     orc.step(19)
     emu.step(19)
     assert np.abs(emu.rows("qpos") - orc.qpos()).max() <= 1e-4 and np.abs(emu.rows("vel") - orc.vel()).max() <= 2e-2
+
+
+def test_lane_box_box_first_touch_and_settling():
+    """The reference's box_box scene (tests/test_rigid_physics.py:82-97, 1031-1053): free fall, first touch (exact-penetration
+    fallback, un-cached pair), multi-contact settling of a cube on a cube against the oracle."""
+    from helpers import box_box_qpos, make_box_box
+
+    B = 3
+    q0 = box_box_qpos(B, seed=3)
+    m, orc, emu = pair(make_box_box, B, lambda m, B: {"qpos": q0})
+    for k in range(3):
+        orc.step(10)
+        emu.step(10)
+        contacts_equal(orc, emu, B)
+    assert np.abs(emu.rows("qpos") - orc.qpos()).max() <= 1e-3 and np.abs(emu.rows("vel") - orc.vel()).max() <= 2e-2

@@ -375,3 +375,26 @@ def test_exact_penetration_fallback_minimum_translation():
         assert abs(np.linalg.norm(b[1]) - 1.0) < 1e-6
         smaller += b[0] < a[0] - 1e-4
     assert smaller >= 3
+
+
+@pytest.mark.parametrize("solver_name", ["Newton", "CG"])
+@pytest.mark.parametrize("integrator_name", ["implicitfast", "Euler", "approximate_implicitfast"])
+def test_box_box_dynamics_reference_expectations(solver_name, integrator_name):
+    """The reference's test_box_box_dynamics (tests/test_rigid_physics.py:1031-1053), its assertions applied to the oracle: a
+    0.4 m cube dropped with a small tilt onto another one comes to rest on it -- |qvel| <= 1e-2 from step 101 on and the upper
+    cube's height is 0.6 +- 2e-3 after 110 steps -- for CG / Newton and Euler / implicitfast (box-box MPR contacts, the
+    multi-contact probes and the exact-penetration fallback on the first touch)."""
+    from helpers import box_box_qpos, make_box_box
+
+    B = 6
+    scene, solver, m = host_model(make_box_box, constraint_solver=getattr(gs.constraint_solver, solver_name),
+                                  integrator=getattr(gs.integrator, integrator_name))
+    orc = oracle_for(solver, m, B, threads=3)
+    orc.set("qpos", box_box_qpos(B, seed=1))
+    orc.step(101)
+    for _ in range(9):
+        orc.step(1)
+        assert np.abs(orc.vel()).max() <= 1e-2
+    q = orc.qpos()
+    np.testing.assert_allclose(q[:, 9], 0.6, atol=2e-3)
+    np.testing.assert_allclose(q[:, 2], 0.2, atol=2e-3)
