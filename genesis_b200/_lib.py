@@ -6,7 +6,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libgsrigid.so")
+LIB_PATH = os.environ.get("GSR_LIB") or os.path.join(_HERE, "csrc", "libgsrigid.so")  # GSR_LIB: developer builds (make trace)
 _lib = None
 
 EXPORTS = (

@@ -45,6 +45,11 @@ struct gsr_handle_s : GsrSpec {
   // staging for gsr_step_host
   float *d_stage = nullptr, *h_stage = nullptr;
   size_t stage_elems = 0;
+  // adaptive on-chip row capacity (reorder_envs): histogram of rows per environment, read back one period later
+  int *d_rows_hist = nullptr, *h_rows_hist = nullptr;
+  cudaEvent_t rows_event = nullptr;
+  bool rows_pending = false, adaptive_rows = true;
+  int rows_default = 0, rows_changes = 0;
   int host_io_mode = 2;  // cfg_host_io: 0 = staged copies + k_scatter / k_gather, 1 = k_step reads / writes dense device staging, 2 = 1 + results posted straight into page-locked caller buffers
   KernelStat stats[K_COUNT] = {{"k_step", 0}, {"k_forward", 0}, {"k_reset", 0}, {"k_init", 0}, {"k_scatter", 0}, {"k_gather", 0},
                               {"k_gather_cost", 0}, {"k_order_flag", 0}};
@@ -159,6 +164,8 @@ int gsr_model_commit(gsr_handle_t h, int device, int n_envs) {
   { int rc_lay = gsr_compute_layouts(h, n_envs); if (rc_lay) return rc_lay; }
   h->reorder_period = (int)h->S("cfg_reorder_period", 16);
   h->host_io_mode = (int)h->S("cfg_host_io", 2);
+  // the caller fixing cfg_smem_rows switches the adaptation off (sweeps); the lane kernel has its own layout
+  h->adaptive_rows = h->S("cfg_adaptive_rows", h->s.count("cfg_smem_rows") ? 0 : 1) != 0 && h->group != 1;
   h->committed = true;
   g_active[device] = nullptr;
   return GSR_OK;
@@ -244,13 +251,64 @@ __global__ void k_iota(int* v, int n) {
 __global__ void k_order_flag(const int* cost_sorted, int* order, int B) {
   if (threadIdx.x == 0 && blockIdx.x == 0) order[B] = (2 * (long long)cost_sorted[0] > 3 * (long long)cost_sorted[B / 2]) ? 1 : 0;
 }
-__global__ void k_gather_cost(const float* state, int B, int field_off, int* dst) {
+#define GSR_ROWS_BINS 32  // rows per environment in buckets of 8 (the last bucket collects everything above 240)
+__global__ void k_gather_cost(const float* state, int B, int field_off, int* dst, int* rows_hist) {
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
-  if (env < B) dst[env] = reinterpret_cast<const int*>(state + (size_t)env * c_h.hot_stride)[field_off];
+  if (env >= B) return;
+  const int* rec = reinterpret_cast<const int*>(state + (size_t)env * c_h.hot_stride);
+  dst[env] = rec[field_off];
+  if (rows_hist) atomicAdd(rows_hist + min((rec[c_h.n_constraints] + 7) >> 3, GSR_ROWS_BINS - 1), 1);
 }
 // sort the environments by their last measured step cost, most expensive first (two tiny kernels + one radix sort)
+static int activate(gsr_handle_t h, cudaStream_t st);
+// Row capacity of the shared-memory workspace follows the workload: when a quarter of the environments carry more
+// constraint rows than fit on chip (their rows then live in the SPILL record and every solver access is an L2 round trip:
+// grasp cluster, 65 rows against 32, measured 4.7 M -> 5.5 M env-steps/s with 72 rows on chip) the capacity is raised to
+// cover 97 % of them, and lowered again when the batch calms down.  Only the shared-memory layout changes (the records
+// in HBM do not), between two launches, from a histogram that is one reorder period old -- no host synchronisation.
+static int adapt_rows(gsr_handle_t h, cudaStream_t st) {
+  const int B = h->B, cur = h->sl.NCS, lenC = h->hm.len_constraints;
+  int cum = 0, b97 = GSR_ROWS_BINS - 1, spilled = 0;
+  for (int b = 0; b < GSR_ROWS_BINS; b++) if (8 * b > cur) spilled += h->h_rows_hist[b];
+  for (int b = 0; b < GSR_ROWS_BINS; b++) { cum += h->h_rows_hist[b]; if (100LL * cum >= 97LL * B) { b97 = b; break; } }
+  int want = 8 * b97;
+  if (b97 == GSR_ROWS_BINS - 1) want = cur;  // beyond the histogram: leave as is
+  if (want < h->rows_default) want = h->rows_default;
+  if (want > lenC) want = lenC;
+  const size_t env_bytes_now = (size_t)h->sl.env_words * 4;
+  const size_t env_bytes_want = env_bytes_now + (size_t)(want - cur) * (h->sl.JS + 8 + GSR_CONTACT_WORDS / 4) * 4;
+  const size_t per_warp = env_bytes_want * (32 / h->group);
+  const bool grow = want > cur && 4LL * spilled >= B && per_warp * 4 <= 220 * 1024;  // keep at least four warps per SM
+  const bool shrink = want + 16 <= cur;
+  if (!grow && !shrink) return GSR_OK;
+  h->s["cfg_smem_rows"] = want;
+  int rc = gsr_compute_layouts(h, B);
+  if (rc) return rc;
+  h->auto_warps = 0;
+  h->rows_changes++;
+  g_active[h->device] = nullptr;  // re-upload the layouts (stream-ordered after the launches that used the old ones)
+  return activate(h, st);
+}
+
 static int reorder_envs(gsr_handle_t h, cudaStream_t st) {
   const int B = h->B;
+  if (h->adaptive_rows) {
+    if (!h->d_rows_hist) {
+      CUDA_OK(cudaMalloc((void**)&h->d_rows_hist, sizeof(int) * GSR_ROWS_BINS));
+      CUDA_OK(cudaHostAlloc((void**)&h->h_rows_hist, sizeof(int) * GSR_ROWS_BINS, cudaHostAllocDefault));
+      CUDA_OK(cudaEventCreateWithFlags(&h->rows_event, cudaEventDisableTiming));
+      h->rows_default = h->sl.NCS;
+    }
+    const bool hist_ready = h->rows_pending && cudaEventQuery(h->rows_event) == cudaSuccess;
+    cudaGetLastError();  // "not ready" is not an error
+    if (hist_ready) {
+      h->rows_pending = false;
+      int rc = adapt_rows(h, st);
+      if (rc) return rc;
+    }
+    if (!h->rows_pending) CUDA_OK(cudaMemsetAsync(h->d_rows_hist, 0, sizeof(int) * GSR_ROWS_BINS, st));
+  }
+  const bool take_hist = h->adaptive_rows && !h->rows_pending;
   if (!h->d_order) {
     CUDA_OK(cudaMalloc((void**)&h->d_order, sizeof(int) * (B + 1))); CUDA_OK(cudaMalloc((void**)&h->d_iota, sizeof(int) * B));
     CUDA_OK(cudaMalloc((void**)&h->d_cost, sizeof(int) * B)); CUDA_OK(cudaMalloc((void**)&h->d_cost_sorted, sizeof(int) * B));
@@ -258,7 +316,12 @@ static int reorder_envs(gsr_handle_t h, cudaStream_t st) {
     CUDA_OK(cudaMalloc(&h->d_sort_tmp, h->sort_tmp_bytes));
     k_iota<<<(B + 255) / 256, 256, 0, st>>>(h->d_iota, B);
   }
-  { Bracket br_(h, K_GATHER_COST, st); k_gather_cost<<<(B + 255) / 256, 256, 0, st>>>(h->state, B, h->lay.step_cost, h->d_cost); }
+  { Bracket br_(h, K_GATHER_COST, st); k_gather_cost<<<(B + 255) / 256, 256, 0, st>>>(h->state, B, h->lay.step_cost, h->d_cost, take_hist ? h->d_rows_hist : nullptr); }
+  if (take_hist) {
+    CUDA_OK(cudaMemcpyAsync(h->h_rows_hist, h->d_rows_hist, sizeof(int) * GSR_ROWS_BINS, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaEventRecord(h->rows_event, st));
+    h->rows_pending = true;
+  }
   CUDA_OK(cub::DeviceRadixSort::SortPairsDescending(h->d_sort_tmp, h->sort_tmp_bytes, h->d_cost, h->d_cost_sorted, h->d_iota, h->d_order, B, 0, 32, st));
   { Bracket br_(h, K_ORDER_FLAG, st); k_order_flag<<<1, 32, 0, st>>>(h->d_cost_sorted, h->d_order, B); }
   CUDA_OK(cudaGetLastError());
@@ -285,8 +348,10 @@ static int auto_warps_per_cta(const gsr_handle_t h, size_t warp_bytes) {
     const int r = ctas * w;
     const long long per_wave = (long long)n_sm * r;
     const double waves = (double)((h->B + per_wave - 1) / per_wave);
-    // ties go to the CTA size closest to 8 warps: 1-2 warp CTAs drift apart in the 20 k-instruction kernel (instruction cache)
-    const double cost = waves * (1.0 + 0.35 * r / 16.0) * (1.0 + 0.002 * (w > 8 ? w - 8 : 8 - w));
+    // ties go to mid-sized CTAs: 1-2 warp CTAs drift apart in the 20 k-instruction kernel (instruction cache, Go2: 11.5 M with
+    // 1 warp against 12.4 M with 8), 8+ warps wait for each other at the phase barriers (grasp cluster, 72 rows on chip: 5.49 M
+    // with 4 warps against 5.34 M with 8)
+    const double cost = waves * (1.0 + 0.35 * r / 16.0) * (1.0 + 0.002 * (w > 6 ? w - 6 : 6 - w));
     if (cost < best - 1e-9) { best = cost; best_w = w; }
   }
   return best_w;
@@ -401,6 +466,7 @@ int gsr_step_host(gsr_handle_t h, int n_substeps, const float* ctrl_pos_host, fl
     const size_t need1 = B * (size_t)(m.nQ + 2 * m.nD);
     if (h->stage_elems < need1) {
       if (h->d_stage) cudaFree(h->d_stage);
+    if (h->d_rows_hist) { cudaFree(h->d_rows_hist); cudaFreeHost(h->h_rows_hist); cudaEventDestroy(h->rows_event); }
       CUDA_OK(cudaMalloc((void**)&h->d_stage, need1 * 4));
       h->stage_elems = need1;
     }
@@ -453,6 +519,14 @@ int gsr_step_host(gsr_handle_t h, int n_substeps, const float* ctrl_pos_host, fl
   CUDA_OK(cudaStreamSynchronize(st));
   return GSR_OK;
 }
+
+#ifdef GSR_SOLVER_TRACE
+int gsr_debug_solver_read(gsr_handle_t h, unsigned long long* out, int n_envs) {  // developer build only (make trace)
+  CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaMemcpyFromSymbol(out, g_solver_dbg, (size_t)n_envs * 16 * sizeof(unsigned long long)));
+  return GSR_OK;
+}
+#endif
 
 int gsr_set_profiling(gsr_handle_t h, int enabled) {
   if (!h) return GSR_EINVAL;

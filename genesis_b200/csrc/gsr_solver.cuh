@@ -326,7 +326,7 @@ __device__ __noinline__ void update_constraint(const Ctx<G>& C, const Rows& R, S
 
 // CS:1394-1452 + CS:1594-1621: H = M + J^T (D active) J (lower), then in-place Cholesky (1 / L_ii kept in WK(Hinv))
 template <int G>
-__device__ __noinline__ void hessian_cholesky(const Ctx<G>& C, const Rows& R) {
+__device__ __noinline__ void hessian_cholesky(const Ctx<G>& C, const Rows& R, long long* t_split = nullptr) {
   const int nD = CM(nD), MS = c_s.MS, lane = C.lane;
   const float EPS = CM(eps);
   float* H = WK(H);
@@ -363,13 +363,21 @@ __device__ __noinline__ void hessian_cholesky(const Ctx<G>& C, const Rows& R) {
     }
   }
   C.sync();
+  if (t_split) *t_split = clock64();
   for (int i = 0; i < nD; i++) {
     // every lane owning a row j >= i forms dot_j = sum_{k<i} H[j][k] H[i][k]; the owner of row i turns its dot into L_ii
     const int owner = i & (G - 1);
     float Lii = 0.f;
     for (int j = i + ((lane - i) & (G - 1)); j < nD; j += G) {
       float dt = 0.f;
-      for (int k = 0; k < i; k++) dt += H[j * MS + k] * H[i * MS + k];
+      const float *Hj = H + j * MS, *Hi = H + i * MS;
+      int k = 0;
+      for (; k + 4 <= i; k += 4) {  // eight loads in flight, then the additions in the original order
+        const float a0 = Hj[k], a1 = Hj[k + 1], a2 = Hj[k + 2], a3 = Hj[k + 3];
+        const float b0 = Hi[k], b1 = Hi[k + 1], b2 = Hi[k + 2], b3 = Hi[k + 3];
+        dt += a0 * b0; dt += a1 * b1; dt += a2 * b2; dt += a3 * b3;
+      }
+      for (; k < i; k++) dt += Hj[k] * Hi[k];
       if (j == i) Lii = sqrtf(fmaxf(H[i * MS + i] - dt, EPS));
       else H[j * MS + i] = H[j * MS + i] - dt;  // scaled below once L_ii is known
     }
@@ -390,6 +398,46 @@ __device__ __noinline__ bool hessian_incremental(const Ctx<G>& C, const Rows& R)
   const float EPS = CM(eps);
   float* H = WK(H);
   float* vec = WK(prev_grad);  // scratch (the CG history is unused by the Newton solver)
+  if (nD <= G) {
+    // one matrix row per lane: lane i keeps vec[i] in a register and is the only one to touch row i of the factor, the
+    // pivot values (vec[k], L_kk) travel by shuffle -- no shared-memory round trip and no barrier per column (the same
+    // operations in the same order as the general loop below)
+    float* Hinv = WK(Hinv);
+    const bool own = lane < nD;
+    for (int base = 0; base < R.n_con; base += G) {
+      const int cl = base + lane;
+      const int a = cl < R.n_con ? R.active[cl] : 0;
+      unsigned bal = C.ballot(((a ^ (a >> 1)) & 1) != 0);
+      while (bal) {
+        const int b = __ffs(bal) - 1;
+        bal &= bal - 1;
+        const int c = base + b;
+        const float sign = (R.active[c] & 1) ? 1.f : -1.f;
+        const float sq = sqrtf(R.D[c]);
+        float v = own ? R.J[c * R.JS + lane] * sq : 0.f;
+        for (int k = 0; k < nD; k++) {
+          const float vk = __shfl_sync(C.gmask, v, k, G);
+          if (fabsf(vk) > EPS) {
+            const float hik = (own && lane >= k) ? H[lane * MS + k] : 0.f;
+            const float Lkk = __shfl_sync(C.gmask, hik, k, G);
+            const float tmp = Lkk * Lkk + sign * vk * vk;
+            if (tmp < EPS) return true;
+            const float r = sqrtf(tmp), cc = r / Lkk, cinv = 1.0f / cc, s = vk / Lkk;
+            if (own && lane > k) {
+              const float Lik = (hik + s * v * sign) * cinv;
+              H[lane * MS + k] = Lik;
+              v = v * cc - s * Lik;
+            } else if (lane == k) {
+              H[k * MS + k] = r;
+              Hinv[k] = 1.0f / r;
+            }
+          }
+        }
+      }
+    }
+    C.sync();
+    return false;
+  }
   for (int base = 0; base < R.n_con; base += G) {
     const int cl = base + lane;
     const int a = cl < R.n_con ? R.active[cl] : 0;
@@ -530,6 +578,58 @@ __device__ __noinline__ LsPoint ls_eval(const Ctx<G>& C, const Rows& R, const So
   if (p.d1 <= 0.f) p.d1 = CM(eps);
   return p;
 }
+// the three candidates of a bracketing round (CS:2226-2354 func_ls_point_fn_3alphas_opt) in ONE sweep over the rows: the row
+// data are loaded once and the nine butterfly reductions interleave, instead of three dependent evaluations back to back
+// (the same additions in the same order per candidate, so the result is bit-identical to three ls_eval calls)
+template <int G>
+__device__ __noinline__ void ls_eval3(const Ctx<G>& C, const Rows& R, const SolverState& X, float a0, float a1, float a2, LsPoint* out) {
+  const float al[3] = {a0, a1, a2};
+  float t0[3] = {0.f, 0.f, 0.f}, t1[3] = {0.f, 0.f, 0.f}, t2[3] = {0.f, 0.f, 0.f};
+  for (int c = R.ne + C.lane; c < R.n_con; c += G) {
+    const float Ja = R.Jaref[c], jv = R.jv[c], D = R.D[c];
+    const float h0 = 0.5f * Ja * Ja, h1 = jv * Ja, h2 = 0.5f * jv * jv;
+    if (c < R.nef) {
+      const float f = R.floss[c], rf = R.R[c] * f;
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const float x = Ja + al[k] * jv;
+        const bool ln = x <= -rf, lp = x >= rf;
+        if (ln || lp) {
+          t0[k] += (ln ? f * (-0.5f * rf - Ja) : 0.f) + (lp ? f * (-0.5f * rf + Ja) : 0.f);
+          t1[k] += (ln ? -f * jv : 0.f) + (lp ? f * jv : 0.f);
+        } else {
+          t0[k] += D * h0; t1[k] += D * h1; t2[k] += D * h2;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const float x = Ja + al[k] * jv;
+        if (x < 0.f) { t0[k] += D * h0; t1[k] += D * h1; t2[k] += D * h2; }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      t0[k] += __shfl_xor_sync(C.gmask, t0[k], o, G);
+      t1[k] += __shfl_xor_sync(C.gmask, t1[k], o, G);
+      t2[k] += __shfl_xor_sync(C.gmask, t2[k], o, G);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const float s0 = t0[k] + X.qg0 + X.es0, s1 = t1[k] + X.qg1 + X.es1, s2 = t2[k] + X.qg2 + X.es2;
+    LsPoint p;
+    p.alpha = al[k];
+    p.cost = al[k] * al[k] * s2 + al[k] * s1 + s0;
+    p.d0 = 2.f * al[k] * s2 + s1;
+    p.d1 = 2.f * s2;
+    if (p.d1 <= 0.f) p.d1 = CM(eps);
+    out[k] = p;
+  }
+}
 // CS:2357-2388
 __device__ __forceinline__ int update_bracket(LsPoint& p, const LsPoint* cand, float& next_alpha) {
   int flag = 0;
@@ -599,7 +699,7 @@ __device__ float linesearch(const Ctx<G>& C, const Rows& R, SolverState& X) {
   float a0 = p1.alpha - p1.d0 / p1.d1, a1 = p1.alpha, a2 = (p1.alpha + p2.alpha) * 0.5f;
   while (X.ls_it < ls_iterations) {
     LsPoint cand[3];
-    cand[0] = ls_eval(C, R, X, a0); cand[1] = ls_eval(C, R, X, a1); cand[2] = ls_eval(C, R, X, a2);
+    ls_eval3(C, R, X, a0, a1, a2, cand);
     X.ls_it += 3;
     float best_alpha = 0.f, best_cost = 0.f;
     bool found = false;
@@ -722,12 +822,24 @@ __device__ __noinline__ void phase_noslip(const Ctx<G>& C, const Rows& R, int n_
 
 // CS:210-245 resolve(): init (CS:2935-3059), monolith body (CS:3163-3190), update_qacc (CS:3240-3261),
 // contact forces (CS:3198-3237)
+#ifdef GSR_SOLVER_TRACE  // developer build (make trace): SM cycles per solver stage and counters, per environment
+__device__ unsigned long long g_solver_dbg[16 * 65536];
+#define DBG_T(k) { const long long t_ = clock64(); dbg[k] += t_ - dbg_t; dbg_t = t_; }
+#define DBG_N(k, n) dbg[k] += (n)
+#else
+#define DBG_T(k)
+#define DBG_N(k, n)
+#endif
 template <int G>
 __device__ void phase_constraints(const Ctx<G>& C) {
+#ifdef GSR_SOLVER_TRACE
+  long long dbg[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, dbg_t = clock64();
+#endif
   const int nD = CM(nD), nL = CM(nL), MS = c_s.MS, lane = C.lane;
   const float EPS = CM(eps);
   Rows R;
   build_rows(C, R);
+  DBG_T(0);
   const int n_con = R.n_con;
   int* SI = C.SI();
   SolverState X;
@@ -753,15 +865,26 @@ __device__ void phase_constraints(const Ctx<G>& C) {
       R.active[c] = 0;
     }
     C.sync();
+    DBG_T(13);
     update_constraint(C, R, X, false);
+    DBG_T(14);
+#ifdef GSR_SOLVER_TRACE
+    long long t_split = 0;
+    if (CM(solver_type) == SOLVER_NEWTON) hessian_cholesky(C, R, &t_split);
+    dbg[15] += t_split - dbg_t; dbg_t = t_split;  // assembly; the factorisation goes to [5] below
+    DBG_T(5);
+#else
     if (CM(solver_type) == SOLVER_NEWTON) hessian_cholesky(C, R);
+#endif
     update_gradient(C);
     for (int d = lane; d < nD; d += G) search[d] = -WK(Mgrad)[d];
     C.sync();
+    DBG_T(1);
     const float tol_scaled = (CM(meaninertia) * (float)max(1, nD)) * CM(tolerance);
     for (int it = 0; it < CM(iterations); it++) {  // CS:3062-3139 func_solve_iter
       iters++;
       const float alpha = linesearch(C, R, X);
+      DBG_T(2); DBG_N(8, X.ls_it); DBG_N(9, 1);
       if (fabsf(alpha) < EPS) break;
       for (int d = lane; d < nD; d += G) {
         qacc[d] += search[d] * alpha;
@@ -771,10 +894,16 @@ __device__ void phase_constraints(const Ctx<G>& C) {
       for (int c = lane; c < n_con; c += G) R.Jaref[c] += R.jv[c] * alpha;
       C.sync();
       update_constraint(C, R, X, true);
+      DBG_T(3);
       if (CM(solver_type) == SOLVER_NEWTON) {
-        if (hessian_incremental(C, R)) { C.sync(); hessian_cholesky(C, R); }
+#ifdef GSR_SOLVER_TRACE
+        for (int c = 0; c < n_con; c++) { const int a = R.active[c]; DBG_N(10, (a ^ (a >> 1)) & 1); }
+#endif
+        if (hessian_incremental(C, R)) { DBG_T(4); DBG_N(11, 1); C.sync(); hessian_cholesky(C, R); DBG_T(5); }
+        else DBG_T(4);
       }
       update_gradient(C);
+      DBG_T(6);
       // CS:2841-2884 termination / new search direction
       float gn = 0.f;
       for (int d = lane; d < nD; d += G) { const float g = WK(grad)[d]; gn += g * g; }
@@ -798,6 +927,11 @@ __device__ void phase_constraints(const Ctx<G>& C) {
     for (int d = lane; d < nD; d += G) WK(qfrc_c)[d] = 0.f;
   }
   C.sync();
+#ifdef GSR_SOLVER_TRACE
+  DBG_T(7);
+  dbg[12] = n_con;
+  if (lane == 0 && C.env < 65536) for (int k = 0; k < 16; k++) g_solver_dbg[16 * C.env + k] = (unsigned long long)dbg[k];
+#endif
   // ---- CS:3240-3261 func_update_qacc
   bool has_nan = false;
   float* acc = WK(acc);

@@ -169,9 +169,6 @@ class RigidSolver:
             buf = self._I if is_int.value else self._F
             shape, strides = ((self._B, items), (stride, istride)) if comps == 1 else ((self._B, items, comps), (stride, istride, 1))
             self._fields[name.value.decode()] = torch.as_strided(buf, shape, strides, seg + off)
-        gi = [ctypes.c_int() for _ in range(4)]
-        _lib.check(h, L.gsr_launch_info(h, *[ctypes.byref(x) for x in gi]))
-        self.launch_info = dict(group_size=gi[0].value, smem_bytes_per_env=gi[1].value, smem_rows=gi[2].value, smem_contacts=gi[3].value)
         _lib.check(h, L.gsr_init_state(h, self._stream()))
         self._is_built = True
         self._init_qpos = self._fields["qpos"].clone()  # (B, nQ)
@@ -212,6 +209,13 @@ class RigidSolver:
     def substep(self, n=1):
         _lib.check(self._handle, _lib.lib().gsr_step(self._handle, n, self._stream()))
         self._n_substeps_total += n
+
+    @property
+    def launch_info(self):
+        """Launch geometry of the step kernel as of now (the on-chip row capacity follows the workload, gsr_api.cu adapt_rows)."""
+        gi = [ctypes.c_int() for _ in range(4)]
+        _lib.check(self._handle, _lib.lib().gsr_launch_info(self._handle, *[ctypes.byref(x) for x in gi]))
+        return dict(group_size=gi[0].value, smem_bytes_per_env=gi[1].value, smem_rows=gi[2].value, smem_contacts=gi[3].value)
 
     def step_host(self, ctrl_pos_host, qpos_host, vel_host, n=1):
         """Reference-facing host-buffer call (bench.py e2e): numpy (B, n) float32 arrays in / out."""
