@@ -63,6 +63,7 @@ static inline int gsr_fill_model(GsrSpec* h) {
   m.iterations = (int)S("cfg_iterations", 50); m.ls_iterations = (int)S("cfg_ls_iterations", 50);
   m.integrator = (int)S("cfg_integrator", INTEGRATOR_APPROX_IMPLICITFAST); m.solver_type = (int)S("cfg_solver_type", SOLVER_NEWTON);
   m.gjk_fallback = (int)S("cfg_gjk_fallback", 1);
+  m.phase_barriers = (int)S("cfg_phase_barriers", 31);
   m.noslip_iterations = (int)S("cfg_noslip_iterations", 0); m.noslip_tolerance = (float)S("cfg_noslip_tolerance", 1e-6);
   m.enable_collision = (int)S("cfg_enable_collision", 1); m.enable_joint_limit = (int)S("cfg_enable_joint_limit", 1);
   m.enable_multi_contact = (int)S("cfg_enable_multi_contact", 1); m.sort_contacts = (int)S("cfg_sort_contacts", 1);

@@ -18,7 +18,7 @@
 // All warps of a CTA walk the phases of the step together (CTA barriers between phases): the step is ~20k instructions of
 // mostly straight-line code per environment, far more than the instruction cache holds, so warps that drift apart each
 // stream the whole kernel from L2 on their own (ncu: stall_no_instruction dominated before this was added).
-#define PHASE_BARRIER() __syncthreads()
+#define PHASE_BARRIER(k) if ((c_m.phase_barriers >> (k)) & 1) __syncthreads()  // CTA-uniform condition
 
 template <int G>
 __device__ __forceinline__ bool make_ctx(Ctx<G>& C, float* state, int B, const DevModel* gm, float* smem, const int* order = nullptr) {
@@ -131,27 +131,27 @@ __global__ void __launch_bounds__(GSR_MAX_WARPS_PER_CTA * 32, 1) k_step(float* s
     const float* src = io.ctrl_pos + (size_t)C.env * nD;
     for (int d = C.lane; d < nD; d += G) IN(ctrl_pos)[d] = __ldcs(src + d);
   }
-  PHASE_BARRIER();
+  PHASE_BARRIER(0);
   PHASE_BEGIN();
   if (live) phase_dynamics(C);
   PHASE_END();
   TRACE_MARK(1);
-  PHASE_BARRIER();
+  PHASE_BARRIER(1);
   PHASE_BEGIN();
   if (live && CM(enable_collision) && CM(nG) > 0) phase_collide(C);
   PHASE_END();
   TRACE_MARK(2);
-  PHASE_BARRIER();
+  PHASE_BARRIER(2);
   PHASE_BEGIN();
   if (live) phase_constraints(C);
   PHASE_END();
   TRACE_MARK(3);
-  PHASE_BARRIER();
+  PHASE_BARRIER(3);
   PHASE_BEGIN();
   if (live) phase_integrate(C);
   PHASE_END();
   TRACE_MARK(4);
-  PHASE_BARRIER();
+  PHASE_BARRIER(4);
   PHASE_BEGIN();
   if (live) step_epilogue(C, clear_ext);
   PHASE_END();

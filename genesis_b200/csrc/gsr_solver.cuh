@@ -365,27 +365,41 @@ __device__ __noinline__ void hessian_cholesky(const Ctx<G>& C, const Rows& R, lo
   C.sync();
   if (t_split) *t_split = clock64();
   for (int i = 0; i < nD; i++) {
-    // every lane owning a row j >= i forms dot_j = sum_{k<i} H[j][k] H[i][k]; the owner of row i turns its dot into L_ii
-    const int owner = i & (G - 1);
-    float Lii = 0.f;
-    for (int j = i + ((lane - i) & (G - 1)); j < nD; j += G) {
-      float dt = 0.f;
-      const float *Hj = H + j * MS, *Hi = H + i * MS;
-      int k = 0;
-      for (; k + 4 <= i; k += 4) {  // eight loads in flight, then the additions in the original order
-        const float a0 = Hj[k], a1 = Hj[k + 1], a2 = Hj[k + 2], a3 = Hj[k + 3];
-        const float b0 = Hi[k], b1 = Hi[k + 1], b2 = Hi[k + 2], b3 = Hi[k + 3];
-        dt += a0 * b0; dt += a1 * b1; dt += a2 * b2; dt += a3 * b3;
+    // Column i: every lane owning a row j >= i forms dot_j = sum_{k<i} H[j][k] H[i][k] and, from the same pivot-row loads,
+    // the pivot's own dot, so that L_ii and 1 / L_ii (one rsqrt) are known to every lane without a shuffle and the column
+    // is scaled in the same pass; the sums run four terms at a time with a predicated tail (the additions keep their order).
+    const int j0 = i + ((lane - i) & (G - 1));
+    const unsigned busy = __ballot_sync(C.gmask, j0 < nD);
+    if (j0 < nD) {
+      const float* Hi = H + i * MS;
+      const float hii = Hi[i];
+      float dii = 0.f, dt0 = 0.f, dt1 = 0.f;
+      const int j1 = j0 + G;
+      const float *Hj0 = H + j0 * MS, *Hj1 = H + (j1 < nD ? j1 : j0) * MS;
+      for (int k = 0; k < i; k += 4) {
+        const bool p1 = k + 1 < i, p2 = k + 2 < i, p3 = k + 3 < i;
+        const float b0 = Hi[k], b1 = p1 ? Hi[k + 1] : 0.f, b2 = p2 ? Hi[k + 2] : 0.f, b3 = p3 ? Hi[k + 3] : 0.f;
+        const float a0 = Hj0[k], a1 = p1 ? Hj0[k + 1] : 0.f, a2 = p2 ? Hj0[k + 2] : 0.f, a3 = p3 ? Hj0[k + 3] : 0.f;
+        dii += b0 * b0; dii += b1 * b1; dii += b2 * b2; dii += b3 * b3;
+        dt0 += a0 * b0; dt0 += a1 * b1; dt0 += a2 * b2; dt0 += a3 * b3;
+        if (G < 32 && j1 < nD) {
+          const float c0 = Hj1[k], c1 = p1 ? Hj1[k + 1] : 0.f, c2 = p2 ? Hj1[k + 2] : 0.f, c3 = p3 ? Hj1[k + 3] : 0.f;
+          dt1 += c0 * b0; dt1 += c1 * b1; dt1 += c2 * b2; dt1 += c3 * b3;
+        }
       }
-      for (; k < i; k++) dt += Hj[k] * Hi[k];
-      if (j == i) Lii = sqrtf(fmaxf(H[i * MS + i] - dt, EPS));
-      else H[j * MS + i] = H[j * MS + i] - dt;  // scaled below once L_ii is known
-    }
-    Lii = __shfl_sync(C.gmask, Lii, owner, G);
-    const float inv = 1.0f / Lii;
-    for (int j = i + ((lane - i) & (G - 1)); j < nD; j += G) {
-      if (j == i) { H[i * MS + i] = Lii; Hinv[i] = inv; }
-      else H[j * MS + i] *= inv;
+      const float x = fmaxf(hii - dii, EPS);
+      const float inv = rsqrtf(x), Lii = x * inv;
+      __syncwarp(busy);  // every lane has read the pivot before its owner overwrites it
+      if (j0 == i) { H[i * MS + i] = Lii; Hinv[i] = inv; }
+      else H[j0 * MS + i] = (H[j0 * MS + i] - dt0) * inv;
+      for (int j = j1; j < nD; j += G) {  // further rows of this lane (nD > G): the second one is already summed
+        float dt = dt1;
+        if (j != j1 || G == 32) {
+          dt = 0.f;
+          for (int k = 0; k < i; k++) dt += H[j * MS + k] * Hi[k];
+        }
+        H[j * MS + i] = (H[j * MS + i] - dt) * inv;
+      }
     }
     C.sync();
   }
@@ -415,24 +429,33 @@ __device__ __noinline__ bool hessian_incremental(const Ctx<G>& C, const Rows& R)
         const float sign = (R.active[c] & 1) ? 1.f : -1.f;
         const float sq = sqrtf(R.D[c]);
         float v = own ? R.J[c * R.JS + lane] * sq : 0.f;
+        // the loads of column k + 1 (own entry, pivot and its cached reciprocal; column k's update does not touch them) are
+        // issued one column ahead, and sqrt / divisions collapse into one rsqrt, so that the dependent chain of a column is
+        // shuffle -> fma -> rsqrt -> fma instead of shuffle -> load -> shuffle -> sqrt -> three divisions
+        C.sync();  // the pivots written by other lanes in the previous update
+        float hik = own ? H[lane * MS] : 0.f, Lkk = H[0], Linv = Hinv[0];
+        bool bad = false;
         for (int k = 0; k < nD; k++) {
+          const int kn = k + 1 < nD ? k + 1 : k;
+          const float hik_n = (own && lane >= kn) ? H[lane * MS + kn] : 0.f, Lkk_n = H[kn * MS + kn], Linv_n = Hinv[kn];
           const float vk = __shfl_sync(C.gmask, v, k, G);
+          const float tmp = Lkk * Lkk + sign * vk * vk;
+          bad |= fabsf(vk) > EPS && tmp < EPS;
+          const float rinv = rsqrtf(fmaxf(tmp, EPS)), r = tmp * rinv;
+          const float cc = r * Linv, cinv = Lkk * rinv, s_ = vk * Linv;
           if (fabsf(vk) > EPS) {
-            const float hik = (own && lane >= k) ? H[lane * MS + k] : 0.f;
-            const float Lkk = __shfl_sync(C.gmask, hik, k, G);
-            const float tmp = Lkk * Lkk + sign * vk * vk;
-            if (tmp < EPS) return true;
-            const float r = sqrtf(tmp), cc = r / Lkk, cinv = 1.0f / cc, s = vk / Lkk;
             if (own && lane > k) {
-              const float Lik = (hik + s * v * sign) * cinv;
+              const float Lik = (hik + s_ * v * sign) * cinv;
               H[lane * MS + k] = Lik;
-              v = v * cc - s * Lik;
+              v = v * cc - s_ * Lik;
             } else if (lane == k) {
               H[k * MS + k] = r;
-              Hinv[k] = 1.0f / r;
+              Hinv[k] = rinv;
             }
           }
+          hik = hik_n; Lkk = Lkk_n; Linv = Linv_n;
         }
+        if (bad) return true;  // degenerate down-date (group-uniform: tmp derives from shuffled values): the caller refactors
       }
     }
     C.sync();

@@ -94,6 +94,8 @@ class RigidSolver:
             self.tuning["warps_per_cta"] = int(os.environ["GSR_WARPS"])
         if "GSR_HOST_IO" in os.environ:  # gsr_step_host: 0 staged + scatter / gather kernels, 1 fused device staging, 2 posted writes to pinned buffers
             self.tuning["host_io"] = int(os.environ["GSR_HOST_IO"])
+        if "GSR_PHASE_BARRIERS" in os.environ:  # bit mask of the CTA barriers between the phases of k_step (sweeps)
+            self.tuning["phase_barriers"] = int(os.environ["GSR_PHASE_BARRIERS"])
         if "GSR_GJK_FALLBACK" in os.environ:  # A/B measurements only: 0 keeps MPR's answer for deep / un-cached pairs
             self.tuning["gjk_fallback"] = int(os.environ["GSR_GJK_FALLBACK"])
         self.model = None
