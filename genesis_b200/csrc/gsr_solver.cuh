@@ -349,12 +349,26 @@ __device__ __noinline__ void hessian_cholesky(const Ctx<G>& C, const Rows& R, lo
       if (t < ntri) tri_decode(t, i, j);
       oi[e] = i; oj[e] = j; acc[e] = 0.f;
     }
-    for (int c = 0; c < R.n_con; c++) {
-      const float wc = w[c];
-      if (wc == 0.f) continue;
-      const float* Jc = R.J + c * R.JS;
+    // two rows per trip: 4 NE independent loads in flight before the first multiply (a row of weight 0 adds exact zeros, the
+    // additions keep the row order), and the skip of inactive rows is decided per pair
+    int c = 0;
+    for (; c + 1 < R.n_con; c += 2) {
+      const float w0 = w[c], w1 = w[c + 1];
+      if (w0 == 0.f && w1 == 0.f) continue;
+      const float *J0 = R.J + c * R.JS, *J1 = J0 + R.JS;
+      float a0[NE], b0[NE], a1[NE], b1[NE];
 #pragma unroll
-      for (int e = 0; e < NE; e++) acc[e] += Jc[oj[e]] * (Jc[oi[e]] * wc);
+      for (int e = 0; e < NE; e++) { a0[e] = J0[oj[e]]; b0[e] = J0[oi[e]]; a1[e] = J1[oj[e]]; b1[e] = J1[oi[e]]; }
+#pragma unroll
+      for (int e = 0; e < NE; e++) { acc[e] += a0[e] * (b0[e] * w0); acc[e] += a1[e] * (b1[e] * w1); }
+    }
+    if (c < R.n_con) {
+      const float wc = w[c];
+      const float* Jc = R.J + c * R.JS;
+      if (wc != 0.f) {
+#pragma unroll
+        for (int e = 0; e < NE; e++) acc[e] += Jc[oj[e]] * (Jc[oi[e]] * wc);
+      }
     }
 #pragma unroll
     for (int e = 0; e < NE; e++) {

@@ -1,10 +1,16 @@
 #!/bin/bash
-# weak-scaling record: Franka 30000 envs per GPU on N = 1, 2, 4, 8 GPUs of one box (the launch the driver uses)
-O=gpurun_out/scale
+# weak-scaling record on one box (the launch the driver uses): Franka 30000 / Go2 4096 envs per GPU on 8 GPUs, and the mixed
+# workload of BASELINE.json configs[4] (65536 envs in total, even ranks Franka, odd ranks Go2) on 2 / 4 / 8 GPUs.
+# Usage: gpurun --gpus 8 -- bash tools/gpu_scale.sh <tag>
+TAG=${1:-scale}
+O=gpurun_out/$TAG
 mkdir -p $O
-python bench.py --gpus 1 --steps 500 --warmup 50 --no-cpu-baseline > $O/scale_1.json 2>$O/scale_1.err
-for N in 2 4 8; do
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N bench.py --gpus $N --steps 500 --warmup 50 --no-cpu-baseline > $O/scale_$N.json 2>$O/scale_$N.err
-done
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29520 bench.py --gpus 8 --workload go2 --steps 500 --warmup 300 --no-cpu-baseline > $O/scale_go2_8.json 2>$O/scale_go2_8.err
-for f in $O/scale_*.json; do tail -1 $f | cut -c1-150; done
+run() {  # N workload steps warmup
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 400)) bench.py --gpus $1 --workload $2 --steps $3 --warmup $4 --no-cpu-baseline > $O/scale_$2_$1.json 2> $O/scale_$2_$1.err
+  tail -1 $O/scale_$2_$1.json | cut -c1-170
+}
+run 8 franka 500 100
+run 8 go2 500 300
+run 8 mixed 500 300
+run 4 mixed 500 300
+run 2 mixed 500 300
