@@ -247,7 +247,9 @@ struct PairDet {
 };
 
 // one detection at the (possibly perturbed) poses in P: analytic capsule pairs, plane support query, or MPR with warm start
-template <int G>
+// MPR = false compiles the portal refinement and the EPA fallback out: models without a convex-convex pair that needs them
+// (gsr_host.h has_mpr; e.g. a robot without self-collision on a plane) run a kernel a few thousand instructions shorter
+template <int G, bool MPR>
 __device__ __forceinline__ void dev_detect(const Ctx<G>& C, const PairDet& D, const PairPose& P, int i_det, bool& is_col, f3& normal, float& pen, f3& cpos) {
   const float EPS = c_m.eps;
   const int ga = D.ga, gb = D.gb;
@@ -262,6 +264,8 @@ __device__ __forceinline__ void dev_detect(const Ctx<G>& C, const PairDet& D, co
     pen = dot(normal, v1 - P.pa);
     cpos = v1 - normal * (0.5f * pen);
     is_col = pen > 0.f;
+  } else if constexpr (!MPR) {
+    is_col = false; normal = f3(); pen = 0.f; cpos = f3();  // unreachable: the host launches this variant only without such pairs
   } else {
     // the perturbed detections read the normal the unperturbed one has just cached (same as the sequential reference flow)
     int* cvalid = reinterpret_cast<int*>(C.cache) + c_h.cache_valid;
@@ -284,7 +288,7 @@ __device__ __forceinline__ void dev_detect(const Ctx<G>& C, const PairDet& D, co
 }
 
 // unperturbed detection of a pair: contact 0, warm-start cache update, perturbation axes
-template <int G>
+template <int G, bool MPR>
 __device__ __noinline__ void dev_pair_det0(const Ctx<G>& C, LaneContacts& out, PairDet& D) {
   const float EPS = c_m.eps;
   const int ga = D.ga, gb = D.gb;
@@ -298,7 +302,7 @@ __device__ __noinline__ void dev_pair_det0(const Ctx<G>& C, LaneContacts& out, P
   bool is_col;
   f3 normal, cpos;
   float pen = 0.f;
-  dev_detect(C, D, P, 0, is_col, normal, pen, cpos);
+  dev_detect<G, MPR>(C, D, P, 0, is_col, normal, pen, cpos);
   D.is_col_0 = is_col; D.normal_0 = normal; D.cpos_0 = cpos;
   if (is_col) {
     out.add(normal, cpos, pen);
@@ -329,7 +333,7 @@ __device__ __noinline__ void dev_pair_det0(const Ctx<G>& C, LaneContacts& out, P
 }
 
 // perturbed detection i_det (1..4) of a colliding pair, corrected back to the unperturbed frame (NP:889-936)
-template <int G>
+template <int G, bool MPR>
 __device__ __noinline__ void dev_pair_perturbed(const Ctx<G>& C, const PairDet& D, int i_det, bool& is_col, f3& normal, float& pen, f3& cpos) {
   const float EPS = c_m.eps;
   const f3 axis = D.axis_0 * (float)(2 * (i_det % 2) - 1) + D.axis_1 * (float)(1 - 2 * ((i_det / 2) % 2));
@@ -338,7 +342,7 @@ __device__ __noinline__ void dev_pair_perturbed(const Ctx<G>& C, const PairDet& 
   P.ga = D.ga; P.gb = D.gb;
   rotate_frame(D.pa0, D.qa0, D.cpos_0, qrot, P.pa, P.qa);
   rotate_frame(D.pb0, D.qb0, D.cpos_0, quat_inv(qrot), P.pb, P.qb);
-  dev_detect(C, D, P, i_det, is_col, normal, pen, cpos);
+  dev_detect<G, MPR>(C, D, P, i_det, is_col, normal, pen, cpos);
   if (is_col) {
     const f3 cpa = rotate((cpos - normal * (0.5f * pen)) - D.cpos_0, quat_inv(qrot)) + D.cpos_0;
     const f3 cpb = rotate((cpos + normal * (0.5f * pen)) - D.cpos_0, qrot) + D.cpos_0;
@@ -382,7 +386,7 @@ __device__ __noinline__ void dev_plane_box(const Ctx<G>& C, LaneContacts& out, i
 }
 
 // narrow phase of up to G queued pairs; appends the contacts (unordered) to the staging records and returns the new count
-template <int G>
+template <int G, bool MPR>
 __device__ int narrow_batch(const Ctx<G>& C, const int* queue, int n_batch, int n_staged) {
   const int lane = C.lane;
   LaneContacts out;
@@ -397,7 +401,7 @@ __device__ int narrow_batch(const Ctx<G>& C, const int* queue, int n_batch, int 
     if (GM(g_type[ga0]) > GM(g_type[gb0])) { ga = gb0; gb = ga0; }
     plane_box = GM(g_type[ga]) == GEOM_PLANE && GM(g_type[gb]) == GEOM_BOX;
     if (plane_box) dev_plane_box(C, out, ga, gb);
-    else { D.ga = ga; D.gb = gb; D.p = p; dev_pair_det0(C, out, D); }
+    else { D.ga = ga; D.gb = gb; D.p = p; dev_pair_det0<G, MPR>(C, out, D); }
   }
   // ---- perturbed detections: task (pair k of the colliding multi-contact pairs, i_det) -> lane, results through the
   // staging area behind the contact staging records, then every pair lane applies the de-duplication in detection order
@@ -427,7 +431,7 @@ __device__ int narrow_batch(const Ctx<G>& C, const int* queue, int n_batch, int 
       bool is_col;
       f3 normal, cpos;
       float pen = 0.f;
-      dev_pair_perturbed(C, T, i_det, is_col, normal, pen, cpos);
+      dev_pair_perturbed<G, MPR>(C, T, i_det, is_col, normal, pen, cpos);
       float* r = stage + ((size_t)src * 4 + (i_det - 1)) * 8;
       r[0] = is_col ? 1.f : 0.f; r[1] = normal.x; r[2] = normal.y; r[3] = normal.z; r[4] = cpos.x; r[5] = cpos.y; r[6] = cpos.z; r[7] = pen;
     }
@@ -481,7 +485,7 @@ __device__ int narrow_batch(const Ctx<G>& C, const int* queue, int n_batch, int 
   return n_new;
 }
 
-template <int G>
+template <int G, bool MPR>
 __device__ void phase_collide(const Ctx<G>& C) {
   const int lane = C.lane;
   const int nP = CM(nP), nG = CM(nG);
@@ -522,7 +526,7 @@ __device__ void phase_collide(const Ctx<G>& C) {
       qn += accepted;
       C.sync();
       if (qn >= G) {
-        n_staged = narrow_batch(C, queue, G, n_staged);
+        n_staged = narrow_batch<G, MPR>(C, queue, G, n_staged);
         C.sync();
         const int rest = qn - G;  // move the tail (< G entries) to the front
         int t = 0;
@@ -533,7 +537,7 @@ __device__ void phase_collide(const Ctx<G>& C) {
         C.sync();
       }
     }
-    if (qn > 0) n_staged = narrow_batch(C, queue, qn, n_staged);
+    if (qn > 0) n_staged = narrow_batch<G, MPR>(C, queue, qn, n_staged);
     if (lane == 0) SI[c_h.n_broad] = n_broad;
   }
   __threadfence_block();

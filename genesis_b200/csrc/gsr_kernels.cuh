@@ -104,7 +104,7 @@ struct HostIO {
   float* vel;             // (B, nD) or null
 };
 
-template <int G>
+template <int G, bool MPR>
 __global__ void __launch_bounds__(GSR_MAX_WARPS_PER_CTA * 32, 1) k_step(float* state, int B, const DevModel* gm, int clear_ext, const int* order,
                                                                         unsigned long long* trace, HostIO io) {
   extern __shared__ __align__(16) float smem[];
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(GSR_MAX_WARPS_PER_CTA * 32, 1) k_step(float* s
   TRACE_MARK(1);
   PHASE_BARRIER(1);
   PHASE_BEGIN();
-  if (live && CM(enable_collision) && CM(nG) > 0) phase_collide(C);
+  if (live && CM(enable_collision) && CM(nG) > 0) phase_collide<G, MPR>(C);
   PHASE_END();
   TRACE_MARK(2);
   PHASE_BARRIER(2);

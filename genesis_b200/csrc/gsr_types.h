@@ -45,6 +45,7 @@ struct DevModel {
   int max_contact_pairs, max_broad_pairs, n_contacts_per_pair, len_constraints;
   int iterations, ls_iterations, integrator, solver_type;
   int noslip_iterations;  // constraint/noslip.py post-solver (0 = off)
+  int has_mpr;            // any valid pair that needs MPR / EPA (neither a plane pair nor an analytic capsule pair): selects the kernel variant
   int phase_barriers;     // bit k: CTA barrier k of k_step (0 after the record load, 1 dynamics, 2 collision, 3 constraints, 4 integration)
   int gjk_fallback;       // exact-penetration fallback after MPR (narrowphase.py:726-733); 0 keeps MPR's answer
   float noslip_tolerance;
