@@ -17,7 +17,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 20 -c 6
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_step -s 10 -c 2 -f -o $O/prof_franka \
    python bench.py --workload franka --steps 20 --warmup 5 --no-cpu-baseline > $O/ncu_full_franka.log 2>&1
 ncu -i $O/prof_franka.ncu-rep --page raw --csv > $O/prof_franka.raw.csv 2>/dev/null
-python tools/ncu_funcs.py $O/prof_franka.ncu-rep k_stepILi8 > $O/prof_franka.funcs.txt 2>&1
-python tools/ncu_lines.py $O/prof_franka.ncu-rep k_stepILi8 40 > $O/prof_franka.lines.txt 2>&1
+python tools/ncu_funcs.py $O/prof_franka.ncu-rep k_stepILi8ELb0 > $O/prof_franka.funcs.txt 2>&1
+python tools/ncu_lines.py $O/prof_franka.ncu-rep k_stepILi8ELb0 40 > $O/prof_franka.lines.txt 2>&1
 rm -f $O/prof_franka.ncu-rep
 ls $O

@@ -28,7 +28,8 @@ GSR_GROUP_SIZE=1 timeout 900 ncu --set full --clock-control none --import-source
      python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $O/ncu_full_franka_lane.log 2>&1
 # gpurun copies back at most 64 MiB: keep the csv exports / attributions, drop the raw reports
 for R in franka go2 franka_lane; do
-  K=k_stepILi8; [ $R = go2 ] && K=k_stepILi32; [ $R = franka_lane ] && K=k_step_lane
+  K=k_stepILi8ELb0; [ $R = go2 ] && K=k_stepILi32ELb1;  # the Franka bench scene has no MPR pair, Go2 with self-collision does
+   [ $R = franka_lane ] && K=k_step_lane
   ncu -i $O/prof_$R.ncu-rep --page raw --csv > $O/prof_$R.raw.csv 2>/dev/null
   python tools/ncu_funcs.py $O/prof_$R.ncu-rep $K > $O/prof_$R.funcs.txt 2>&1
   python tools/ncu_lines.py $O/prof_$R.ncu-rep $K 40 > $O/prof_$R.lines.txt 2>&1
