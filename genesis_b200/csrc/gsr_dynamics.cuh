@@ -265,8 +265,8 @@ __device__ void phase_geoms(const Ctx<G>& C) {
 template <int G>
 __device__ __noinline__ void mass_solve(const Ctx<G>& C, float* x) {
   const int nD = CM(nD), MS = c_s.MS;
-  const float* L = WK(L);
-  const float* Dinv = WK(Dinv);
+  const float* L = WKS(L);
+  const float* Dinv = WKS(Dinv);
   if (nD <= G) {
     // one lane per unknown, the running right-hand side in a register; the pivot value travels by shuffle, so the
     // 2 (nD - 1) elimination steps need no shared-memory round trip and no barrier (same products, same order)
@@ -326,8 +326,8 @@ __device__ __noinline__ void mass_solve(const Ctx<G>& C, float* x) {
 template <int G>
 __device__ __noinline__ void mass_factor(const Ctx<G>& C) {
   const int nD = CM(nD), MS = c_s.MS;
-  float* L = WK(L);
-  float* Dinv = WK(Dinv);
+  float* L = WKS(L);
+  float* Dinv = WKS(Dinv);
   for (int i = nD - 1; i >= 0; i--) {
     const float dinv = 1.0f / L[i * MS + i];
     // (j, k), k <= j < i, over the ancestor dofs of i only: entries of other branches are structurally zero and stay zero

@@ -87,3 +87,12 @@ __device__ __forceinline__ f3 link_ipos(const Ctx<G>& C, int l, bool shifted) {
 // results in 16-20 parity tests (profiles/README.md, r1e) -- left as it is until that is understood.
 #define IN(field) (C.S + c_h.field)   // IN part of the record, mirrored in shared memory
 #define WK(field) (C.S + c_s.field)   // workspace regions
+// Shared-space variant for the self-contained dense-algebra routines (factorisations, triangular solves, rank-1 updates:
+// explicit warp barriers between dependent steps): LDS / STS instead of generic LD / ST, Franka 73.8 -> 75.9 M env-steps/s.
+// Applied to ALL accessors it produced wrong results in 16-20 parity tests (profiles/README.md item 13), hence the opt-in.
+#ifndef GSR_NO_LDS_ROUTINES
+__device__ __forceinline__ float* smem_ptr(float* p) { __builtin_assume(__isShared(p)); return p; }
+#define WKS(field) (smem_ptr(C.S) + c_s.field)
+#else
+#define WKS(field) WK(field)
+#endif

@@ -329,9 +329,9 @@ template <int G>
 __device__ __noinline__ void hessian_cholesky(const Ctx<G>& C, const Rows& R, long long* t_split = nullptr) {
   const int nD = CM(nD), MS = c_s.MS, lane = C.lane;
   const float EPS = CM(eps);
-  float* H = WK(H);
-  float* Hinv = WK(Hinv);
-  const float* M = WK(M);
+  float* H = WKS(H);
+  float* Hinv = WKS(Hinv);
+  const float* M = WKS(M);
   const int ntri = nD * (nD + 1) / 2;
   // every lane accumulates up to NE lower-triangle entries at once, so one sweep over the rows (with the row weight
   // D_c * active_c loaded once, inactive rows skipped by a group-uniform branch) serves NE * G entries
@@ -424,13 +424,13 @@ template <int G>
 __device__ __noinline__ bool hessian_incremental(const Ctx<G>& C, const Rows& R) {
   const int nD = CM(nD), MS = c_s.MS, lane = C.lane;
   const float EPS = CM(eps);
-  float* H = WK(H);
+  float* H = WKS(H);
   float* vec = WK(prev_grad);  // scratch (the CG history is unused by the Newton solver)
   if (nD <= G) {
     // one matrix row per lane: lane i keeps vec[i] in a register and is the only one to touch row i of the factor, the
     // pivot values (vec[k], L_kk) travel by shuffle -- no shared-memory round trip and no barrier per column (the same
     // operations in the same order as the general loop below)
-    float* Hinv = WK(Hinv);
+    float* Hinv = WKS(Hinv);
     const bool own = lane < nD;
     for (int base = 0; base < R.n_con; base += G) {
       const int cl = base + lane;
@@ -521,8 +521,8 @@ __device__ __noinline__ void update_gradient(const Ctx<G>& C) {
   if (CM(solver_type) == SOLVER_CG) {
     mass_solve(C, Mgrad);
   } else {
-    const float* H = WK(H);
-    const float* Hinv = WK(Hinv);
+    const float* H = WKS(H);
+    const float* Hinv = WKS(Hinv);
     if (nD <= G) {
       // one lane per unknown with the running right-hand side in a register and the pivot broadcast by shuffle: no
       // shared-memory round trip or barrier per column (same products in the same order as the column sweeps below)
