@@ -82,9 +82,9 @@ __device__ __forceinline__ f3 link_ipos(const Ctx<G>& C, int l, bool shifted) {
   return p;
 }
 
-// IN / WK reach shared memory through a generic pointer (generic LD / ST in SASS, no LDS / STS): telling the compiler the
-// address space (`__builtin_assume(__isShared(C.S))`) produced LDS / STS, 8 fewer registers and +5 % on Franka, but wrong
-// results in 16-20 parity tests (profiles/README.md, r1e) -- left as it is until that is understood.
+// IN / WK reach shared memory through a generic pointer (generic LD / ST in SASS): telling the compiler the address space of
+// EVERY access (`__builtin_assume(__isShared(C.S))` in both macros) gave wrong results in 16-20 parity tests, for either half
+// of the accessors (profiles/README.md item 13); the routines that are known to be safe use WKS below.
 #define IN(field) (C.S + c_h.field)   // IN part of the record, mirrored in shared memory
 #define WK(field) (C.S + c_s.field)   // workspace regions
 // Shared-space variant for the self-contained dense-algebra routines (factorisations, triangular solves, rank-1 updates:
