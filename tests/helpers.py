@@ -182,3 +182,31 @@ def box_box_qpos(n, seed=0):
         q[b, 7:10] = (0, 0, 0.65 + 0.1 * rng.random())
         q[b, 10:14] = mul(mul(qx, qy), qz_)
     return q
+
+
+def multi_pendulum_urdf(n=2, joint_damping=0.0, joint_friction=0.0):
+    """The reference's `_build_multi_pendulum` fixture (tests/test_rigid_physics.py:230-292): n massless 1 m arms hinged about x,
+    each carrying a 1 kg point mass at its tip."""
+    out = ['<robot name="multi_pendulum">', '<link name="base"/>']
+    parent = "base"
+    for i in range(n):
+        out.append(f'<joint name="PendulumJoint_{i}" type="continuous"><origin xyz="0 0 0" rpy="0 0 0"/><axis xyz="1 0 0"/>'
+                   f'<parent link="{parent}"/><child link="PendulumArm_{i}"/><limit effort="{100.0 * (n - i)}" velocity="30.0"/>'
+                   f'<dynamics damping="{joint_damping}" friction="{joint_friction}"/></joint>')
+        out.append(f'<link name="PendulumArm_{i}"><inertial><origin xyz="0 0 0" rpy="0 0 0"/><mass value="0.0"/>'
+                   '<inertia ixx="0.0" ixy="0.0" ixz="0.0" iyy="0.0" iyz="0.0" izz="0.0"/></inertial></link>')
+        out.append(f'<joint name="PendulumMassJoint_{i}" type="fixed"><origin xyz="0 0 1.0" rpy="0 0 0"/>'
+                   f'<parent link="PendulumArm_{i}"/><child link="PendulumMass_{i}"/></joint>')
+        out.append(f'<link name="PendulumMass_{i}"><inertial><origin xyz="0 0 0" rpy="0 0 0"/><mass value="1.0"/>'
+                   '<inertia ixx="1e-12" ixy="0.0" ixz="0.0" iyy="1e-12" iyz="0.0" izz="1e-12"/></inertial></link>')
+        parent = f"PendulumMass_{i}"
+    out.append("</robot>")
+    return "\n".join(out)
+
+
+def make_double_pendulum(n_envs, build=True, **rigid_kwargs):
+    scene = gs.Scene(rigid_options=gs.options.RigidOptions(dt=0.01, **rigid_kwargs))
+    ent = scene.add_entity(gs.morphs.URDF(file=write_tmp(multi_pendulum_urdf(2), ".urdf"), merge_fixed_links=False, fixed=True))
+    if build:
+        scene.build(n_envs=n_envs)
+    return scene, ent

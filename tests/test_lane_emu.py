@@ -340,3 +340,25 @@ def test_lane_box_box_first_touch_and_settling():
         emu.step(10)
         contacts_equal(orc, emu, B)
     assert np.abs(emu.rows("qpos") - orc.qpos()).max() <= 1e-3 and np.abs(emu.rows("vel") - orc.vel()).max() <= 2e-2
+
+
+def test_lane_double_pendulum_link_accelerations():
+    """The reference's double pendulum (tests/test_rigid_physics.py:230-297, fixed links kept, CG + Euler): every quantity of a
+    step and the link accelerations along a 50-step swing against the oracle (which satisfies the reference's closed-form
+    assertions, tests/test_oracle_analytic.py)."""
+    from helpers import make_double_pendulum
+
+    B = 3
+    rng = np.random.default_rng(1)
+    q0, v0 = rng.random((B, 2)), rng.random((B, 2))
+    m, orc, emu = pair(make_double_pendulum, B, lambda m, B: {"qpos": q0, "vel": v0}, constraint_solver=gs.constraint_solver.CG,
+                       integrator=gs.integrator.Euler)
+    orc.step(1)
+    emu.step(1)
+    check_all_quantities(m, orc, emu)
+    orc.step(49)
+    emu.step(49)
+    assert np.abs(emu.rows("qpos") - orc.qpos()).max() <= 1e-4 and np.abs(emu.rows("vel") - orc.vel()).max() <= 1e-3
+    for name in ("cacc_lin", "cacc_ang"):
+        a = emu.rows(name)
+        close(a, orc.get(name, (m.n_links, 3)).reshape(a.shape), TOL_SOLVER, name)

@@ -398,3 +398,45 @@ def test_box_box_dynamics_reference_expectations(solver_name, integrator_name):
     q = orc.qpos()
     np.testing.assert_allclose(q[:, 9], 0.6, atol=2e-3)
     np.testing.assert_allclose(q[:, 2], 0.2, atol=2e-3)
+
+
+def test_double_pendulum_link_accelerations_reference_closed_form():
+    """The reference's test_double_pendulum_links_acc (tests/test_rigid_physics.py:955-1020; CG, Euler, fixed links kept), its
+    closed-form assertions applied to the oracle for 100 steps from a random state: angular accelerations of the links, the
+    spatial linear acceleration carried in the COM frame (`cacc_lin`), and the classical acceleration of the point masses
+    (the `get_links_acc` formula) in the rotating frames.  Poses and velocities are the ones the accelerations were computed
+    from (the state before the step: what the reference's MuJoCo-compatible test fixture reads back)."""
+    from helpers import make_double_pendulum
+
+    scene, solver, m = host_model(make_double_pendulum, constraint_solver=gs.constraint_solver.CG, integrator=gs.integrator.Euler)
+    assert (m.n_links, m.n_dofs) == (5, 2)
+    orc = oracle_for(solver, m, 1, double=True)
+    rng = np.random.default_rng(0)
+    orc.set("qpos", rng.random(2))
+    orc.set("vel", rng.random(2))
+    orc.step(1)
+    L, sel, tol = m.n_links, [0, 2, 4], 1e-9
+    for _ in range(100):
+        theta, theta_dot = orc.qpos()[0].copy(), orc.vel()[0].copy()
+        pos, com = orc.get("links_pos", (L, 3), 0)[sel], orc.get("root_COM", (L, 3), 0)[-1]
+        ang, vel = orc.get("cd_ang", (L, 3), 0)[sel], orc.get("cd_vel", (L, 3), 0)[sel]
+        orc.step(1)
+        tdd = orc.get("acc", 2, 0)
+        acc_ang = orc.get("cacc_ang", (L, 3), 0)
+        cacc = orc.get("cacc_lin", (L, 3), 0)[sel]
+        np.testing.assert_allclose(acc_ang[0], 0, atol=tol)
+        np.testing.assert_allclose(acc_ang[1], [tdd[0], 0, 0], atol=tol)
+        np.testing.assert_allclose(acc_ang[-1], [tdd.sum(), 0, 0], atol=tol)
+        np.testing.assert_allclose(cacc[1], np.cross(acc_ang[2], com), atol=tol)
+        spatial = cacc + np.cross(acc_ang[sel], pos - com)
+        np.testing.assert_allclose(spatial[0], 0, atol=tol)
+        tw = theta.cumsum()
+        R = np.array([[np.ones(2), np.zeros(2), np.zeros(2)], [np.zeros(2), np.cos(tw), np.sin(tw)], [np.zeros(2), -np.sin(tw), np.cos(tw)]])
+        local = np.matmul(np.moveaxis(R, 2, 0), spatial[1:, :, None])[..., 0]
+        np.testing.assert_allclose(local[0], [0, -tdd[0], 0], atol=tol)
+        np.testing.assert_allclose(local[1], R[..., 1] @ (R[..., 0].T @ np.array([0, -tdd[0], theta_dot[0] * theta_dot[1]])) + np.array([0, -tdd.sum(), 0]), atol=tol)
+        classical = spatial + np.cross(ang, vel + np.cross(ang, pos - com))
+        np.testing.assert_allclose(classical[0], 0, atol=tol)
+        local = np.matmul(np.moveaxis(R, 2, 0), classical[1:, :, None])[..., 0]
+        np.testing.assert_allclose(local[0], [0, -tdd[0], -(theta_dot[0] ** 2)], atol=tol)
+        np.testing.assert_allclose(local[1], R[..., 1] @ classical[1] + np.array([0, -tdd.sum(), -(theta_dot.sum() ** 2)]), atol=tol)
