@@ -210,3 +210,29 @@ def make_double_pendulum(n_envs, build=True, **rigid_kwargs):
     if build:
         scene.build(n_envs=n_envs)
     return scene, ent
+
+# the reference's `two_aligned_hinges` fixture (tests/test_rigid_physics.py:170-182)
+TWO_HINGES_XML = """
+<mujoco model="two_aligned_hinges">
+  <option timestep="0.05"/>
+  <default><geom contype="1" conaffinity="1" condim="3"/></default>
+  <worldbody>
+    <body name="body0">
+      <geom type="capsule" fromto="0 0 0 0.5 0 0" size="0.05"/>
+      <joint type="hinge" name="joint0" axis="0 0 1"/>
+      <body name="body1" pos="0.5 0 0">
+        <geom type="capsule" fromto="0 0 0 0.5 0 0" size="0.05"/>
+        <joint type="hinge" name="joint1" axis="0 0 1"/>
+      </body>
+    </body>
+  </worldbody>
+</mujoco>
+"""
+
+
+def make_two_hinges(n_envs, build=True, **rigid_kwargs):
+    scene = gs.Scene(rigid_options=gs.options.RigidOptions(dt=0.05, **rigid_kwargs))
+    ent = scene.add_entity(gs.morphs.MJCF(file=write_tmp(TWO_HINGES_XML, ".xml")))
+    if build:
+        scene.build(n_envs=n_envs)
+    return scene, ent

@@ -440,3 +440,47 @@ def test_double_pendulum_link_accelerations_reference_closed_form():
         local = np.matmul(np.moveaxis(R, 2, 0), classical[1:, :, None])[..., 0]
         np.testing.assert_allclose(local[0], [0, -tdd[0], -(theta_dot[0] ** 2)], atol=tol)
         np.testing.assert_allclose(local[1], R[..., 1] @ classical[1] + np.array([0, -tdd.sum(), -(theta_dot.sum() ** 2)]), atol=tol)
+
+
+def test_link_velocity_reference_expectations():
+    """The reference's test_link_velocity (tests/test_rigid_physics.py:826-896, `two_aligned_hinges`): subtree COM, link
+    origins and the COM-frame spatial velocities `cd_vel` / `cd_ang` for its special cases and its random configuration, plus
+    the link-origin velocity formula of `get_links_vel`."""
+    from helpers import make_two_hinges
+
+    scene, solver, m = host_model(make_two_hinges, constraint_solver=gs.constraint_solver.CG, integrator=gs.integrator.Euler)
+    orc = oracle_for(solver, m, 1, double=True)
+    L, tol = m.n_links, 1e-9
+
+    def state(q, v):
+        orc.set("qpos", q)
+        orc.set("vel", v)
+        orc.forward_dynamics(0)
+        return [orc.get(k, (L, 3), 0) for k in ("cd_vel", "cd_ang", "root_COM", "links_pos")]
+
+    cvel, _, _, _ = state([0.0, 0.0], [0.0, 1.0])
+    np.testing.assert_allclose(cvel, 0, atol=tol)
+    cvel, _, _, _ = state([0.0, 0.0], [1.0, 0.0])
+    np.testing.assert_allclose(cvel, [[0.0, 0.5, 0.0]] * 2, atol=tol)
+    cvel, _, com, pos = state([0.0, np.pi / 2.0], [0.0, 1.2])
+    np.testing.assert_allclose(com[0], [0.375, 0.125, 0.0], atol=tol)
+    np.testing.assert_allclose(pos[1], [0.5, 0.0, 0.0], atol=tol)  # = xanchor of joint 1
+    np.testing.assert_allclose(cvel[0], 0, atol=tol)
+    np.testing.assert_allclose(cvel[1], [-1.2 * (0.125 - 0.0), 1.2 * (0.375 - 0.5), 0.0], atol=tol)
+    # random configuration
+    t0, t1 = -0.7, 0.2
+    cvel, cang, com, pos = state([t0, t1], [3.0, 13.0])
+    xanchor = pos[1]
+    np.testing.assert_allclose(xanchor, [0.5 * np.cos(t0), 0.5 * np.sin(t0), 0.0], atol=tol)
+    com0 = np.array([0.25 * np.cos(t0), 0.25 * np.sin(t0), 0.0])
+    com1 = np.array([0.5 * np.cos(t0) + 0.25 * np.cos(t0 + t1), 0.5 * np.sin(t0) + 0.25 * np.sin(t0 + t1), 0.0])
+    COM = com[0]
+    np.testing.assert_allclose(COM, 0.5 * (com0 + com1), atol=tol)
+    w0, w1 = cang[0, 2], cang[1, 2]
+    assert w0 == pytest.approx(3.0, abs=tol) and w1 - w0 == pytest.approx(13.0, abs=tol)
+    np.testing.assert_allclose(cvel[0], w0 * np.array([-COM[1], COM[0], 0.0]), atol=tol)
+    np.testing.assert_allclose(cvel[1], cvel[0] + (w1 - w0) * np.array([xanchor[1] - COM[1], COM[0] - xanchor[0], 0.0]), atol=tol)
+    np.testing.assert_allclose(pos[0], 0, atol=tol)
+    xvel = cvel + np.cross(cang, pos - com)  # get_links_vel (abd/accessor.py): velocity of the link origin
+    np.testing.assert_allclose(xvel[0], 0, atol=tol)
+    np.testing.assert_allclose(xvel[1], w0 * np.array([-xanchor[1], xanchor[0], 0.0]), atol=tol)
