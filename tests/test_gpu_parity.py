@@ -425,3 +425,31 @@ def test_box_box_dynamics_reference_expectations(solver_name, integrator_name):
     q = ent.get_qpos().cpu().numpy()
     np.testing.assert_allclose(q[:, 9], 0.6, atol=2e-3)
     np.testing.assert_allclose(q[:, 2], 0.2, atol=2e-3)
+
+
+def test_double_pendulum_link_accelerations():
+    """The reference's double pendulum (tests/test_rigid_physics.py:230-297, 955-1020: massless arms, fixed links kept, CG +
+    Euler) on the CUDA path: a 50-step swing and the link accelerations (`get_links_acc_ang`, `cacc_lin`) against the oracle,
+    which satisfies the reference's closed-form assertions (tests/test_oracle_analytic.py)."""
+    from helpers import make_double_pendulum
+
+    B = 16
+    scene, ent = make_double_pendulum(B, constraint_solver=gs.constraint_solver.CG, integrator=gs.integrator.Euler)
+    rng = np.random.default_rng(1)
+    ent.set_qpos(torch.tensor(rng.random((B, 2)), dtype=torch.float32, device=gs.device))
+    ent.set_dofs_velocity(torch.tensor(rng.random((B, 2)), dtype=torch.float32, device=gs.device))
+    orc = mirror_oracle(scene)
+    for _ in range(50):
+        scene.step()
+    orc.step(50)
+    assert np.abs(gpu_field(scene, "qpos") - orc.qpos()).max() <= TRAJ_QPOS_FREE
+    assert np.abs(gpu_field(scene, "vel") - orc.vel()).max() <= TRAJ_QVEL_FREE
+    nL = scene.rigid_solver.model.n_links
+    assert nL == 5
+    for name in ("cacc_lin", "cacc_ang"):
+        a = gpu_field(scene, name)
+        assert_close(a, orc.get(name, (nL, 3)).reshape(a.shape), 5e-4, name)
+    acc_ang = scene.rigid_solver.get_links_acc_ang().cpu().numpy()
+    acc = gpu_field(scene, "acc")
+    np.testing.assert_allclose(acc_ang[:, 1, 0], acc[:, 0], atol=1e-4)  # reference: acc_ang[1] = (theta_ddot_0, 0, 0)
+    np.testing.assert_allclose(acc_ang[:, -1, 0], acc[:, 0] + acc[:, 1], atol=1e-4)
