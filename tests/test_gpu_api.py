@@ -164,3 +164,41 @@ def test_collider_and_constraint_solver_facades():
     assert cs.qacc_ws.shape == (B, 18)
     assert (cs.n_constraints >= 4 * n).all() and (cs.n_constraints_equality == 0).all()
     assert (cs.n_iterations >= 1).all()
+
+
+def test_link_velocity_reference_expectations():
+    """The reference's test_link_velocity (tests/test_rigid_physics.py:826-896, `two_aligned_hinges`) through the accessors:
+    set_qpos / set_dofs_velocity refresh the kinematics, get_links_pos / get_links_vel / get_links_ang / get_links_root_COM
+    return what the reference asserts (5e-5, its fp32 tolerance)."""
+    from helpers import make_two_hinges
+
+    B, tol = 2, 5e-5
+    scene, ent = make_two_hinges(B, constraint_solver=gs.constraint_solver.CG, integrator=gs.integrator.Euler)
+    s = scene.rigid_solver
+
+    def state(q, v):
+        ent.set_qpos(torch.tensor([q] * B, dtype=torch.float32, device=gs.device))
+        ent.set_dofs_velocity(torch.tensor([v] * B, dtype=torch.float32, device=gs.device))
+        return [x[0].cpu().numpy().astype(np.float64) for x in (s.field("cd_vel"), s.get_links_ang(), s.get_links_root_COM(), s.get_links_pos(), s.get_links_vel())]
+
+    cvel = state([0.0, 0.0], [0.0, 1.0])[0]
+    np.testing.assert_allclose(cvel, 0, atol=tol)
+    cvel = state([0.0, 0.0], [1.0, 0.0])[0]
+    np.testing.assert_allclose(cvel, [[0.0, 0.5, 0.0]] * 2, atol=tol)
+    cvel, _, com, pos, _ = state([0.0, np.pi / 2.0], [0.0, 1.2])
+    np.testing.assert_allclose(com[0], [0.375, 0.125, 0.0], atol=tol)
+    np.testing.assert_allclose(pos[1], [0.5, 0.0, 0.0], atol=tol)
+    np.testing.assert_allclose(cvel[1], [-1.2 * 0.125, 1.2 * (0.375 - 0.5), 0.0], atol=tol)
+    t0, t1 = -0.7, 0.2
+    cvel, cang, com, pos, xvel = state([t0, t1], [3.0, 13.0])
+    xanchor, COM = pos[1], com[0]
+    np.testing.assert_allclose(xanchor, [0.5 * np.cos(t0), 0.5 * np.sin(t0), 0.0], atol=tol)
+    com0 = np.array([0.25 * np.cos(t0), 0.25 * np.sin(t0), 0.0])
+    com1 = np.array([0.5 * np.cos(t0) + 0.25 * np.cos(t0 + t1), 0.5 * np.sin(t0) + 0.25 * np.sin(t0 + t1), 0.0])
+    np.testing.assert_allclose(COM, 0.5 * (com0 + com1), atol=tol)
+    w0, w1 = cang[0, 2], cang[1, 2]
+    assert abs(w0 - 3.0) <= tol and abs(w1 - w0 - 13.0) <= 2e-4  # 16.0 in fp32
+    np.testing.assert_allclose(cvel[0], w0 * np.array([-COM[1], COM[0], 0.0]), atol=2e-4)
+    np.testing.assert_allclose(cvel[1], cvel[0] + (w1 - w0) * np.array([xanchor[1] - COM[1], COM[0] - xanchor[0], 0.0]), atol=2e-4)
+    np.testing.assert_allclose(xvel[0], 0, atol=2e-4)
+    np.testing.assert_allclose(xvel[1], w0 * np.array([-xanchor[1], xanchor[0], 0.0]), atol=2e-4)
