@@ -362,3 +362,20 @@ def test_lane_double_pendulum_link_accelerations():
     for name in ("cacc_lin", "cacc_ang"):
         a = emu.rows(name)
         close(a, orc.get(name, (m.n_links, 3)).reshape(a.shape), TOL_SOLVER, name)
+
+
+def test_lane_all_fixed_scene_steps():
+    """The reference's test_all_fixed (tests/test_rigid_physics.py:2093-2115): a scene whose only entity is a fixed box (no dofs,
+    no qs) builds and steps; the box stays where it is (oracle and lane kernel)."""
+    from helpers import scene_from_morphs
+
+    scene, _ = scene_from_morphs([gs.morphs.Box(size=(0.1, 0.1, 0.1), pos=(0.0, 0.0, 0.0), fixed=True)], dt=0.01)
+    solver = scene.rigid_solver
+    m = solver.build_model()
+    assert (m.n_links, m.n_dofs, m.n_qs, m.n_geoms) == (1, 0, 0, 1)
+    orc = oracle_for(solver, m, 2)
+    emu = LaneEmu(m, 2, solver.model_options())
+    orc.step(3)
+    emu.step(3)
+    assert np.abs(orc.get("links_pos", (1, 3))).max() == 0.0 and np.abs(emu.field("links_pos")).max() == 0.0
+    assert int(emu.field("errno_").max()) == 0
