@@ -208,6 +208,8 @@ class ModelBuilder:
             lgeoms = geoms[link["geom_start"]: link["geom_end"]]
             if link["inertial_mass"] is None or link["inertial_pos"] is None or link["inertial_i"] is None:
                 rho = ent.rho if ent.rho is not None else (RHO_ROBOT if ent.is_robot else RHO_OBJECT)
+                if link.get("geom_density"):  # MJCF body without <inertial>: MuJoCo's geom density, whatever the material says
+                    rho = link["geom_density"]
                 if not link["is_fixed"] and lgeoms:
                     mass, com, I = _compose_inertial([(*_geom_inertial(g, rho), g["pos"], g["quat"]) for g in lgeoms])
                 else:

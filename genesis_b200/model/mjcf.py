@@ -23,6 +23,7 @@ from ..constants import EQUALITY_TYPE, GEOM_TYPE, JOINT_TYPE
 
 # MuJoCo defaults
 _DEFAULT_SOLIMP = np.array([0.9, 0.95, 0.001, 0.5, 2.0])
+RHO_MUJOCO = 1000.0  # MuJoCo's default geom density (rigid_link.py:25)
 
 
 def _floats(s, n=None):
@@ -123,7 +124,10 @@ def parse_mjcf(path, default_armature=0.1, scale=1.0):
                 l_info["inertial_quat"] = iq
                 l_info["inertial_i"] = np.diag(_floats(inertial.attrib["diaginertia"])) * scale**5
         else:
-            l_info.update(inertial_mass=None, inertial_pos=None, inertial_quat=None, inertial_i=None)
+            # no <inertial>: MuJoCo's compiler infers mass / COM / inertia from the body's geoms with its default geom density
+            # (1000 kg/m^3) and the reference takes body_mass / body_ipos / body_inertia as they are (utils/mjcf.py:240-243),
+            # so the entity's material density plays no role for such links
+            l_info.update(inertial_mass=None, inertial_pos=None, inertial_quat=None, inertial_i=None, geom_density=RHO_MUJOCO)
 
         idx = len(l_infos)
         l_infos.append(l_info)

@@ -236,3 +236,28 @@ def make_two_hinges(n_envs, build=True, **rigid_kwargs):
     if build:
         scene.build(n_envs=n_envs)
     return scene, ent
+
+# the reference's `hinge_slide` fixture (tests/test_rigid_physics.py:351-365): joint friction loss, damping and a spring
+HINGE_SLIDE_XML = """
+<mujoco model="hinge_slide">
+  <default><joint damping="0.01"/></default>
+  <worldbody>
+    <body name="pendulum" pos="0.15 0.0 0.0">
+      <joint name="hinge" type="hinge" axis="0 1 0" frictionloss="0.08"/>
+      <geom name="geom1" type="capsule" size="0.02" fromto="0.0 0.0 0.0 0.1 0.0 0.0"/>
+      <body name="link1" pos="0.1 0.0 0.0">
+        <joint name="slide" type="slide" axis="1 0 0" frictionloss="0.3" stiffness="200.0"/>
+        <geom name="geom2" type="capsule" size="0.015" fromto="-0.1 0.0 0.0 0.1 0.0 0.0"/>
+      </body>
+    </body>
+  </worldbody>
+</mujoco>
+"""
+
+
+def make_hinge_slide(n_envs, build=True, **rigid_kwargs):
+    scene = gs.Scene(rigid_options=gs.options.RigidOptions(dt=0.002, **rigid_kwargs))  # MuJoCo's default timestep
+    ent = scene.add_entity(gs.morphs.MJCF(file=write_tmp(HINGE_SLIDE_XML, ".xml"), default_armature=None))  # as tests/utils.py:596
+    if build:
+        scene.build(n_envs=n_envs)
+    return scene, ent

@@ -484,3 +484,24 @@ def test_link_velocity_reference_expectations():
     xvel = cvel + np.cross(cang, pos - com)  # get_links_vel (abd/accessor.py): velocity of the link origin
     np.testing.assert_allclose(xvel[0], 0, atol=tol)
     np.testing.assert_allclose(xvel[1], w0 * np.array([-xanchor[1], xanchor[0], 0.0]), atol=tol)
+
+
+@pytest.mark.parametrize("solver_name", ["CG", "Newton"])
+@pytest.mark.parametrize("integrator_name", ["implicitfast", "Euler"])
+def test_frictionloss_reference_expectation(solver_name, integrator_name):
+    """The reference's test_frictionloss (tests/test_rigid_physics.py:509-520, `hinge_slide`: joint friction loss 0.08 / 0.3, damping,
+    a 200 N/m spring; MuJoCo's default time step and no default armature like its fixture): started with qvel = (0.7, -0.9)
+    the mechanism is at rest after 2000 steps, |qvel| <= 1e-2.  (The step-by-step comparison with MuJoCo of the same test
+    cannot run here.)  Also pins the link masses MuJoCo's compiler infers from the capsule geoms (density 1000)."""
+    from helpers import make_hinge_slide
+
+    scene, solver, m = host_model(make_hinge_slide, constraint_solver=getattr(gs.constraint_solver, solver_name),
+                                  integrator=getattr(gs.integrator, integrator_name))
+    vol = lambda r, half: np.pi * r * r * 2 * half + 4.0 / 3.0 * np.pi * r**3
+    np.testing.assert_allclose(np.asarray(m.links_inertial_mass)[1:], [1000 * vol(0.02, 0.05), 1000 * vol(0.015, 0.1)], rtol=1e-9)
+    assert list(m.dofs_armature) == [0.0, 0.0]
+    orc = oracle_for(solver, m, 1, double=True)
+    orc.set("vel", [0.7, -0.9])
+    orc.step(2000)
+    assert np.abs(orc.vel()).max() <= 1e-2
+    assert orc.get("n_constraints", 1, 0)[0] == 2  # the two friction-loss rows
