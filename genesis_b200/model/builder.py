@@ -211,7 +211,14 @@ class ModelBuilder:
                 if link.get("geom_density"):  # MJCF body without <inertial>: MuJoCo's geom density, whatever the material says
                     rho = link["geom_density"]
                 if not link["is_fixed"] and lgeoms:
-                    mass, com, I = _compose_inertial([(*_geom_inertial(g, rho), g["pos"], g["quat"]) for g in lgeoms])
+                    def one(g):
+                        if not link.get("geom_density"):
+                            return _geom_inertial(g, rho)
+                        mg, cg, Ig = _geom_inertial(g, g.get("density", rho))
+                        if g.get("mass") is not None and mg > 0:  # an explicit geom mass overrides its density
+                            Ig, mg = Ig * (g["mass"] / mg), g["mass"]
+                        return mg, cg, Ig
+                    mass, com, I = _compose_inertial([(*one(g), g["pos"], g["quat"]) for g in lgeoms])
                 else:
                     mass, com, I = 0.0, np.zeros(3), np.zeros((3, 3))
                 if link["inertial_mass"] is None:

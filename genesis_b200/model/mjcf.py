@@ -216,6 +216,11 @@ def parse_mjcf(path, default_armature=0.1, scale=1.0):
             if "solimp" in attrs:
                 s = _floats(attrs["solimp"])
                 g_info["sol_params"][2 : 2 + len(s)] = s
+            # per-geom density / mass of MuJoCo's inertia inference (used only for bodies without <inertial>)
+            if "density" in attrs:
+                g_info["density"] = float(attrs["density"])
+            if "mass" in attrs:
+                g_info["mass"] = float(attrs["mass"]) * scale**3
             if gtype == "mesh":
                 mpath, mscale = meshes[attrs["mesh"]]
                 verts, faces = meshio.convex_hull(meshio.load_vertices(mpath) * mscale * scale)

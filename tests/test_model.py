@@ -79,3 +79,28 @@ def test_unknown_option_is_rejected():
     scene.add_entity(gs.morphs.Plane())
     with pytest.raises(gs.GenesisException):
         scene.rigid_solver.build_model()
+
+
+def test_mjcf_inertia_inferred_from_geoms_like_mujoco():
+    """Bodies without <inertial>: mass / COM from the geoms at MuJoCo's default density 1000 kg/m^3, per-geom `density` and
+    `mass` attributes honoured (the reference reads body_mass / body_ipos from the MuJoCo compiler, utils/mjcf.py:240-243);
+    the material density of the entity plays no role for them."""
+    from helpers import scene_from_morphs, write_tmp
+
+    xml = """
+    <mujoco><worldbody>
+      <body name="a" pos="0 0 1"><freejoint/><geom type="box" size="0.1 0.2 0.3"/></body>
+      <body name="b" pos="1 0 1"><freejoint/><geom type="sphere" size="0.1" density="200"/><geom type="box" size="0.1 0.1 0.1" pos="0.5 0 0" mass="2.0"/></body>
+      <body name="c" pos="2 0 1"><freejoint/><inertial pos="0 0 0" mass="3.0" diaginertia="0.1 0.1 0.1"/><geom type="sphere" size="0.1"/></body>
+    </worldbody></mujoco>"""
+    scene, _ = scene_from_morphs([gs.morphs.MJCF(file=write_tmp(xml, ".xml"))], dt=0.01)
+    m = scene.rigid_solver.build_model()
+    mass = np.asarray(m.links_inertial_mass)
+    names = list(scene.rigid_solver._entities[0]._info.link_names)
+    ia, ib, ic = names.index("a"), names.index("b"), names.index("c")
+    assert mass[ia] == pytest.approx(1000 * 0.2 * 0.4 * 0.6, rel=1e-9)
+    m_sphere = 200 * 4.0 / 3.0 * np.pi * 0.1**3
+    assert mass[ib] == pytest.approx(m_sphere + 2.0, rel=1e-9)
+    ipos = np.asarray(m.links_inertial_pos).reshape(-1, 3)
+    assert ipos[ib, 0] == pytest.approx(2.0 * 0.5 / (m_sphere + 2.0), rel=1e-9)
+    assert mass[ic] == pytest.approx(3.0, rel=1e-9)
