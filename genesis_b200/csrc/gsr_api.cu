@@ -21,7 +21,7 @@ struct KernelStat {
   long long launches;
 };
 
-enum { K_STEP = 0, K_FORWARD = 1, K_RESET = 2, K_INIT = 3, K_SCATTER = 4, K_GATHER = 5, K_GATHER_COST = 6, K_ORDER_FLAG = 7, K_COUNT = 8 };
+enum { K_STEP = 0, K_FORWARD = 1, K_RESET = 2, K_INIT = 3, K_SCATTER = 4, K_GATHER = 5, K_GATHER_COST = 6, K_ORDER_FLAG = 7, K_DIAG = 8, K_COUNT = 9 };
 
 }  // namespace
 
@@ -52,15 +52,15 @@ struct gsr_handle_s : GsrSpec {
   int rows_default = 0, rows_changes = 0;
   int host_io_mode = 2;  // cfg_host_io: 0 = staged copies + k_scatter / k_gather, 1 = k_step reads / writes dense device staging, 2 = 1 + results posted straight into page-locked caller buffers
   KernelStat stats[K_COUNT] = {{"k_step", 0}, {"k_forward", 0}, {"k_reset", 0}, {"k_init", 0}, {"k_scatter", 0}, {"k_gather", 0},
-                              {"k_gather_cost", 0}, {"k_order_flag", 0}};
+                              {"k_gather_cost", 0}, {"k_order_flag", 0}, {"k_diag", 0}};
   long long total_launches = 0;
   // optional per-kernel event timing (gsr_set_profiling)
   bool profiling = false;
   struct Span { int k; cudaEvent_t a, b; };
   std::vector<Span> spans;
   std::vector<cudaEvent_t> event_pool;
-  double time_ms[K_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
-  long long timed[K_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double time_ms[K_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long timed[K_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   cudaStream_t prof_stream = nullptr;
 };
 
@@ -105,6 +105,12 @@ static int activate(gsr_handle_t h, cudaStream_t st) {
     g_active[h->device] = h;
   }
   return GSR_OK;
+}
+
+#define GSR_ROWS_BINS 32  // rows per environment in buckets of 8 (the last bucket collects everything above 240)
+__global__ void k_iota(int* v, int n) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) v[t] = t;
 }
 
 extern "C" {
@@ -166,6 +172,28 @@ int gsr_model_commit(gsr_handle_t h, int device, int n_envs) {
   h->host_io_mode = (int)h->S("cfg_host_io", 2);
   // the caller fixing cfg_smem_rows switches the adaptation off (sweeps); the lane kernel has its own layout
   h->adaptive_rows = h->S("cfg_adaptive_rows", h->s.count("cfg_smem_rows") ? 0 : 1) != 0 && h->group != 1;
+  // every buffer of the cost-ordered launch, the adaptive row capacity and gsr_step_host is allocated here: nothing on the
+  // step path calls cudaMalloc / cudaHostAlloc / cudaEventCreate (those serialise the device and used to land inside timed loops)
+  if (h->group != 1) {
+    const int B = n_envs;
+    CUDA_OK(cudaMalloc((void**)&h->d_order, sizeof(int) * (B + 1))); CUDA_OK(cudaMalloc((void**)&h->d_iota, sizeof(int) * B));
+    CUDA_OK(cudaMalloc((void**)&h->d_cost, sizeof(int) * B)); CUDA_OK(cudaMalloc((void**)&h->d_cost_sorted, sizeof(int) * B));
+    CUDA_OK(cub::DeviceRadixSort::SortPairsDescending(nullptr, h->sort_tmp_bytes, h->d_cost, h->d_cost_sorted, h->d_iota, h->d_order, B, 0, 32, (cudaStream_t)0));
+    CUDA_OK(cudaMalloc(&h->d_sort_tmp, h->sort_tmp_bytes));
+    k_iota<<<(B + 255) / 256, 256>>>(h->d_iota, B);
+    k_iota<<<(B + 255) / 256, 256>>>(h->d_order, B);
+    CUDA_OK(cudaMemset(h->d_order + B, 0, sizeof(int)));  // flag 0 = identity order until the first sort
+    CUDA_OK(cudaMalloc((void**)&h->d_rows_hist, sizeof(int) * GSR_ROWS_BINS));
+    CUDA_OK(cudaHostAlloc((void**)&h->h_rows_hist, sizeof(int) * GSR_ROWS_BINS, cudaHostAllocDefault));
+    CUDA_OK(cudaEventCreateWithFlags(&h->rows_event, cudaEventDisableTiming));
+    h->rows_default = h->sl.NCS;
+  }
+  {
+    const size_t need = (size_t)n_envs * (size_t)(m.nQ + 2 * m.nD);
+    CUDA_OK(cudaMalloc((void**)&h->d_stage, need * 4));
+    h->stage_elems = need;
+  }
+  CUDA_OK(cudaDeviceSynchronize());
   h->committed = true;
   g_active[device] = nullptr;
   return GSR_OK;
@@ -243,15 +271,10 @@ static int lane_launch(gsr_handle_t h, cudaStream_t st, int clear_ext) {
   return GSR_OK;
 }
 
-__global__ void k_iota(int* v, int n) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n) v[t] = t;
-}
 // order[B] = 1 when the most expensive environment costs at least 1.5x the median one
 __global__ void k_order_flag(const int* cost_sorted, int* order, int B) {
   if (threadIdx.x == 0 && blockIdx.x == 0) order[B] = (2 * (long long)cost_sorted[0] > 3 * (long long)cost_sorted[B / 2]) ? 1 : 0;
 }
-#define GSR_ROWS_BINS 32  // rows per environment in buckets of 8 (the last bucket collects everything above 240)
 __global__ void k_gather_cost(const float* state, int B, int field_off, int* dst, int* rows_hist) {
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= B) return;
@@ -293,12 +316,6 @@ static int adapt_rows(gsr_handle_t h, cudaStream_t st) {
 static int reorder_envs(gsr_handle_t h, cudaStream_t st) {
   const int B = h->B;
   if (h->adaptive_rows) {
-    if (!h->d_rows_hist) {
-      CUDA_OK(cudaMalloc((void**)&h->d_rows_hist, sizeof(int) * GSR_ROWS_BINS));
-      CUDA_OK(cudaHostAlloc((void**)&h->h_rows_hist, sizeof(int) * GSR_ROWS_BINS, cudaHostAllocDefault));
-      CUDA_OK(cudaEventCreateWithFlags(&h->rows_event, cudaEventDisableTiming));
-      h->rows_default = h->sl.NCS;
-    }
     const bool hist_ready = h->rows_pending && cudaEventQuery(h->rows_event) == cudaSuccess;
     cudaGetLastError();  // "not ready" is not an error
     if (hist_ready) {
@@ -309,13 +326,6 @@ static int reorder_envs(gsr_handle_t h, cudaStream_t st) {
     if (!h->rows_pending) CUDA_OK(cudaMemsetAsync(h->d_rows_hist, 0, sizeof(int) * GSR_ROWS_BINS, st));
   }
   const bool take_hist = h->adaptive_rows && !h->rows_pending;
-  if (!h->d_order) {
-    CUDA_OK(cudaMalloc((void**)&h->d_order, sizeof(int) * (B + 1))); CUDA_OK(cudaMalloc((void**)&h->d_iota, sizeof(int) * B));
-    CUDA_OK(cudaMalloc((void**)&h->d_cost, sizeof(int) * B)); CUDA_OK(cudaMalloc((void**)&h->d_cost_sorted, sizeof(int) * B));
-    CUDA_OK(cub::DeviceRadixSort::SortPairsDescending(nullptr, h->sort_tmp_bytes, h->d_cost, h->d_cost_sorted, h->d_iota, h->d_order, B, 0, 32, st));
-    CUDA_OK(cudaMalloc(&h->d_sort_tmp, h->sort_tmp_bytes));
-    k_iota<<<(B + 255) / 256, 256, 0, st>>>(h->d_iota, B);
-  }
   { Bracket br_(h, K_GATHER_COST, st); k_gather_cost<<<(B + 255) / 256, 256, 0, st>>>(h->state, B, h->lay.step_cost, h->d_cost, take_hist ? h->d_rows_hist : nullptr); }
   if (take_hist) {
     CUDA_OK(cudaMemcpyAsync(h->h_rows_hist, h->d_rows_hist, sizeof(int) * GSR_ROWS_BINS, cudaMemcpyDeviceToHost, st));
@@ -380,6 +390,10 @@ static int group_launch(gsr_handle_t h, int which, cudaStream_t st, const uint8_
       Bracket br_(h, K_STEP, st);                                                                        \
       k_step<GG, false><<<grid, block, smem, st>>>(h->state, h->B, h->d_model, clear_ext, h->d_order, h->d_trace, io);           \
     }                                                                                                    \
+  } else if (which == K_DIAG) {                                                                          \
+    CUDA_OK(set_smem(k_diag<GG>, smem));                                                                 \
+    Bracket br_(h, K_DIAG, st);                                                                          \
+    k_diag<GG><<<grid, block, smem, st>>>(h->state, h->B, h->d_model);                                   \
   } else {                                                                                               \
     CUDA_OK(set_smem(k_forward<GG>, smem));                                                              \
     Bracket br_(h, K_FORWARD, st);                                                                       \
@@ -443,6 +457,14 @@ int gsr_forward_kinematics(gsr_handle_t h, const uint8_t* env_mask_dev, void* cu
   return group_launch(h, K_FORWARD, st, env_mask_dev, 0);
 }
 
+int gsr_compute_diagnostics(gsr_handle_t h, void* cuda_stream) {
+  if (!h || !h->state) return fail(h, GSR_ESTATE, "state not bound");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  int rc = activate(h, st);
+  if (rc) return rc;
+  return group_launch(h, K_DIAG, st, nullptr, 0);
+}
+
 int gsr_reset_envs(gsr_handle_t h, const uint8_t* env_mask_dev, void* cuda_stream) {
   if (!h || !h->state) return fail(h, GSR_ESTATE, "state not bound");
   cudaStream_t st = (cudaStream_t)cuda_stream;
@@ -472,7 +494,6 @@ int gsr_step_host(gsr_handle_t h, int n_substeps, const float* ctrl_pos_host, fl
     const size_t need1 = B * (size_t)(m.nQ + 2 * m.nD);
     if (h->stage_elems < need1) {
       if (h->d_stage) cudaFree(h->d_stage);
-    if (h->d_rows_hist) { cudaFree(h->d_rows_hist); cudaFreeHost(h->h_rows_hist); cudaEventDestroy(h->rows_event); }
       CUDA_OK(cudaMalloc((void**)&h->d_stage, need1 * 4));
       h->stage_elems = need1;
     }
@@ -587,8 +608,9 @@ void gsr_destroy(gsr_handle_t h) {
     cudaSetDevice(h->device);
     if (g_active[h->device] == h) g_active[h->device] = nullptr;
     cudaFree(h->d_verts); cudaFree(h->d_support); cudaFree(h->d_pairs); cudaFree(h->d_pair_idx); cudaFree(h->d_model); cudaFree(h->d_fac); if (h->d_trace) cudaFree(h->d_trace);
-    if (h->d_order) { cudaFree(h->d_order); cudaFree(h->d_iota); cudaFree(h->d_cost); cudaFree(h->d_cost_sorted); cudaFree(h->d_sort_tmp); }
-    if (h->d_stage) cudaFree(h->d_stage);
+    if (h->d_order) { cudaFree(h->d_order); cudaFree(h->d_iota); cudaFree(h->d_cost); cudaFree(h->d_cost_sorted); cudaFree(h->d_sort_tmp); h->d_order = nullptr; }
+    if (h->d_rows_hist) { cudaFree(h->d_rows_hist); cudaFreeHost(h->h_rows_hist); cudaEventDestroy(h->rows_event); h->d_rows_hist = nullptr; h->h_rows_hist = nullptr; h->rows_event = nullptr; }
+    if (h->d_stage) { cudaFree(h->d_stage); h->d_stage = nullptr; }
     for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : h->event_pool) cudaEventDestroy(e);
   }

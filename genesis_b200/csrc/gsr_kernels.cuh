@@ -176,6 +176,35 @@ __global__ void __launch_bounds__(GSR_MAX_WARPS_PER_CTA * 32, 1) k_step(float* s
 #undef PHASE_BEGIN
 }
 
+// Diagnostic outputs (cfg_diagnostics = 1: every step, with the reference's timing -- the mass matrix and the smooth forces of
+// the configuration the step STARTED from; cfg_diagnostics = 0, the default: only on demand by k_diag for the current state).
+template <int G>
+__device__ __forceinline__ void write_dynamics_diagnostics(const Ctx<G>& C) {
+  const int nD = CM(nD), MS = c_s.MS, lane = C.lane;
+  float* rec = C.rec;
+  for (int d = lane; d < nD; d += G) {
+    rec[c_h.acc_smooth + d] = WK(acc_smooth)[d];
+    rec[c_h.qf_smooth + d] = WK(force)[d];
+    rec[c_h.qf_passive + d] = WK(qf_passive)[d];
+    rec[c_h.qf_bias + d] = WK(qf_bias)[d];
+    rec[c_h.mass_Dinv + d] = WK(Dinv)[d];
+  }
+  for (int i = 0; i < nD; i++)
+    for (int j = lane; j < nD; j += G) rec[c_h.mass_mat + i * nD + j] = WK(M)[i * MS + j];
+}
+template <int G>
+__device__ __forceinline__ void write_geom_poses(const Ctx<G>& C) {
+  const int nG = CM(nG);
+  float* rec = C.rec;
+  for (int g = C.lane; g < nG; g += G) {
+    const int l = GM(g_link[g]);
+    const f3 lp = ld3(IN(links_pos), l);
+    const f4 lq = ld4(IN(links_quat), l);
+    st3(rec + c_h.geoms_pos, g, lp + rotate(f3(GM(g_pos[g][0]), GM(g_pos[g][1]), GM(g_pos[g][2])), lq));
+    st4(rec + c_h.geoms_quat, g, quat_compose(f4(GM(g_quat[g][0]), GM(g_quat[g][1]), GM(g_quat[g][2]), GM(g_quat[g][3])), lq));
+  }
+}
+
 template <int G>
 __device__ __forceinline__ void step_epilogue(const Ctx<G>& C, int clear_ext) {
   // ---- outputs that live in scratch recycled by the kinematics
@@ -191,29 +220,10 @@ __device__ __forceinline__ void step_epilogue(const Ctx<G>& C, int clear_ext) {
     st3(rec + c_h.cacc_lin, l, ld3(WK(cacc), 2 * l));
     st3(rec + c_h.cacc_ang, l, ld3(WK(cacc), 2 * l + 1));
   }
-  if (CM(diagnostics)) {
-    for (int d = lane; d < nD; d += G) {
-      rec[c_h.acc_smooth + d] = WK(acc_smooth)[d];
-      rec[c_h.qf_smooth + d] = WK(force)[d];
-      rec[c_h.qf_passive + d] = WK(qf_passive)[d];
-      rec[c_h.qf_bias + d] = WK(qf_bias)[d];
-      rec[c_h.mass_Dinv + d] = WK(Dinv)[d];
-    }
-    for (int i = 0; i < nD; i++)
-      for (int j = lane; j < nD; j += G) rec[c_h.mass_mat + i * nD + j] = WK(M)[i * MS + j];
-  }
+  if (CM(diagnostics)) write_dynamics_diagnostics(C);
   C.sync();
   phase_kinematics(C);
-  if (CM(diagnostics)) {  // geoms_state.pos / quat of the post-integration configuration (FK:828-864)
-    const int nG = CM(nG);
-    for (int g = lane; g < nG; g += G) {
-      const int l = GM(g_link[g]);
-      const f3 lp = ld3(IN(links_pos), l);
-      const f4 lq = ld4(IN(links_quat), l);
-      st3(rec + c_h.geoms_pos, g, lp + rotate(f3(GM(g_pos[g][0]), GM(g_pos[g][1]), GM(g_pos[g][2])), lq));
-      st4(rec + c_h.geoms_quat, g, quat_compose(f4(GM(g_quat[g][0]), GM(g_quat[g][1]), GM(g_quat[g][2]), GM(g_quat[g][3])), lq));
-    }
-  }
+  if (CM(diagnostics)) write_geom_poses(C);  // geoms_state.pos / quat of the post-integration configuration (FK:828-864)
   if (clear_ext && C.SI()[c_h.has_ext_force]) {  // RS:2603-2612 clear_external_force
     for (int i = lane; i < 3 * nL; i += G) { rec[c_h.cfrc_applied_vel + i] = 0.f; rec[c_h.cfrc_applied_ang + i] = 0.f; }
     C.sync();
@@ -242,6 +252,25 @@ __global__ void __launch_bounds__(GSR_MAX_WARPS_PER_CTA * 32) k_forward(float* s
     const float4* src = reinterpret_cast<const float4*>(C.S);
     for (int i = C.lane; i < c_h.n_in / 4; i += G) dst[i] = src[i];
   }
+}
+
+// On-demand diagnostics of the CURRENT state (get_mass_mat, geoms_state.pos / quat, qf_* with cfg_diagnostics = 0): smooth
+// dynamics from the kinematic cache of the record, outputs into the diagnostic fields; the state itself is not touched.
+template <int G>
+__global__ void __launch_bounds__(GSR_MAX_WARPS_PER_CTA * 32) k_diag(float* state, int B, const DevModel* gm) {
+  extern __shared__ __align__(16) float smem[];
+  Ctx<G> C;
+  if (!make_ctx(C, state, B, gm, smem)) return;
+  {
+    const float4* src = reinterpret_cast<const float4*>(C.rec);
+    float4* dst = reinterpret_cast<float4*>(C.S);
+    for (int i = C.lane; i < c_h.n_in / 4; i += G) dst[i] = src[i];
+    C.sync();
+  }
+  phase_dynamics(C);
+  C.sync();
+  write_dynamics_diagnostics(C);
+  write_geom_poses(C);
 }
 
 // collider.clear + constraint_solver.reset for masked envs (collider.py:563-607, solver.py:114-179)

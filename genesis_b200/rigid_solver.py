@@ -81,11 +81,13 @@ class RigidSolver:
         self._gravity = rigid_options.gravity or sim_options.gravity
         self._handle = None
         self._n_substeps_total = 0
+        self._errno_host = self._errno_event = None
+        self._errno_pending = False
         # launch tuning of libgsrigid (0 = library default): lanes per environment, constraint rows kept in shared
         # memory, and whether the diagnostic fields (mass_mat, qf_*, acc_smooth, geom poses) are written every step
         import os
 
-        self.tuning = dict(group_size=int(os.environ.get("GSR_GROUP_SIZE", 0)), diagnostics=int(os.environ.get("GSR_DIAGNOSTICS", 1)))
+        self.tuning = dict(group_size=int(os.environ.get("GSR_GROUP_SIZE", 0)), diagnostics=int(os.environ.get("GSR_DIAGNOSTICS", 0)))
         if os.environ.get("GSR_SMEM_ROWS"):
             self.tuning["smem_rows"] = int(os.environ["GSR_SMEM_ROWS"])
         if os.environ.get("GSR_REORDER_PERIOD"):
@@ -254,10 +256,30 @@ class RigidSolver:
     def get_error_envs_mask(self):
         return self._fields["errno_"][:, 0] > 0
 
-    def check_errno(self):
-        """rigid_solver.py:985-1009 (polled every RATE_CHECK_ERRNO substeps by Scene.step)."""
-        errno = int(self._fields["errno_"].max().item()) if self._B else 0
-        if errno == 0:
+    def check_errno(self, deferred=False):
+        """rigid_solver.py:985-1009 (polled every RATE_CHECK_ERRNO substeps by Scene.step).
+
+        `deferred=True` (the poll of Simulator.step) never stalls the stream: it evaluates the OR-reduction enqueued by the
+        previous poll (complete long ago: it was recorded RATE_CHECK_ERRNO substeps earlier) and enqueues the next one into a
+        pinned word, so an error surfaces one poll period later than in the reference and the step loop has no host sync."""
+        if not self._B:
+            return
+        if deferred:
+            if self._errno_host is None:
+                self._errno_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+                self._errno_event = torch.cuda.Event()
+                self._errno_pending = False
+            bits = 0
+            if self._errno_pending:
+                self._errno_event.synchronize()
+                bits = int(self._errno_host[0])
+            # errno bits are OR-ed per env; max > 0 flags an error, the exact bits are gathered only on the error path
+            self._errno_host.copy_(self._fields["errno_"].max().reshape(1), non_blocking=True)
+            self._errno_event.record(torch.cuda.current_stream(self.device))
+            self._errno_pending = True
+            if bits == 0:
+                return
+        elif int(self._fields["errno_"].max().item()) == 0:
             return
         bits = int(np.bitwise_or.reduce(self._fields["errno_"][:, 0].cpu().numpy()))
         if bits & ErrorCode.OVERFLOW_CANDIDATE_CONTACTS:
@@ -654,7 +676,25 @@ class RigidSolver:
     def get_links_net_contact_force(self, links_idx=None, envs_idx=None):
         return self._get("links_contact_force", links_idx, envs_idx, self.model.n_links, comps=3)
 
+    DIAG_FIELDS = ("acc_smooth", "qf_smooth", "qf_passive", "qf_bias", "mass_mat", "mass_Dinv", "geoms_pos", "geoms_quat")
+
+    def refresh_diagnostics(self):
+        """With cfg_diagnostics = 0 (default) the step kernel does not write the diagnostic fields (mass_mat, mass_Dinv, qf_*,
+        acc_smooth, geoms_pos / quat); the accessors that expose them recompute them for the CURRENT state on demand (k_diag).
+        With GSR_DIAGNOSTICS=1 they are written every step with the reference's timing and this is a no-op."""
+        if not self.tuning.get("diagnostics"):
+            _lib.check(self._handle, _lib.lib().gsr_compute_diagnostics(self._handle, self._stream()))
+
+    def get_geoms_pos(self, geoms_idx=None, envs_idx=None):
+        self.refresh_diagnostics()
+        return self._get("geoms_pos", geoms_idx, envs_idx, self.model.n_geoms, comps=3)
+
+    def get_geoms_quat(self, geoms_idx=None, envs_idx=None):
+        self.refresh_diagnostics()
+        return self._get("geoms_quat", geoms_idx, envs_idx, self.model.n_geoms, comps=4)
+
     def get_mass_mat(self, dofs_idx=None, envs_idx=None):
+        self.refresh_diagnostics()
         nD = self.model.n_dofs
         M = self._fields["mass_mat"].reshape(self._B, nD, nD)
         envs = self._envs(envs_idx)

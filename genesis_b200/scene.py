@@ -24,7 +24,7 @@ class Simulator:
     def step(self):
         # simulator.py:277-283: errno poll every RATE_CHECK_ERRNO substeps, then `substeps` rigid substeps
         if self.cur_substep_global > 0 and self.cur_substep_global % RATE_CHECK_ERRNO < self.options.substeps and self.scene._check_errno:
-            self.rigid_solver.check_errno()
+            self.rigid_solver.check_errno(deferred=True)
         self.rigid_solver.substep(self.options.substeps)
         self.cur_substep_global += self.options.substeps
 

@@ -19,6 +19,14 @@ from helpers import gs, make_capsules, make_jumble, make_weld, make_franka, make
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True)
+def _diagnostics_on(monkeypatch):
+    """The parity tests read the intermediate quantities (mass_mat, qf_*, acc_smooth, geoms_pos) of the step that produced the
+    state: cfg_diagnostics = 1 writes them every step (the product default is 0: on demand, see test_lazy_diagnostics)."""
+    monkeypatch.setenv("GSR_DIAGNOSTICS", "1")
+
+
 TRAJ_QPOS_FREE, TRAJ_QVEL_FREE = 1e-4, 1e-3
 TRAJ_QPOS_CONTACT, TRAJ_QVEL_CONTACT = 1e-3, 2e-2
 JACCARD_MIN = 0.98
@@ -453,3 +461,25 @@ def test_double_pendulum_link_accelerations():
     acc = gpu_field(scene, "acc")
     np.testing.assert_allclose(acc_ang[:, 1, 0], acc[:, 0], atol=1e-4)  # reference: acc_ang[1] = (theta_ddot_0, 0, 0)
     np.testing.assert_allclose(acc_ang[:, -1, 0], acc[:, 0] + acc[:, 1], atol=1e-4)
+
+
+def test_lazy_diagnostics_match_per_step_diagnostics(monkeypatch):
+    """cfg_diagnostics = 0 (the default): get_mass_mat / geoms poses / qf_* are recomputed on demand for the current state by
+    k_diag.  They must equal what a cfg_diagnostics = 1 scene writes during the step that starts from the same state."""
+    scene_a, fa = make_go2(16, seed=3)            # diagnostics on (fixture)
+    monkeypatch.setenv("GSR_DIAGNOSTICS", "0")
+    scene_b, fb = make_go2(16, seed=3)
+    sa, sb = scene_a.rigid_solver, scene_b.rigid_solver
+    assert sa.tuning["diagnostics"] == 1 and sb.tuning["diagnostics"] == 0
+    for _ in range(5):
+        scene_a.step(); scene_b.step()
+    assert torch.equal(sa.field("qpos"), sb.field("qpos"))
+    Mb = sb.get_mass_mat()                                   # lazy: smooth dynamics of the current state
+    gp, gq = sb.get_geoms_pos(), sb.get_geoms_quat()
+    lazy = {k: sb.field(k).clone() for k in ("qf_bias", "qf_passive", "acc_smooth", "mass_Dinv")}
+    assert torch.equal(gp, sa.field("geoms_pos")) and torch.equal(gq, sa.field("geoms_quat"))  # both post-integration poses
+    scene_a.step()                                           # eager: written by the step that starts from that state
+    assert torch.equal(Mb, sa.get_mass_mat())
+    for k, v in lazy.items():
+        assert torch.equal(v, sa.field(k)), k
+    assert sb.kernel_launches()["k_diag"] >= 1 and sa.kernel_launches()["k_diag"] == 0

@@ -116,4 +116,32 @@ def test_grasp_8192_determinism_launch_order_and_sanity():
     assert torch.isfinite(qpos).all()
     z = qpos[:, 9 + 2::7][:, :4]  # z of the four free boxes
     assert (z > 0.015).all() and (z < 0.2).all()
-    assert float(outs[0][1].float().mean()) >= 16.0  # four boxes x four corner contacts at least
+    assert float(outs[0][1].float().mean()) > 20.0  # four boxes x four corner contacts + finger-box and box-box contacts
+
+
+def test_step_host_after_device_steps_keeps_adaptive_rows_alive():
+    """Regression for the use-after-free of round 1 (gsr_api.cu: the first gsr_step_host after >= 16 device steps freed the row
+    histogram of the adaptive on-chip capacity).  Grasp scene: 40 device steps (two reorder periods: the histogram exists and
+    the capacity has been raised once), then 64 host-buffer steps; the capacity must still follow the workload and the results
+    must equal a scene that only ever took device steps."""
+    from helpers import make_franka_grasp
+
+    B = 2048
+    scene_a, fa, _ = make_franka_grasp(B)
+    scene_b, fb, _ = make_franka_grasp(B)
+    sa, sb = scene_a.rigid_solver, scene_b.rigid_solver
+    rows0 = sb.launch_info["smem_rows"]
+    for _ in range(40):
+        scene_a.step(); scene_b.step()
+    keep = [torch.empty((B, n), dtype=torch.float32).pin_memory() for n in (sb.model.n_dofs, sb.model.n_qs, sb.model.n_dofs)]
+    ctrl, qpos, vel = (t.numpy() for t in keep)
+    ctrl[:] = sb.field("ctrl_pos").cpu().numpy()
+    for _ in range(64):
+        scene_a.step()
+        sb.step_host(ctrl, qpos, vel)
+    assert np.array_equal(sa.field("qpos").cpu().numpy(), qpos) and np.array_equal(sa.field("vel").cpu().numpy(), vel)
+    assert int(sb.field("errno_").max()) == 0
+    mean_rows = float(sb.field("n_constraints").float().mean())
+    if mean_rows > rows0:  # the batch needs more rows than the default capacity: the adaptation must have happened and survived
+        assert sb.launch_info["smem_rows"] > rows0, (rows0, sb.launch_info, mean_rows)
+    assert sb.launch_info == sa.launch_info
