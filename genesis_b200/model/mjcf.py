@@ -185,6 +185,18 @@ def parse_mjcf(path, default_armature=0.1, scale=1.0):
                     dofs_armature=np.array([armature]),
                     dofs_frictionloss=np.array([float(attrs.get("frictionloss", 0.0))]),
                 )
+            elif jtype == "ball":
+                # spherical joint: qpos = local quaternion, three body-frame angular dofs (utils/mjcf.py parse_link, mjJNT_BALL)
+                armature = float(attrs["armature"]) if "armature" in j.attrib else (
+                    default_armature if default_armature is not None else float(attrs.get("armature", 0.0))
+                )
+                j_info.update(
+                    type=JOINT_TYPE.SPHERICAL, n_qs=4, n_dofs=3, init_qpos=np.array([1.0, 0.0, 0.0, 0.0]),
+                    dofs_motion_ang=np.eye(3), dofs_motion_vel=np.zeros((3, 3)),
+                    dofs_limit=np.tile([-np.inf, np.inf], (3, 1)), dofs_stiffness=np.zeros(3),
+                    dofs_damping=np.full(3, float(attrs.get("damping", 0.0))), dofs_armature=np.full(3, armature),
+                    dofs_frictionloss=np.full(3, float(attrs.get("frictionloss", 0.0))),
+                )
             else:
                 raise ValueError(f"Unsupported MJCF joint type '{jtype}'")
             n = j_info["n_dofs"]

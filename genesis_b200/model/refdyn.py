@@ -44,8 +44,11 @@ def forward_kinematics(m, qpos):
                 xanchor[j] = gn.rotate(m.joints_pos[j], lq) + lp
                 xaxis[j] = gn.rotate(axis, lq)
                 lp = lp + xaxis[j] * (qpos[qs] - m.qpos0[qs])
-            else:
-                raise NotImplementedError("spherical joints are not on the configs' path")
+            elif t == JOINT_TYPE.SPHERICAL:  # forward_kinematics.py:700-716: rotate about the anchor by the local quaternion
+                xanchor[j] = gn.rotate(m.joints_pos[j], lq) + lp
+                xaxis[j] = [0, 0, 1]
+                lq = gn.quat_normalize(gn.quat_mul(lq, gn.quat_normalize(qpos[qs: qs + 4])))
+                lp = xanchor[j] - gn.rotate(m.joints_pos[j], lq)
         pos[l], quat[l] = lp, lq
     return pos, quat, xanchor, xaxis
 
@@ -84,6 +87,11 @@ def com_and_cdof(m, pos, quat, xanchor, xaxis):
                 for i in range(3):
                     cdof_ang[ds + 3 + i] = RT[i]
                     cdof_vel[ds + 3 + i] = np.cross(RT[i], off)
+            elif t == JOINT_TYPE.SPHERICAL:  # body-frame angular dofs (forward_kinematics.py:559-562)
+                RT = gn.quat_to_R(quat[l]).T
+                for i in range(3):
+                    cdof_ang[ds + i] = RT[i]
+                    cdof_vel[ds + i] = np.cross(RT[i], off)
     return i_pos, i_quat, root_com, cdof_ang, cdof_vel
 
 
