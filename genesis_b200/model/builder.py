@@ -137,7 +137,8 @@ class ModelBuilder:
         self.entities: list[EntityInfo] = []
 
     # ------------------------------------------------------------------ entities
-    def add_entity(self, name, l_infos, eqs_info=(), is_robot=True, rho=None, friction=None, local_collision_mask=False):
+    def add_entity(self, name, l_infos, eqs_info=(), is_robot=True, rho=None, friction=None, local_collision_mask=False,
+                   morph_pos=None, morph_quat=None):
         # Drop the virtual world link when it carries nothing (rigid_entity.py:623-641)
         l_infos = list(l_infos)
         if (len(l_infos) > 1 and not l_infos[0]["joints"] and not l_infos[0]["geoms"] and l_infos[0]["parent_idx"] == -1
@@ -153,6 +154,19 @@ class ModelBuilder:
         for li in l_infos:
             if li["joints"] and all(j["type"] == JOINT_TYPE.FREE for j in li["joints"]):
                 li["parent_idx"] = -1
+        # morph.pos / morph.quat offset every base link (rigid_entity.py:744-767) -- AFTER the virtual world link is gone and the free
+        # links hang off the world, so that the offset lands on the bodies that actually exist
+        if morph_pos is not None or morph_quat is not None:
+            pos_off = np.zeros(3) if morph_pos is None else np.asarray(morph_pos, float)
+            quat_off = np.array([1.0, 0, 0, 0]) if morph_quat is None else np.asarray(morph_quat, float)
+            for li in l_infos:
+                if li["parent_idx"] < 0:
+                    li["pos"], li["quat"] = gn.transform_pos_quat(li["pos"], li["quat"], pos_off, quat_off)
+        for li in l_infos:
+            if li["parent_idx"] < 0:
+                for j in li["joints"]:
+                    if j["type"] == JOINT_TYPE.FREE:
+                        j["init_qpos"] = np.concatenate([np.asarray(li["pos"], float), np.asarray(li["quat"], float)])
         ent = EntityInfo(name=name, l_infos=l_infos, eqs_info=list(eqs_info), is_robot=is_robot, rho=rho, friction=friction,
                          local_collision_mask=local_collision_mask)
         self.entities.append(ent)
@@ -223,6 +237,8 @@ class ModelBuilder:
                     mass, com, I = 0.0, np.zeros(3), np.zeros((3, 3))
                 if link["inertial_mass"] is None:
                     link["inertial_mass"] = mass
+                elif mass > 0:  # only the mass was given: the inferred inertia is rescaled to it (rigid_link.py:737)
+                    I = I * (link["inertial_mass"] / mass)
                 link["inertial_pos"], link["inertial_i"] = com, I
                 link["inertial_quat"] = np.array([1.0, 0, 0, 0])
             link["inertial_mass"] = max(link["inertial_mass"], EPS32)

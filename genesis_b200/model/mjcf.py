@@ -176,7 +176,7 @@ def parse_mjcf(path, default_armature=0.1, scale=1.0):
                 )
                 j_info.update(
                     type=JOINT_TYPE.REVOLUTE if jtype == "hinge" else JOINT_TYPE.PRISMATIC, n_qs=1, n_dofs=1,
-                    init_qpos=np.array([float(attrs.get("ref", 0.0))]),
+                    init_qpos=np.array([float(attrs.get("ref", 0.0)) * (angle_scale if jtype == "hinge" else scale)]),
                     dofs_motion_ang=np.array([axis]) if jtype == "hinge" else np.zeros((1, 3)),
                     dofs_motion_vel=np.zeros((1, 3)) if jtype == "hinge" else np.array([axis]),
                     dofs_limit=np.array([rng]) if is_limited else np.array([[-np.inf, np.inf]]),

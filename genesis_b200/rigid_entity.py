@@ -247,16 +247,39 @@ class RigidEntity:
     def set_dofs_velocity(self, velocity=None, dofs_idx_local=None, envs_idx=None, *, skip_forward=False):
         self._solver.set_dofs_velocity(velocity, self._dofs(dofs_idx_local), envs_idx, skip_forward=skip_forward)
 
-    def set_pos(self, pos, envs_idx=None, *, zero_velocity=True):
-        """Base position of a free-floating entity (qpos[0:3])."""
+    def _base_kind(self):
+        """'free' when the base link hangs off a free joint (its pose IS qpos[0:7]), 'fixed' when it is a fixed root link (its pose is
+        a user-settable link state that FK keeps, forward_kinematics.py:732-736)."""
+        from .constants import JOINT_TYPE
+
+        m, l0 = self._solver.model, self._info.link_start
+        js, je = int(m.links_joint_start[l0]), int(m.links_joint_end[l0])
+        if je > js and int(m.joints_type[js]) == JOINT_TYPE.FREE:
+            return "free"
+        if int(m.links_parent[l0]) == -1 and int(m.links_is_fixed[l0]):
+            return "fixed"
+        return "articulated"
+
+    def _set_base(self, value, comps, envs_idx, zero_velocity):
+        """rigid_entity.py set_pos / set_quat -> set_base_links_pos / quat: a free base writes qpos, a fixed base moves the root link
+        (joint coordinates are never touched: writing a pose into qpos[0:7] of a fixed-base arm would overwrite joint angles)."""
+        kind = self._base_kind()
+        if kind == "articulated":
+            from .rigid_solver import GenesisException
+
+            raise GenesisException("set_pos / set_quat: the base link of this entity is neither free-floating nor fixed.")
         if zero_velocity:
             self._solver.set_dofs_velocity(None, self._dofs(None), envs_idx, skip_forward=True)
-        self._solver.set_qpos(pos, self._qs([0, 1, 2]), envs_idx)
+        if kind == "free":
+            self._solver.set_qpos(value, self._qs(comps), envs_idx)
+        else:
+            self._solver.set_base_link_pose(self._info.link_start, value, "links_pos" if len(comps) == 3 else "links_quat", envs_idx)
+
+    def set_pos(self, pos, envs_idx=None, *, zero_velocity=True):
+        self._set_base(pos, [0, 1, 2], envs_idx, zero_velocity)
 
     def set_quat(self, quat, envs_idx=None, *, zero_velocity=True):
-        if zero_velocity:
-            self._solver.set_dofs_velocity(None, self._dofs(None), envs_idx, skip_forward=True)
-        self._solver.set_qpos(quat, self._qs([3, 4, 5, 6]), envs_idx)
+        self._set_base(quat, [3, 4, 5, 6], envs_idx, zero_velocity)
 
     def control_dofs_position(self, position, dofs_idx_local=None, envs_idx=None):
         self._solver.control_dofs_position(position, self._dofs(dofs_idx_local), envs_idx)
@@ -327,8 +350,8 @@ class RigidEntity:
     def get_links_inertial_mass(self, links_idx_local=None, envs_idx=None):
         return self._solver.get_links_inertial_mass(self._links_idx(links_idx_local))
 
-    def apply_links_external_force(self, force, links_idx_local=None, envs_idx=None):
-        self._solver.apply_links_external_force(force, self._links_idx(links_idx_local), envs_idx)
+    def apply_links_external_force(self, force, links_idx_local=None, envs_idx=None, *, ref="link_origin", local=False):
+        self._solver.apply_links_external_force(force, self._links_idx(links_idx_local), envs_idx, ref=ref, local=local)
 
     def apply_links_external_torque(self, torque, links_idx_local=None, envs_idx=None, *, ref="link_origin", local=False):
         self._solver.apply_links_external_torque(torque, self._links_idx(links_idx_local), envs_idx, ref=ref, local=local)

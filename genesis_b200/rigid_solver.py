@@ -47,26 +47,8 @@ def _morph_to_infos(morph):
             if loaded is None:
                 raise GenesisException(f"Asset '{morph.file}' not found and no pre-compiled model is bundled for it.")
             l_infos, eqs = loaded
-        _apply_morph_pose(l_infos, morph)
         return l_infos, eqs, True, is_mjcf
     raise GenesisException(f"Unsupported morph: {morph!r}")
-
-
-def _apply_morph_pose(l_infos, morph):
-    """rigid_entity.py:744-767: offset the base link pose by morph.pos / morph.quat."""
-    from .model import geom_np as gn
-    from .constants import JOINT_TYPE
-
-    if morph.pos is None and morph.quat is None:
-        return
-    for li in l_infos:
-        if li["parent_idx"] < 0:
-            pos_off = np.zeros(3) if morph.pos is None else np.asarray(morph.pos, float)
-            quat_off = np.array([1.0, 0, 0, 0]) if morph.quat is None else np.asarray(morph.quat, float)
-            li["pos"], li["quat"] = gn.transform_pos_quat(li["pos"], li["quat"], pos_off, quat_off)
-            for j in li["joints"]:
-                if j["type"] == JOINT_TYPE.FREE:
-                    j["init_qpos"] = np.concatenate([li["pos"], li["quat"]])
 
 
 class RigidSolver:
@@ -128,8 +110,10 @@ class RigidSolver:
             l_infos, eqs, is_robot, local_mask = _morph_to_infos(ent.morph)
             rho = getattr(ent.material, "rho", None)
             friction = getattr(ent.material, "friction", None)
+            file_morph = isinstance(ent.morph, (_morphs.MJCF, _morphs.URDF))  # primitives bake pos / quat into their l_infos
             ent._info = b.add_entity(type(ent.morph).__name__.lower(), l_infos, eqs, is_robot=is_robot, rho=rho,
-                                     friction=friction, local_collision_mask=local_mask)
+                                     friction=friction, local_collision_mask=local_mask,
+                                     morph_pos=ent.morph.pos if file_morph else None, morph_quat=ent.morph.quat if file_morph else None)
             ent._info.gravity_compensation = getattr(ent.material, "gravity_compensation", 0.0)
         self.model = b.build()
         return self.model
@@ -359,6 +343,21 @@ class RigidSolver:
         if not skip_forward:
             self._forward(envs_idx)
 
+    def set_base_link_pose(self, link_idx, value, field, envs_idx=None):
+        """kernel_set_links_pos / kernel_set_links_quat for a FIXED root link (abd/accessor.py): its world pose is state, FK of
+        the subtree follows from it."""
+        f = self._fields[field]
+        envs = self._envs(envs_idx)
+        nb = self._B if envs is None else len(envs)
+        v = torch.broadcast_to(torch.as_tensor(value, dtype=torch.float32, device=self.device), (nb, f.shape[-1]))
+        if field == "links_quat":
+            v = v / v.norm(dim=-1, keepdim=True)
+        if envs is None:
+            f[:, link_idx] = v
+        else:
+            f[envs, link_idx] = v
+        self._forward(envs_idx)
+
     def set_dofs_position(self, position, dofs_idx=None, envs_idx=None):
         """dofs_state.pos -> qpos (rigid_solver.py set_dofs_position / kernel_set_dofs_position)."""
         from .constants import JOINT_TYPE
@@ -409,18 +408,33 @@ class RigidSolver:
         self._set("ctrl_mode", int(CTRL_MODE.FORCE), dofs_idx, envs_idx, n, dtype=torch.int32)
         self._set("ctrl_force", force, dofs_idx, envs_idx, n)
 
-    def apply_links_external_force(self, force, links_idx=None, envs_idx=None):
-        """World-frame force at each link's COM -> c-frame wrench (rigid_solver.py:1110-1193, abd/accessor.py)."""
+    def apply_links_external_force(self, force, links_idx=None, envs_idx=None, *, ref="link_origin", local=False):
+        """External linear force on a set of links (rigid_solver.py:1110-1150, abd/misc.py:692-712): accumulated into the c-frame
+        wrench about the subtree COM, `cfrc_applied_vel -= F`, `cfrc_applied_ang -= r x F` with r = the link origin
+        (`ref="link_origin"`, the default), the link COM (`"link_com"`) or zero (`"root_com"`), all relative to root_COM.
+        `local=True` expresses F in the link's inertial frame (the reference rotates by links_state.i_quat for both refs)."""
+        if ref not in ("link_origin", "link_com", "root_com"):
+            raise GenesisException("'ref' must be one of 'link_origin', 'link_com', 'root_com'.")
+        if ref == "root_com" and local:
+            raise ValueError("'local=True' not compatible with ref='root_com'.")
         m = self.model
         links = self._idx(links_idx, m.n_links)
         envs = self._envs(envs_idx)
         nb = self._B if envs is None else len(envs)
         force = torch.broadcast_to(torch.as_tensor(force, dtype=torch.float32, device=self.device), (nb, len(links), 3))
-        # c-frame wrench about root_COM: ang += (com_link - root_COM) x F ; vel += F  (sign follows cfrc_applied = -f_ext)
-        pos = self._get_links_com(links, envs)  # (nb, nl, 3)
-        root = self._fields["root_COM"][:, links]
-        root = root if envs is None else root[envs]
-        torque = torch.cross(pos - root, force, dim=-1)
+        sel = (lambda f: f[:, links]) if envs is None else (lambda f: f[envs][:, links])
+        if local:
+            iq = torch.tensor(m.links_inertial_quat, dtype=torch.float32, device=self.device)[links]
+            quat = sel(self._fields["links_quat"])
+            force = _rotate_torch(force, _quat_mul_torch(quat, iq[None].expand(quat.shape[0], -1, -1)))
+        root = sel(self._fields["root_COM"])
+        if ref == "link_com":
+            arm = self._get_links_com(links, envs) - root
+        elif ref == "link_origin":
+            arm = sel(self._fields["links_pos"]) - root
+        else:
+            arm = torch.zeros_like(force)
+        torque = torch.cross(arm, force, dim=-1)
         e = self._envs_all if envs is None else envs
         self._fields["cfrc_applied_vel"][e[:, None], links[None, :]] -= force
         self._fields["cfrc_applied_ang"][e[:, None], links[None, :]] -= torque

@@ -59,6 +59,7 @@ class LaneEmu:
             L.gsr_model_set_scalar(h, f"gravity_{ax}".encode(), float(model.gravity[i]))
         for k, v in (options or {}).items():
             L.gsr_model_set_scalar(h, f"cfg_{k}".encode(), float(v))
+        L.gsr_model_set_scalar(h, b"cfg_diagnostics", 1.0)  # the emulation tests read the intermediate quantities of every step
         rc = L.gsr_model_commit(h, 0, n_envs)
         assert rc == 0, L.gsr_last_error(h)
         nw = ctypes.c_size_t()

@@ -202,3 +202,49 @@ def test_link_velocity_reference_expectations():
     np.testing.assert_allclose(cvel[1], cvel[0] + (w1 - w0) * np.array([xanchor[1] - COM[1], COM[0] - xanchor[0], 0.0]), atol=2e-4)
     np.testing.assert_allclose(xvel[0], 0, atol=2e-4)
     np.testing.assert_allclose(xvel[1], w0 * np.array([-xanchor[1], xanchor[0], 0.0]), atol=2e-4)
+
+
+def test_external_force_reference_frames():
+    """apply_links_external_force(ref=..., local=...) builds the c-frame wrench of abd/misc.py:692-712: the default reference is
+    the LINK ORIGIN (torque arm = links_pos - root_COM), 'link_com' uses the link's COM, 'root_com' no arm at all; local=True
+    rotates the force by the link's inertial-frame orientation.  Checked on a Franka link whose COM is offset from its origin."""
+    from helpers import make_franka
+
+    scene, franka = make_franka(2)
+    s = scene.rigid_solver
+    l = 5
+    F = torch.tensor([1.0, -2.0, 0.5], device=gs.device)
+    pos, root = s.field("links_pos")[:, l], s.field("root_COM")[:, l]
+    com = s._get_links_com(torch.tensor([l], device=gs.device), None)[:, 0]
+    assert (com - pos).norm(dim=-1).min() > 1e-3  # the COM really is offset
+    for ref, arm in (("link_origin", pos - root), ("link_com", com - root), ("root_com", torch.zeros_like(pos))):
+        s.field("cfrc_applied_vel").zero_(); s.field("cfrc_applied_ang").zero_()
+        s.apply_links_external_force(F, links_idx=[l], ref=ref)
+        assert torch.allclose(s.field("cfrc_applied_vel")[:, l], -F.expand(2, 3))
+        assert torch.allclose(s.field("cfrc_applied_ang")[:, l], -torch.cross(arm, F.expand(2, 3), dim=-1), atol=1e-6), ref
+    # default == link_origin (the reference's default), and the entity forwarder takes the same keywords
+    s.field("cfrc_applied_ang").zero_()
+    franka.apply_links_external_force(F, links_idx_local=[l - 1])
+    assert torch.allclose(s.field("cfrc_applied_ang")[:, l], -torch.cross(pos - root, F.expand(2, 3), dim=-1), atol=1e-6)
+    with pytest.raises(ValueError):
+        s.apply_links_external_force(F, links_idx=[l], ref="root_com", local=True)
+
+
+def test_set_pos_on_fixed_base_moves_the_base_not_the_joints():
+    """RigidEntity.set_pos / set_quat on a fixed-base arm move the (fixed) root link and leave the joint coordinates alone; on a
+    free body they write qpos[0:7] (rigid_entity.py set_pos -> set_base_links_pos)."""
+    from helpers import make_franka, scene_from_morphs
+
+    scene, franka = make_franka(2)
+    s = scene.rigid_solver
+    q_before = franka.get_qpos().clone()
+    hand_before = s.get_links_pos()[:, -3].clone()
+    franka.set_pos(torch.tensor([0.5, -0.25, 0.1], device=gs.device))
+    assert torch.equal(franka.get_qpos(), q_before)
+    base = s.get_links_pos()[:, franka._info.link_start]
+    assert torch.allclose(base, torch.tensor([0.5, -0.25, 0.1], device=gs.device).expand(2, 3))
+    assert torch.allclose(s.get_links_pos()[:, -3] - hand_before, torch.tensor([0.5, -0.25, 0.1], device=gs.device).expand(2, 3), atol=1e-6)
+    scene2, (plane, box) = scene_from_morphs([gs.morphs.Plane(), gs.morphs.Box(size=(0.1, 0.1, 0.1), pos=(0, 0, 1.0))], dt=0.01)
+    scene2.build(n_envs=2)
+    box.set_pos(torch.tensor([1.0, 2.0, 3.0], device=gs.device))
+    assert torch.allclose(box.get_qpos()[:, :3], torch.tensor([1.0, 2.0, 3.0], device=gs.device).expand(2, 3))

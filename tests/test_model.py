@@ -104,3 +104,21 @@ def test_mjcf_inertia_inferred_from_geoms_like_mujoco():
     ipos = np.asarray(m.links_inertial_pos).reshape(-1, 3)
     assert ipos[ib, 0] == pytest.approx(2.0 * 0.5 / (m_sphere + 2.0), rel=1e-9)
     assert mass[ic] == pytest.approx(3.0, rel=1e-9)
+
+
+def test_mjcf_morph_pose_offsets_the_real_base_links():
+    """rigid_entity.py:623-651 then 744-767: the virtual MJCF 'world' link is dropped BEFORE morph.pos / morph.quat offset the base
+    links, so a fixed-base arm placed at (1, 2, 0.5) has its link0 there, and a free body's init_qpos carries the offset."""
+    from helpers import BOX_BOX_XML, write_tmp
+
+    scene = gs.Scene()
+    scene.add_entity(gs.morphs.MJCF(file="xml/franka_emika_panda/panda.xml", pos=(1.0, 2.0, 0.5), quat=(0.70710678, 0.0, 0.0, 0.70710678)))
+    m = scene.rigid_solver.build_model()
+    np.testing.assert_allclose(m.links_pos[0], [1.0, 2.0, 0.5])
+    np.testing.assert_allclose(m.links_quat[0], [0.70710678, 0, 0, 0.70710678], atol=1e-7)
+    np.testing.assert_allclose(m.links_pos[1], [0.0, 0.0, 0.333])  # children stay relative to their parent
+    scene = gs.Scene()
+    scene.add_entity(gs.morphs.MJCF(file=write_tmp(BOX_BOX_XML, ".xml"), pos=(1.0, 0.0, 0.5)))
+    m = scene.rigid_solver.build_model()
+    np.testing.assert_allclose(m.qpos0[:3], [1.0, 0.0, 0.7])
+    np.testing.assert_allclose(m.qpos0[7:10], [1.0, 0.0, 1.3])
