@@ -370,6 +370,59 @@ class Leg:
         torch.cuda.empty_cache()
 
 
+def accessors_leg(B, K, W, rank, world, clocks, barrier, max_over_ranks):
+    """The reference's `franka_accessors` benchmark (tests/test_rigid_benchmarks.py:362-394): every step reads eight observation
+    getters, resets 2 % of the environments with set_state(..., partial=True) and re-applies targets / gains / masked qpos and
+    velocities with skip_forward=True -- the RL-loop boundary (scope row f3)."""
+    import torch
+    import genesis_b200 as gs
+    from genesis_b200.bench_scenes import make_franka
+
+    scene, franka = make_franka(B, randomized=True, seed=rank)
+    s = scene.rigid_solver
+    qpos0 = torch.tensor([0, 0, 0, -1.0, 0, 1.0, 0, 0.02, 0.02], device=gs.device).repeat(B, 1)
+    vel0 = s.field("vel").clone()
+    state0 = s.get_state()
+    g = torch.Generator(device="cpu").manual_seed(rank)
+    idx = torch.randperm(B, generator=g)[: max(int(0.02 * B), 1)].to(gs.device)
+    mask = torch.zeros(B, dtype=torch.bool, device=gs.device)
+    mask[idx] = True
+    stiff, damp = franka.get_dofs_stiffness(), franka.get_dofs_damping()
+
+    def step():
+        scene.step()
+        franka.get_ang(); franka.get_vel(); franka.get_dofs_position(); franka.get_dofs_velocity()
+        franka.get_links_pos(); franka.get_links_quat(); franka.get_links_vel(); franka.get_contacts()
+        s.set_state(0, state0, envs_idx=mask, partial=True)
+        franka.control_dofs_position(qpos0)
+        franka.set_dofs_stiffness(stiff); franka.set_dofs_damping(damp)
+        franka.set_dofs_velocity(vel0, envs_idx=mask, skip_forward=True)
+        franka.set_qpos(qpos0, envs_idx=mask, zero_velocity=False, skip_forward=True)
+
+    for _ in range(INTERNAL_WARMUP + W):
+        step()
+    l0 = s.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    clocks.mark(True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(K):
+        step()
+    e1.record()
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    clocks.mark(False)
+    ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms))
+    out = {"value": world * B * K / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms / K, "steps": K,
+           "config": {"workload": f"franka_accessors-{B}", "reset_fraction": 0.02,
+                      "step_body": "tests/test_rigid_benchmarks.py:377-394 (8 getters incl. get_contacts, set_state(partial=True), masked setters, skip_forward)"},
+           "gsr_launches_per_step": (s.launch_count() - l0) / K, "timer": "max(CUDA events, host wall clock): get_contacts reads the contact count on the host, as in the reference"}
+    s.destroy()
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -425,6 +478,7 @@ def main():
             g = Leg("go2", WORKLOADS["go2"][0], rank, world, clocks, barrier, max_over_ranks)
             extras["go2"] = g.run(K, W, cpu_baseline_seconds=cpu_s)
             g.free()
+            extras["franka_accessors"] = accessors_leg(WORKLOADS["franka"][0], max(K, 20), W, rank, world, clocks, barrier, max_over_ranks)
             if world > 1:
                 mx = Leg("mixed", 0, rank, world, clocks, barrier, max_over_ranks)
                 extras["mixed"] = mx.run(K, W)

@@ -53,21 +53,32 @@ def make_go2(n_envs, randomized=True, build=True, seed=0, **rigid_kwargs):
     return scene, robot
 
 
-def make_franka_grasp(n_envs, n_boxes=4, build=True, **rigid_kwargs):
-    """Config 4: plane + panda + a cluster of 4 cm boxes near (0.65, 0, 0.02) (pattern of tests/test_rigid_physics.py:2123-2191)."""
+# joint angles that put the hand at (0.65, 0, 0.135) / (0.65, 0, 0.30) pointing down (quat (0, 1, 0, 0)): the inverse-kinematics targets of
+# the reference's test_contact_forces (tests/test_rigid_physics.py:2160-2186), solved once offline with the model's own FK
+GRASP_Q_DOWN = [-0.5161, 0.8579, 0.5578, -1.7541, -0.6506, 2.4193, 1.1756]
+GRASP_Q_LIFT = [-0.6480, 0.5776, 0.7431, -1.7814, -0.4656, 2.1753, 1.0716]
+GRASP_BOXES = [(0.65, 0.0, 0.02),      # the cube between the fingers
+               (0.74, 0.0, 0.02), (0.74, 0.0, 0.06),  # a stacked pair behind it: box-box contacts
+               (0.74, 0.05, 0.02)]     # and a neighbour on the plane
+
+
+def make_franka_grasp(n_envs, n_boxes=4, build=True, close_fingers=True, **rigid_kwargs):
+    """Config 4: plane + panda + a cluster of 4 cm boxes near (0.65, 0, 0.02); the hand hovers over the first box with its fingers
+    straddling it and closes them (pattern of tests/test_rigid_physics.py:2123-2191: hold, grasp): finger-box contacts through the
+    convex-convex narrow phase (fingertip boxes and pads against the cube), box-box contacts in the stacked pair, plane-box corners."""
     scene = gs.Scene(rigid_options=gs.options.RigidOptions(dt=0.01, **rigid_kwargs))
     scene.add_entity(gs.morphs.Plane())
     franka = scene.add_entity(gs.morphs.MJCF(file="xml/franka_emika_panda/panda.xml"))
     boxes = []
     for i in range(n_boxes):
-        dx, dy = (i % 2) * 0.06 - 0.03, (i // 2) * 0.06 - 0.03
-        boxes.append(scene.add_entity(gs.morphs.Box(size=(0.04, 0.04, 0.04), pos=(0.65 + dx, dy, 0.02))))
+        boxes.append(scene.add_entity(gs.morphs.Box(size=(0.04, 0.04, 0.04), pos=GRASP_BOXES[i % len(GRASP_BOXES)])))
     if not build:
         return scene, franka, boxes
     scene.build(n_envs=n_envs)
-    q = torch.tensor([-0.0, 0.45, 0.0, -2.2, 0.0, 2.65, 0.78, 0.04, 0.04], dtype=torch.float32, device=gs.device)
+    q = torch.tensor(GRASP_Q_DOWN + [0.04, 0.04], dtype=torch.float32, device=gs.device)
+    tgt = torch.tensor(GRASP_Q_DOWN + ([0.0, 0.0] if close_fingers else [0.04, 0.04]), dtype=torch.float32, device=gs.device)
     if n_envs > 0:
-        q = q.repeat(n_envs, 1)
+        q, tgt = q.repeat(n_envs, 1), tgt.repeat(n_envs, 1)
     franka.set_qpos(q)
-    franka.control_dofs_position(q)
+    franka.control_dofs_position(tgt)
     return scene, franka, boxes

@@ -21,7 +21,7 @@ struct KernelStat {
   long long launches;
 };
 
-enum { K_STEP = 0, K_FORWARD = 1, K_RESET = 2, K_INIT = 3, K_SCATTER = 4, K_GATHER = 5, K_GATHER_COST = 6, K_ORDER_FLAG = 7, K_DIAG = 8, K_COUNT = 9 };
+enum { K_STEP = 0, K_FORWARD = 1, K_RESET = 2, K_INIT = 3, K_SCATTER = 4, K_GATHER = 5, K_GATHER_COST = 6, K_ORDER_FLAG = 7, K_DIAG = 8, K_SET_STATE = 9, K_GATHER_FIELDS = 10, K_COUNT = 11 };
 
 }  // namespace
 
@@ -31,6 +31,7 @@ struct gsr_handle_s : GsrSpec {
   float* state = nullptr;
   DevModel* d_model = nullptr;  // global-memory copy for lane-varying table reads
   float *d_verts = nullptr, *d_support = nullptr;
+  int* d_support_vid = nullptr;
   unsigned short* d_fac = nullptr;
   unsigned long long* d_trace = nullptr;  // gsr_debug_trace
   // cost-ordered scheduling of the lane-group step kernel: every `reorder_period` steps the environments are sorted by the
@@ -52,15 +53,15 @@ struct gsr_handle_s : GsrSpec {
   int rows_default = 0, rows_changes = 0;
   int host_io_mode = 2;  // cfg_host_io: 0 = staged copies + k_scatter / k_gather, 1 = k_step reads / writes dense device staging, 2 = 1 + results posted straight into page-locked caller buffers
   KernelStat stats[K_COUNT] = {{"k_step", 0}, {"k_forward", 0}, {"k_reset", 0}, {"k_init", 0}, {"k_scatter", 0}, {"k_gather", 0},
-                              {"k_gather_cost", 0}, {"k_order_flag", 0}, {"k_diag", 0}};
+                              {"k_gather_cost", 0}, {"k_order_flag", 0}, {"k_diag", 0}, {"k_set_state", 0}, {"k_gather_fields", 0}};
   long long total_launches = 0;
   // optional per-kernel event timing (gsr_set_profiling)
   bool profiling = false;
   struct Span { int k; cudaEvent_t a, b; };
   std::vector<Span> spans;
   std::vector<cudaEvent_t> event_pool;
-  double time_ms[K_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  long long timed[K_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  double time_ms[K_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long timed[K_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   cudaStream_t prof_stream = nullptr;
 };
 
@@ -159,13 +160,14 @@ int gsr_model_commit(gsr_handle_t h, int device, int n_envs) {
   {
     auto& v = h->f["verts"]; CUDA_OK(upload(v.empty() ? nullptr : v.data(), v.size() * 4, (void**)&h->d_verts));
     auto& sv = h->f["support_v"]; CUDA_OK(upload(sv.empty() ? nullptr : sv.data(), sv.size() * 4, (void**)&h->d_support));
+    auto& svid = h->i["support_vid"]; CUDA_OK(upload(svid.empty() ? nullptr : svid.data(), svid.size() * 4, (void**)&h->d_support_vid));
     auto& pr = h->i["pairs"]; CUDA_OK(upload(pr.empty() ? nullptr : pr.data(), pr.size() * 4, (void**)&h->d_pairs));
     auto& pi = h->i["pair_idx"]; CUDA_OK(upload(pi.empty() ? nullptr : pi.data(), pi.size() * 4, (void**)&h->d_pair_idx));
     CUDA_OK(upload(h->fac_tasks.empty() ? nullptr : h->fac_tasks.data(), h->fac_tasks.size() * sizeof(unsigned short), (void**)&h->d_fac));
     CUDA_OK(cudaMalloc((void**)&h->d_model, sizeof(DevModel)));
   }
   m.fac_tasks = h->d_fac;
-  m.verts = h->d_verts; m.support_v = h->d_support; m.pairs = h->d_pairs; m.pair_idx = h->d_pair_idx;
+  m.verts = h->d_verts; m.support_v = h->d_support; m.support_vid = h->d_support_vid; m.pairs = h->d_pairs; m.pair_idx = h->d_pair_idx;
 
   { int rc_lay = gsr_compute_layouts(h, n_envs); if (rc_lay) return rc_lay; }
   h->reorder_period = (int)h->S("cfg_reorder_period", 16);
@@ -367,7 +369,8 @@ static int auto_warps_per_cta(const gsr_handle_t h, size_t warp_bytes) {
   return best_w;
 }
 
-static int group_launch(gsr_handle_t h, int which, cudaStream_t st, const uint8_t* mask, int clear_ext, HostIO io = HostIO{nullptr, nullptr, nullptr}) {
+static int group_launch(gsr_handle_t h, int which, cudaStream_t st, const uint8_t* mask, int clear_ext, HostIO io = HostIO{nullptr, nullptr, nullptr},
+                        StateIO sio = StateIO{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}) {
   if (h->group == 1 && which == K_STEP) return lane_launch(h, st, clear_ext);
   const int G = h->group == 1 ? 8 : h->group, EPW = 32 / G;  // the (cold) forward-kinematics paths of a lane model use the group kernel
   const size_t warp_bytes = (size_t)EPW * h->sl.env_words * sizeof(float);
@@ -390,6 +393,10 @@ static int group_launch(gsr_handle_t h, int which, cudaStream_t st, const uint8_
       Bracket br_(h, K_STEP, st);                                                                        \
       k_step<GG, false><<<grid, block, smem, st>>>(h->state, h->B, h->d_model, clear_ext, h->d_order, h->d_trace, io);           \
     }                                                                                                    \
+  } else if (which == K_SET_STATE) {                                                                     \
+    CUDA_OK(set_smem(k_set_state<GG>, smem));                                                            \
+    Bracket br_(h, K_SET_STATE, st);                                                                     \
+    k_set_state<GG><<<grid, block, smem, st>>>(h->state, h->B, h->d_model, mask, sio, clear_ext);        \
   } else if (which == K_DIAG) {                                                                          \
     CUDA_OK(set_smem(k_diag<GG>, smem));                                                                 \
     Bracket br_(h, K_DIAG, st);                                                                          \
@@ -455,6 +462,40 @@ int gsr_forward_kinematics(gsr_handle_t h, const uint8_t* env_mask_dev, void* cu
   int rc = activate(h, st);
   if (rc) return rc;
   return group_launch(h, K_FORWARD, st, env_mask_dev, 0);
+}
+
+int gsr_set_state(gsr_handle_t h, const uint8_t* env_mask_dev, const float* qpos, const float* dofs_vel, const float* dofs_acc,
+                  const float* links_pos, const float* links_quat, const float* i_pos_shift, const float* mass_shift,
+                  const float* friction_ratio, int partial, void* cuda_stream) {
+  if (!h || !h->state) return fail(h, GSR_ESTATE, "state not bound");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  int rc = activate(h, st);
+  if (rc) return rc;
+  return group_launch(h, K_SET_STATE, st, env_mask_dev, partial ? 1 : 0, HostIO{nullptr, nullptr, nullptr},
+                      StateIO{qpos, dofs_vel, dofs_acc, links_pos, links_quat, i_pos_shift, mass_shift, friction_ratio});
+}
+
+int gsr_gather_fields(gsr_handle_t h, int n, const char* const* names, void* const* dst_dev, void* cuda_stream) {
+  if (!h || !h->state) return fail(h, GSR_ESTATE, "state not bound");
+  if (n <= 0 || n > GSR_MAX_GATHER || !names || !dst_dev) return fail(h, GSR_EINVAL, "gsr_gather_fields: 1..16 fields");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  int rc = activate(h, st);
+  if (rc) return rc;
+  GatherIO io;
+  memset(&io, 0, sizeof(io));
+  io.n = n;
+  for (int k = 0; k < n; k++) {
+    const GsrFieldInfo* f = nullptr;
+    for (const auto& c : h->fields) if (c.name == names[k]) { f = &c; break; }
+    if (!f || f->seg_base != 0 || f->item_stride != f->comps) return fail(h, GSR_EINVAL, std::string("gsr_gather_fields: not a HOT-record field: ") + names[k]);
+    io.off[k] = (int)f->offset; io.width[k] = (int)(f->items * f->comps); io.start[k + 1] = io.start[k] + io.width[k];
+    io.dst[k] = (float*)dst_dev[k];
+    if (!io.dst[k]) return fail(h, GSR_EINVAL, "gsr_gather_fields: null destination");
+  }
+  const long long total = (long long)h->B * io.start[n];
+  { Bracket br_(h, K_GATHER_FIELDS, st); k_gather_fields<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(h->state, h->B, io); }
+  CUDA_OK(cudaGetLastError());
+  return GSR_OK;
 }
 
 int gsr_compute_diagnostics(gsr_handle_t h, void* cuda_stream) {
@@ -607,7 +648,7 @@ void gsr_destroy(gsr_handle_t h) {
   if (h->committed) {
     cudaSetDevice(h->device);
     if (g_active[h->device] == h) g_active[h->device] = nullptr;
-    cudaFree(h->d_verts); cudaFree(h->d_support); cudaFree(h->d_pairs); cudaFree(h->d_pair_idx); cudaFree(h->d_model); cudaFree(h->d_fac); if (h->d_trace) cudaFree(h->d_trace);
+    cudaFree(h->d_verts); cudaFree(h->d_support); cudaFree(h->d_support_vid); cudaFree(h->d_pairs); cudaFree(h->d_pair_idx); cudaFree(h->d_model); cudaFree(h->d_fac); if (h->d_trace) cudaFree(h->d_trace);
     if (h->d_order) { cudaFree(h->d_order); cudaFree(h->d_iota); cudaFree(h->d_cost); cudaFree(h->d_cost_sorted); cudaFree(h->d_sort_tmp); h->d_order = nullptr; }
     if (h->d_rows_hist) { cudaFree(h->d_rows_hist); cudaFreeHost(h->h_rows_hist); cudaEventDestroy(h->rows_event); h->d_rows_hist = nullptr; h->h_rows_hist = nullptr; h->rows_event = nullptr; }
     if (h->d_stage) { cudaFree(h->d_stage); h->d_stage = nullptr; }

@@ -13,6 +13,7 @@
 #pragma once
 #include "gsr_group.cuh"
 #include "gsr_epa.cuh"
+#include "gsr_gjk.cuh"
 
 // SF:138-180 support point of a mesh-backed geom from its 180x180 direction table (L2 resident, read-only path)
 template <int G>
@@ -33,6 +34,31 @@ __device__ __noinline__ f3 dev_support_mesh(const Ctx<G>& C, f3 d, int g) {
     const f3 v = g3(tab + 3 * (i * res + j));
     const float dt = dot(v, d);
     if (dt > dot_max) { best = v; dot_max = dt; }
+  }
+  return best;
+}
+
+// the same lookup with the identity of the winning vertex (support_field.py support_vid: index inside the geom), for GJK
+template <int G>
+__device__ __noinline__ f3 dev_support_mesh_id(const Ctx<G>& C, f3 d, int g, int& vid) {
+  const float PI = 3.14159265358979323846f;
+  const float theta = atan2f(d.y, d.x), phi = acosf(d.z);
+  const int res = 180;
+  const float ii = (theta + PI) / PI / 2.f * res, jj = phi / PI * res;
+  float dot_max = -1e20f;
+  f3 best;
+  const int start = GM(g_support_start[g]);
+  const float* tab = CM(support_v) + 3 * (size_t)start;
+  const int* ids = CM(support_vid) + start;
+  vid = 0;
+  for (int i4 = 0; i4 < 4; i4++) {
+    int i = (i4 & 1) ? ((int)ceilf(ii)) % res : ((int)floorf(ii)) % res;
+    int j;
+    if (i4 >> 1) { j = (int)fminf(fmaxf(ceilf(jj), 0.f), (float)(res - 1)); if (j == res - 1) j = res - 2; }
+    else { j = (int)fminf(fmaxf(floorf(jj), 0.f), (float)(res - 1)); if (j == 0) j = 1; }
+    const f3 v = g3(tab + 3 * (i * res + j));
+    const float dt = dot(v, d);
+    if (dt > dot_max) { best = v; dot_max = dt; vid = __ldg(ids + i * res + j); }
   }
   return best;
 }
@@ -85,6 +111,48 @@ struct GroupSupport {  // support functor of the pair for gsr_epa.cuh
   const Ctx<G>& C;
   const PairPose& P;
   __device__ __forceinline__ void operator()(f3 d, f3& v, f3& v1, f3& v2) const { mpr_support(C, P, d, v, v1, v2); }
+};
+// the pair as gsr_gjk.cuh sees it (gjk_support.py:66-112 support_driver, gjk.py:1648-1698 discrete vertices, :1841-1900 counts)
+template <int G>
+struct GroupGeo {
+  const Ctx<G>& C;
+  const PairPose& P;
+  int ta, tb;
+  __device__ __forceinline__ float eps() const { return c_m.eps; }
+  __device__ __forceinline__ bool discrete() const { return (ta == GEOM_MESH || ta == GEOM_BOX) && (tb == GEOM_MESH || tb == GEOM_BOX); }
+  __device__ void support(f3 d, int which, f3& v, int& vid) const {
+    const int g = which ? P.gb : P.ga, type = which ? tb : ta;
+    const f3 pos = which ? P.pb : P.pa;
+    const f4 quat = which ? P.qb : P.qa;
+    vid = -1;
+    if (type == GEOM_BOX) {
+      const f3 db = rotate_inv(d, quat);
+      const f3 vl((db.x < 0.f ? -1.f : 1.f) * GM(g_data[g][0]) * 0.5f, (db.y < 0.f ? -1.f : 1.f) * GM(g_data[g][1]) * 0.5f,
+                  (db.z < 0.f ? -1.f : 1.f) * GM(g_data[g][2]) * 0.5f);
+      vid = (vl.x > 0.f ? 1 : 0) + (vl.y > 0.f ? 2 : 0) + (vl.z > 0.f ? 4 : 0) + GM(g_vert_start[g]);
+      v = transform(vl, pos, quat);
+    } else if (type == GEOM_SPHERE || type == GEOM_ELLIPSOID || type == GEOM_CAPSULE) {
+      v = dev_support(C, d, g, pos, quat);
+    } else {
+      v = transform(dev_support_mesh_id(C, rotate_inv(d, quat), g, vid), pos, quat);
+    }
+  }
+  __device__ int count_support(f3 dir) const {  // boxes: 2^(zero components); the reference's mesh count always answers 1
+    int count = 1;
+    if (ta == GEOM_BOX) { const f3 db = rotate_inv(dir, P.qa); count <<= (db.x == 0.f) + (db.y == 0.f) + (db.z == 0.f); }
+    if (tb == GEOM_BOX) { const f3 db = rotate_inv(-dir, P.qb); count <<= (db.x == 0.f) + (db.y == 0.f) + (db.z == 0.f); }
+    return count;
+  }
+  __device__ __forceinline__ int n_verts(int which) const { const int g = which ? P.gb : P.ga; return GM(g_vert_end[g]) - GM(g_vert_start[g]); }
+  __device__ void vertex(int which, int iv, f3& v, int& id) const {
+    const int g = which ? P.gb : P.ga, type = which ? tb : ta;
+    f3 vl;
+    if (type == GEOM_BOX) vl = f3(((iv & 1) ? 1.f : -1.f) * GM(g_data[g][0]) * 0.5f, ((iv & 2) ? 1.f : -1.f) * GM(g_data[g][1]) * 0.5f,
+                                  ((iv & 4) ? 1.f : -1.f) * GM(g_data[g][2]) * 0.5f);
+    else vl = g3(CM(verts) + 3 * (size_t)(GM(g_vert_start[g]) + iv));
+    id = GM(g_vert_start[g]) + iv;
+    v = transform(vl, which ? P.pb : P.pa, which ? P.qb : P.qa);
+  }
 };
 __device__ __forceinline__ f3 portal_dir(const Simplex& s) { return normalized(cross(s.v[2] - s.v[1], s.v[3] - s.v[1])); }
 __device__ __forceinline__ bool reach_tolerance(const Simplex& s, f3 v, f3 dir) {  // MPR:134-143
@@ -278,11 +346,18 @@ __device__ __forceinline__ void dev_detect(const Ctx<G>& C, const PairDet& D, co
     dev_mpr_contact(C, P, normal_ws, is_col, normal, pen, cpos, sx, tetra);
     if (i_det == 0 && !is_col && guess) { dev_mpr_contact(C, P, f3(), is_col, normal, pen, cpos, sx, tetra); guess_used = false; }
     // NP:726-733: MPR's answer is replaced by the exact one when the overlap is large or no direction was cached
-    if (c_m.gjk_fallback && is_col && tetra && pen > D.tolerance && (!guess_used || c_m.mc_tolerance * pen >= 0.25f * D.tolerance)) {
-      const GroupSupport<G> sup{C, P};
-      f3 n2, c2;
-      float p2 = 0.f;
-      if (epa_penetration(sx.v, sx.v1, sx.v2, sup, n2, p2, c2)) { normal = n2; pen = p2; cpos = c2; is_col = p2 > 0.f; }
+    if (c_m.gjk_fallback && is_col && pen > D.tolerance && (!guess_used || c_m.mc_tolerance * pen >= 0.25f * D.tolerance)) {
+      if (c_m.gjk_fallback == 2) {  // round-1 approximation (EPA seeded with MPR's final portal), kept for A/B runs
+        if (tetra) {
+          const GroupSupport<G> sup{C, P};
+          f3 n2, c2;
+          float p2 = 0.f;
+          if (epa_penetration(sx.v, sx.v1, sx.v2, sup, n2, p2, c2)) { normal = n2; pen = p2; cpos = c2; is_col = p2 > 0.f; }
+        }
+      } else {  // the reference's path: a fresh safe-GJK query and safe EPA from its tetrahedron (gsr_gjk.cuh)
+        const GroupGeo<G> geo{C, P, D.ta, D.tb};
+        gjk_contact(geo, is_col, normal, pen, cpos);
+      }
     }
   }
 }

@@ -397,10 +397,10 @@ __device__ void phase_dynamics(const Ctx<G>& C) {
     float v = 0.f;
     if (bit64(GM(l_dofmask[GM(d_link[i])]), j)) v = dot(ld3(fdof, 2 * i), ld3(cda, j)) + dot(ld3(fdof, 2 * i + 1), ld3(cdv, j));
     if (i == j) {
-      v += GM(d_armature[i]);
+      v += dof_armature(C, i);
       if (CM(integrator) == INTEGRATOR_APPROX_IMPLICITFAST) {
-        v += GM(d_damping[i]) * dt;
-        if (mode[i] <= CTRL_VELOCITY) v -= GM(d_act_bias[i][2]) * dt;
+        v += dof_damping(C, i) * dt;
+        if (mode[i] <= CTRL_VELOCITY) v -= dof_bias(C, i, 2) * dt;
       }
     }
     M[i * MS + j] = v; M[j * MS + i] = v; L[i * MS + j] = v;
@@ -417,7 +417,7 @@ __device__ void phase_dynamics(const Ctx<G>& C) {
     const int jt = GM(j_type[j]), ds = GM(j_dof_start[j]);
     const int md = mode[d];
     const float v = vel[d], dp = dofs_pos[d];
-    const float kp = GM(d_kp[d]), b0 = GM(d_act_bias[d][0]), b1 = GM(d_act_bias[d][1]), b2 = GM(d_act_bias[d][2]);
+    const float kp = dof_kp(C, d), b0 = dof_bias(C, d, 0), b1 = dof_bias(C, d, 1), b2 = dof_bias(C, d, 2);
     float force = 0.f;
     if (md == CTRL_FORCE) force = IN(ctrl_force)[d];
     else if (md == CTRL_VELOCITY) force = -b2 * (IN(ctrl_vel)[d] - v);
@@ -433,9 +433,9 @@ __device__ void phase_dynamics(const Ctx<G>& C) {
       const f3 rv = quat_to_rotvec(quat_compose(xyz_to_quat(cxyz), quat_inv(xyz_to_quat(xyz))), CM(eps));
       force = kp * comp(rv, d - ds - 3) + b0 + (kp + b1) * dp + b2 * (v - IN(ctrl_vel)[d]);
     }
-    qf_applied[d] = fminf(fmaxf(force, GM(d_force_range[d][0])), GM(d_force_range[d][1]));
-    float passive = -GM(d_damping[d]) * v;
-    if (jt != JOINT_FREE && jt != JOINT_FIXED) passive += -dp * GM(d_stiffness[d]);
+    qf_applied[d] = fminf(fmaxf(force, dof_force_range(C, d, 0)), dof_force_range(C, d, 1));
+    float passive = -dof_damping(C, d) * v;
+    if (jt != JOINT_FREE && jt != JOINT_FIXED) passive += -dp * dof_stiffness(C, d);
     qf_passive[d] = passive;
   }
   // ---- RNE bias forces (FD:1186-1486)
@@ -510,7 +510,7 @@ __device__ void phase_integrate(const Ctx<G>& C) {
     // FD:1787-1859 func_implicit_damping: refactor M + dt (damping - d act / d vel) and re-solve acc = M'^-1 force
     const int* mode = C.SI() + c_h.ctrl_mode;
     auto dof_damped = [&](int k) {
-      return CM(d_damping[k]) > EPS || (CM(integrator) != INTEGRATOR_EULER && mode[k] <= CTRL_VELOCITY && fabsf(CM(d_act_bias[k][2])) > EPS);
+      return dof_damping(C, k) > EPS || (CM(integrator) != INTEGRATOR_EULER && mode[k] <= CTRL_VELOCITY && fabsf(dof_bias(C, k, 2)) > EPS);
     };
     // the reference refactors entity by entity and skips entities without damping / velocity-dependent actuation (FD:1806-1832)
     auto ent_active = [&](int e) {
@@ -531,8 +531,8 @@ __device__ void phase_integrate(const Ctx<G>& C) {
         tri_decode(t, i, j);
         float v = M[i * MS + j];
         if (i == j && ent_active(GM(d_entity[i]))) {
-          v += GM(d_damping[i]) * dt;
-          if (CM(integrator) == INTEGRATOR_IMPLICITFAST && mode[i] <= CTRL_VELOCITY) v -= GM(d_act_bias[i][2]) * dt;
+          v += dof_damping(C, i) * dt;
+          if (CM(integrator) == INTEGRATOR_IMPLICITFAST && mode[i] <= CTRL_VELOCITY) v -= dof_bias(C, i, 2) * dt;
         }
         L[i * MS + j] = v;
       }

@@ -43,10 +43,10 @@ static inline size_t gsr_round4(size_t x) { return (x + 3) & ~(size_t)3; }
 
 static inline int gsr_fill_model(GsrSpec* h) {
   DevModel& m = h->hm;
-  const float* keep_verts = m.verts; const float* keep_support = m.support_v; const int* keep_pairs = m.pairs; const int* keep_pidx = m.pair_idx;
+  const float* keep_verts = m.verts; const float* keep_support = m.support_v; const int* keep_svid = m.support_vid; const int* keep_pairs = m.pairs; const int* keep_pidx = m.pair_idx;
   const unsigned short* keep_fac = m.fac_tasks;
   memset(&m, 0, sizeof(m));
-  m.verts = keep_verts; m.support_v = keep_support; m.pairs = keep_pairs; m.pair_idx = keep_pidx; m.fac_tasks = keep_fac;
+  m.verts = keep_verts; m.support_v = keep_support; m.support_vid = keep_svid; m.pairs = keep_pairs; m.pair_idx = keep_pidx; m.fac_tasks = keep_fac;
   auto S = [&](const char* k, double d) { auto it = h->s.find(k); return it == h->s.end() ? d : it->second; };
   m.nL = (int)S("n_links", 0); m.nJ = (int)S("n_joints", 0); m.nD = (int)S("n_dofs", 0); m.nQ = (int)S("n_qs", 0);
   m.nG = (int)S("n_geoms", 0); m.nE = (int)S("n_entities", 0); m.nEq = (int)S("n_equalities", 0); m.nP = (int)S("n_pairs", 0);
@@ -74,6 +74,8 @@ static inline int gsr_fill_model(GsrSpec* h) {
   m.ccd_eps = 1e-9f; m.ccd_tolerance = 1e-6f; m.ccd_iterations = 50;  // mpr.py:13-19
   m.n_cache_words = (m.nP + 31) / 32 > 0 ? (m.nP + 31) / 32 : 1;
   m.diagnostics = (int)S("cfg_diagnostics", 1);
+  m.batch_dofs = (int)S("cfg_batch_dofs_info", 0);
+  m.disable_constraint = (int)S("cfg_disable_constraint", 0);
 
   bool missing = false;
   std::string missing_name;
@@ -197,6 +199,7 @@ static inline int gsr_compute_layouts(GsrSpec* h, int n_envs) {
 
   // ---- HOT record layout
   const int nL = m.nL, nD = m.nD, nQ = m.nQ, nG = m.nG;
+  const int nBD = m.batch_dofs ? nD : 0;
   HotLayout& L = h->lay;
   memset(&L, 0, sizeof(L));
   h->fields.clear();

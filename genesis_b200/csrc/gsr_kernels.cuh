@@ -131,6 +131,14 @@ __global__ void __launch_bounds__(GSR_MAX_WARPS_PER_CTA * 32, 1) k_step(float* s
     const float* src = io.ctrl_pos + (size_t)C.env * nD;
     for (int d = C.lane; d < nD; d += G) IN(ctrl_pos)[d] = __ldcs(src + d);
   }
+  // qpos / vel written with skip_forward=True or by set_state(partial=True): the reference defers the forward kinematics to
+  // kernel_step_1 (is_forward_pos_updated = False, rigid_solver.py:2738-2765); the flag is per environment here
+  if (live && C.SI()[c_h.fk_dirty]) {  // group-uniform
+    C.sync();
+    phase_kinematics(C);
+    if (C.lane == 0) C.SI()[c_h.fk_dirty] = 0;
+    C.sync();
+  }
   PHASE_BARRIER(0);
   PHASE_BEGIN();
   if (live) phase_dynamics(C);
@@ -246,12 +254,112 @@ __global__ void __launch_bounds__(GSR_MAX_WARPS_PER_CTA * 32) k_forward(float* s
   }
   phase_kinematics(C);
   phase_geoms(C);
+  if (C.lane == 0) C.SI()[c_h.fk_dirty] = 0;
   C.sync();
   {
     float4* dst = reinterpret_cast<float4*>(C.rec);
     const float4* src = reinterpret_cast<const float4*>(C.S);
     for (int i = C.lane; i < c_h.n_in / 4; i += G) dst[i] = src[i];
   }
+}
+
+// RigidSolver.set_state (rigid_solver.py:1458-1579) for the masked environments in ONE launch: collider.reset / clear and
+// constraint_solver.reset / clear, errno = 0, state from dense (B, n) buffers (qpos, dofs_vel, dofs_acc, links_pos / quat of the
+// fixed root links, i_pos_shift, mass_shift, friction_ratio), ctrl_force = 0 / ctrl_mode = FORCE, external wrenches cleared,
+// then -- unless `partial` -- the forward kinematics of the new configuration; with `partial` the kinematics are left to the
+// next step (fk_dirty), as the reference does.
+struct StateIO {
+  const float *qpos, *vel, *acc, *links_pos, *links_quat, *i_pos_shift, *mass_shift, *friction_ratio;
+};
+template <int G>
+__global__ void __launch_bounds__(GSR_MAX_WARPS_PER_CTA * 32) k_set_state(float* state, int B, const DevModel* gm, const uint8_t* mask, StateIO io, int partial) {
+  extern __shared__ __align__(16) float smem[];
+  Ctx<G> C;
+  if (!make_ctx(C, state, B, gm, smem)) return;
+  if (mask && !mask[C.env]) return;
+  const int nD = CM(nD), nQ = CM(nQ), nL = CM(nL), nG = CM(nG), lane = C.lane, env = C.env;
+  float* rec = C.rec;
+  int* reci = reinterpret_cast<int*>(rec);
+  // collider.reset (warm-start cache) / constraint_solver.reset (warm start); clear additionally drops contacts and row counts
+  for (int d = lane; d < nD; d += G) rec[c_h.qacc_ws + d] = 0.f;
+  int* cv = reinterpret_cast<int*>(C.cache) + c_h.cache_valid;
+  for (int w = lane; w < CM(n_cache_words); w += G) cv[w] = 0;
+  if (!partial) {
+    const int nc = reci[c_h.n_contacts];
+    for (int i = lane; i < nc * GSR_CONTACT_WORDS; i += G) {
+      const int k = i % GSR_CONTACT_WORDS;
+      if (k < 4) reinterpret_cast<int*>(C.contacts)[i] = -1; else C.contacts[i] = 0.f;
+    }
+  }
+  bool any_shift = false;
+  for (int q = lane; q < nQ; q += G) if (io.qpos) rec[c_h.qpos + q] = io.qpos[(size_t)env * nQ + q];
+  for (int d = lane; d < nD; d += G) {
+    if (io.vel) rec[c_h.vel + d] = io.vel[(size_t)env * nD + d];
+    if (io.acc) rec[c_h.acc + d] = io.acc[(size_t)env * nD + d];
+    rec[c_h.ctrl_force + d] = 0.f;
+    reci[c_h.ctrl_mode + d] = CTRL_FORCE;
+  }
+  for (int l = lane; l < nL; l += G) {
+    if (GM(l_parent[l]) == -1 && GM(l_is_fixed[l])) {  // only fixed roots keep a user-set pose; every other pose follows from qpos
+      if (io.links_pos) for (int k = 0; k < 3; k++) rec[c_h.links_pos + 3 * l + k] = io.links_pos[((size_t)env * nL + l) * 3 + k];
+      if (io.links_quat) for (int k = 0; k < 4; k++) rec[c_h.links_quat + 4 * l + k] = io.links_quat[((size_t)env * nL + l) * 4 + k];
+    }
+    for (int k = 0; k < 3; k++) {
+      if (io.i_pos_shift) { const float v = io.i_pos_shift[((size_t)env * nL + l) * 3 + k]; rec[c_h.com_shift + 3 * l + k] = v; any_shift |= v != 0.f; }
+      rec[c_h.cfrc_applied_vel + 3 * l + k] = 0.f; rec[c_h.cfrc_applied_ang + 3 * l + k] = 0.f;
+    }
+    if (io.mass_shift) { const float v = io.mass_shift[(size_t)env * nL + l]; rec[c_h.mass_shift + l] = v; any_shift |= v != 0.f; }
+  }
+  for (int g = lane; g < nG; g += G) if (io.friction_ratio) rec[c_h.friction_ratio + g] = io.friction_ratio[(size_t)env * nG + g];
+  any_shift = C.any(any_shift);
+  if (lane == 0) {
+    reci[c_h.is_warmstart] = 0; reci[c_h.errno_] = 0; reci[c_h.has_ext_force] = 0;
+    if (io.i_pos_shift || io.mass_shift) reci[c_h.has_shift] = any_shift ? 1 : 0;
+    if (!partial) {
+      reci[c_h.n_contacts] = 0; reci[c_h.n_broad] = 0;
+      reci[c_h.n_constraints] = 0; reci[c_h.n_constraints_equality] = 0; reci[c_h.n_constraints_frictionloss] = 0;
+    }
+    reci[c_h.fk_dirty] = partial ? 1 : 0;
+  }
+  __threadfence_block();
+  C.sync();
+  if (partial) return;
+  {
+    const float4* src = reinterpret_cast<const float4*>(rec);
+    float4* dst = reinterpret_cast<float4*>(C.S);
+    for (int i = lane; i < c_h.n_in / 4; i += G) dst[i] = src[i];
+    C.sync();
+  }
+  phase_kinematics(C);
+  phase_geoms(C);
+  C.sync();
+  {
+    float4* dst = reinterpret_cast<float4*>(rec);
+    const float4* src = reinterpret_cast<const float4*>(C.S);
+    for (int i = lane; i < c_h.n_in / 4; i += G) dst[i] = src[i];
+  }
+}
+
+// Several fields of every environment's HOT record into dense (B, n) buffers in ONE launch: kernel_get_state
+// (abd/accessor.py) and the observation getters of an RL loop (qpos, dofs position / velocity, link poses and velocities ...).
+#define GSR_MAX_GATHER 16
+struct GatherIO {
+  int n;                        // number of segments
+  int off[GSR_MAX_GATHER];      // word offset inside the HOT record
+  int width[GSR_MAX_GATHER];    // words per environment
+  int start[GSR_MAX_GATHER + 1];  // prefix sum of the widths
+  float* dst[GSR_MAX_GATHER];   // dense (B, width) destinations
+};
+__global__ void k_gather_fields(const float* state, int B, GatherIO io) {
+  const int total = io.start[io.n];
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)B * total) return;
+  const int env = (int)(t / total), w = (int)(t - (long long)env * total);
+  int s = 0;
+#pragma unroll
+  for (int k = 1; k < GSR_MAX_GATHER; k++) if (k < io.n && w >= io.start[k]) s = k;
+  const int i = w - io.start[s];
+  io.dst[s][(size_t)env * io.width[s] + i] = state[(size_t)env * c_h.hot_stride + io.off[s] + i];
 }
 
 // On-demand diagnostics of the CURRENT state (get_mass_mat, geoms_state.pos / quat, qf_* with cfg_diagnostics = 0): smooth
@@ -305,6 +413,13 @@ __global__ void k_init(float* state, int B) {
   for (int q = 0; q < c_m.nQ; q++) rec[c_h.qpos + q] = c_m.qpos0[q];
   for (int d = 0; d < c_m.nD; d++) reci[c_h.ctrl_mode + d] = CTRL_FORCE;
   for (int g = 0; g < c_m.nG; g++) rec[c_h.friction_ratio + g] = 1.0f;
+  if (c_m.batch_dofs)  // RigidOptions.batch_dofs_info: every environment starts from the model's dof parameters
+    for (int d = 0; d < c_m.nD; d++) {
+      rec[c_h.bd_kp + d] = c_m.d_kp[d]; rec[c_h.bd_armature + d] = c_m.d_armature[d]; rec[c_h.bd_damping + d] = c_m.d_damping[d];
+      rec[c_h.bd_stiffness + d] = c_m.d_stiffness[d]; rec[c_h.bd_frictionloss + d] = c_m.d_frictionloss[d]; rec[c_h.bd_invweight + d] = c_m.d_invweight[d];
+      for (int k = 0; k < 3; k++) rec[c_h.bd_bias + 3 * d + k] = c_m.d_act_bias[d][k];
+      for (int k = 0; k < 2; k++) { rec[c_h.bd_limit + 2 * d + k] = c_m.d_limit[d][k]; rec[c_h.bd_force_range + 2 * d + k] = c_m.d_force_range[d][k]; }
+    }
   for (int l = 0; l < c_m.nL; l++) {
     for (int k = 0; k < 3; k++) rec[c_h.links_pos + 3 * l + k] = c_m.l_pos[l][k];
     for (int k = 0; k < 4; k++) rec[c_h.links_quat + 4 * l + k] = c_m.l_quat[l][k];

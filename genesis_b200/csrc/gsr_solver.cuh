@@ -75,19 +75,20 @@ __device__ __noinline__ void build_rows(const Ctx<G>& C, Rows& R) {
   const float EPS = CM(eps);
   const float* qpos = IN(qpos);
   const float* vel = IN(vel);
-  const int n_contacts = CM(enable_collision) ? C.SI()[c_h.n_contacts] : 0;
+  const bool off = CM(disable_constraint) != 0;  // RigidOptions.disable_constraint: collision detection still runs, no rows are built
+  const int n_contacts = (CM(enable_collision) && !off) ? C.SI()[c_h.n_contacts] : 0;
   // ---- static counts: equality rows and friction-loss rows
   int n_eq = 0;
-  for (int i = 0; i < CM(nEq); i++) n_eq += CM(eq_type[i]) == EQ_JOINT ? 1 : (CM(eq_type[i]) == EQ_CONNECT ? 3 : (CM(eq_type[i]) == EQ_WELD ? 6 : 0));
-  const int n_dyn = min(max(C.SI()[c_h.n_dyn_eq], 0), GSR_MAX_DYN_EQ);
+  for (int i = 0; i < (off ? 0 : CM(nEq)); i++) n_eq += CM(eq_type[i]) == EQ_JOINT ? 1 : (CM(eq_type[i]) == EQ_CONNECT ? 3 : (CM(eq_type[i]) == EQ_WELD ? 6 : 0));
+  const int n_dyn = off ? 0 : min(max(C.SI()[c_h.n_dyn_eq], 0), GSR_MAX_DYN_EQ);
   n_eq += 6 * n_dyn;
   int n_floss = 0;
-  for (int d = 0; d < nD; d++) n_floss += CM(d_frictionloss[d]) > EPS ? 1 : 0;
+  for (int d = 0; d < (off ? 0 : nD); d++) n_floss += dof_frictionloss(C, d) > EPS ? 1 : 0;
   // ---- joint limits that are violated (CS:1176-1233), in joint order
   int n_lim = 0;
   const int lim_base = n_eq + n_floss + 4 * n_contacts;
   // first pass only counts, second pass (below) fills once the storage is chosen
-  if (CM(enable_joint_limit)) {
+  if (CM(enable_joint_limit) && !off) {
     for (int base = 0; base < nJ; base += G) {
       const int j = base + lane;
       bool viol = false;
@@ -96,7 +97,7 @@ __device__ __noinline__ void build_rows(const Ctx<G>& C, Rows& R) {
         if (type == JOINT_REVOLUTE || type == JOINT_PRISMATIC) {
           const int q = GM(j_q_start[j]), d = GM(j_dof_start[j]);
           const float qv = qpos[q];
-          viol = fminf(qv - GM(d_limit[d][0]), GM(d_limit[d][1]) - qv) < 0.f;
+          viol = fminf(qv - dof_limit(C, d, 0), dof_limit(C, d, 1) - qv) < 0.f;
         }
       }
       n_lim += __popc(C.ballot(viol));
@@ -144,7 +145,7 @@ __device__ __noinline__ void build_rows(const Ctx<G>& C, Rows& R) {
         J[row * JS + d1] = 1.0f;
         J[row * JS + d2] = -deriv;
         const float jac_qvel = vel[d1] + (-deriv) * vel[d2];
-        const float invweight = CM(d_invweight[d1]) + CM(d_invweight[d2]);
+        const float invweight = dof_invweight(C, d1) + dof_invweight(C, d2);
         float imp, aref;
         imp_aref(CM(eq_sol[i]), -fabsf(pos), jac_qvel, pos, imp, aref);
         const float diag = fmaxf(invweight * (1.0f - imp) / imp, EPS);
@@ -190,11 +191,11 @@ __device__ __noinline__ void build_rows(const Ctx<G>& C, Rows& R) {
   if (n_floss > 0 && lane == 0) {
     int r = n_eq;
     for (int d = 0; d < nD; d++)
-      if (CM(d_frictionloss[d]) > EPS) {
+      if (dof_frictionloss(C, d) > EPS) {
         float imp, aref;
         imp_aref(CM(j_sol[CM(d_joint[d])]), 0.f, vel[d], 0.f, imp, aref);
-        const float diag = fmaxf(CM(d_invweight[d]) * (1.0f - imp) / imp, EPS);
-        R.R[r] = diag; R.aref[r] = aref; R.D[r] = 1.0f / diag; R.floss[r] = CM(d_frictionloss[d]);
+        const float diag = fmaxf(dof_invweight(C, d) * (1.0f - imp) / imp, EPS);
+        R.R[r] = diag; R.aref[r] = aref; R.D[r] = 1.0f / diag; R.floss[r] = dof_frictionloss(C, d);
         J[r * JS + d] = 1.0f;
         r++;
       }
@@ -259,7 +260,7 @@ __device__ __noinline__ void build_rows(const Ctx<G>& C, Rows& R) {
           const int q = GM(j_q_start[j]);
           d = GM(j_dof_start[j]);
           const float qv = qpos[q];
-          pmin = qv - GM(d_limit[d][0]); pmax = GM(d_limit[d][1]) - qv;
+          pmin = qv - dof_limit(C, d, 0); pmax = dof_limit(C, d, 1) - qv;
           viol = fminf(pmin, pmax) < 0.f;
         }
       }
@@ -273,7 +274,7 @@ __device__ __noinline__ void build_rows(const Ctx<G>& C, Rows& R) {
         for (int k = 0; k < 7; k++) sol[k] = GM(j_sol[j][k]);
         float imp, aref;
         imp_aref(sol, pd, jac * vel[d], pd, imp, aref);
-        const float diag = fmaxf(GM(d_invweight[d]) * (1.0f - imp) / imp, EPS);
+        const float diag = fmaxf(dof_invweight(C, d) * (1.0f - imp) / imp, EPS);
         R.R[c] = diag; R.aref[c] = aref; R.D[c] = 1.0f / diag; R.floss[c] = 0.f;
         J[c * JS + d] = jac;
       }
@@ -985,7 +986,7 @@ __device__ void phase_constraints(const Ctx<G>& C) {
     out[c_h.n_constraints] = n_con; out[c_h.n_constraints_equality] = R.ne; out[c_h.n_constraints_frictionloss] = R.nef - R.ne;
     out[c_h.solver_iters] = iters;
   }
-  const int nc = CM(enable_collision) ? SI[c_h.n_contacts] : 0;
+  const int nc = (CM(enable_collision) && !CM(disable_constraint)) ? SI[c_h.n_contacts] : 0;
   if (CM(noslip_iterations) > 0 && n_con > 0) { C.sync(); phase_noslip(C, R, nc); }  // CS:237-238
   // ---- CS:3198-3237 func_update_contact_force: per-contact force (global record) and per-link totals
   for (int ic = lane; ic < nc; ic += G) {

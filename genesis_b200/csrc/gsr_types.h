@@ -50,6 +50,8 @@ struct DevModel {
   int gjk_fallback;       // exact-penetration fallback after MPR (narrowphase.py:726-733); 0 keeps MPR's answer
   float noslip_tolerance;
   int enable_collision, enable_joint_limit, enable_multi_contact, sort_contacts, has_cc, n_cache_words, diagnostics;
+  int batch_dofs;          // RigidOptions.batch_dofs_info: per-environment dof parameters live in the record (bd_* fields)
+  int disable_constraint;  // RigidOptions.disable_constraint: no rows at all (rigid_solver.py:1026-1042)
   float meaninertia, dt, eps, tolerance, ls_tolerance, mc_perturbation, mc_tolerance;
   float gravity[3];
   float ccd_eps, ccd_tolerance;
@@ -92,6 +94,7 @@ struct DevModel {
   // large read-only tables in global memory
   const float* verts;      // [nV][3]
   const float* support_v;  // [n_support_cells][3]
+  const int* support_vid;  // [n_support_cells] vertex index (inside its geom) of every support cell
   const int* pairs;        // [nP][2]
   const int* pair_idx;     // [nG][nG]
   // L^T D L elimination tasks of pivot i: fac_tasks[fac_start[i] .. fac_start[i + 1]) = (j << 8) | k over the ancestor dofs
@@ -108,7 +111,7 @@ struct DevModel {
   X(qpos, 0, nQ, 1) X(vel, 0, nD, 1) X(ctrl_pos, 0, nD, 1) X(ctrl_vel, 0, nD, 1) X(ctrl_force, 0, nD, 1)           \
   X(ctrl_mode, 1, nD, 1) X(qacc_ws, 0, nD, 1)                                                                      \
   X(is_warmstart, 1, 1, 1) X(errno_, 1, 1, 1) X(n_contacts, 1, 1, 1) X(n_broad, 1, 1, 1)                           \
-  X(has_ext_force, 1, 1, 1) X(has_shift, 1, 1, 1) X(n_dyn_eq, 1, 1, 1)                                             \
+  X(has_ext_force, 1, 1, 1) X(has_shift, 1, 1, 1) X(n_dyn_eq, 1, 1, 1) X(fk_dirty, 1, 1, 1)                                           \
   /* kinematic cache written by the FK at the end of a step and consumed by the next step */                       \
   X(dofs_pos, 0, nD, 1) X(root_COM, 0, nL, 3) X(cdof_ang, 0, nD, 3) X(cdof_vel, 0, nD, 3) X(cdofd_ang, 0, nD, 3)   \
   X(cdofd_vel, 0, nD, 3) X(links_pos, 0, nL, 3) X(links_quat, 0, nL, 4) X(cinr_I, 0, nL, 6) X(cinr_pos, 0, nL, 3)  \
@@ -122,6 +125,9 @@ struct DevModel {
   /* dynamic weld equalities (add_weld_constraint, solver.py:1293-1340): n_dyn_eq records of GSR_DYN_EQ_WORDS words   \
      [link1, link2, eq_data[11], sol_params[7]] */                                                                    \
   X(dyn_eq, 0, GSR_MAX_DYN_EQ, GSR_DYN_EQ_WORDS)                                                                    \
+  /* per-environment dof parameters (RigidOptions.batch_dofs_info, array_class.py:1347-1364): nBD = nD when on, else 0 */ \
+  X(bd_kp, 0, nBD, 1) X(bd_bias, 0, nBD, 3) X(bd_armature, 0, nBD, 1) X(bd_damping, 0, nBD, 1) X(bd_stiffness, 0, nBD, 1)   \
+  X(bd_frictionloss, 0, nBD, 1) X(bd_limit, 0, nBD, 2) X(bd_force_range, 0, nBD, 2) X(bd_invweight, 0, nBD, 1)              \
   X(acc, 0, nD, 1) X(force, 0, nD, 1) X(qf_applied, 0, nD, 1) X(qf_constraint, 0, nD, 1)                           \
   X(cacc_lin, 0, nL, 3) X(cacc_ang, 0, nL, 3) X(links_contact_force, 0, nL, 3)                                     \
   X(aabb_min, 0, nG, 3) X(aabb_max, 0, nG, 3)                                                                      \

@@ -346,17 +346,19 @@ class ModelBuilder:
         dirs = np.stack(
             [np.sin(phi)[None, :] * np.cos(theta)[:, None], np.sin(phi)[None, :] * np.sin(theta)[:, None],
              np.broadcast_to(np.cos(phi)[None, :], (SUPPORT_RES, SUPPORT_RES))], axis=-1).reshape(-1, 3)
-        cell_start, sup_v, n_cells = [], [], 0
+        cell_start, sup_v, sup_vid, n_cells = [], [], [], 0
         for g, v in zip(geoms, verts_all):
             if g["type"] in (GEOM_TYPE.MESH, GEOM_TYPE.CYLINDER):
                 idx = np.argmax(dirs @ v.T, axis=1)
                 cell_start.append(n_cells)
                 sup_v.append(v[idx])
+                sup_vid.append(idx)  # support_field.py:62-70 support_vid: vertex index inside the geom (simplex-vertex identity in GJK)
                 n_cells += len(idx)
             else:
                 cell_start.append(-1)
         m.geoms_support_start = np.array(cell_start, I32).reshape(nG)
         m.support_v = np.concatenate(sup_v, axis=0) if sup_v else np.zeros((0, 3))
+        m.support_vid = np.concatenate(sup_vid).astype(I32) if sup_vid else np.zeros(0, I32)
         m.n_support_cells = n_cells
 
         # ---- equalities (entity-local names -> global joint/link ids)

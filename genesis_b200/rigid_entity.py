@@ -128,8 +128,13 @@ class RigidEntity:
     def _global(self, idx_local, n, start):
         """rigid_entity.py:1214-1261 _get_global_idx."""
         if idx_local is None:
-            return torch.arange(start, start + n)
-        if isinstance(idx_local, (slice, range)):
+            return slice(start, start + n)  # contiguous columns of the record: the solver reads / writes strided views, no gather
+        if isinstance(idx_local, slice):
+            a, b, st = idx_local.indices(n)
+            if st == 1:
+                return slice(start + a, start + max(a, b))
+            return torch.arange(start, start + n)[idx_local]
+        if isinstance(idx_local, range):
             return torch.arange(start, start + n)[idx_local]
         idx = torch.as_tensor(idx_local, dtype=torch.long).reshape(-1).cpu()
         if len(idx) and (idx.min() < -n or idx.max() >= n):
@@ -312,10 +317,10 @@ class RigidEntity:
         self._solver.set_dofs_stiffness(stiffness, self._dofs(dofs_idx_local), envs_idx)
 
     def get_dofs_stiffness(self, dofs_idx_local=None, envs_idx=None):
-        return torch.tensor(self._solver.model.dofs_stiffness, dtype=torch.float32)[self._dofs(dofs_idx_local)]
+        return self._solver.get_dofs_stiffness(self._dofs(dofs_idx_local), envs_idx)
 
     def get_dofs_damping(self, dofs_idx_local=None, envs_idx=None):
-        return torch.tensor(self._solver.model.dofs_damping, dtype=torch.float32)[self._dofs(dofs_idx_local)]
+        return self._solver.get_dofs_damping(self._dofs(dofs_idx_local), envs_idx)
 
     def set_dofs_frictionloss(self, frictionloss, dofs_idx_local=None, envs_idx=None):
         self._solver.set_dofs_frictionloss(frictionloss, self._dofs(dofs_idx_local), envs_idx)
@@ -324,10 +329,10 @@ class RigidEntity:
         self._solver.set_dofs_limit(lower, upper, self._dofs(dofs_idx_local), envs_idx)
 
     def get_dofs_armature(self, dofs_idx_local=None, envs_idx=None):
-        return self._solver.get_dofs_armature(self._dofs(dofs_idx_local))
+        return self._solver.get_dofs_armature(self._dofs(dofs_idx_local), envs_idx)
 
     def get_dofs_frictionloss(self, dofs_idx_local=None, envs_idx=None):
-        return self._solver.get_dofs_frictionloss(self._dofs(dofs_idx_local))
+        return self._solver.get_dofs_frictionloss(self._dofs(dofs_idx_local), envs_idx)
 
     def get_dofs_force_range(self, dofs_idx_local=None, envs_idx=None):
         return self._solver.get_dofs_force_range(self._dofs(dofs_idx_local))
@@ -360,7 +365,7 @@ class RigidEntity:
         """rigid_entity.py: per-environment friction scale, one value per link, applied to all the link's geoms."""
         m = self._solver.model
         links = self._links_idx(links_idx_local)
-        links = torch.as_tensor(links).reshape(-1).tolist()
+        links = list(range(links.start, links.stop)) if isinstance(links, slice) else torch.as_tensor(links).reshape(-1).tolist()
         ratio = torch.as_tensor(friction_ratio, dtype=torch.float32)
         geoms, cols = [], []
         for k, l in enumerate(links):

@@ -51,6 +51,31 @@ def _morph_to_infos(morph):
     raise GenesisException(f"Unsupported morph: {morph!r}")
 
 
+class RigidSolverState:
+    """Dynamic state queried from a RigidSolver (genesis/engine/states/solvers.py:83-106): (B, n) tensors on the device."""
+
+    FIELDS = ("qpos", "dofs_vel", "dofs_acc", "links_pos", "links_quat", "i_pos_shift", "mass_shift", "friction_ratio")
+
+    def __init__(self, scene=None, s_global=0):
+        self.scene, self._s_global = scene, s_global
+        for k in self.FIELDS:
+            setattr(self, k, None)
+
+    @property
+    def s_global(self):
+        return self._s_global
+
+    def __getitem__(self, key):  # the dict-style access of round 1 keeps working
+        return getattr(self, key)
+
+    def serializable(self):
+        self.scene = None
+        for k in self.FIELDS:
+            v = getattr(self, k)
+            if v is not None:
+                setattr(self, k, v.detach())
+
+
 class RigidSolver:
     def __init__(self, scene, sim_options, rigid_options):
         self._scene = scene
@@ -64,6 +89,7 @@ class RigidSolver:
         self._handle = None
         self._n_substeps_total = 0
         self._errno_host = self._errno_event = None
+        self._obs_valid, self._obs = False, None
         self._errno_pending = False
         # launch tuning of libgsrigid (0 = library default): lanes per environment, constraint rows kept in shared
         # memory, and whether the diagnostic fields (mass_mat, qf_*, acc_smooth, geom poses) are written every step
@@ -94,6 +120,8 @@ class RigidSolver:
 
     def build_model(self):
         o = self._options
+        if (o.batch_dofs_info or o.batch_links_info) and self.tuning.get("group_size") == 1:
+            raise GenesisException("batch_dofs_info / batch_links_info need the lane-group step kernel (unset GSR_GROUP_SIZE=1).")
         if o.use_contact_island or o.use_hibernation or o.enable_mujoco_compatibility or o.use_gjk_collision:
             raise GenesisException(
                 "contact islands, hibernation, mujoco-compatibility and GJK-first collision are outside the "
@@ -124,6 +152,7 @@ class RigidSolver:
                     integrator=int(o.integrator), solver_type=int(o.constraint_solver), enable_collision=int(o.enable_collision),
                     enable_joint_limit=int(o.enable_joint_limit), enable_multi_contact=int(o.enable_multi_contact),
                     noslip_iterations=int(o.noslip_iterations), noslip_tolerance=float(o.noslip_tolerance),
+                    batch_dofs_info=int(bool(o.batch_dofs_info)), disable_constraint=int(bool(o.disable_constraint)),
                     sort_contacts=1, **self.tuning)
 
     def build(self, n_envs, device):
@@ -197,6 +226,7 @@ class RigidSolver:
     def substep(self, n=1):
         _lib.check(self._handle, _lib.lib().gsr_step(self._handle, n, self._stream()))
         self._n_substeps_total += n
+        self._obs_valid = False
 
     @property
     def launch_info(self):
@@ -210,6 +240,7 @@ class RigidSolver:
         p = lambda a: ctypes.c_void_p(a.ctypes.data) if a is not None else None
         _lib.check(self._handle, _lib.lib().gsr_step_host(self._handle, n, p(ctrl_pos_host), p(qpos_host), p(vel_host), self._stream()))
         self._n_substeps_total += n
+        self._obs_valid = False
 
     def launch_count(self):
         return int(_lib.lib().gsr_launch_count(self._handle))
@@ -294,29 +325,84 @@ class RigidSolver:
             return torch.as_tensor(list(idx), device=self.device, dtype=torch.long)
         return torch.as_tensor(idx, device=self.device, dtype=torch.long).reshape(-1)
 
+    # fields the observation getters of an RL loop read: gathered into dense (B, n) tensors by ONE launch the first time any of them
+    # is asked for after a step / setter (k_gather_fields); the getters then return copies of those dense tensors
+    OBS_FIELDS = ("qpos", "dofs_pos", "vel", "links_pos", "links_quat", "cd_vel", "cd_ang", "root_COM", "acc", "force", "qf_applied",
+                  "cacc_lin", "cacc_ang", "links_contact_force")
+
+    def _observed(self, name):
+        if name not in self.OBS_FIELDS:
+            return self._fields[name]
+        if not self._obs_valid:
+            self._obs = self.gather_fields(list(self.OBS_FIELDS), out=self._obs)
+            self._obs_valid = True
+        return self._obs[name]
+
     def _get(self, name, idx, envs_idx, n, comps=1):
         """(B, len(idx)[, comps]) copy of a field."""
-        f = self._fields[name]
-        out = f[:, self._idx(idx, n)]
-        envs = self._envs(envs_idx)
-        out = out.clone() if envs is None else out[envs]
+        f = self._observed(name)
+        view = idx is None or isinstance(idx, slice)
+        out = f if idx is None else (f[:, idx] if view else f[:, self._idx(idx, n)])
+        if envs_idx is None:
+            out = out.clone() if view else out  # an index_select result is a copy already
+        elif self._is_mask(envs_idx):
+            out = out[envs_idx.to(self.device)]
+        else:
+            out = out[self._envs(envs_idx)]
         if self.n_envs == 0:
             out = out[0]
         return out
 
+    def _is_mask(self, envs_idx):
+        return isinstance(envs_idx, torch.Tensor) and envs_idx.dtype == torch.bool
+
     def _set(self, name, value, idx, envs_idx, n, dtype=torch.float32):
         f = self._fields[name]
-        idx = self._idx(idx, n)
+        full = idx is None or (isinstance(idx, slice) and len(range(*idx.indices(n))) == n)
+        if isinstance(idx, slice) and self._envs_is_all_or_mask(envs_idx):
+            n_sel = len(range(*idx.indices(n)))  # contiguous columns: plain strided writes, no index tensor
+        else:
+            idx = self._idx(idx, n)
+            n_sel = len(idx)
+        value = torch.as_tensor(value, dtype=dtype, device=self.device)
+        if self._is_mask(envs_idx):  # boolean env mask: a masked select on the device, no index extraction (no host sync)
+            mask = envs_idx.to(self.device)
+            cur = f if full else f[:, idx]
+            value = torch.broadcast_to(value, cur.shape).to(f.dtype)
+            new = torch.where(mask.reshape((-1,) + (1,) * (cur.dim() - 1)), value, cur)
+            if full:
+                f.copy_(new)
+            else:
+                f[:, idx] = new
+            return
         envs = self._envs(envs_idx)
         nb = self._B if envs is None else len(envs)
-        value = torch.as_tensor(value, dtype=dtype, device=self.device)
-        value = torch.broadcast_to(value, (nb, len(idx))).to(f.dtype)
+        value = torch.broadcast_to(value, (nb, n_sel)).to(f.dtype)
         if envs is None:
-            f[:, idx] = value
+            if full:
+                f.copy_(value)
+            else:
+                f[:, idx] = value
         else:
             f[envs[:, None], idx[None, :]] = value
 
+    def _envs_is_all_or_mask(self, envs_idx):
+        return envs_idx is None or self._is_mask(envs_idx)
+
+    def _mark_fk_dirty(self, envs_idx):
+        """qpos / vel written with skip_forward=True: the next step runs the forward kinematics of these environments first
+        (the reference's is_forward_pos_updated = False, rigid_solver.py:2738-2765)."""
+        d = self._fields["fk_dirty"]
+        if envs_idx is None:
+            d.fill_(1)
+        elif self._is_mask(envs_idx):
+            d[:, 0] = torch.where(envs_idx.to(self.device), torch.ones_like(d[:, 0]), d[:, 0])
+        else:
+            d[self._envs(envs_idx)] = 1
+
     def _env_mask(self, envs_idx):
+        if self._is_mask(envs_idx):
+            return envs_idx.to(self.device).to(torch.uint8)
         envs = self._envs(envs_idx)
         if envs is None:
             return None
@@ -333,15 +419,21 @@ class RigidSolver:
     def set_qpos(self, qpos, qs_idx=None, envs_idx=None, *, skip_forward=False):
         self._set("qpos", qpos, qs_idx, envs_idx, self.model.n_qs)
         self._reset_warmstart(envs_idx)
+        self._obs_valid = False
         if not skip_forward:
             self._forward(envs_idx)
+        else:
+            self._mark_fk_dirty(envs_idx)
 
     def set_dofs_velocity(self, velocity, dofs_idx=None, envs_idx=None, *, skip_forward=False):
         if velocity is None:
             velocity = 0.0
         self._set("vel", velocity, dofs_idx, envs_idx, self.model.n_dofs)
+        self._obs_valid = False
         if not skip_forward:
             self._forward(envs_idx)
+        else:
+            self._mark_fk_dirty(envs_idx)
 
     def set_base_link_pose(self, link_idx, value, field, envs_idx=None):
         """kernel_set_links_pos / kernel_set_links_quat for a FIXED root link (abd/accessor.py): its world pose is state, FK of
@@ -473,10 +565,13 @@ class RigidSolver:
     def _set_model_array(self, name, values, dofs_idx, width=None):
         m = self.model
         arr = getattr(m, name)
-        idx = self._idx(dofs_idx, m.n_dofs).cpu().numpy()
+        idx = np.arange(m.n_dofs)[dofs_idx] if isinstance(dofs_idx, slice) else self._idx(dofs_idx, m.n_dofs).cpu().numpy()
         vals = np.asarray(torch.as_tensor(values).detach().cpu().numpy(), dtype=np.float64)
         if vals.ndim >= 1 and self.n_envs > 0 and vals.ndim == (2 if width is None else 3):
             vals = vals[0]  # unbatched parameters: envs must agree
+        cur = arr[idx] if width is None else arr[idx, width]
+        if np.array_equal(np.broadcast_to(vals, np.shape(cur)).astype(np.float32), np.asarray(cur, np.float32)):
+            return  # unchanged (an RL loop re-applying its gains every step): no model upload
         if width is None:
             arr[idx] = vals
         else:
@@ -486,35 +581,84 @@ class RigidSolver:
         L.gsr_model_set_f32(self._handle, name.encode(), a.ctypes.data, a.size)
         _lib.check(self._handle, L.gsr_model_refresh(self._handle))
 
+    # per-dof parameters: model constants shared by every environment (default), or -- RigidOptions.batch_dofs_info -- fields of each
+    # environment's record (dofs_info of shape (n_dofs, B) in the reference, array_class.py:1347-1364)
+    @property
+    def _batch_dofs(self):
+        return bool(self._options.batch_dofs_info)
+
+    def _set_dof_param(self, field, model_name, values, dofs_idx, envs_idx, width=None, comps=1):
+        if not self._batch_dofs:
+            if envs_idx is not None:
+                raise GenesisException("Per-environment dof parameters need RigidOptions(batch_dofs_info=True).")
+            return self._set_model_array(model_name, values, dofs_idx, width)
+        f = self._fields[field]
+        n = self.model.n_dofs
+        cols = self._idx(dofs_idx, n) if not isinstance(dofs_idx, slice) else torch.arange(n, device=self.device)[dofs_idx]
+        if comps > 1:
+            cols = cols * comps + width
+        tgt = f.reshape(self._B, -1)
+        v = torch.as_tensor(values, dtype=torch.float32, device=self.device)
+        if self._is_mask(envs_idx):
+            cur = tgt[:, cols]
+            tgt[:, cols] = torch.where(envs_idx.to(self.device)[:, None], torch.broadcast_to(v, cur.shape), cur)
+            return
+        envs = self._envs(envs_idx)
+        nb = self._B if envs is None else len(envs)
+        v = torch.broadcast_to(v, (nb, len(cols)))
+        if envs is None:
+            tgt[:, cols] = v
+        else:
+            tgt[envs[:, None], cols[None, :]] = v
+
+    def _get_dof_param(self, field, model_values, dofs_idx, envs_idx, width=None, comps=1):
+        n = self.model.n_dofs
+        if not self._batch_dofs:
+            return torch.tensor(np.asarray(model_values), dtype=torch.float32, device=self.device)[self._idx(dofs_idx, n)]
+        cols = self._idx(dofs_idx, n) if not isinstance(dofs_idx, slice) else torch.arange(n, device=self.device)[dofs_idx]
+        if comps > 1:
+            cols = cols * comps + width
+        out = self._fields[field].reshape(self._B, -1)[:, cols]
+        if envs_idx is not None:
+            out = out[envs_idx.to(self.device)] if self._is_mask(envs_idx) else out[self._envs(envs_idx)]
+        return out[0] if self.n_envs == 0 else out
+
     def set_dofs_kp(self, kp, dofs_idx=None, envs_idx=None):
         """abd/accessor.py:566-583: act_gain = kp, act_bias[1] = -kp."""
-        self._set_model_array("dofs_kp", kp, dofs_idx)
-        self._set_model_array("dofs_act_bias", -np.asarray(torch.as_tensor(kp).cpu().numpy()), dofs_idx, width=1)
+        kp = torch.as_tensor(kp, dtype=torch.float32)
+        self._set_dof_param("bd_kp", "dofs_kp", kp, dofs_idx, envs_idx)
+        self._set_dof_param("bd_bias", "dofs_act_bias", -kp, dofs_idx, envs_idx, width=1, comps=3)
 
     def set_dofs_kv(self, kv, dofs_idx=None, envs_idx=None):
-        self._set_model_array("dofs_act_bias", -np.asarray(torch.as_tensor(kv).cpu().numpy()), dofs_idx, width=2)
+        self._set_dof_param("bd_bias", "dofs_act_bias", -torch.as_tensor(kv, dtype=torch.float32), dofs_idx, envs_idx, width=2, comps=3)
 
     def set_dofs_force_range(self, lower, upper, dofs_idx=None, envs_idx=None):
-        self._set_model_array("dofs_force_range", lower, dofs_idx, width=0)
-        self._set_model_array("dofs_force_range", upper, dofs_idx, width=1)
+        self._set_dof_param("bd_force_range", "dofs_force_range", lower, dofs_idx, envs_idx, width=0, comps=2)
+        self._set_dof_param("bd_force_range", "dofs_force_range", upper, dofs_idx, envs_idx, width=1, comps=2)
 
     def set_dofs_frictionloss(self, frictionloss, dofs_idx=None, envs_idx=None):
         """rigid_solver.py:2100-2120: dofs with a positive friction loss get one constraint row each (solver.py:1236-1286)."""
-        self._set_model_array("dofs_frictionloss", frictionloss, dofs_idx)
+        self._set_dof_param("bd_frictionloss", "dofs_frictionloss", frictionloss, dofs_idx, envs_idx)
 
     def set_dofs_limit(self, lower, upper, dofs_idx=None, envs_idx=None):
-        self._set_model_array("dofs_limit", lower, dofs_idx, width=0)
-        self._set_model_array("dofs_limit", upper, dofs_idx, width=1)
+        self._set_dof_param("bd_limit", "dofs_limit", lower, dofs_idx, envs_idx, width=0, comps=2)
+        self._set_dof_param("bd_limit", "dofs_limit", upper, dofs_idx, envs_idx, width=1, comps=2)
         self._dofs_limit = torch.tensor(self.model.dofs_limit, dtype=torch.float32, device=self.device).reshape(-1, 2)
 
     def set_dofs_armature(self, armature, dofs_idx=None, envs_idx=None):
-        self._set_model_array("dofs_armature", armature, dofs_idx)
+        self._set_dof_param("bd_armature", "dofs_armature", armature, dofs_idx, envs_idx)
 
     def set_dofs_damping(self, damping, dofs_idx=None, envs_idx=None):
-        self._set_model_array("dofs_damping", damping, dofs_idx)
+        self._set_dof_param("bd_damping", "dofs_damping", damping, dofs_idx, envs_idx)
 
     def set_dofs_stiffness(self, stiffness, dofs_idx=None, envs_idx=None):
-        self._set_model_array("dofs_stiffness", stiffness, dofs_idx)
+        self._set_dof_param("bd_stiffness", "dofs_stiffness", stiffness, dofs_idx, envs_idx)
+
+    @property
+    def dofs_info(self):
+        """`rigid_solver.dofs_info.<field>.to_numpy() / from_numpy()` as the reference's tests use it (shape (n_dofs, B) when
+        batch_dofs_info, else (n_dofs,); array_class.py:1332-1364)."""
+        return _DofsInfoFacade(self)
 
     # ------------------------------------------------------------------ getters (kinematic_solver.py:940-1003, rigid_solver.py:2323-2580)
     def get_qpos(self, qs_idx=None, envs_idx=None):
@@ -537,10 +681,10 @@ class RigidSolver:
         return self._dofs_limit[idx, 0].clone(), self._dofs_limit[idx, 1].clone()
 
     def get_dofs_kp(self, dofs_idx=None, envs_idx=None):
-        return torch.tensor(self.model.dofs_kp, dtype=torch.float32, device=self.device)[self._idx(dofs_idx, self.model.n_dofs)]
+        return self._get_dof_param("bd_kp", self.model.dofs_kp, dofs_idx, envs_idx)
 
     def get_dofs_kv(self, dofs_idx=None, envs_idx=None):
-        return -torch.tensor(self.model.dofs_act_bias[:, 2], dtype=torch.float32, device=self.device)[self._idx(dofs_idx, self.model.n_dofs)]
+        return -self._get_dof_param("bd_bias", np.asarray(self.model.dofs_act_bias).reshape(-1, 3)[:, 2], dofs_idx, envs_idx, width=2, comps=3)
 
     def get_links_pos(self, links_idx=None, envs_idx=None):
         return self._get("links_pos", links_idx, envs_idx, self.model.n_links, comps=3)
@@ -577,11 +721,17 @@ class RigidSolver:
     def get_links_root_COM(self, links_idx=None, envs_idx=None):
         return self._get("root_COM", links_idx, envs_idx, self.model.n_links, comps=3)
 
-    def get_dofs_armature(self, dofs_idx=None):
-        return torch.tensor(self.model.dofs_armature, dtype=torch.float32, device=self.device)[self._idx(dofs_idx, self.model.n_dofs)]
+    def get_dofs_armature(self, dofs_idx=None, envs_idx=None):
+        return self._get_dof_param("bd_armature", self.model.dofs_armature, dofs_idx, envs_idx)
 
-    def get_dofs_frictionloss(self, dofs_idx=None):
-        return torch.tensor(self.model.dofs_frictionloss, dtype=torch.float32, device=self.device)[self._idx(dofs_idx, self.model.n_dofs)]
+    def get_dofs_frictionloss(self, dofs_idx=None, envs_idx=None):
+        return self._get_dof_param("bd_frictionloss", self.model.dofs_frictionloss, dofs_idx, envs_idx)
+
+    def get_dofs_damping(self, dofs_idx=None, envs_idx=None):
+        return self._get_dof_param("bd_damping", self.model.dofs_damping, dofs_idx, envs_idx)
+
+    def get_dofs_stiffness(self, dofs_idx=None, envs_idx=None):
+        return self._get_dof_param("bd_stiffness", self.model.dofs_stiffness, dofs_idx, envs_idx)
 
     def get_dofs_force_range(self, dofs_idx=None):
         fr = torch.tensor(self.model.dofs_force_range, dtype=torch.float32, device=self.device).reshape(-1, 2)[self._idx(dofs_idx, self.model.n_dofs)]
@@ -760,10 +910,59 @@ class RigidSolver:
         return _ConstraintSolverFacade(self)
 
     # ------------------------------------------------------------------ state (rigid_solver.py:1430-1579)
-    def get_state(self):
-        f = self._fields
-        return dict(qpos=f["qpos"].clone(), dofs_vel=f["vel"].clone(), dofs_acc=f["acc"].clone(),
-                    links_pos=f["links_pos"].clone(), links_quat=f["links_quat"].clone())
+    STATE_FIELDS = (("qpos", "qpos"), ("dofs_vel", "vel"), ("dofs_acc", "acc"), ("links_pos", "links_pos"), ("links_quat", "links_quat"),
+                    ("i_pos_shift", "com_shift"), ("mass_shift", "mass_shift"), ("friction_ratio", "friction_ratio"))
+
+    def gather_fields(self, names, out=None):
+        """{name: dense (B, items[, comps]) tensor} of several record fields in ONE launch (gsr_gather_fields)."""
+        out = out or {}
+        bufs = []
+        for nme in names:
+            f = self._fields[nme]
+            t = out.get(nme)
+            if t is None:
+                t = torch.empty(f.shape, dtype=torch.float32, device=self.device)
+            bufs.append(t)
+        for k in range(0, len(names), 16):
+            chunk, cb = names[k: k + 16], bufs[k: k + 16]
+            arr_n = (ctypes.c_char_p * len(chunk))(*[c.encode() for c in chunk])
+            arr_p = (ctypes.c_void_p * len(chunk))(*[b.data_ptr() for b in cb])
+            _lib.check(self._handle, _lib.lib().gsr_gather_fields(self._handle, len(chunk), arr_n, arr_p, self._stream()))
+        return dict(zip(names, bufs))
+
+    def get_state(self, f=None):
+        """RigidSolverState of the current step (kernel_get_state, abd/accessor.py): one fused gather."""
+        got = self.gather_fields([src for _, src in self.STATE_FIELDS])
+        st = RigidSolverState(self._scene, self._n_substeps_total)
+        for dst, src in self.STATE_FIELDS:
+            setattr(st, dst, got[src])
+        return st
+
+    def set_state(self, f, state=None, envs_idx=None, *, partial=False):
+        """rigid_solver.py:1458-1579 `set_state(f, state, envs_idx, *, partial)`: one fused launch (k_set_state) does the collider
+        / constraint-solver reset (partial) or clear, writes the state of the selected environments, zeroes the control forces
+        and external wrenches and -- unless partial -- runs the forward kinematics.  `envs_idx`: None, indices, or a boolean mask
+        (used as is on the device)."""
+        if state is None or isinstance(f, (RigidSolverState, dict)):  # tolerate the old (state, envs_idx) calling convention
+            f, state, envs_idx = 0, f, state if envs_idx is None else envs_idx
+        get = (lambda k: state.get(k)) if isinstance(state, dict) else (lambda k: getattr(state, k, None))
+        ptrs, keep = [], []
+        for dst, src in self.STATE_FIELDS:
+            v = get(dst)
+            if v is None:
+                ptrs.append(None)
+                continue
+            shape = self._fields[src].shape
+            t = torch.as_tensor(v, dtype=torch.float32, device=self.device)
+            if self.n_envs == 0 and t.dim() == len(shape) - 1:
+                t = t[None]
+            t = torch.broadcast_to(t, shape).contiguous()
+            keep.append(t)
+            ptrs.append(ctypes.c_void_p(t.data_ptr()))
+        mask = self._env_mask(envs_idx)
+        mptr = ctypes.c_void_p(mask.data_ptr()) if mask is not None else None
+        _lib.check(self._handle, _lib.lib().gsr_set_state(self._handle, mptr, *ptrs, int(bool(partial)), self._stream()))
+        self._obs_valid = False
 
     def _restore(self, values, envs_idx):
         f = self._fields
@@ -778,11 +977,7 @@ class RigidSolver:
         f["has_ext_force"][rows] = 0
         self._reset_warmstart(envs_idx)
         self._forward(envs_idx)
-
-    def set_state(self, state, envs_idx=None, partial=False):
-        """rigid_solver.py:1458-1579."""
-        self._restore(dict(qpos=state["qpos"], vel=state["dofs_vel"], acc=state["dofs_acc"], links_pos=state["links_pos"],
-                           links_quat=state["links_quat"]), envs_idx)
+        self._obs_valid = False
 
     def reset(self, envs_idx=None):
         self._restore(dict(qpos=self._init_qpos, vel=0.0, acc=0.0), envs_idx)
@@ -797,6 +992,39 @@ class RigidSolver:
             self.destroy()
         except Exception:
             pass
+
+
+class _QdFieldFacade:
+    """to_numpy / from_numpy of one dof parameter in the reference's `[dof, env]` orientation."""
+
+    def __init__(self, solver, field, model_name, comps=1):
+        self._s, self._field, self._model_name, self._comps = solver, field, model_name, comps
+
+    def to_numpy(self):
+        s = self._s
+        if s._batch_dofs:
+            a = s.field(self._field).cpu().numpy()  # (B, nD[, comps])
+            return np.moveaxis(a, 0, 1).copy()
+        return np.asarray(getattr(s.model, self._model_name), np.float32).copy()
+
+    def from_numpy(self, arr):
+        s = self._s
+        arr = np.asarray(arr, np.float32)
+        if s._batch_dofs:
+            s.field(self._field).copy_(torch.as_tensor(np.moveaxis(arr, 1, 0).copy(), device=s.device))
+        else:
+            getattr(s.model, self._model_name)[...] = arr.reshape(np.shape(getattr(s.model, self._model_name)))
+            a = np.ascontiguousarray(getattr(s.model, self._model_name), dtype=np.float32)
+            _lib.lib().gsr_model_set_f32(s._handle, self._model_name.encode(), a.ctypes.data, a.size)
+            _lib.check(s._handle, _lib.lib().gsr_model_refresh(s._handle))
+
+
+class _DofsInfoFacade:
+    def __init__(self, solver):
+        f = lambda field, name, comps=1: _QdFieldFacade(solver, field, name, comps)
+        self.armature, self.damping, self.stiffness = f("bd_armature", "dofs_armature"), f("bd_damping", "dofs_damping"), f("bd_stiffness", "dofs_stiffness")
+        self.frictionloss, self.invweight, self.act_gain = f("bd_frictionloss", "dofs_frictionloss"), f("bd_invweight", "dofs_invweight"), f("bd_kp", "dofs_kp")
+        self.act_bias, self.limit, self.force_range = f("bd_bias", "dofs_act_bias", 3), f("bd_limit", "dofs_limit", 2), f("bd_force_range", "dofs_force_range", 2)
 
 
 class _ColliderFacade:

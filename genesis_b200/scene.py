@@ -89,7 +89,7 @@ class Scene:
 
     def reset(self, state=None, envs_idx=None):
         if state is not None:
-            self.rigid_solver.set_state(state, envs_idx)
+            self.rigid_solver.set_state(0, state, envs_idx)
         else:
             self.rigid_solver.reset(envs_idx)
         if envs_idx is None:

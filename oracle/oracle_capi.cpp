@@ -45,6 +45,7 @@ static bool get_field(Oracle<T>& o, int b, const std::string& n, double* out) {
   if (n == "jac") return cp(e.jac.data(), (size_t)e.n_con * o.m.nD);
   if (n == "ctrl_mode") { for (size_t i = 0; i < e.ctrl_mode.size(); i++) out[i] = e.ctrl_mode[i]; return true; }
   if (n == "n_contacts") { out[0] = e.n_contacts; return true; }
+  if (n == "n_broad") { out[0] = e.n_broad; return true; }
   if (n == "n_constraints") { out[0] = e.n_con; out[1] = e.n_eq; out[2] = e.n_floss; return true; }
   if (n == "n_iter") { out[0] = e.n_iter; return true; }
   if (n == "errno") { out[0] = e.errno_; return true; }

@@ -60,7 +60,7 @@ struct Model {
   std::vector<int> dofs_link, dofs_joint, dofs_entity;
   std::vector<int> entities_link_start, entities_link_end, entities_dof_start, entities_dof_end, entities_geom_start, entities_geom_end;
   std::vector<T> entities_gravity_compensation;
-  std::vector<int> geoms_link, geoms_type, geoms_is_fixed, geoms_vert_start, geoms_vert_end, geoms_support_start;
+  std::vector<int> geoms_link, geoms_type, geoms_is_fixed, geoms_vert_start, geoms_vert_end, geoms_support_start, support_vid;
   std::vector<T> geoms_pos, geoms_quat, geoms_data, geoms_friction, geoms_sol_params, geoms_center, geoms_init_aabb, verts, support_v;
   std::vector<int> eq_type, eq_obj1, eq_obj2;
   std::vector<T> eq_data, eq_sol_params;
@@ -93,6 +93,7 @@ struct Model {
     LI(geoms_link); LI(geoms_type); LI(geoms_is_fixed); LI(geoms_vert_start); LI(geoms_vert_end); LI(geoms_support_start);
     LF(geoms_pos); LF(geoms_quat); LF(geoms_data); LF(geoms_friction); LF(geoms_sol_params); LF(geoms_center); LF(geoms_init_aabb);
     LF(verts); LF(support_v);
+    if (r.i.count("support_vid")) support_vid = r.i.at("support_vid");
     LI(eq_type); LI(eq_obj1); LI(eq_obj2); LF(eq_data); LF(eq_sol_params);
     LI(pairs); LI(pair_idx);
 #undef LI
@@ -955,6 +956,415 @@ struct Oracle {
     return true;
   }
 
+
+  // ---- a17 proper: the reference's safe GJK + safe EPA (gjk.py:170-446 func_gjk_contact non-MuJoCo branch, :1209-1425
+  // func_safe_gjk, :1425-1900 helpers; epa.py:970-1183 func_safe_epa, :1184-1249 witness, :1251-1387 init / attach, :274-433
+  // horizon; gjk_utils.py:45-235; gjk_support.py).  Constants of gjk.py:53-110.
+  struct GjkVert { V obj1, obj2, mink; int id1, id2; };
+  struct GjkFace { int v[3], adj[3]; V normal; T dist2; int map_idx; };
+  static constexpr int GJK_MAX_ITER = 50, EPA_MAX_ITER = 50, POLY_MAX_FACES = 300, POLY_MAX_VERTS = 64;
+  struct GjkState {
+    GjkVert sv[4]; int nverts = 0;            // simplex
+    GjkVert pv[POLY_MAX_VERTS]; int npv = 0;  // polytope vertices
+    GjkFace pf[POLY_MAX_FACES]; int nfaces = 0;
+    int fmap[POLY_MAX_FACES]; int nfmap = 0;
+    int hz_face[POLY_MAX_FACES], hz_edge[POLY_MAX_FACES]; int nhz = 0;
+    int st_face[3 * POLY_MAX_FACES], st_edge[3 * POLY_MAX_FACES];
+    int last_searched = 0;
+    V w1, w2; int n_witness = 0; T distance = 0;
+  };
+  T gjk_FLOAT_MIN() const { return T(1e-15); }
+  T gjk_FLOAT_MAX() const { return T(1e15); }
+  bool is_discrete(int g) const { return m.geoms_type[g] == GEOM_MESH || m.geoms_type[g] == GEOM_BOX; }
+  // gjk_support.py:66-112 support_driver (non-MuJoCo): support point in world frame + vertex identity (-1 for smooth shapes)
+  void gjk_support_driver(const V& d, int g, const V& pos, const Q& quat, V& v, int& vid) {
+    const int type = m.geoms_type[g];
+    vid = -1;
+    if (type == GEOM_BOX) {
+      V db = inv_transform_by_quat(d, quat);
+      V vl((db.x < 0 ? T(-1) : T(1)) * m.geoms_data[7 * g] * T(0.5), (db.y < 0 ? T(-1) : T(1)) * m.geoms_data[7 * g + 1] * T(0.5),
+           (db.z < 0 ? T(-1) : T(1)) * m.geoms_data[7 * g + 2] * T(0.5));
+      vid = (vl.x > 0 ? 1 : 0) + (vl.y > 0 ? 2 : 0) + (vl.z > 0 ? 4 : 0) + m.geoms_vert_start[g];  // SF:298-309
+      v = transform_by_trans_quat(vl, pos, quat);
+    } else if (type == GEOM_SPHERE || type == GEOM_ELLIPSOID || type == GEOM_CAPSULE) {
+      v = support_driver(d, g, pos, quat);
+    } else {  // support field (mesh / cylinder): SF:121-180, identity = support_vid of the winning cell
+      V dm = transform_by_quat(d, inv_quat(quat));
+      const T PI = T(3.14159265358979323846);
+      T theta = std::atan2(dm.y, dm.x), phi = std::acos(dm.z);
+      const int res = 180;
+      T ii = (theta + PI) / PI / 2 * res, jj = phi / PI * res;
+      T dot_max = T(-1e20);
+      V best;
+      int bid = 0;
+      for (int i4 = 0; i4 < 4; i4++) {
+        int i, j;
+        if (i4 % 2) i = f2i(std::ceil(ii)) % res; else i = f2i(std::floor(ii)) % res;
+        if (i4 / 2 > 0) { j = f2i(std::fmin(std::fmax(std::ceil(jj), T(0)), T(res - 1))); if (j == res - 1) j = res - 2; }
+        else { j = f2i(std::fmin(std::fmax(std::floor(jj), T(0)), T(res - 1))); if (j == 0) j = 1; }
+        int idx = m.geoms_support_start[g] + i * res + j;
+        V p(m.support_v[3 * idx], m.support_v[3 * idx + 1], m.support_v[3 * idx + 2]);
+        T dot = p.dot(dm);
+        if (dot > dot_max) { best = p; dot_max = dot; bid = m.support_vid.empty() ? idx : m.support_vid[idx]; }
+      }
+      vid = bid;
+      v = transform_by_trans_quat(best, pos, quat);
+    }
+  }
+  // gjk.py:1870-1900 func_count_support: boxes have 2^(zero components) candidate vertices; _func_count_supports_mesh never
+  // updates its running maximum, so it always answers 1 (SF:330-376) -- restated as is
+  int gjk_count_support(const V& dir, int ga, int gb, const Q& qa, const Q& qb) {
+    int count = 1;
+    for (int i = 0; i < 2; i++) {
+      const int g = i == 0 ? ga : gb;
+      if (m.geoms_type[g] == GEOM_BOX) {
+        V db = inv_transform_by_quat(i == 0 ? dir : -dir, i == 0 ? qa : qb);
+        int z = (db.x == 0 ? 1 : 0) + (db.y == 0 ? 1 : 0) + (db.z == 0 ? 1 : 0);
+        count *= (1 << z);
+      }
+    }
+    return count;
+  }
+  bool gjk_vertex_duplicate(const GjkState& S, int id1, int id2) {  // gjk.py:1451-1470
+    for (int i = 0; i < S.nverts; i++) {
+      if (id1 == -1 || S.sv[i].id1 != id1) continue;
+      if (id2 == -1 || S.sv[i].id2 != id2) continue;
+      return true;
+    }
+    return false;
+  }
+  bool gjk_vertex_degenerate(const GjkState& S, const V& mink) {  // gjk.py:1473-1514
+    const T deg2 = T(1e-5) * T(1e-5);
+    for (int i = 0; i < S.nverts; i++) { V d = S.sv[i].mink - mink; if (d.dot(d) < deg2) return true; }
+    if (S.nverts == 2) {
+      V e1 = S.sv[1].mink - S.sv[0].mink, e2 = mink - S.sv[0].mink, n = e1.cross(e2);
+      return n.dot(n) < deg2 * e1.dot(e1) * e2.dot(e2);
+    }
+    if (S.nverts == 3) {
+      V e1 = (S.sv[1].mink - S.sv[0].mink).normalized(), e2 = (S.sv[2].mink - S.sv[0].mink).normalized(), n = e1.cross(e2), diff = mink - S.sv[0].mink;
+      T nd = n.dot(diff);
+      return nd * nd < deg2 * n.dot(n) * diff.dot(diff);
+    }
+    return false;
+  }
+  bool gjk_vertex_valid(const GjkState& S, int id1, int id2, const V& mink) { return !gjk_vertex_duplicate(S, id1, id2) && !gjk_vertex_degenerate(S, mink); }
+  // gjk.py:1733-1838 func_safe_gjk_support
+  GjkVert gjk_safe_support(GjkState& S, int ga, int gb, const V& pa, const Q& qa, const V& pb, const Q& qb, const V& dir) {
+    GjkVert r; r.id1 = r.id2 = -1;
+    for (int i = 0; i < 9; i++) {
+      V nd = dir;
+      if (i > 0) {
+        const int j = i - 1;
+        nd.x += -(T(1) - T(2) * T(j & 1)) * EPS;
+        nd.y += -(T(1) - T(2) * T(j & 2)) * EPS;
+        nd.z += -(T(1) - T(2) * T(j & 4)) * EPS;
+      }
+      nd = nd * (T(2) - nd.dot(dir));
+      const int num = gjk_count_support(nd, ga, gb, qa, qb);
+      if (i > 0 && num > 1) continue;
+      gjk_support_driver(nd, ga, pa, qa, r.obj1, r.id1);
+      gjk_support_driver(-nd, gb, pb, qb, r.obj2, r.id2);
+      r.mink = r.obj1 - r.obj2;
+      if (i == 0) { if (num > 1) continue; else break; }
+      if (i == 8) break;
+      if (gjk_vertex_valid(S, r.id1, r.id2, r.mink)) break;
+    }
+    return r;
+  }
+  // gjk.py:1660-1698 func_get_discrete_geom_vertex
+  void gjk_discrete_vertex(int g, const V& pos, const Q& quat, int iv, V& v) {
+    V vl;
+    if (m.geoms_type[g] == GEOM_BOX)
+      vl = V(((iv & 1) ? T(1) : T(-1)) * m.geoms_data[7 * g] * T(0.5), ((iv & 2) ? T(1) : T(-1)) * m.geoms_data[7 * g + 1] * T(0.5),
+             ((iv & 4) ? T(1) : T(-1)) * m.geoms_data[7 * g + 2] * T(0.5));
+    else { const int k = m.geoms_vert_start[g] + iv; vl = V(m.verts[3 * k], m.verts[3 * k + 1], m.verts[3 * k + 2]); }
+    v = transform_by_trans_quat(vl, pos, quat);
+  }
+  // gjk.py:1545-1645 func_search_valid_simplex_vertex
+  bool gjk_search_valid_vertex(GjkState& S, int ga, int gb, const V& pa, const Q& qa, const V& pb, const Q& qb, GjkVert& r) {
+    r = GjkVert(); r.id1 = r.id2 = -1;
+    if (is_discrete(ga) && is_discrete(gb)) {
+      const int n0 = m.geoms_vert_end[ga] - m.geoms_vert_start[ga], n1 = m.geoms_vert_end[gb] - m.geoms_vert_start[gb];
+      const int num = n0 * n1;
+      for (int k = 0; k < num; k++) {
+        const int mm = (k + S.last_searched) % num, i = mm / n1, j = mm % n1;
+        r.id1 = m.geoms_vert_start[ga] + i; r.id2 = m.geoms_vert_start[gb] + j;
+        gjk_discrete_vertex(ga, pa, qa, i, r.obj1);
+        gjk_discrete_vertex(gb, pb, qb, j, r.obj2);
+        r.mink = r.obj1 - r.obj2;
+        if (gjk_vertex_valid(S, r.id1, r.id2, r.mink)) { S.last_searched = (mm + 1) % num; return true; }
+      }
+      return false;
+    }
+    if (S.nverts == 3) {
+      V dir = (S.sv[2].mink - S.sv[0].mink).cross(S.sv[1].mink - S.sv[0].mink).normalized();
+      for (int i = 0; i < 2; i++) {
+        r = gjk_safe_support(S, ga, gb, pa, qa, pb, qb, i == 0 ? dir : -dir);
+        if (gjk_vertex_valid(S, r.id1, r.id2, r.mink)) return true;
+      }
+    }
+    return false;
+  }
+  // gjk.py:1209-1425 func_safe_gjk: true when the origin is inside the final tetrahedron
+  bool safe_gjk(GjkState& S, int ga, int gb, const V& pa, const Q& qa, const V& pb, const Q& qb) {
+    S.nverts = 0;
+    bool init_ok = true;
+    for (int i = 0; i < 4; i++) {
+      V dir; dir[2 - i / 2] = T(1) - T(2) * T(i % 2);
+      GjkVert r = gjk_safe_support(S, ga, gb, pa, qa, pb, qb, dir);
+      if (!gjk_vertex_valid(S, r.id1, r.id2, r.mink)) {
+        if (!gjk_search_valid_vertex(S, ga, gb, pa, qa, pb, qb, r)) { init_ok = false; break; }
+      }
+      S.sv[i] = r;
+      S.nverts++;
+    }
+    bool intersect = false;
+    if (init_ok) {
+      int si[4] = {0, 1, 2, 3};
+      for (int it = 0; it < GJK_MAX_ITER; it++) {
+        V nrm[4]; T sd[4];
+        for (int j = 0; j < 4; j++) {
+          int s0 = si[2], s1 = si[1], s2 = si[3], ap = si[0];
+          if (j == 1) { s0 = si[0]; s1 = si[2]; s2 = si[3]; ap = si[1]; }
+          else if (j == 2) { s0 = si[1]; s1 = si[0]; s2 = si[3]; ap = si[2]; }
+          else if (j == 3) { s0 = si[0]; s1 = si[1]; s2 = si[2]; ap = si[3]; }
+          const V v1 = S.sv[s0].mink, v2 = S.sv[s1].mink, v3 = S.sv[s2].mink, apex = S.sv[ap].mink;  // gjk.py:1701-1730
+          V n = (v3 - v1).cross(v2 - v1).normalized();
+          if (n.dot(apex - v1) > 0) n = -n;
+          nrm[j] = n; sd[j] = n.dot(v1);
+        }
+        int min_i = 0;
+        for (int j = 1; j < 4; j++) if (sd[j] < sd[min_i]) min_i = j;
+        const int min_si = si[min_i];
+        const V min_normal = nrm[min_i];
+        if (sd[min_i] >= 0) { intersect = true; break; }
+        S.nverts = 3;
+        if (min_si != 3) S.sv[min_si] = S.sv[3];
+        GjkVert r = gjk_safe_support(S, ga, gb, pa, qa, pb, qb, min_normal);
+        if (gjk_vertex_duplicate(S, r.id1, r.id2)) break;
+        if (gjk_vertex_degenerate(S, r.mink)) break;
+        if (r.mink.dot(min_normal) < 0) break;
+        S.sv[3] = r;
+        S.nverts = 4;
+      }
+    }
+    S.distance = intersect ? T(0) : gjk_FLOAT_MAX();
+    return intersect;
+  }
+  // epa.py:1389-1427 func_plane_normal
+  bool epa_plane_normal(const V& v1, const V& v2, const V& v3, V& normal) {
+    const V d21 = v2 - v1, d31 = v3 - v1, d32 = v3 - v2;
+    for (int i = 0; i < 3; i++) {
+      V n = i == 0 ? d32.cross(d21) : (i == 1 ? d21.cross(d31) : d31.cross(d32));
+      const T nn = n.norm();
+      if (nn == 0) return false;
+      if (nn > gjk_FLOAT_MIN()) { normal = n.normalized(); return true; }
+    }
+    return false;
+  }
+  // epa.py:1304-1386 func_safe_attach_face_to_polytope
+  bool epa_attach_face(GjkState& S, int v1, int v2, int v3, int a1, int a2, int a3) {
+    const int n = S.nfaces;
+    GjkFace& f = S.pf[n];
+    f.v[0] = v1; f.v[1] = v2; f.v[2] = v3; f.adj[0] = a1; f.adj[1] = a2; f.adj[2] = a3;
+    S.nfaces++;
+    V normal;
+    if (!epa_plane_normal(S.pv[v3].mink, S.pv[v2].mink, S.pv[v1].mink, normal)) return false;
+    const V center = (S.pv[v1].mink + S.pv[v2].mink + S.pv[v3].mink) / T(3);
+    T max_orient = -normal.dot(center), max_abs = std::abs(max_orient);
+    for (int iv = 0; iv < S.npv; iv++) {
+      if (iv != v1 && iv != v2 && iv != v3) {
+        const T orient = normal.dot(S.pv[iv].mink - center);
+        if (std::abs(orient) > max_abs) { max_abs = std::abs(orient); max_orient = orient; }
+      }
+    }
+    if (max_orient > 0) normal = -normal;
+    f.normal = normal;
+    T min_d2 = gjk_FLOAT_MAX();
+    const int vs[3] = {v1, v2, v3};
+    for (int i = 0; i < 3; i++) { const T d = normal.dot(S.pv[vs[i]].mink); if (d * d < min_d2) min_d2 = d * d; }
+    f.dist2 = min_d2;
+    f.map_idx = -1;
+    return true;
+  }
+  void epa_delete_face(GjkState& S, int i_f) {  // epa.py:384-405
+    const int mi = S.pf[i_f].map_idx;
+    if (mi >= 0) {
+      const int last = S.fmap[S.nfmap - 1];
+      S.fmap[mi] = last;
+      S.pf[last].map_idx = mi;
+      S.nfmap--;
+    }
+    S.pf[i_f].map_idx = -2;
+  }
+  // epa.py:274-341 func_epa_horizon (depth-first walk over the faces visible from w; the horizon edges come out as a loop)
+  void epa_horizon(GjkState& S, const V& w, int nearest) {
+    S.st_face[0] = nearest; S.st_edge[0] = 0;
+    int top = 1;
+    bool is_first = true;
+    while (top > 0) {
+      const int i_f = S.st_face[top - 1], i_e = S.st_edge[top - 1];
+      const V v = S.pv[S.pf[i_f].v[0]].mink;
+      top--;
+      const bool deleted = S.pf[i_f].map_idx == -2;
+      if (!is_first && deleted) continue;
+      const bool visible = S.pf[i_f].normal.dot(w - v) > gjk_FLOAT_MIN();
+      if (visible || is_first) {
+        epa_delete_face(S, i_f);
+        for (int k = is_first ? 0 : 1; k < 3; k++) {
+          const int e2 = (i_e + k) % 3, adj = S.pf[i_f].adj[e2];
+          if (S.pf[adj].map_idx != -2) {
+            const int start_v = S.pf[i_f].v[(e2 + 1) % 3];
+            const int ae = S.pf[adj].v[0] == start_v ? 0 : (S.pf[adj].v[1] == start_v ? 1 : 2);  // epa.py:362-381
+            S.st_face[top] = adj; S.st_edge[top] = ae; top++;
+          }
+        }
+      } else {
+        S.hz_edge[S.nhz] = i_e; S.hz_face[S.nhz] = i_f; S.nhz++;
+      }
+      is_first = false;
+    }
+  }
+  // gjk_utils.py:45-100 func_triangle_affine_coords, :183-235 func_project_origin_to_plane
+  V tri_affine_coords(const V& point, const V& t1, const V& t2, const V& t3) {
+    T ms[3];
+    for (int i = 0; i < 3; i++) {
+      int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+      if (i == 1) std::swap(i1, i2);
+      ms[i] = t2[i1] * t3[i2] - t2[i2] * t3[i1] - t1[i1] * t3[i2] + t1[i2] * t3[i1] + t1[i1] * t2[i2] - t1[i2] * t2[i1];
+    }
+    T m_max = 0;
+    int ix = 0, iy = 0;
+    for (int i = 0; i < 3; i++) {
+      if (std::abs(ms[i]) >= std::abs(ms[(i + 1) % 3]) && std::abs(ms[i]) >= std::abs(ms[(i + 2) % 3])) {
+        m_max = ms[i]; ix = (i + 1) % 3; iy = (i + 2) % 3;
+        if (i == 1) std::swap(ix, iy);
+        break;
+      }
+    }
+    V cs;
+    for (int i = 0; i < 3; i++) {
+      const V& a = i == 0 ? t2 : (i == 1 ? t3 : t1);
+      const V& b = i == 0 ? t3 : (i == 1 ? t1 : t2);
+      cs[i] = point[ix] * a[iy] + point[iy] * b[ix] + a[ix] * b[iy] - point[ix] * b[iy] - point[iy] * a[ix] - b[ix] * a[iy];
+    }
+    return cs / m_max;
+  }
+  bool project_origin_to_plane(const V& v1, const V& v2, const V& v3, V& point) {
+    const V d21 = v2 - v1, d31 = v3 - v1, d32 = v3 - v2;
+    point = V();
+    for (int i = 0; i < 3; i++) {
+      V n, v;
+      if (i == 0) { n = d32.cross(d21); v = v2; } else if (i == 1) { n = d21.cross(d31); v = v1; } else { n = d31.cross(d32); v = v3; }
+      const T nv = n.dot(v), nn = n.dot(n);
+      if (nn == 0) return false;
+      if (nn > gjk_FLOAT_MIN()) { point = n * (nv / nn); return true; }
+      if (i == 2) { if (nn < gjk_FLOAT_MIN()) return false; point = n * (nv / nn); return true; }
+    }
+    return true;
+  }
+  // epa.py:970-1183 func_safe_epa (+ :1251-1301 init from the GJK tetrahedron, :1184-1249 witness points)
+  void safe_epa(GjkState& S, int ga, int gb, const V& pa, const Q& qa, const V& pb, const Q& qb) {
+    S.npv = 0; S.nfaces = 0; S.nfmap = 0; S.nhz = 0;
+    for (int i = 0; i < 4; i++) S.pv[S.npv++] = S.sv[i];
+    {
+      const int fv[4][3] = {{0, 1, 2}, {0, 3, 1}, {0, 2, 3}, {3, 2, 1}}, fa[4][3] = {{1, 3, 2}, {2, 3, 0}, {0, 3, 1}, {2, 0, 1}};
+      for (int i = 0; i < 4; i++) epa_attach_face(S, fv[i][0], fv[i][1], fv[i][2], fa[i][0], fa[i][1], fa[i][2]);
+      for (int i = 0; i < 4; i++) { S.fmap[i] = i; S.pf[i].map_idx = i; }
+      S.nfmap = 4;
+    }
+    T upper = gjk_FLOAT_MAX(), upper2 = gjk_FLOAT_MAX() * gjk_FLOAT_MAX(), lower = 0;
+    T tolerance = T(1e-6);
+    int nearest = -1, prev_nearest = -1;
+    const bool discrete = is_discrete(ga) && is_discrete(gb);
+    if (discrete) tolerance = EPS;
+    for (int k = 0; k < EPA_MAX_ITER; k++) {
+      prev_nearest = nearest;
+      T lower2 = gjk_FLOAT_MAX() * gjk_FLOAT_MAX();
+      for (int i = 0; i < S.nfmap; i++) {
+        const int i_f = S.fmap[i];
+        if (S.pf[i_f].dist2 < lower2) { lower2 = S.pf[i_f].dist2; nearest = i_f; }
+      }
+      if (lower2 > upper2 || nearest == -1) { nearest = prev_nearest; break; }
+      lower = std::sqrt(lower2);
+      const V dir = S.pf[nearest].normal;
+      // epa.py:810-883 func_epa_support(dir, 1.0): plain support pair (no perturbation), appended to the polytope
+      if (S.npv >= POLY_MAX_VERTS) break;
+      const int wi = S.npv;
+      {
+        GjkVert& r = S.pv[wi];
+        gjk_support_driver(dir, ga, pa, qa, r.obj1, r.id1);
+        gjk_support_driver(-dir, gb, pb, qb, r.obj2, r.id2);
+        r.mink = r.obj1 - r.obj2;
+        S.npv++;
+      }
+      const V w = S.pv[wi].mink;
+      const T upper_k = w.dot(dir);
+      if (upper_k < upper) { upper = upper_k; upper2 = upper * upper; }
+      if ((upper - lower) < tolerance) break;
+      if (discrete) {
+        bool repeated = false;
+        for (int i = 0; i < S.npv; i++) {
+          if (i == wi) continue;
+          if (S.pv[i].id1 == S.pv[wi].id1 && S.pv[i].id2 == S.pv[wi].id2) { repeated = true; break; }
+        }
+        if (repeated) break;
+      }
+      epa_horizon(S, w, nearest);
+      if (S.nhz < 3) { nearest = -1; break; }
+      const int nfaces = S.nfaces, nedges = S.nhz;
+      if (nfaces + nedges >= POLY_MAX_FACES) break;
+      bool attach_ok = true;
+      for (int i = 0; i < nedges; i++) {
+        const int i_f0 = nfaces + i, i_f1 = nfaces + (i + 1) % nedges;
+        const int hf = S.hz_face[i], he = S.hz_edge[i];
+        const int hv1 = S.pf[hf].v[he], hv2 = S.pf[hf].v[(he + 1) % 3];
+        S.pf[hf].adj[he] = i_f0;
+        const int adj0 = i > 0 ? i_f0 - 1 : nfaces + nedges - 1;
+        if (!epa_attach_face(S, wi, hv2, hv1, i_f1, hf, adj0)) { attach_ok = false; break; }
+        const T d2 = S.pf[S.nfaces - 1].dist2;
+        if (d2 >= lower2 - EPS && d2 <= upper2 + EPS) { S.fmap[S.nfmap] = i_f0; S.pf[i_f0].map_idx = S.nfmap; S.nfmap++; }
+      }
+      if (!attach_ok) { nearest = -1; break; }
+      S.nhz = 0;
+      if (S.nfmap == 0 || nearest == -1) { nearest = -1; break; }
+    }
+    S.n_witness = 0; S.distance = 0;
+    if (nearest != -1) {
+      const GjkFace& f = S.pf[nearest];
+      const V f1 = S.pv[f.v[0]].mink, f2 = S.pv[f.v[1]].mink, f3 = S.pv[f.v[2]].mink;
+      V proj;
+      project_origin_to_plane(f1, f2, f3, proj);
+      const V lam = tri_affine_coords(proj, f1, f2, f3);
+      const V back = f1 * lam[0] + f2 * lam[1] + f3 * lam[2];
+      const T err = (proj - back).norm();
+      const T e12 = (f1 - f2).dot(f1 - f2), e23 = (f2 - f3).dot(f2 - f3), e31 = (f3 - f1).dot(f3 - f1);
+      const T inv_len = T(1) / std::sqrt(std::max(std::max(e12, e23), std::max(e31, gjk_FLOAT_MIN() * gjk_FLOAT_MIN())));
+      if (!(err * inv_len > T(1e-4) && err > T(1e-4))) {
+        S.w1 = S.pv[f.v[0]].obj1 * lam[0] + S.pv[f.v[1]].obj1 * lam[1] + S.pv[f.v[2]].obj1 * lam[2];
+        S.w2 = S.pv[f.v[0]].obj2 * lam[0] + S.pv[f.v[1]].obj2 * lam[1] + S.pv[f.v[2]].obj2 * lam[2];
+        S.n_witness = 1;
+        S.distance = -std::sqrt(f.dist2);
+      }
+    }
+  }
+  // gjk.py:170-446 func_gjk_contact (non-MuJoCo branch): is_col, penetration, contact position and normal
+  void gjk_contact(int ga, int gb, const V& pa, const Q& qa, const V& pb, const Q& qb, bool& is_col, V& normal, T& pen, V& pos) {
+    GjkState* Sp = new GjkState();
+    GjkState& S = *Sp;
+    if (safe_gjk(S, ga, gb, pa, qa, pb, qb)) safe_epa(S, ga, gb, pa, qa, pb, qb);
+    is_col = S.distance < 0;
+    pen = is_col ? -S.distance : T(0);
+    int n_contacts = 0;
+    if (is_col && S.n_witness > 0) {
+      const V d = S.w2 - S.w1;
+      const T len = d.norm();
+      if (!(len < gjk_FLOAT_MIN())) { pos = (S.w1 + S.w2) * T(0.5); normal = d / len; n_contacts = 1; }
+    }
+    if (n_contacts == 0) { is_col = false; pen = 0; }
+    delete Sp;
+  }
+
   // CT:181-222 func_add_contact
   void add_contact(Env<T>& e, int ga, int gb, const V& normal, const V& pos, T pen, int i_pair) {
     int c = e.n_contacts;
@@ -1119,12 +1529,16 @@ struct Oracle {
             if (!updated) { mpr_contact(ga, gb, normal_ws, ga_pos, ga_quat, gb_pos, gb_quat, is_col, normal, pen, cpos, last_simplex, last_simplex_valid); updated = true; }
           }
           // NP:726-733: MPR's answer is replaced by the exact one when the overlap is large or no direction was cached
-          if (cfg.gjk_fallback && is_col && pen > tolerance && last_simplex_valid) {
+          if (cfg.gjk_fallback && is_col && pen > tolerance) {
             const bool prefer_gjk = !guess || (T(cfg.mc_tolerance) * pen >= T(cfg.mpr_to_gjk_overlap_ratio) * tolerance);
-            V n2, c2;
-            T p2 = 0;
-            if (prefer_gjk && epa_penetration(last_simplex, ga, gb, ga_pos, ga_quat, gb_pos, gb_quat, n2, p2, c2)) {
-              normal = n2; pen = p2; cpos = c2; is_col = p2 > 0;
+            if (prefer_gjk) {
+              if (cfg.gjk_fallback == 2) {  // round-1 approximation kept for A/B: EPA seeded with MPR's final portal
+                V n2, c2;
+                T p2 = 0;
+                if (epa_penetration(last_simplex, ga, gb, ga_pos, ga_quat, gb_pos, gb_quat, n2, p2, c2)) { normal = n2; pen = p2; cpos = c2; is_col = p2 > 0; }
+              } else {          // the reference's path: a fresh GJK distance query, then EPA from its tetrahedron (NP:756-850)
+                gjk_contact(ga, gb, ga_pos, ga_quat, gb_pos, gb_quat, is_col, normal, pen, cpos);
+              }
             }
           }
         }

@@ -261,3 +261,26 @@ def make_hinge_slide(n_envs, build=True, **rigid_kwargs):
     if build:
         scene.build(n_envs=n_envs)
     return scene, ent
+
+
+import torch  # noqa: E402
+
+
+def make_franka_cluster_r1(n_envs, n_boxes=4, build=True, **rigid_kwargs):
+    """Round-1 box cluster (arm hovering over four boxes, fingers open): kept for the frozen lane-kernel emulation tests."""
+    scene = gs.Scene(rigid_options=gs.options.RigidOptions(dt=0.01, **rigid_kwargs))
+    scene.add_entity(gs.morphs.Plane())
+    franka = scene.add_entity(gs.morphs.MJCF(file="xml/franka_emika_panda/panda.xml"))
+    boxes = []
+    for i in range(n_boxes):
+        dx, dy = (i % 2) * 0.06 - 0.03, (i // 2) * 0.06 - 0.03
+        boxes.append(scene.add_entity(gs.morphs.Box(size=(0.04, 0.04, 0.04), pos=(0.65 + dx, dy, 0.02))))
+    if not build:
+        return scene, franka, boxes
+    scene.build(n_envs=n_envs)
+    q = torch.tensor([-0.0, 0.45, 0.0, -2.2, 0.0, 2.65, 0.78, 0.04, 0.04], dtype=torch.float32, device=gs.device)
+    if n_envs > 0:
+        q = q.repeat(n_envs, 1)
+    franka.set_qpos(q)
+    franka.control_dofs_position(q)
+    return scene, franka, boxes

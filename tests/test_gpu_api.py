@@ -248,3 +248,113 @@ def test_set_pos_on_fixed_base_moves_the_base_not_the_joints():
     scene2.build(n_envs=2)
     box.set_pos(torch.tensor([1.0, 2.0, 3.0], device=gs.device))
     assert torch.allclose(box.get_qpos()[:, :3], torch.tensor([1.0, 2.0, 3.0], device=gs.device).expand(2, 3))
+
+
+def _accessor_step(scene, franka, state0, mask, qpos0, vel0, stiff, damp):
+    """The body of the reference's `franka_accessors` benchmark step (tests/test_rigid_benchmarks.py:377-394), verbatim."""
+    scene.step()
+    franka.get_ang()
+    franka.get_vel()
+    franka.get_dofs_position()
+    franka.get_dofs_velocity()
+    franka.get_links_pos()
+    franka.get_links_quat()
+    franka.get_links_vel()
+    franka.get_contacts()
+    scene.rigid_solver.set_state(0, state0, envs_idx=mask, partial=True)
+    franka.control_dofs_position(qpos0)
+    franka.set_dofs_stiffness(stiff)
+    franka.set_dofs_damping(damp)
+    franka.set_dofs_velocity(vel0, envs_idx=mask, skip_forward=True)
+    franka.set_qpos(qpos0, envs_idx=mask, zero_velocity=False, skip_forward=True)
+
+
+def test_franka_accessors_reference_step_body_runs_and_resets():
+    """RL-loop boundary (scope row f3): the reference's franka_accessors step body runs unmodified -- RigidSolverState from
+    get_state(), set_state(f, state, envs_idx=<bool mask>, partial=True), masked setters with skip_forward=True (the forward
+    kinematics of the reset environments are deferred to the next step) -- and the reset environments then replay the trajectory
+    of the initial state bit for bit, while the others are untouched."""
+    from helpers import make_franka
+
+    B = 64
+    scene, franka = make_franka(B, randomized=True, seed=5)
+    s = scene.rigid_solver
+    qpos0 = torch.tensor([0, 0, 0, -1.0, 0, 1.0, 0, 0.02, 0.02], device=gs.device).repeat(B, 1)
+    vel0 = s.field("vel").clone()
+    state0 = s.get_state()
+    assert type(state0).__name__ == "RigidSolverState"
+    for k in ("qpos", "dofs_vel", "dofs_acc", "links_pos", "links_quat", "i_pos_shift", "mass_shift", "friction_ratio"):
+        assert getattr(state0, k).shape[0] == B
+    assert torch.equal(state0.qpos, s.field("qpos")) and torch.equal(state0.links_quat, s.field("links_quat"))
+    mask = torch.zeros(B, dtype=torch.bool, device=gs.device)
+    mask[::7] = True
+    stiff, damp = franka.get_dofs_stiffness(), franka.get_dofs_damping()
+    # reference trajectory of the initial state: 6 plain steps of an identical scene
+    scene_ref, _ = make_franka(B, randomized=True, seed=5)
+    traj = []
+    for _ in range(6):
+        scene_ref.step()
+        traj.append(scene_ref.rigid_solver.field("qpos").clone())
+    launches0 = s.kernel_launches()
+    for _ in range(4):
+        _accessor_step(scene, franka, state0, mask, qpos0, vel0, stiff, damp)
+    launches = s.kernel_launches()
+    assert launches["k_set_state"] - launches0["k_set_state"] == 4       # one fused launch per masked reset
+    assert launches["k_gather_fields"] - launches0["k_gather_fields"] == 4  # the eight getters share one gather per step
+    assert launches["k_forward"] == launches0["k_forward"]               # skip_forward: no eager FK launch
+    # the masked envs were reset after step 4: two more steps replay steps 1-2 of the initial state; the others are at step 6
+    scene.step(); scene.step()
+    q = s.field("qpos")
+    assert torch.equal(q[mask], traj[1][mask]), "reset environments do not replay the initial trajectory"
+    assert torch.equal(q[~mask], traj[5][~mask]), "environments outside the mask were disturbed"
+    assert int(s.field("errno_").max()) == 0
+
+
+def test_set_state_full_and_skip_forward_semantics():
+    from helpers import make_go2
+
+    B = 8
+    scene, robot = make_go2(B, seed=1)
+    s = scene.rigid_solver
+    st = s.get_state()
+    for _ in range(10):
+        scene.step()
+    after10 = s.field("qpos").clone()
+    s.set_state(0, st, envs_idx=[1, 3])               # partial=False: contacts cleared, FK run for the two envs
+    assert int(s.field("n_contacts")[1, 0]) == 0 and int(s.field("n_contacts")[0, 0]) >= 0
+    assert torch.equal(s.field("qpos")[1], st.qpos[1]) and torch.equal(s.field("qpos")[0], after10[0])
+    assert torch.allclose(s.field("links_pos")[1, 1], st.qpos[1, :3])  # base link pose == free-joint qpos: FK was run
+    assert int(s.field("ctrl_mode")[1].min()) == int(gs.CTRL_MODE.FORCE) and int(s.field("fk_dirty")[1, 0]) == 0
+    # skip_forward=True defers the kinematics to the next step and gives the same step result as the eager path
+    scene_b, robot_b = make_go2(B, seed=1)
+    q = st.qpos.clone(); q[:, 2] += 0.05
+    robot.set_qpos(q, skip_forward=True); robot_b.set_qpos(q)
+    assert int(s.field("fk_dirty").min()) == 1
+    s.field("ctrl_mode").copy_(scene_b.rigid_solver.field("ctrl_mode")); s.field("vel").copy_(scene_b.rigid_solver.field("vel"))
+    scene.step(); scene_b.step()
+    assert torch.equal(s.field("qpos"), scene_b.rigid_solver.field("qpos"))
+    assert int(s.field("fk_dirty").max()) == 0
+
+
+def test_batch_dofs_info_per_environment_gains():
+    """RigidOptions(batch_dofs_info=True) (array_class.py:1347-1364): kp / kv / armature per environment.  Env 0 gets the gains of
+    the reference's test_position_control (tests/test_rigid_physics.py:1417-1440); it must step exactly like an unbatched scene
+    built with those gains, env 1 like the default scene."""
+    from helpers import make_franka
+
+    KP = torch.tensor([4500.0, 4500.0, 3500.0, 3500.0, 2000.0, 2000.0, 2000.0, 100.0, 100.0], device=gs.device)
+    KD = torch.tensor([450.0, 450.0, 350.0, 350.0, 200.0, 200.0, 200.0, 10.0, 10.0], device=gs.device)
+    tgt = torch.tensor([0.69, -0.11, -0.72, -2.73, -0.15, 2.64, 0.89, 0.04, 0.04], device=gs.device)
+    scene, franka = make_franka(2, batch_dofs_info=True, disable_constraint=True)
+    franka.set_dofs_kp(KP, envs_idx=[0]); franka.set_dofs_kv(KD, envs_idx=[0])
+    franka.control_dofs_position(tgt)
+    ref_a, fa = make_franka(1, disable_constraint=True); fa.set_dofs_kp(KP); fa.set_dofs_kv(KD); fa.control_dofs_position(tgt)
+    ref_b, fb = make_franka(1, disable_constraint=True); fb.control_dofs_position(tgt)
+    assert scene.rigid_solver.dofs_info.armature.to_numpy().shape == (9, 2)
+    for _ in range(20):
+        scene.step(); ref_a.step(); ref_b.step()
+    q = scene.rigid_solver.field("qpos")
+    assert torch.equal(q[0], ref_a.rigid_solver.field("qpos")[0])
+    assert torch.equal(q[1], ref_b.rigid_solver.field("qpos")[0])
+    assert not torch.equal(q[0], q[1])
+    assert torch.allclose(franka.get_dofs_kp(envs_idx=[0])[0], KP) and int(scene.rigid_solver.field("n_constraints").max()) == 0

@@ -31,7 +31,7 @@ def model_digest(m):
     h = hashlib.sha256()
     for k in sorted(m.__dict__):
         v = m.__dict__[k]
-        if isinstance(v, np.ndarray) and k not in ("support_v",):
+        if isinstance(v, np.ndarray) and k not in ("support_v", "support_vid"):
             h.update(k.encode()); h.update(np.ascontiguousarray(np.round(np.asarray(v, np.float64), 9)).tobytes())
     return h.hexdigest()[:16]
 
@@ -105,6 +105,8 @@ def test_oracle_matches_reference_fixture(name):
         np.testing.assert_array_equal(nc[:, 1].astype(int), ref["n_constraints_equality"][k])
         np.testing.assert_array_equal(nc[:, 2].astype(int), ref["n_constraints_frictionloss"][k])
         assert int(orc.get("errno", 1).max()) == int(ref["errno"][k].max())
+        # scope row a13: the broad phase hands the same number of candidate pairs to the narrow phase
+        np.testing.assert_array_equal(orc.get("n_broad", 1)[:, 0].astype(int), ref["n_broad_pairs"][k], err_msg=f"{name} step {k}: broad-phase candidates")
         for b in range(B):
             match_contacts(orc.contacts(b), ref, b, k, *((loose["contact"], loose["post"]) if loose else ()))
 
