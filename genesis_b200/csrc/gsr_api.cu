@@ -404,7 +404,7 @@ static int group_launch(gsr_handle_t h, int which, cudaStream_t st, const uint8_
   } else {                                                                                               \
     CUDA_OK(set_smem(k_forward<GG>, smem));                                                              \
     Bracket br_(h, K_FORWARD, st);                                                                       \
-    k_forward<GG><<<grid, block, smem, st>>>(h->state, h->B, h->d_model, mask);                          \
+    k_forward<GG><<<grid, block, smem, st>>>(h->state, h->B, h->d_model, mask, clear_ext);               \
   }
   if (G == 32) { LAUNCH(32) } else if (G == 16) { LAUNCH(16) } else { LAUNCH(8) }
 #undef LAUNCH
@@ -504,6 +504,14 @@ int gsr_compute_diagnostics(gsr_handle_t h, void* cuda_stream) {
   int rc = activate(h, st);
   if (rc) return rc;
   return group_launch(h, K_DIAG, st, nullptr, 0);
+}
+
+int gsr_forward_kinematics_dirty(gsr_handle_t h, void* cuda_stream) {
+  if (!h || !h->state) return fail(h, GSR_ESTATE, "state not bound");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  int rc = activate(h, st);
+  if (rc) return rc;
+  return group_launch(h, K_FORWARD, st, nullptr, 1);
 }
 
 int gsr_reset_envs(gsr_handle_t h, const uint8_t* env_mask_dev, void* cuda_stream) {

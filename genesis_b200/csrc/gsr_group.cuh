@@ -83,9 +83,14 @@ __device__ __forceinline__ f3 link_ipos(const Ctx<G>& C, int l, bool shifted) {
 }
 
 // dof parameters: model constants, or the environment's own values when RigidOptions.batch_dofs_info is on (uniform branch)
+#ifdef GSR_NO_BATCH_DOFS
+#define GSR_BD(x) false
+#else
+#define GSR_BD(x) (x)
+#endif
 #define GSR_DOF_PARAM(fn, field, expr)                                                                     \
   template <int G>                                                                                         \
-  __device__ __forceinline__ float fn(const Ctx<G>& C, int d) { return CM(batch_dofs) ? C.rec[c_h.field + d] : (expr); }
+  __device__ __forceinline__ float fn(const Ctx<G>& C, int d) { return GSR_BD(CM(batch_dofs)) ? C.rec[c_h.field + d] : (expr); }
 GSR_DOF_PARAM(dof_kp, bd_kp, GM(d_kp[d]))
 GSR_DOF_PARAM(dof_armature, bd_armature, GM(d_armature[d]))
 GSR_DOF_PARAM(dof_damping, bd_damping, GM(d_damping[d]))
@@ -94,11 +99,11 @@ GSR_DOF_PARAM(dof_frictionloss, bd_frictionloss, GM(d_frictionloss[d]))
 GSR_DOF_PARAM(dof_invweight, bd_invweight, GM(d_invweight[d]))
 #undef GSR_DOF_PARAM
 template <int G>
-__device__ __forceinline__ float dof_bias(const Ctx<G>& C, int d, int k) { return CM(batch_dofs) ? C.rec[c_h.bd_bias + 3 * d + k] : GM(d_act_bias[d][k]); }
+__device__ __forceinline__ float dof_bias(const Ctx<G>& C, int d, int k) { return GSR_BD(CM(batch_dofs)) ? C.rec[c_h.bd_bias + 3 * d + k] : GM(d_act_bias[d][k]); }
 template <int G>
-__device__ __forceinline__ float dof_limit(const Ctx<G>& C, int d, int k) { return CM(batch_dofs) ? C.rec[c_h.bd_limit + 2 * d + k] : GM(d_limit[d][k]); }
+__device__ __forceinline__ float dof_limit(const Ctx<G>& C, int d, int k) { return GSR_BD(CM(batch_dofs)) ? C.rec[c_h.bd_limit + 2 * d + k] : GM(d_limit[d][k]); }
 template <int G>
-__device__ __forceinline__ float dof_force_range(const Ctx<G>& C, int d, int k) { return CM(batch_dofs) ? C.rec[c_h.bd_force_range + 2 * d + k] : GM(d_force_range[d][k]); }
+__device__ __forceinline__ float dof_force_range(const Ctx<G>& C, int d, int k) { return GSR_BD(CM(batch_dofs)) ? C.rec[c_h.bd_force_range + 2 * d + k] : GM(d_force_range[d][k]); }
 
 // IN / WK reach shared memory through a generic pointer (generic LD / ST in SASS): telling the compiler the address space of
 // EVERY access (`__builtin_assume(__isShared(C.S))` in both macros) gave wrong results in 16-20 parity tests, for either half

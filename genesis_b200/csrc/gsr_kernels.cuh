@@ -131,14 +131,6 @@ __global__ void __launch_bounds__(GSR_MAX_WARPS_PER_CTA * 32, 1) k_step(float* s
     const float* src = io.ctrl_pos + (size_t)C.env * nD;
     for (int d = C.lane; d < nD; d += G) IN(ctrl_pos)[d] = __ldcs(src + d);
   }
-  // qpos / vel written with skip_forward=True or by set_state(partial=True): the reference defers the forward kinematics to
-  // kernel_step_1 (is_forward_pos_updated = False, rigid_solver.py:2738-2765); the flag is per environment here
-  if (live && C.SI()[c_h.fk_dirty]) {  // group-uniform
-    C.sync();
-    phase_kinematics(C);
-    if (C.lane == 0) C.SI()[c_h.fk_dirty] = 0;
-    C.sync();
-  }
   PHASE_BARRIER(0);
   PHASE_BEGIN();
   if (live) phase_dynamics(C);
@@ -241,11 +233,13 @@ __device__ __forceinline__ void step_epilogue(const Ctx<G>& C, int clear_ext) {
 }
 
 template <int G>
-__global__ void __launch_bounds__(GSR_MAX_WARPS_PER_CTA * 32) k_forward(float* state, int B, const DevModel* gm, const uint8_t* mask) {
+__global__ void __launch_bounds__(GSR_MAX_WARPS_PER_CTA * 32) k_forward(float* state, int B, const DevModel* gm, const uint8_t* mask, int dirty_only) {
   extern __shared__ __align__(16) float smem[];
   Ctx<G> C;
   if (!make_ctx(C, state, B, gm, smem)) return;
   if (mask && !mask[C.env]) return;
+  // deferred kinematics (set_qpos(..., skip_forward=True), set_state(..., partial=True)): only the environments flagged in their record
+  if (dirty_only && !reinterpret_cast<const int*>(C.rec)[c_h.fk_dirty]) return;
   {  // masked environments are few: plain vector copies
     const float4* src = reinterpret_cast<const float4*>(C.rec);
     float4* dst = reinterpret_cast<float4*>(C.S);

@@ -90,6 +90,7 @@ class RigidSolver:
         self._n_substeps_total = 0
         self._errno_host = self._errno_event = None
         self._obs_valid, self._obs = False, None
+        self._fk_dirty_any = False
         self._errno_pending = False
         # launch tuning of libgsrigid (0 = library default): lanes per environment, constraint rows kept in shared
         # memory, and whether the diagnostic fields (mass_mat, qf_*, acc_smooth, geom poses) are written every step
@@ -223,7 +224,13 @@ class RigidSolver:
         return self._fields[name].reshape(self._B, -1)
 
     # ------------------------------------------------------------------ stepping
+    def _flush_deferred_fk(self):
+        if self._fk_dirty_any:
+            _lib.check(self._handle, _lib.lib().gsr_forward_kinematics_dirty(self._handle, self._stream()))
+            self._fk_dirty_any = False
+
     def substep(self, n=1):
+        self._flush_deferred_fk()
         _lib.check(self._handle, _lib.lib().gsr_step(self._handle, n, self._stream()))
         self._n_substeps_total += n
         self._obs_valid = False
@@ -238,6 +245,7 @@ class RigidSolver:
     def step_host(self, ctrl_pos_host, qpos_host, vel_host, n=1):
         """Reference-facing host-buffer call (bench.py e2e): numpy (B, n) float32 arrays in / out."""
         p = lambda a: ctypes.c_void_p(a.ctypes.data) if a is not None else None
+        self._flush_deferred_fk()
         _lib.check(self._handle, _lib.lib().gsr_step_host(self._handle, n, p(ctrl_pos_host), p(qpos_host), p(vel_host), self._stream()))
         self._n_substeps_total += n
         self._obs_valid = False
@@ -393,6 +401,7 @@ class RigidSolver:
         """qpos / vel written with skip_forward=True: the next step runs the forward kinematics of these environments first
         (the reference's is_forward_pos_updated = False, rigid_solver.py:2738-2765)."""
         d = self._fields["fk_dirty"]
+        self._fk_dirty_any = True
         if envs_idx is None:
             d.fill_(1)
         elif self._is_mask(envs_idx):
@@ -963,6 +972,8 @@ class RigidSolver:
         mptr = ctypes.c_void_p(mask.data_ptr()) if mask is not None else None
         _lib.check(self._handle, _lib.lib().gsr_set_state(self._handle, mptr, *ptrs, int(bool(partial)), self._stream()))
         self._obs_valid = False
+        if partial:
+            self._fk_dirty_any = True
 
     def _restore(self, values, envs_idx):
         f = self._fields

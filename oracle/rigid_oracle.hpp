@@ -114,6 +114,7 @@ struct Config {
   double mc_perturbation = 1e-2, mc_tolerance = 1e-2, mpr_to_gjk_overlap_ratio = 0.25;  // collider.py:85-87
   double ccd_eps = 1e-9, ccd_tolerance = 1e-6;  // mpr.py:13-19
   int ccd_iterations = 50;
+  int broadphase_sap = 0;     // 1: sweep-and-prune traversal of the CPU backend (BP:142-396); 0: all-vs-all over the valid-pair table (BP:400-460)
   int gjk_fallback = 1;       // exact-penetration fallback after MPR (NP:726-733); 0 keeps MPR's answer (A/B tests)
   int noslip_iterations = 0;  // options/solvers.py:506-507
   double noslip_tolerance = 1e-6;
@@ -156,6 +157,7 @@ struct Env {
   std::vector<V> contact_cache_normal;
   std::vector<int> broad_pairs;
   int n_broad = 0;
+  std::vector<T> sap_value; std::vector<int> sap_geom; std::vector<uint8_t> sap_is_max;  // persistent SAP sort buffer
   std::vector<Contact<T>> contacts;
   int n_contacts = 0;
   // constraints
@@ -234,6 +236,7 @@ struct Oracle {
     for (auto& n : e.contact_cache_normal) n = V();
     e.n_contacts = 0; e.n_con = 0; e.n_eq = 0; e.n_floss = 0;
     e.errno_ = 0;
+    e.sap_value.clear();  // collider.clear: first_time = True (the next SAP sweep rebuilds its sort buffer)
   }
 
   void init_fixed_geoms(Env<T>& e) {  // RS.build: _func_update_geoms(force_update_fixed_geoms=True), RS:348
@@ -622,7 +625,71 @@ struct Oracle {
   }
 
   // BP:74-139 (clear) + BP:400-460 (all-vs-all traversal, visited in valid-pair order => deterministic)
+  // BP:33-70 func_check_collision_valid: a valid static pair that is not tied by a dynamically registered weld
+  bool pair_valid(const Env<T>& e, int ga, int gb) const {
+    if (m.pair_idx[ga * m.nG + gb] == -1) return false;
+    const int la = m.geoms_link[ga], lb = m.geoms_link[gb];
+    for (const auto& w : e.dyn_welds)
+      if ((w.l1 == la && w.l2 == lb) || (w.l1 == lb && w.l2 == la)) return false;
+    return true;
+  }
+  // BP:142-396 _func_broad_phase_sap (the traversal gs.cpu uses, rigid_solver.py:370-372): geoms sorted along x by an insertion
+  // sort that is warm-started from the previous step's order, then one sweep with an active list.  Same candidate SET as the
+  // all-vs-all traversal of the GPU backend (BP:400-460), in sweep order.
+  void broad_phase_sap(Env<T>& e) {
+    for (int c = 0; c < e.n_contacts; c++) {
+      Contact<T>& ct = e.contacts[c];
+      ct.link_a = ct.link_b = ct.geom_a = ct.geom_b = -1;
+      ct.penetration = 0; ct.pos = V(); ct.normal = V(); ct.force = V();
+    }
+    e.n_contacts = 0;
+    const int nG = m.nG, axis = 0;
+    if (e.sap_value.empty()) {  // first_time: [min, max] of every geom in geom order
+      e.sap_value.resize(2 * nG); e.sap_geom.resize(2 * nG); e.sap_is_max.resize(2 * nG);
+      for (int g = 0; g < nG; g++) {
+        e.sap_value[2 * g] = e.aabb_min[g][axis]; e.sap_geom[2 * g] = g; e.sap_is_max[2 * g] = 0;
+        e.sap_value[2 * g + 1] = e.aabb_max[g][axis]; e.sap_geom[2 * g + 1] = g; e.sap_is_max[2 * g + 1] = 1;
+      }
+    } else {
+      for (int i = 0; i < 2 * nG; i++) e.sap_value[i] = e.sap_is_max[i] ? e.aabb_max[e.sap_geom[i]][axis] : e.aabb_min[e.sap_geom[i]][axis];
+    }
+    for (int i = 1; i < 2 * nG; i++) {  // insertion sort: near O(n) on a nearly sorted buffer
+      const T kv = e.sap_value[i];
+      const uint8_t km = e.sap_is_max[i];
+      const int kg = e.sap_geom[i];
+      int j = i - 1;
+      while (j >= 0 && kv < e.sap_value[j]) {
+        e.sap_value[j + 1] = e.sap_value[j]; e.sap_is_max[j + 1] = e.sap_is_max[j]; e.sap_geom[j + 1] = e.sap_geom[j];
+        j--;
+      }
+      e.sap_value[j + 1] = kv; e.sap_is_max[j + 1] = km; e.sap_geom[j + 1] = kg;
+    }
+    e.n_broad = 0;
+    std::vector<int> active;
+    for (int i = 0; i < 2 * nG; i++) {
+      if (!e.sap_is_max[i]) {
+        bool overflow = false;
+        for (size_t j = 0; j < active.size(); j++) {
+          int ga = active[j], gb = e.sap_geom[i];
+          if (ga > gb) std::swap(ga, gb);
+          if (!pair_valid(e, ga, gb)) continue;
+          bool sep = false;
+          for (int k = 0; k < 3; k++) if (e.aabb_max[ga][k] <= e.aabb_min[gb][k] || e.aabb_min[ga][k] >= e.aabb_max[gb][k]) sep = true;
+          if (sep) { e.contact_cache_normal[m.pair_idx[ga * m.nG + gb]] = V(); continue; }
+          if (e.n_broad == m.max_broad_pairs) { e.errno_ |= ERR_BROAD_OVERFLOW; overflow = true; break; }
+          e.broad_pairs[2 * e.n_broad] = ga; e.broad_pairs[2 * e.n_broad + 1] = gb; e.n_broad++;
+        }
+        (void)overflow;
+        active.push_back(e.sap_geom[i]);
+      } else {
+        for (size_t j = 0; j < active.size(); j++)
+          if (active[j] == e.sap_geom[i]) { active.erase(active.begin() + j); break; }
+      }
+    }
+  }
+
   void broad_phase(Env<T>& e) {
+    if (cfg.broadphase_sap) { broad_phase_sap(e); return; }
     for (int c = 0; c < e.n_contacts; c++) {
       Contact<T>& ct = e.contacts[c];
       ct.link_a = ct.link_b = ct.geom_a = ct.geom_b = -1;
@@ -632,6 +699,7 @@ struct Oracle {
     e.n_broad = 0;
     for (int p = 0; p < m.nP; p++) {
       int ga = m.pairs[2 * p], gb = m.pairs[2 * p + 1];
+      if (!e.dyn_welds.empty() && !pair_valid(e, ga, gb)) continue;  // BP:46-56: pairs tied by a dynamically registered weld
       bool sep = false;  // collider/utils.py func_is_geom_aabbs_overlap
       for (int k = 0; k < 3; k++) if (e.aabb_max[ga][k] <= e.aabb_min[gb][k] || e.aabb_min[ga][k] >= e.aabb_max[gb][k]) sep = true;
       if (sep) { e.contact_cache_normal[p] = V(); continue; }

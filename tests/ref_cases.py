@@ -208,6 +208,18 @@ def case_box_noslip():
     return s, m, dict(qpos=np.asarray(m.qpos0, float)[None].copy(), vel=np.zeros((1, 6))), 5, dict(noslip_iterations=5)
 
 
+def case_go2_drop_sap():
+    """The same drop with the sweep-and-prune broad phase of the CPU backend (broadphase.py:142-396): the insertion sort is warm-started
+    from the previous step, the candidate pairs come out in sweep order."""
+    s, m, init, K, opts = case_go2_drop()
+    return s, m, init, K, dict(opts, _broadphase="sap")
+
+
+def case_jumble_deep_sap():
+    s, m, init, K, opts = case_jumble_deep()
+    return s, m, init, K, dict(opts, _broadphase="sap")
+
+
 CASES = {name[5:]: fn for name, fn in list(globals().items()) if name.startswith("case_")}
 
 # per-step quantities recorded by the reference run, with the oracle field (orc.get name, shape per env) they pin and the scope

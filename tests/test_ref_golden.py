@@ -81,7 +81,7 @@ def test_oracle_matches_reference_fixture(name):
     B = len(init["qpos"])
     loose = ref_cases.GJK_PATH_TOL.get(name)
     tol_post = loose["post"] if loose else TOL_POST
-    orc = oracle_for(solver, m, B, double=True, sort_contacts=0)
+    orc = oracle_for(solver, m, B, double=True, sort_contacts=0, broadphase_sap=int(opts.get("_broadphase") == "sap"))
     for k_ in ("qpos", "vel", "ctrl_pos", "ctrl_vel", "ctrl_force", "ctrl_mode"):
         if k_ in init:
             np.testing.assert_array_equal(init[k_], ref["init_" + k_])
