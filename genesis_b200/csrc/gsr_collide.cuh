@@ -14,6 +14,15 @@
 #include "gsr_group.cuh"
 #include "gsr_epa.cuh"
 #include "gsr_gjk.cuh"
+#undef IN
+#undef WK
+#if GSR_LDS_MASK & 2
+#define IN(field) IN_SHARED(field)
+#define WK(field) WK_SHARED(field)
+#else
+#define IN(field) IN_GENERIC(field)
+#define WK(field) WK_GENERIC(field)
+#endif
 
 // SF:138-180 support point of a mesh-backed geom from its 180x180 direction table (L2 resident, read-only path)
 template <int G>

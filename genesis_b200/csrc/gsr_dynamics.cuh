@@ -9,6 +9,15 @@
 // jumping in ceil(log2(depth)) rounds.
 #pragma once
 #include "gsr_group.cuh"
+#undef IN
+#undef WK
+#if GSR_LDS_MASK & 1
+#define IN(field) IN_SHARED(field)
+#define WK(field) WK_SHARED(field)
+#else
+#define IN(field) IN_GENERIC(field)
+#define WK(field) WK_GENERIC(field)
+#endif
 
 // ---------------------------------------------------------------------------------------------------------------------
 // FK:580-736 one link's pose from its parent's world pose (pp, pq); also joint anchors / axes and dofs_pos when `final`.

@@ -108,13 +108,21 @@ __device__ __forceinline__ float dof_force_range(const Ctx<G>& C, int d, int k) 
 // IN / WK reach shared memory through a generic pointer (generic LD / ST in SASS): telling the compiler the address space of
 // EVERY access (`__builtin_assume(__isShared(C.S))` in both macros) gave wrong results in 16-20 parity tests, for either half
 // of the accessors (profiles/README.md item 13); the routines that are known to be safe use WKS below.
-#define IN(field) (C.S + c_h.field)   // IN part of the record, mirrored in shared memory
-#define WK(field) (C.S + c_s.field)   // workspace regions
+__device__ __forceinline__ float* smem_ptr(float* p) { __builtin_assume(__isShared(p)); return p; }
+#define IN_GENERIC(field) (C.S + c_h.field)
+#define WK_GENERIC(field) (C.S + c_s.field)
+#define IN_SHARED(field) (smem_ptr(C.S) + c_h.field)
+#define WK_SHARED(field) (smem_ptr(C.S) + c_s.field)
+// GSR_LDS_MASK (developer builds): bit 0 dynamics, 1 collide, 2 solver, 3 kernels -- which files address the workspace as shared
+#ifndef GSR_LDS_MASK
+#define GSR_LDS_MASK 0
+#endif
+#define IN(field) IN_GENERIC(field)   // IN part of the record, mirrored in shared memory
+#define WK(field) WK_GENERIC(field)   // workspace regions
 // Shared-space variant for the self-contained dense-algebra routines (factorisations, triangular solves, rank-1 updates:
 // explicit warp barriers between dependent steps): LDS / STS instead of generic LD / ST, Franka 73.8 -> 75.9 M env-steps/s.
 // Applied to ALL accessors it produced wrong results in 16-20 parity tests (profiles/README.md item 13), hence the opt-in.
 #ifndef GSR_NO_LDS_ROUTINES
-__device__ __forceinline__ float* smem_ptr(float* p) { __builtin_assume(__isShared(p)); return p; }
 #define WKS(field) (smem_ptr(C.S) + c_s.field)
 #else
 #define WKS(field) WK(field)

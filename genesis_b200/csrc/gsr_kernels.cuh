@@ -13,6 +13,15 @@
 #include "gsr_dynamics.cuh"
 #include "gsr_collide.cuh"
 #include "gsr_solver.cuh"
+#undef IN
+#undef WK
+#if GSR_LDS_MASK & 8
+#define IN(field) IN_SHARED(field)
+#define WK(field) WK_SHARED(field)
+#else
+#define IN(field) IN_GENERIC(field)
+#define WK(field) WK_GENERIC(field)
+#endif
 
 #define GSR_MAX_WARPS_PER_CTA 16
 // All warps of a CTA walk the phases of the step together (CTA barriers between phases): the step is ~20k instructions of

@@ -11,6 +11,15 @@
 #pragma once
 #include "gsr_group.cuh"
 #include "gsr_dynamics.cuh"
+#undef IN
+#undef WK
+#if GSR_LDS_MASK & 4
+#define IN(field) IN_SHARED(field)
+#define WK(field) WK_SHARED(field)
+#else
+#define IN(field) IN_GENERIC(field)
+#define WK(field) WK_GENERIC(field)
+#endif
 
 struct Rows {
   float* J; int JS;
@@ -513,12 +522,13 @@ __device__ __noinline__ bool hessian_incremental(const Ctx<G>& C, const Rows& R)
 
 // CS:2721-2750 gradient and preconditioned gradient (Newton: Cholesky solve CS:1892-1910; CG: M^-1 via L^T D L)
 template <int G>
-__device__ __noinline__ void update_gradient(const Ctx<G>& C) {
+__device__ __noinline__ void update_gradient(const Ctx<G>& C, bool solve = true) {
   const int nD = CM(nD), MS = c_s.MS, lane = C.lane;
   float* grad = WK(grad);
   float* Mgrad = WK(Mgrad);
   for (int d = lane; d < nD; d += G) { const float g = WK(Ma)[d] - WK(force)[d] - WK(qfrc_c)[d]; grad[d] = g; Mgrad[d] = g; }
   C.sync();
+  if (!solve) return;  // the caller only needs the gradient (termination test); the preconditioned one follows if it goes on
   if (CM(solver_type) == SOLVER_CG) {
     mass_solve(C, Mgrad);
   } else {
@@ -933,6 +943,16 @@ __device__ void phase_constraints(const Ctx<G>& C) {
       C.sync();
       update_constraint(C, R, X, true);
       DBG_T(3);
+      // CS:2841-2884 termination test first: it needs the gradient only (Ma, force, J^T f) -- not the Hessian.  The reference
+      // updates the factor and solves for the preconditioned gradient before it tests; on the last iteration of every solve
+      // (for most environments: the only one) that work is never used, so it is done here only when the iteration goes on.
+      update_gradient(C, false);
+      float gn = 0.f;
+      for (int d = lane; d < nD; d += G) { const float g = WK(grad)[d]; gn += g * g; }
+      gn = sqrtf(C.sum(gn));
+      const bool improved = gn > tol_scaled && (X.prev_cost - X.cost) > tol_scaled;
+      DBG_T(6);
+      if (!improved) break;
       if (CM(solver_type) == SOLVER_NEWTON) {
 #ifdef GSR_SOLVER_TRACE
         for (int c = 0; c < n_con; c++) { const int a = R.active[c]; DBG_N(10, (a ^ (a >> 1)) & 1); }
@@ -941,13 +961,6 @@ __device__ void phase_constraints(const Ctx<G>& C) {
         else DBG_T(4);
       }
       update_gradient(C);
-      DBG_T(6);
-      // CS:2841-2884 termination / new search direction
-      float gn = 0.f;
-      for (int d = lane; d < nD; d += G) { const float g = WK(grad)[d]; gn += g * g; }
-      gn = sqrtf(C.sum(gn));
-      const bool improved = gn > tol_scaled && (X.prev_cost - X.cost) > tol_scaled;
-      if (!improved) break;
       if (CM(solver_type) == SOLVER_NEWTON) {
         for (int d = lane; d < nD; d += G) search[d] = -WK(Mgrad)[d];
       } else {
