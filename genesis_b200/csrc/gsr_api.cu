@@ -384,7 +384,11 @@ static int group_launch(gsr_handle_t h, int which, cudaStream_t st, const uint8_
   dim3 grid((h->B + envs_per_cta - 1) / envs_per_cta), block(warps * 32);
 #define LAUNCH(GG)                                                                                       \
   if (which == K_STEP) {                                                                                 \
-    if (h->hm.has_mpr) {                                                                                 \
+    if (h->hm.has_box_box) {                                                                             \
+      CUDA_OK((set_smem(k_step<GG, true, true>, smem)));                                                 \
+      Bracket br_(h, K_STEP, st);                                                                        \
+      k_step<GG, true, true><<<grid, block, smem, st>>>(h->state, h->B, h->d_model, clear_ext, h->d_order, h->d_trace, io);      \
+    } else if (h->hm.has_mpr) {                                                                          \
       CUDA_OK((set_smem(k_step<GG, true>, smem)));                                                       \
       Bracket br_(h, K_STEP, st);                                                                        \
       k_step<GG, true><<<grid, block, smem, st>>>(h->state, h->B, h->d_model, clear_ext, h->d_order, h->d_trace, io);            \

@@ -439,6 +439,8 @@ __device__ __noinline__ void dev_pair_perturbed(const Ctx<G>& C, const PairDet& 
   }
 }
 
+#include "gsr_boxbox.cuh"  // BOX:100-785 func_box_box_contact (needs LaneContacts)
+
 // BOX:24-96 func_plane_box_contact
 template <int G>
 __device__ __noinline__ void dev_plane_box(const Ctx<G>& C, LaneContacts& out, int ga, int gb) {
@@ -470,7 +472,8 @@ __device__ __noinline__ void dev_plane_box(const Ctx<G>& C, LaneContacts& out, i
 }
 
 // narrow phase of up to G queued pairs; appends the contacts (unordered) to the staging records and returns the new count
-template <int G, bool MPR>
+// BB: RigidOptions.box_box_detection and the pair table holds a box-box pair (gsr_boxbox.cuh)
+template <int G, bool MPR, bool BB>
 __device__ int narrow_batch(const Ctx<G>& C, const int* queue, int n_batch, int n_staged) {
   const int lane = C.lane;
   LaneContacts out;
@@ -483,8 +486,12 @@ __device__ int narrow_batch(const Ctx<G>& C, const int* queue, int n_batch, int 
     const int ga0 = __ldg(CM(pairs) + 2 * p), gb0 = __ldg(CM(pairs) + 2 * p + 1);
     ga = ga0; gb = gb0;
     if (GM(g_type[ga0]) > GM(g_type[gb0])) { ga = gb0; gb = ga0; }
-    plane_box = GM(g_type[ga]) == GEOM_PLANE && GM(g_type[gb]) == GEOM_BOX;
-    if (plane_box) dev_plane_box(C, out, ga, gb);
+    // convex specialisations (NP:2135-2189): their contacts follow those of the convex-convex pass in the contact list
+    const bool is_plane_box = GM(g_type[ga]) == GEOM_PLANE && GM(g_type[gb]) == GEOM_BOX;
+    const bool is_box_box = BB && GM(g_type[ga]) == GEOM_BOX && GM(g_type[gb]) == GEOM_BOX;
+    plane_box = is_plane_box || is_box_box;
+    if (is_plane_box) dev_plane_box(C, out, ga, gb);
+    else if (is_box_box) { if constexpr (BB) dev_box_box(C, out, ga, gb); }
     else { D.ga = ga; D.gb = gb; D.p = p; dev_pair_det0<G, MPR>(C, out, D); }
   }
   // ---- perturbed detections: task (pair k of the colliding multi-contact pairs, i_det) -> lane, results through the
@@ -569,7 +576,7 @@ __device__ int narrow_batch(const Ctx<G>& C, const int* queue, int n_batch, int 
   return n_new;
 }
 
-template <int G, bool MPR>
+template <int G, bool MPR, bool BB>
 __device__ void phase_collide(const Ctx<G>& C) {
   const int lane = C.lane;
   const int nP = CM(nP), nG = CM(nG);
@@ -610,7 +617,7 @@ __device__ void phase_collide(const Ctx<G>& C) {
       qn += accepted;
       C.sync();
       if (qn >= G) {
-        n_staged = narrow_batch<G, MPR>(C, queue, G, n_staged);
+        n_staged = narrow_batch<G, MPR, BB>(C, queue, G, n_staged);
         C.sync();
         const int rest = qn - G;  // move the tail (< G entries) to the front
         int t = 0;
@@ -621,7 +628,7 @@ __device__ void phase_collide(const Ctx<G>& C) {
         C.sync();
       }
     }
-    if (qn > 0) n_staged = narrow_batch<G, MPR>(C, queue, qn, n_staged);
+    if (qn > 0) n_staged = narrow_batch<G, MPR, BB>(C, queue, qn, n_staged);
     if (lane == 0) SI[c_h.n_broad] = n_broad;
   }
   __threadfence_block();

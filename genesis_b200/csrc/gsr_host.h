@@ -172,11 +172,15 @@ static inline int gsr_fill_model(GsrSpec* h) {
   // has_cc: any valid pair that is not plane-box (collider.py:449-459) -> contacts are x-sorted (collider.py:804-808)
   m.has_cc = 0;
   m.has_mpr = 0;
+  m.has_box_box = 0;
+  const bool box_box_detection = h->S("cfg_box_box_detection", 0) != 0;  // options/solvers.py:511
   {
     const int* pr = IV("pairs", 2 * (size_t)m.nP);
     for (int p = 0; p < m.nP; p++) {
       int ta = m.g_type[pr[2 * p]], tb = m.g_type[pr[2 * p + 1]];
       if (ta > tb) { int t = ta; ta = tb; tb = t; }
+      const bool box_box = box_box_detection && ta == GEOM_BOX && tb == GEOM_BOX;  // specialised like plane-box (collider.py:456-459)
+      if (box_box) { m.has_box_box = 1; continue; }
       if (!(ta == GEOM_PLANE && tb == GEOM_BOX)) m.has_cc = 1;
       const bool analytic = (ta == GEOM_CAPSULE && tb == GEOM_CAPSULE) || (ta == GEOM_SPHERE && tb == GEOM_CAPSULE) || (ta == GEOM_CAPSULE && tb == GEOM_SPHERE);
       if (ta != GEOM_PLANE && tb != GEOM_PLANE && !analytic) m.has_mpr = 1;

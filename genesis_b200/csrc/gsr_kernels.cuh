@@ -113,8 +113,14 @@ struct HostIO {
   float* vel;             // (B, nD) or null
 };
 
-template <int G, bool MPR>
-__global__ void __launch_bounds__(GSR_MAX_WARPS_PER_CTA * 32, 1) k_step(float* state, int B, const DevModel* gm, int clear_ext, const int* order,
+// launch bounds of the step kernel (developer builds may override: ptxas fits the kernel into 96 registers without spilling, so
+// shared memory, not registers, bounds the number of resident CTAs)
+#ifndef GSR_LB_T
+#define GSR_LB_T (GSR_MAX_WARPS_PER_CTA * 32)
+#define GSR_LB_B 1
+#endif
+template <int G, bool MPR, bool BB = false>
+__global__ void __launch_bounds__(GSR_LB_T, GSR_LB_B) k_step(float* state, int B, const DevModel* gm, int clear_ext, const int* order,
                                                                         unsigned long long* trace, HostIO io) {
   extern __shared__ __align__(16) float smem[];
   Ctx<G> C;
@@ -147,7 +153,7 @@ __global__ void __launch_bounds__(GSR_MAX_WARPS_PER_CTA * 32, 1) k_step(float* s
   TRACE_MARK(1);
   PHASE_BARRIER(1);
   PHASE_BEGIN();
-  if (live && CM(enable_collision) && CM(nG) > 0) phase_collide<G, MPR>(C);
+  if (live && CM(enable_collision) && CM(nG) > 0) phase_collide<G, MPR, BB>(C);
   PHASE_END();
   TRACE_MARK(2);
   PHASE_BARRIER(2);

@@ -46,6 +46,7 @@ struct DevModel {
   int iterations, ls_iterations, integrator, solver_type;
   int noslip_iterations;  // constraint/noslip.py post-solver (0 = off)
   int has_mpr;            // any valid pair that needs MPR / EPA (neither a plane pair nor an analytic capsule pair): selects the kernel variant
+  int has_box_box;        // RigidOptions.box_box_detection and a valid box-box pair: the variant with func_box_box_contact compiled in
   int phase_barriers;     // bit k: CTA barrier k of k_step (0 after the record load, 1 dynamics, 2 collision, 3 constraints, 4 integration)
   int gjk_fallback;       // exact-penetration fallback after MPR (narrowphase.py:726-733); 0 keeps MPR's answer
   float noslip_tolerance;

@@ -123,6 +123,8 @@ class RigidSolver:
         o = self._options
         if (o.batch_dofs_info or o.batch_links_info) and self.tuning.get("group_size") == 1:
             raise GenesisException("batch_dofs_info / batch_links_info need the lane-group step kernel (unset GSR_GROUP_SIZE=1).")
+        if o.box_box_detection and self.tuning.get("group_size") == 1:
+            raise GenesisException("box_box_detection needs the lane-group step kernel (unset GSR_GROUP_SIZE=1).")
         if o.use_contact_island or o.use_hibernation or o.enable_mujoco_compatibility or o.use_gjk_collision:
             raise GenesisException(
                 "contact islands, hibernation, mujoco-compatibility and GJK-first collision are outside the "
@@ -154,6 +156,7 @@ class RigidSolver:
                     enable_joint_limit=int(o.enable_joint_limit), enable_multi_contact=int(o.enable_multi_contact),
                     noslip_iterations=int(o.noslip_iterations), noslip_tolerance=float(o.noslip_tolerance),
                     batch_dofs_info=int(bool(o.batch_dofs_info)), disable_constraint=int(bool(o.disable_constraint)),
+                    box_box_detection=int(bool(o.box_box_detection)),
                     sort_contacts=1, **self.tuning)
 
     def build(self, n_envs, device):

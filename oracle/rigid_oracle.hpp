@@ -29,6 +29,7 @@
 #include <limits>
 #include <thread>
 #include "vecmath.hpp"
+#include "box_box.hpp"
 
 namespace orc {
 
@@ -116,6 +117,7 @@ struct Config {
   int ccd_iterations = 50;
   int broadphase_sap = 0;     // 1: sweep-and-prune traversal of the CPU backend (BP:142-396); 0: all-vs-all over the valid-pair table (BP:400-460)
   int gjk_fallback = 1;       // exact-penetration fallback after MPR (NP:726-733); 0 keeps MPR's answer (A/B tests)
+  int box_box_detection = 0;  // options/solvers.py:511: box-box pairs through func_box_box_contact (BOX:100-785) instead of MPR
   int noslip_iterations = 0;  // options/solvers.py:506-507
   double noslip_tolerance = 1e-6;
 };
@@ -1552,6 +1554,7 @@ struct Oracle {
   // NP:519-970 func_convex_convex_contact (MPR ccd with the exact-penetration fallback of NP:726-733)
   void convex_convex_contact(Env<T>& e, int ga, int gb) {
     if (m.geoms_type[ga] == GEOM_PLANE && m.geoms_type[gb] == GEOM_BOX) return;
+    if (cfg.box_box_detection && m.geoms_type[ga] == GEOM_BOX && m.geoms_type[gb] == GEOM_BOX) return;  // NP:2028-2032
     bool multi_contact = cfg.enable_multi_contact && m.geoms_type[ga] != GEOM_SPHERE && m.geoms_type[ga] != GEOM_ELLIPSOID &&
                          m.geoms_type[gb] != GEOM_SPHERE && m.geoms_type[gb] != GEOM_ELLIPSOID;
     T tolerance = compute_tolerance(ga, gb, (T)cfg.mc_tolerance);
@@ -1673,6 +1676,27 @@ struct Oracle {
     }
   }
 
+  // BOX:100-785 func_box_box_contact: candidates from box_box_detect (oracle/box_box.hpp); duplicate filter and contact records here
+  void box_box_contact(Env<T>& e, int ga, int gb, int i_pair) {
+    BoxBoxContacts<T> bb;
+    const V ha(m.geoms_data[7 * ga] / 2, m.geoms_data[7 * ga + 1] / 2, m.geoms_data[7 * ga + 2] / 2);
+    const V hb(m.geoms_data[7 * gb] / 2, m.geoms_data[7 * gb + 1] / 2, m.geoms_data[7 * gb + 2] / 2);
+    if (!box_box_detect(e.g_pos[ga], e.g_quat[ga], ha, e.g_pos[gb], e.g_quat[gb], hb, EPS, bb)) return;
+    int n_added = 0;
+    const int n_start = e.n_contacts;
+    for (int i = 0; i < bb.n; i++) {
+      if (n_added >= m.n_contacts_per_pair) continue;
+      bool is_valid = true;
+      for (int j_ = 0; j_ < n_added; j_++) {  // BOX:437-441, 763-767
+        const int j = n_start + j_;
+        if (j >= m.max_contact_pairs) continue;
+        const V d = bb.pos[i] - e.contacts[j].pos;
+        if (std::abs(d.x) < EPS && std::abs(d.y) < EPS && std::abs(d.z) < EPS) is_valid = false;
+      }
+      if (is_valid) { add_contact(e, ga, gb, -bb.normal, bb.pos[i], -bb.dist[i], i_pair); n_added++; }
+    }
+  }
+
   // CT:439-538 func_sort_contacts (stable insertion sort of pair groups by x of the group's first contact)
   void sort_contacts(Env<T>& e) {
     int n = e.n_contacts;
@@ -1703,7 +1727,8 @@ struct Oracle {
     for (int p = 0; p < m.nP; p++) {
       int ta = m.geoms_type[m.pairs[2 * p]], tb = m.geoms_type[m.pairs[2 * p + 1]];
       if (ta > tb) std::swap(ta, tb);
-      if (!(ta == GEOM_PLANE && tb == GEOM_BOX)) has_cc = true;
+      const bool specialized = (ta == GEOM_PLANE && tb == GEOM_BOX) || (cfg.box_box_detection && ta == GEOM_BOX && tb == GEOM_BOX);  // collider.py:456-459
+      if (!specialized) has_cc = true;
     }
     for (int i = 0; i < e.n_broad; i++) {  // NP:1989-2060
       int ga = e.broad_pairs[2 * i], gb = e.broad_pairs[2 * i + 1];
@@ -1714,6 +1739,7 @@ struct Oracle {
       int ga = e.broad_pairs[2 * i], gb = e.broad_pairs[2 * i + 1];
       if (m.geoms_type[ga] > m.geoms_type[gb]) std::swap(ga, gb);
       if (m.geoms_type[ga] == GEOM_PLANE && m.geoms_type[gb] == GEOM_BOX) plane_box_contact(e, ga, gb, i);
+      if (cfg.box_box_detection && m.geoms_type[ga] == GEOM_BOX && m.geoms_type[gb] == GEOM_BOX) box_box_contact(e, ga, gb, i);  // NP:2175-2189
     }
     if (has_cc && cfg.sort_contacts) sort_contacts(e);  // collider.py:804-808 (GPU split path)
   }

@@ -208,6 +208,39 @@ def case_box_noslip():
     return s, m, dict(qpos=np.asarray(m.qpos0, float)[None].copy(), vel=np.zeros((1, 6))), 5, dict(noslip_iterations=5)
 
 
+# box-box pairs through the reference's func_box_box_contact (RigidOptions.box_box_detection, box_contact.py:100-785):
+# boxes of different sizes thrown together at arbitrary orientations -- face / vertex, face / edge and edge / edge contacts
+BOXBOX_PILE_XML = """
+<mujoco model="boxbox_pile">
+  <option gravity="0 0 -9.81"/>
+  <worldbody>
+    <geom name="floor" type="plane" size="5 5 0.1"/>
+    <body name="a" pos="0 0 0.30"><freejoint/><geom type="box" size="0.10 0.08 0.05"/></body>
+    <body name="b" pos="0.09 0.05 0.385" euler="7 41 -13"><freejoint/><geom type="box" size="0.06 0.07 0.04"/></body>
+    <body name="c" pos="-0.07 -0.04 0.39" euler="40 35 20"><freejoint/><geom type="box" size="0.05 0.05 0.05"/></body>
+    <body name="d" pos="0.0 0.11 0.29" euler="52 -9 31"><freejoint/><geom type="box" size="0.03 0.09 0.03"/></body>
+    <body name="e" pos="0.02 -0.02 0.21" euler="5 -8 60"><freejoint/><geom type="box" size="0.07 0.07 0.04"/></body>
+  </worldbody>
+</mujoco>
+"""
+
+
+def case_boxbox_stack():
+    """The reference's box_box fixture with box_box_detection=True: the upper cube rests on the lower one face to face (aligned: every
+    edge axis degenerate; yawed: eight candidate points, five kept), or touches it with an edge / a corner first (tilted)."""
+    s, m = _scene(xml=BOX_BOX_XML, box_box_detection=True)
+    q = box_box_qpos(4, seed=7)
+    q[0, 10:14] = (1, 0, 0, 0)                                  # aligned
+    q[1, 10:14] = (np.cos(0.35), 0, 0, np.sin(0.35))            # yawed by 0.7 rad, flat
+    q[:, 9] = [0.598, 0.597, 0.615, 0.62]                       # all four start in contact
+    return s, m, dict(qpos=q, vel=np.zeros((4, 12))), 4, dict(box_box_detection=True)
+
+
+def case_boxbox_pile():
+    s, m = _scene(xml=BOXBOX_PILE_XML, box_box_detection=True)
+    return s, m, dict(qpos=np.asarray(m.qpos0, float)[None].copy(), vel=np.zeros((1, m.n_dofs))), 4, dict(box_box_detection=True)
+
+
 def case_go2_drop_sap():
     """The same drop with the sweep-and-prune broad phase of the CPU backend (broadphase.py:142-396): the insertion sort is warm-started
     from the previous step, the candidate pairs come out in sweep order."""

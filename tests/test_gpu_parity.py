@@ -435,6 +435,60 @@ def test_box_box_dynamics_reference_expectations(solver_name, integrator_name):
     np.testing.assert_allclose(q[:, 2], 0.2, atol=2e-3)
 
 
+def test_box_box_detection_contact_records_and_stack():
+    """RigidOptions.box_box_detection (scope row f4, box_contact.py:100-785): (1) a pile of boxes at arbitrary orientations -- face /
+    vertex, face / edge and edge / edge contacts -- gives the oracle's contact records one by one (the oracle itself is pinned to
+    the reference's func_box_box_contact by tests/golden/ref_boxbox_*.npz); (2) the reference's stacked cubes follow the oracle through the first touch
+    and stay stacked (upper cube at z = 0.6 +- 2e-3)."""
+    import ref_cases
+    from helpers import box_box_qpos, make_box_box, write_tmp
+
+    scene = gs.Scene(rigid_options=gs.options.RigidOptions(dt=0.01, box_box_detection=True))
+    ent = scene.add_entity(gs.morphs.MJCF(file=write_tmp(ref_cases.BOXBOX_PILE_XML, ".xml")))
+    B = 8
+    scene.build(n_envs=B)
+    s = scene.rigid_solver
+    rng = np.random.default_rng(3)
+    q = np.tile(np.asarray(s.model.qpos0, np.float32), (B, 1))
+    q[:, 0::7][:, :5] += rng.uniform(-0.01, 0.01, (B, 5)).astype(np.float32)  # jitter x of every box: different contact sets per env
+    s.set_qpos(torch.tensor(q, device=gs.device))
+    orc = mirror_oracle(scene)
+    scene.step()
+    orc.step(1)
+    con = ent.get_contacts()
+    n = s.field("n_contacts")[:, 0].cpu().numpy()
+    n_bb = 0
+    for b in range(B):
+        c = orc.contacts(b)
+        assert n[b] == len(c["geom_a"]) > 0
+        np.testing.assert_array_equal(con["geom_a"][b, : n[b]].cpu().numpy(), c["geom_a"])
+        np.testing.assert_array_equal(con["geom_b"][b, : n[b]].cpu().numpy(), c["geom_b"])
+        np.testing.assert_allclose(con["position"][b, : n[b]].cpu().numpy(), c["position"], atol=1e-5)
+        np.testing.assert_allclose(con["normal"][b, : n[b]].cpu().numpy(), c["normal"], atol=1e-5)
+        np.testing.assert_allclose(con["penetration"][b, : n[b]].cpu().numpy(), c["penetration"], atol=1e-5)
+        n_bb += int((np.asarray(c["geom_a"]) > 0).sum())
+    assert n_bb >= 4 * B  # box-box contacts, not only plane contacts
+    assert int(s.field("errno_").max()) == 0
+
+    B = 32
+    scene, ent = make_box_box(B, box_box_detection=True)
+    ent.set_qpos(torch.tensor(box_box_qpos(B, seed=5), dtype=torch.float32, device=gs.device))
+    orc = mirror_oracle(scene)
+    for _ in range(25):
+        scene.step()
+    orc.step(25)
+    dq = np.abs(gpu_field(scene, "qpos") - orc.qpos()).max(axis=1)
+    assert (dq <= TRAJ_QPOS_CONTACT).mean() >= 0.95, f"qpos outliers: {np.sort(dq)[-5:]}"
+    # the stack holds: with five of the eight face-face candidates kept per pair the reference's algorithm leaves the upper cube
+    # rocking at ~0.1 rad/s for good (fp32 oracle: max |qvel| 0.10-0.16 between steps 100 and 400), so no rest criterion here
+    for i in range(25, 200):
+        scene.step()
+    q = ent.get_qpos().cpu().numpy()
+    np.testing.assert_allclose(q[:, 9], 0.6, atol=2e-3)
+    np.testing.assert_allclose(q[:, 2], 0.2, atol=2e-3)
+    assert float(ent.get_dofs_velocity().abs().max()) <= 0.5
+
+
 def test_double_pendulum_link_accelerations():
     """The reference's double pendulum (tests/test_rigid_physics.py:230-297, 955-1020: massless arms, fixed links kept, CG +
     Euler) on the CUDA path: a 50-step swing and the link accelerations (`get_links_acc_ang`, `cacc_lin`) against the oracle,
