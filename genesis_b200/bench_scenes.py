@@ -33,10 +33,14 @@ def make_franka(n_envs, self_collision=False, randomized=False, controlled=True,
     return scene, franka
 
 
-def make_go2(n_envs, randomized=True, build=True, seed=0, **rigid_kwargs):
-    """Config 3: plane + go2.urdf, joints uniform within limits, PD targets (test_rigid_benchmarks.py:240-256)."""
+def make_go2(n_envs, randomized=True, build=True, seed=0, terrain=None, **rigid_kwargs):
+    """Config 3: plane + go2.urdf, joints uniform within limits, PD targets (test_rigid_benchmarks.py:240-256).
+    terrain = (height_field, horizontal_scale, vertical_scale, pos) puts the robot on a height field instead of the plane."""
     scene = gs.Scene(rigid_options=gs.options.RigidOptions(dt=0.01, **rigid_kwargs))
-    scene.add_entity(gs.morphs.Plane())
+    if terrain is None:
+        scene.add_entity(gs.morphs.Plane())
+    else:
+        scene.add_entity(gs.morphs.Terrain(height_field=terrain[0], horizontal_scale=terrain[1], vertical_scale=terrain[2], pos=terrain[3]))
     robot = scene.add_entity(gs.morphs.URDF(file="urdf/go2/urdf/go2.urdf"))
     if not build:
         return scene, robot

@@ -30,7 +30,7 @@ struct gsr_handle_s : GsrSpec {
   int device = 0, B = 0;
   float* state = nullptr;
   DevModel* d_model = nullptr;  // global-memory copy for lane-varying table reads
-  float *d_verts = nullptr, *d_support = nullptr;
+  float *d_verts = nullptr, *d_support = nullptr, *d_terrain = nullptr;
   int* d_support_vid = nullptr;
   unsigned short* d_fac = nullptr;
   unsigned long long* d_trace = nullptr;  // gsr_debug_trace
@@ -161,6 +161,7 @@ int gsr_model_commit(gsr_handle_t h, int device, int n_envs) {
     auto& v = h->f["verts"]; CUDA_OK(upload(v.empty() ? nullptr : v.data(), v.size() * 4, (void**)&h->d_verts));
     auto& sv = h->f["support_v"]; CUDA_OK(upload(sv.empty() ? nullptr : sv.data(), sv.size() * 4, (void**)&h->d_support));
     auto& svid = h->i["support_vid"]; CUDA_OK(upload(svid.empty() ? nullptr : svid.data(), svid.size() * 4, (void**)&h->d_support_vid));
+    auto& thf = h->f["terrain_hf"]; CUDA_OK(upload(thf.empty() ? nullptr : thf.data(), thf.size() * 4, (void**)&h->d_terrain));
     auto& pr = h->i["pairs"]; CUDA_OK(upload(pr.empty() ? nullptr : pr.data(), pr.size() * 4, (void**)&h->d_pairs));
     auto& pi = h->i["pair_idx"]; CUDA_OK(upload(pi.empty() ? nullptr : pi.data(), pi.size() * 4, (void**)&h->d_pair_idx));
     CUDA_OK(upload(h->fac_tasks.empty() ? nullptr : h->fac_tasks.data(), h->fac_tasks.size() * sizeof(unsigned short), (void**)&h->d_fac));
@@ -168,6 +169,7 @@ int gsr_model_commit(gsr_handle_t h, int device, int n_envs) {
   }
   m.fac_tasks = h->d_fac;
   m.verts = h->d_verts; m.support_v = h->d_support; m.support_vid = h->d_support_vid; m.pairs = h->d_pairs; m.pair_idx = h->d_pair_idx;
+  m.terrain_hf = h->d_terrain;
 
   { int rc_lay = gsr_compute_layouts(h, n_envs); if (rc_lay) return rc_lay; }
   h->reorder_period = (int)h->S("cfg_reorder_period", 16);
@@ -660,6 +662,7 @@ void gsr_destroy(gsr_handle_t h) {
   if (h->committed) {
     cudaSetDevice(h->device);
     if (g_active[h->device] == h) g_active[h->device] = nullptr;
+    cudaFree(h->d_terrain);
     cudaFree(h->d_verts); cudaFree(h->d_support); cudaFree(h->d_support_vid); cudaFree(h->d_pairs); cudaFree(h->d_pair_idx); cudaFree(h->d_model); cudaFree(h->d_fac); if (h->d_trace) cudaFree(h->d_trace);
     if (h->d_order) { cudaFree(h->d_order); cudaFree(h->d_iota); cudaFree(h->d_cost); cudaFree(h->d_cost_sorted); cudaFree(h->d_sort_tmp); h->d_order = nullptr; }
     if (h->d_rows_hist) { cudaFree(h->d_rows_hist); cudaFreeHost(h->h_rows_hist); cudaEventDestroy(h->rows_event); h->d_rows_hist = nullptr; h->h_rows_hist = nullptr; h->rows_event = nullptr; }

@@ -176,15 +176,16 @@ __device__ __forceinline__ void expand_portal(Simplex& s, f3 v, f3 v1, f3 v2) { 
   else is = dot(s.v[3], v4v0) > 0.f ? 2 : 1;
   simplex_set(s, is, v, v1, v2);
 }
-// MPR:445-598
-template <int G>
-__device__ int discover_portal(const Ctx<G>& C, Simplex& s, const PairPose& P, f3 ca, f3 cb) {
+// MPR:445-598.  `sup(d, v, v1, v2)` is the support mapping of the pair: GroupSupport for two posed geoms, TerrainSupport for a geom
+// against one prism of the height field.
+template <int G, class Sup>
+__device__ int discover_portal(const Ctx<G>& C, Simplex& s, const Sup& sup, f3 ca, f3 cb) {
   const float CE = c_m.ccd_eps;
   s.v1[0] = ca; s.v2[0] = cb; s.v[0] = ca - cb;
   if (fabsf(s.v[0].x) < CE && fabsf(s.v[0].y) < CE && fabsf(s.v[0].z) < CE) s.v[0].x += 10.0f * CE;
   f3 dir = -normalized(s.v[0]);
   f3 v, v1, v2;
-  mpr_support(C, P, dir, v, v1, v2);
+  sup(dir, v, v1, v2);
   s.v[1] = v; s.v1[1] = v1; s.v2[1] = v2;
   if (dot(v, dir) < CE) return -1;
   dir = cross(s.v[0], s.v[1]);
@@ -193,7 +194,7 @@ __device__ int discover_portal(const Ctx<G>& C, Simplex& s, const PairPose& P, f
     return 2;
   }
   dir = normalized(dir);
-  mpr_support(C, P, dir, v, v1, v2);
+  sup(dir, v, v1, v2);
   if (dot(v, dir) < CE) return -1;
   s.v[2] = v; s.v1[2] = v1; s.v2[2] = v2;
   dir = normalized(cross(s.v[1] - s.v[0], s.v[2] - s.v[0]));
@@ -206,7 +207,7 @@ __device__ int discover_portal(const Ctx<G>& C, Simplex& s, const PairPose& P, f
   }
   int num_trials = 0;
   while (true) {
-    mpr_support(C, P, dir, v, v1, v2);
+    sup(dir, v, v1, v2);
     if (dot(v, dir) < CE) return -1;
     bool cont = false;
     if (dot(cross(s.v[1], v), s.v[0]) < -CE) { s.v[2] = v; s.v1[2] = v1; s.v2[2] = v2; cont = true; }
@@ -220,6 +221,50 @@ __device__ int discover_portal(const Ctx<G>& C, Simplex& s, const PairPose& P, f
     }
   }
 }
+// MPR:686-765 func_mpr_contact_from_centers (portal discovery / refinement + penetration)
+template <int G, class Sup>
+__device__ __forceinline__ void dev_mpr_from_centers(const Ctx<G>& C, const Sup& sup, f3 ca, f3 cb, bool& is_col, f3& normal, float& pen, f3& pos,
+                                                     Simplex& s, bool& tetra) {
+  const float CE = c_m.ccd_eps;
+  int res = discover_portal(C, s, sup, ca, cb);
+  is_col = false; pos = f3(); normal = f3(); pen = 0.f;
+  tetra = false;  // true when s ends as the interior point + final portal, a tetrahedron around the origin (EPA seed)
+  if (res == 1) { is_col = true; normal = -normalized(s.v[0]); pos = (s.v1[1] + s.v2[1]) * 0.5f; }
+  else if (res == 2) { is_col = true; pen = norm(s.v[1]); normal = -normalized(s.v[1]); pos = (s.v1[1] + s.v2[1]) * 0.5f; }
+  else if (res == 0) {
+    while (true) {  // MPR:232-278 refine portal
+      const f3 dir = portal_dir(s);
+      if (dot(s.v[1], dir) > -CE) { res = 0; break; }
+      f3 v, v1, v2;
+      sup(dir, v, v1, v2);
+      if (!(dot(v, dir) > -CE) || reach_tolerance(s, v, dir)) { res = -1; break; }
+      expand_portal(s, v, v1, v2);
+    }
+    if (res >= 0) {
+      int it = 0;
+      while (true) {  // MPR:338-423 find penetration
+        const f3 dir = portal_dir(s);
+        f3 v, v1, v2;
+        sup(dir, v, v1, v2);
+        if (reach_tolerance(s, v, dir) || it > c_m.ccd_iterations) {
+          pen = dot(dir, s.v[1]);
+          normal = -dir;
+          is_col = true;
+          // MPR:281-316 find_pos: barycentric weights of the origin's projection on the portal
+          const float b1 = dot(cross(s.v[2], s.v[3]), dir), b2 = dot(cross(s.v[3], s.v[1]), dir), b3 = dot(cross(s.v[1], s.v[2]), dir);
+          const float sum = b1 + b2 + b3;
+          const f3 p1 = s.v1[1] * b1 + s.v1[2] * b2 + s.v1[3] * b3, p2 = s.v2[1] * b1 + s.v2[2] * b2 + s.v2[3] * b3;
+          pos = (p1 + p2) * (0.5f / sum);
+          tetra = true;
+          break;
+        }
+        expand_portal(s, v, v1, v2);
+        it++;
+      }
+    }
+  }
+}
+
 // MPR:601-819 func_mpr_contact (centre guess + portal discovery/refinement + penetration)
 template <int G>
 __device__ __noinline__ void dev_mpr_contact(const Ctx<G>& C, const PairPose& P, f3 normal_ws, bool& is_col, f3& normal, float& pen, f3& pos,
@@ -248,43 +293,7 @@ __device__ __noinline__ void dev_mpr_contact(const Ctx<G>& C, const PairPose& P,
       }
     }
   }
-  int res = discover_portal(C, s, P, ca, cb);
-  is_col = false; pos = f3(); normal = f3(); pen = 0.f;
-  tetra = false;  // true when s ends as the interior point + final portal, a tetrahedron around the origin (EPA seed)
-  if (res == 1) { is_col = true; normal = -normalized(s.v[0]); pos = (s.v1[1] + s.v2[1]) * 0.5f; }
-  else if (res == 2) { is_col = true; pen = norm(s.v[1]); normal = -normalized(s.v[1]); pos = (s.v1[1] + s.v2[1]) * 0.5f; }
-  else if (res == 0) {
-    while (true) {  // MPR:232-278 refine portal
-      const f3 dir = portal_dir(s);
-      if (dot(s.v[1], dir) > -CE) { res = 0; break; }
-      f3 v, v1, v2;
-      mpr_support(C, P, dir, v, v1, v2);
-      if (!(dot(v, dir) > -CE) || reach_tolerance(s, v, dir)) { res = -1; break; }
-      expand_portal(s, v, v1, v2);
-    }
-    if (res >= 0) {
-      int it = 0;
-      while (true) {  // MPR:338-423 find penetration
-        const f3 dir = portal_dir(s);
-        f3 v, v1, v2;
-        mpr_support(C, P, dir, v, v1, v2);
-        if (reach_tolerance(s, v, dir) || it > c_m.ccd_iterations) {
-          pen = dot(dir, s.v[1]);
-          normal = -dir;
-          is_col = true;
-          // MPR:281-316 find_pos: barycentric weights of the origin's projection on the portal
-          const float b1 = dot(cross(s.v[2], s.v[3]), dir), b2 = dot(cross(s.v[3], s.v[1]), dir), b3 = dot(cross(s.v[1], s.v[2]), dir);
-          const float sum = b1 + b2 + b3;
-          const f3 p1 = s.v1[1] * b1 + s.v1[2] * b2 + s.v1[3] * b3, p2 = s.v2[1] * b1 + s.v2[2] * b2 + s.v2[3] * b3;
-          pos = (p1 + p2) * (0.5f / sum);
-          tetra = true;
-          break;
-        }
-        expand_portal(s, v, v1, v2);
-        it++;
-      }
-    }
-  }
+  dev_mpr_from_centers(C, GroupSupport<G>{C, P}, ca, cb, is_col, normal, pen, pos, s, tetra);
 }
 
 // contacts found by one lane for one pair (registers / local memory)
@@ -441,6 +450,8 @@ __device__ __noinline__ void dev_pair_perturbed(const Ctx<G>& C, const PairDet& 
 
 #include "gsr_boxbox.cuh"  // BOX:100-785 func_box_box_contact (needs LaneContacts)
 
+#include "gsr_terrain.cuh"  // NP:346-517 func_contact_mpr_terrain (needs LaneContacts, dev_tolerance, dev_mpr_from_centers)
+
 // BOX:24-96 func_plane_box_contact
 template <int G>
 __device__ __noinline__ void dev_plane_box(const Ctx<G>& C, LaneContacts& out, int ga, int gb) {
@@ -472,7 +483,8 @@ __device__ __noinline__ void dev_plane_box(const Ctx<G>& C, LaneContacts& out, i
 }
 
 // narrow phase of up to G queued pairs; appends the contacts (unordered) to the staging records and returns the new count
-// BB: RigidOptions.box_box_detection and the pair table holds a box-box pair (gsr_boxbox.cuh)
+// BB: the "full" variant -- RigidOptions.box_box_detection with a box-box pair in the table (gsr_boxbox.cuh) or a height-field
+// terrain (gsr_terrain.cuh)
 template <int G, bool MPR, bool BB>
 __device__ int narrow_batch(const Ctx<G>& C, const int* queue, int n_batch, int n_staged) {
   const int lane = C.lane;
@@ -488,10 +500,12 @@ __device__ int narrow_batch(const Ctx<G>& C, const int* queue, int n_batch, int 
     if (GM(g_type[ga0]) > GM(g_type[gb0])) { ga = gb0; gb = ga0; }
     // convex specialisations (NP:2135-2189): their contacts follow those of the convex-convex pass in the contact list
     const bool is_plane_box = GM(g_type[ga]) == GEOM_PLANE && GM(g_type[gb]) == GEOM_BOX;
-    const bool is_box_box = BB && GM(g_type[ga]) == GEOM_BOX && GM(g_type[gb]) == GEOM_BOX;
-    plane_box = is_plane_box || is_box_box;
+    const bool is_box_box = BB && c_m.box_box_detection && GM(g_type[ga]) == GEOM_BOX && GM(g_type[gb]) == GEOM_BOX;
+    const bool is_terrain = BB && GM(g_type[gb]) == GEOM_TERRAIN;  // NP:2193-2239: after the specialisations
+    plane_box = is_terrain ? 2 : ((is_plane_box || is_box_box) ? 1 : 0);
     if (is_plane_box) dev_plane_box(C, out, ga, gb);
     else if (is_box_box) { if constexpr (BB) dev_box_box(C, out, ga, gb); }
+    else if (is_terrain) { if constexpr (BB) dev_terrain(C, out, ga, gb); }
     else { D.ga = ga; D.gb = gb; D.p = p; dev_pair_det0<G, MPR>(C, out, D); }
   }
   // ---- perturbed detections: task (pair k of the colliding multi-contact pairs, i_det) -> lane, results through the

@@ -45,7 +45,9 @@ static inline int gsr_fill_model(GsrSpec* h) {
   DevModel& m = h->hm;
   const float* keep_verts = m.verts; const float* keep_support = m.support_v; const int* keep_svid = m.support_vid; const int* keep_pairs = m.pairs; const int* keep_pidx = m.pair_idx;
   const unsigned short* keep_fac = m.fac_tasks;
+  const float* keep_terrain = m.terrain_hf;
   memset(&m, 0, sizeof(m));
+  m.terrain_hf = keep_terrain;
   m.verts = keep_verts; m.support_v = keep_support; m.support_vid = keep_svid; m.pairs = keep_pairs; m.pair_idx = keep_pidx; m.fac_tasks = keep_fac;
   auto S = [&](const char* k, double d) { auto it = h->s.find(k); return it == h->s.end() ? d : it->second; };
   m.nL = (int)S("n_links", 0); m.nJ = (int)S("n_joints", 0); m.nD = (int)S("n_dofs", 0); m.nQ = (int)S("n_qs", 0);
@@ -170,17 +172,27 @@ static inline int gsr_fill_model(GsrSpec* h) {
   }
 
   // has_cc: any valid pair that is not plane-box (collider.py:449-459) -> contacts are x-sorted (collider.py:804-808)
+  {  // height-field terrain tables (model arrays terrain_rc / terrain_scale / terrain_xyz_maxmin; the heights go to the device in gsr_model_commit)
+    auto rc = h->i.find("terrain_rc");
+    auto sc = h->f.find("terrain_scale");
+    auto mm = h->f.find("terrain_xyz_maxmin");
+    if (rc != h->i.end() && rc->second.size() == 2 && sc != h->f.end() && sc->second.size() == 2 && mm != h->f.end() && mm->second.size() == 6) {
+      m.terrain_rows = rc->second[0]; m.terrain_cols = rc->second[1]; m.terrain_hs = sc->second[0];
+      for (int k = 0; k < 6; k++) m.terrain_maxmin[k] = mm->second[k];
+    }
+  }
   m.has_cc = 0;
   m.has_mpr = 0;
   m.has_box_box = 0;
   const bool box_box_detection = h->S("cfg_box_box_detection", 0) != 0;  // options/solvers.py:511
+  m.box_box_detection = box_box_detection ? 1 : 0;
   {
     const int* pr = IV("pairs", 2 * (size_t)m.nP);
     for (int p = 0; p < m.nP; p++) {
       int ta = m.g_type[pr[2 * p]], tb = m.g_type[pr[2 * p + 1]];
       if (ta > tb) { int t = ta; ta = tb; tb = t; }
       const bool box_box = box_box_detection && ta == GEOM_BOX && tb == GEOM_BOX;  // specialised like plane-box (collider.py:456-459)
-      if (box_box) { m.has_box_box = 1; continue; }
+      if (box_box || tb == GEOM_TERRAIN) { m.has_box_box = 1; continue; }  // terrain: not convex, its own narrow-phase pass
       if (!(ta == GEOM_PLANE && tb == GEOM_BOX)) m.has_cc = 1;
       const bool analytic = (ta == GEOM_CAPSULE && tb == GEOM_CAPSULE) || (ta == GEOM_SPHERE && tb == GEOM_CAPSULE) || (ta == GEOM_CAPSULE && tb == GEOM_SPHERE);
       if (ta != GEOM_PLANE && tb != GEOM_PLANE && !analytic) m.has_mpr = 1;

@@ -30,7 +30,7 @@
 #define GSR_MAX_DYN_EQ 8      /* RigidOptions.max_dynamic_constraints (options/solvers.py) */
 #define GSR_DYN_EQ_WORDS 20
 
-enum { GEOM_PLANE = 0, GEOM_SPHERE = 1, GEOM_ELLIPSOID = 2, GEOM_CYLINDER = 3, GEOM_CAPSULE = 4, GEOM_BOX = 5, GEOM_MESH = 6 };
+enum { GEOM_PLANE = 0, GEOM_SPHERE = 1, GEOM_ELLIPSOID = 2, GEOM_CYLINDER = 3, GEOM_CAPSULE = 4, GEOM_BOX = 5, GEOM_MESH = 6, GEOM_TERRAIN = 7 };
 enum { JOINT_FIXED = 0, JOINT_REVOLUTE = 1, JOINT_PRISMATIC = 2, JOINT_SPHERICAL = 3, JOINT_FREE = 4 };
 enum { EQ_CONNECT = 0, EQ_WELD = 1, EQ_JOINT = 2 };
 enum { CTRL_POSITION = 0, CTRL_VELOCITY = 1, CTRL_FORCE = 2 };
@@ -46,7 +46,13 @@ struct DevModel {
   int iterations, ls_iterations, integrator, solver_type;
   int noslip_iterations;  // constraint/noslip.py post-solver (0 = off)
   int has_mpr;            // any valid pair that needs MPR / EPA (neither a plane pair nor an analytic capsule pair): selects the kernel variant
-  int has_box_box;        // RigidOptions.box_box_detection and a valid box-box pair: the variant with func_box_box_contact compiled in
+  int has_box_box;        // a box-box pair under RigidOptions.box_box_detection or a terrain pair: the "full" variant (func_box_box_contact,
+                          // func_contact_mpr_terrain compiled in)
+  int box_box_detection;  // options/solvers.py:511
+  // height-field terrain (collider.py:541-561): scaled heights (rows x cols, device), cell size, [x_max, y_max, z_max, x_min, y_min, z_min - 1]
+  const float* terrain_hf;
+  int terrain_rows, terrain_cols;
+  float terrain_hs, terrain_maxmin[6];
   int phase_barriers;     // bit k: CTA barrier k of k_step (0 after the record load, 1 dynamics, 2 collision, 3 constraints, 4 integration)
   int gjk_fallback;       // exact-penetration fallback after MPR (narrowphase.py:726-733); 0 keeps MPR's answer
   float noslip_tolerance;

@@ -320,7 +320,7 @@ class ModelBuilder:
         nV = 0
         for g in geoms:
             v = np.asarray(g["verts"], np.float64)
-            if g["type"] == GEOM_TYPE.PLANE or len(v) < 4:
+            if g["type"] in (GEOM_TYPE.PLANE, GEOM_TYPE.TERRAIN) or len(v) < 4:
                 center = v.mean(axis=0)
             else:
                 vol, com, _ = meshio.mesh_mass_properties(v, np.asarray(g["faces"]))
@@ -334,6 +334,17 @@ class ModelBuilder:
             vend.append(nV)
             verts_all.append(v)
         m.geoms_center = np.array(centers, np.float64).reshape(nG, 3)
+        # height-field terrain (collider.py:541-561): at most one, as in the reference (the tables live in collider_info)
+        ter = [g for g in geoms if g["type"] == GEOM_TYPE.TERRAIN]
+        if len(ter) > 1:
+            raise ValueError("only one Terrain entity per scene (collider.py:541-561 keeps a single height field)")
+        if ter:
+            hf = np.asarray(ter[0]["terrain"]["hf"], np.float64)
+            hs, vs = ter[0]["terrain"]["scale"]
+            m.terrain_hf = hf.copy()
+            m.terrain_rc = np.array(hf.shape, I32)
+            m.terrain_scale = np.array([hs, vs], np.float64)
+            m.terrain_xyz_maxmin = np.array([hf.shape[0] * hs, hf.shape[1] * hs, hf.max(), 0.0, 0.0, hf.min() - 1.0], np.float64)
         m.geoms_init_aabb = np.array(aabbs, np.float64).reshape(nG, 8, 3)
         m.geoms_vert_start = np.array(vstart, I32).reshape(nG)
         m.geoms_vert_end = np.array(vend, I32).reshape(nG)
@@ -498,6 +509,22 @@ def box_l_infos(size, pos, quat=(1.0, 0.0, 0.0, 0.0), fixed=False):
         j["init_qpos"] = np.concatenate([np.asarray(pos, float), np.asarray(quat, float)])
         joints = [j]
     return [dict(name="box_baselink", pos=np.asarray(pos, float), quat=np.asarray(quat, float), parent_idx=-1, joints=joints,
+                 geoms=[geom], inertial_mass=None, inertial_pos=None, inertial_quat=None, inertial_i=None, invweight=None)]
+
+
+def terrain_l_infos(height_field, horizontal_scale, vertical_scale, pos, quat=(1.0, 0.0, 0.0, 0.0)):
+    """Fixed height-field terrain entity (rigid_entity.py `_load_terrain`; collider.py:541-561 keeps the scaled heights, the
+    grid shape and the scales for func_contact_mpr_terrain).  The geom's vertices are the grid points (AABB, centre)."""
+    hf = np.asarray(height_field, np.float64)
+    if hf.ndim != 2 or hf.shape[0] < 2 or hf.shape[1] < 2:
+        raise ValueError("Terrain height_field must be a 2-D array of at least 2 x 2 samples")
+    hs, vs = float(horizontal_scale), float(vertical_scale)
+    rr, cc = np.meshgrid(np.arange(hf.shape[0]) * hs, np.arange(hf.shape[1]) * hs, indexing="ij")
+    verts = np.stack([rr, cc, hf * vs], axis=-1).reshape(-1, 3)
+    geom = dict(type=GEOM_TYPE.TERRAIN, pos=np.zeros(3), quat=np.array([1.0, 0, 0, 0]), data=np.zeros(7), verts=verts,
+                faces=np.zeros((0, 3), np.int64), friction=1.0, contype=0xFFFF, conaffinity=0xFFFF,
+                sol_params=np.array([0.0, 1.0, 0.9, 0.95, 0.001, 0.5, 2.0]), terrain=dict(hf=hf * vs, scale=(hs, vs)))
+    return [dict(name="terrain_baselink", pos=np.asarray(pos, float), quat=np.asarray(quat, float), parent_idx=-1, joints=[],
                  geoms=[geom], inertial_mass=None, inertial_pos=None, inertial_quat=None, inertial_i=None, invweight=None)]
 
 

@@ -31,6 +31,17 @@ class Sphere(Morph):
 
 
 @dataclass
+class Terrain(Morph):
+    """Height-field terrain (genesis/options/morphs.py:916+, the `height_field` form): `height_field[r, c]` in units of
+    vertical_scale at x = r * horizontal_scale, y = c * horizontal_scale in the terrain's frame.  The procedural sub-terrain
+    generators of the reference (utils/terrain.py) produce such an array and are outside the hot-path scope."""
+    height_field: object = None
+    horizontal_scale: float = 0.25
+    vertical_scale: float = 0.005
+    fixed: bool = True
+
+
+@dataclass
 class MJCF(Morph):
     file: str = ""
     scale: float = 1.0

@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 from .constants import CTRL_MODE, ErrorCode
-from .model import ModelBuilder, box_l_infos, parse_mjcf, parse_urdf, plane_l_infos, sphere_l_infos
+from .model import ModelBuilder, box_l_infos, parse_mjcf, parse_urdf, plane_l_infos, sphere_l_infos, terrain_l_infos
 from .model.compiled import load_compiled, resolve_asset
 from . import morphs as _morphs
 
@@ -31,6 +31,9 @@ def _morph_to_infos(morph):
         return plane_l_infos(morph.pos or (0, 0, 0), morph.quat or (1, 0, 0, 0), morph.normal, morph.plane_size), [], False, False
     if isinstance(morph, _morphs.Box):
         return box_l_infos(morph.size, morph.pos or (0, 0, 0), morph.quat or (1, 0, 0, 0), morph.fixed), [], False, False
+    if isinstance(morph, _morphs.Terrain):
+        return terrain_l_infos(morph.height_field, morph.horizontal_scale, morph.vertical_scale, morph.pos or (0, 0, 0),
+                               morph.quat or (1, 0, 0, 0)), [], False, False
     if isinstance(morph, _morphs.Sphere):
         return sphere_l_infos(morph.radius, morph.pos or (0, 0, 0), morph.fixed), [], False, False
     if isinstance(morph, (_morphs.MJCF, _morphs.URDF)):
@@ -123,8 +126,8 @@ class RigidSolver:
         o = self._options
         if (o.batch_dofs_info or o.batch_links_info) and self.tuning.get("group_size") == 1:
             raise GenesisException("batch_dofs_info / batch_links_info need the lane-group step kernel (unset GSR_GROUP_SIZE=1).")
-        if o.box_box_detection and self.tuning.get("group_size") == 1:
-            raise GenesisException("box_box_detection needs the lane-group step kernel (unset GSR_GROUP_SIZE=1).")
+        if self.tuning.get("group_size") == 1 and (o.box_box_detection or any(isinstance(e.morph, _morphs.Terrain) for e in self._entities)):
+            raise GenesisException("box_box_detection / Terrain need the lane-group step kernel (unset GSR_GROUP_SIZE=1).")
         if o.use_contact_island or o.use_hibernation or o.enable_mujoco_compatibility or o.use_gjk_collision:
             raise GenesisException(
                 "contact islands, hibernation, mujoco-compatibility and GJK-first collision are outside the "

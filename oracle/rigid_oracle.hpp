@@ -33,7 +33,7 @@
 
 namespace orc {
 
-enum { GEOM_PLANE = 0, GEOM_SPHERE = 1, GEOM_ELLIPSOID = 2, GEOM_CYLINDER = 3, GEOM_CAPSULE = 4, GEOM_BOX = 5, GEOM_MESH = 6 };
+enum { GEOM_PLANE = 0, GEOM_SPHERE = 1, GEOM_ELLIPSOID = 2, GEOM_CYLINDER = 3, GEOM_CAPSULE = 4, GEOM_BOX = 5, GEOM_MESH = 6, GEOM_TERRAIN = 7 };
 enum { JOINT_FIXED = 0, JOINT_REVOLUTE = 1, JOINT_PRISMATIC = 2, JOINT_SPHERICAL = 3, JOINT_FREE = 4 };
 enum { EQ_CONNECT = 0, EQ_WELD = 1, EQ_JOINT = 2 };
 enum { CTRL_POSITION = 0, CTRL_VELOCITY = 1, CTRL_FORCE = 2 };
@@ -66,6 +66,10 @@ struct Model {
   std::vector<int> eq_type, eq_obj1, eq_obj2;
   std::vector<T> eq_data, eq_sol_params;
   std::vector<int> pairs, pair_idx;
+  // height-field terrain (collider.py:541-561): heights already scaled (rows x cols), grid shape, (horizontal, vertical) scale,
+  // [x_max, y_max, z_max, x_min, y_min, z_min - 1] in the terrain's frame
+  std::vector<T> terrain_hf, terrain_scale, terrain_xyz_maxmin;
+  std::vector<int> terrain_rc;
   T meaninertia = 1;
 
   static std::vector<T> cv(const std::vector<double>& v) { return std::vector<T>(v.begin(), v.end()); }
@@ -97,6 +101,7 @@ struct Model {
     if (r.i.count("support_vid")) support_vid = r.i.at("support_vid");
     LI(eq_type); LI(eq_obj1); LI(eq_obj2); LF(eq_data); LF(eq_sol_params);
     LI(pairs); LI(pair_idx);
+    LF(terrain_hf); LF(terrain_scale); LF(terrain_xyz_maxmin); LI(terrain_rc);
 #undef LI
 #undef LF
   }
@@ -742,9 +747,21 @@ struct Oracle {
     return best;
   }
 
+  // the prism of the height field under test (collider_state.prism): bottom triangle [0..3), top triangle [3..6), terrain frame
+  static V* terrain_prism() { static thread_local V prism[6]; return prism; }
+  // SF:268-285 _func_support_prism
+  V support_prism(const V& d) {
+    const V* prism = terrain_prism();
+    int istart = d.z < 0 ? 0 : 3, ibest = istart;
+    T best = prism[istart].dot(d);
+    for (int i = istart + 1; i < istart + 3; i++) { T dot = prism[i].dot(d); if (dot > best) { ibest = i; best = dot; } }
+    return prism[ibest];
+  }
+
   // MPR:146-176 support_driver (+ SF:183-309)
   V support_driver(const V& d, int g, const V& pos, const Q& quat) {
     int type = m.geoms_type[g];
+    if (type == GEOM_TERRAIN) return support_prism(d);  // MPR:168-172: does not depend on pos / quat
     if (type == GEOM_SPHERE) return pos + d * m.geoms_data[7 * g];
     if (type == GEOM_ELLIPSOID) {
       T a = m.geoms_data[7 * g], b = m.geoms_data[7 * g + 1], c = m.geoms_data[7 * g + 2];
@@ -916,6 +933,11 @@ struct Oracle {
                    Simplex& last_simplex, bool& last_simplex_valid) {
     V ca, cb;
     guess_centers(ga, gb, pa, qa, pb, qb, normal_ws, ca, cb);
+    mpr_contact_from_centers(ga, gb, ca, cb, pa, qa, pb, qb, is_col, normal, pen, pos, last_simplex, last_simplex_valid);
+  }
+  // MPR:686-765 func_mpr_contact_from_centers
+  void mpr_contact_from_centers(int ga, int gb, const V& ca, const V& cb, const V& pa, const Q& qa, const V& pb, const Q& qb, bool& is_col,
+                                V& normal, T& pen, V& pos, Simplex& last_simplex, bool& last_simplex_valid) {
     Simplex s;
     int res = discover_portal(s, ga, gb, ca, cb, pa, qa, pb, qb);
     is_col = false; pos = V(); normal = V(); pen = 0;
@@ -1555,6 +1577,7 @@ struct Oracle {
   void convex_convex_contact(Env<T>& e, int ga, int gb) {
     if (m.geoms_type[ga] == GEOM_PLANE && m.geoms_type[gb] == GEOM_BOX) return;
     if (cfg.box_box_detection && m.geoms_type[ga] == GEOM_BOX && m.geoms_type[gb] == GEOM_BOX) return;  // NP:2028-2032
+    if (m.geoms_type[gb] == GEOM_TERRAIN) return;  // NP:2024-2027: terrain pairs go to func_narrow_phase_any_vs_terrain
     bool multi_contact = cfg.enable_multi_contact && m.geoms_type[ga] != GEOM_SPHERE && m.geoms_type[ga] != GEOM_ELLIPSOID &&
                          m.geoms_type[gb] != GEOM_SPHERE && m.geoms_type[gb] != GEOM_ELLIPSOID;
     T tolerance = compute_tolerance(ga, gb, (T)cfg.mc_tolerance);
@@ -1697,6 +1720,80 @@ struct Oracle {
     }
   }
 
+  // NP:346-497 func_contact_mpr_terrain: geom `ga` against the prisms of the height-field cells under its bounding box
+  void terrain_contact(Env<T>& e, int ga, int gb) {
+    const V ga_pos = e.g_pos[ga], gb_pos = e.g_pos[gb];
+    const Q ga_quat = e.g_quat[ga], gb_quat = e.g_quat[gb];
+    const T margin = 0;
+    const T tolerance = compute_tolerance(ga, gb, (T)cfg.mc_tolerance);
+    // into the terrain's frame (gu.qd_transform_pos_quat_by_trans_quat with the inverse terrain rotation)
+    const Q inv_b = inv_quat(gb_quat);
+    const V pa = transform_by_quat(ga_pos - gb_pos, inv_b);
+    const Q qa = transform_quat_by_quat(ga_quat, inv_b);
+    const V pb;
+    const Q qb;
+    const V center_a = transform_by_trans_quat(m.v3(m.geoms_center, ga), pa, qa);
+    const std::vector<T>& tmm = m.terrain_xyz_maxmin;
+    V* prism = terrain_prism();
+    T xyz[6];
+    for (int i_axis = 0; i_axis < 3; i_axis++)
+      for (int i_m = 0; i_m < 2; i_m++) {
+        V direction;
+        direction[i_axis] = i_m == 0 ? T(1) : T(-1);
+        const V v1 = support_driver(direction, ga, pa, qa);
+        xyz[3 * i_m + i_axis] = v1[i_axis];
+      }
+    bool is_return = false;
+    for (int i = 0; i < 3; i++) {
+      prism[i].z = tmm[5];
+      if (tmm[i] < xyz[i + 3] - margin || tmm[i + 3] > xyz[i] + margin) is_return = true;
+    }
+    if (is_return) return;
+    const T sh = m.terrain_scale[0];
+    int r_min = (int)std::floor((xyz[3] - tmm[3]) / sh), r_max = (int)std::ceil((xyz[0] - tmm[3]) / sh);
+    int c_min = (int)std::floor((xyz[4] - tmm[4]) / sh), c_max = (int)std::ceil((xyz[1] - tmm[4]) / sh);
+    r_min = std::max(0, r_min); c_min = std::max(0, c_min);
+    r_max = std::min(m.terrain_rc[0] - 1, r_max); c_max = std::min(m.terrain_rc[1] - 1, c_max);
+    const int ncols = m.terrain_rc[1];
+    int n_con = 0;
+    for (int r = r_min; r < r_max; r++) {
+      int nvert = 0;
+      for (int c = c_min; c <= c_max; c++)
+        for (int i = 0; i < 2; i++) {
+          if (n_con >= m.n_contacts_per_pair) continue;
+          nvert++;
+          {  // NP:499-517 func_add_prism_vert
+            const T x = sh * (r + i) + tmm[3], y = sh * c + tmm[4], z = m.terrain_hf[(size_t)(r + i) * ncols + c] + margin;
+            prism[0] = prism[1]; prism[1] = prism[2]; prism[3] = prism[4]; prism[4] = prism[5];
+            prism[2].x = x; prism[5].x = x; prism[2].y = y; prism[5].y = y; prism[5].z = z;
+          }
+          if (nvert > 2 && (prism[3].z >= xyz[5] || prism[4].z >= xyz[5] || prism[5].z >= xyz[5])) {
+            V center_b;
+            for (int k = 0; k < 6; k++) center_b = center_b + prism[k];
+            center_b = center_b / T(6);
+            bool is_col, sv;
+            V normal, cpos;
+            T pen;
+            Simplex simplex;
+            mpr_contact_from_centers(ga, gb, center_a, center_b, pa, qa, pb, qb, is_col, normal, pen, cpos, simplex, sv);
+            if (is_col) {
+              normal = transform_by_quat(normal, gb_quat);
+              cpos = transform_by_quat(cpos, gb_quat) + gb_pos;
+              bool valid = true;
+              const int i_c = e.n_contacts;
+              for (int j = 0; j < n_con; j++)
+                if (i_c - j - 1 >= 0 && (cpos - e.contacts[i_c - j - 1].pos).norm() < tolerance) { valid = false; break; }
+              if (valid) {
+                const int i_pair = m.pair_idx[(ga > gb ? gb : ga) * m.nG + (ga > gb ? ga : gb)];
+                add_contact(e, ga, gb, normal, cpos, pen, i_pair);
+                n_con++;
+              }
+            }
+          }
+        }
+    }
+  }
+
   // CT:439-538 func_sort_contacts (stable insertion sort of pair groups by x of the group's first contact)
   void sort_contacts(Env<T>& e) {
     int n = e.n_contacts;
@@ -1728,7 +1825,7 @@ struct Oracle {
       int ta = m.geoms_type[m.pairs[2 * p]], tb = m.geoms_type[m.pairs[2 * p + 1]];
       if (ta > tb) std::swap(ta, tb);
       const bool specialized = (ta == GEOM_PLANE && tb == GEOM_BOX) || (cfg.box_box_detection && ta == GEOM_BOX && tb == GEOM_BOX);  // collider.py:456-459
-      if (!specialized) has_cc = true;
+      if (!specialized && tb != GEOM_TERRAIN) has_cc = true;  // terrain is not convex (collider.py:449-459)
     }
     for (int i = 0; i < e.n_broad; i++) {  // NP:1989-2060
       int ga = e.broad_pairs[2 * i], gb = e.broad_pairs[2 * i + 1];
@@ -1740,6 +1837,11 @@ struct Oracle {
       if (m.geoms_type[ga] > m.geoms_type[gb]) std::swap(ga, gb);
       if (m.geoms_type[ga] == GEOM_PLANE && m.geoms_type[gb] == GEOM_BOX) plane_box_contact(e, ga, gb, i);
       if (cfg.box_box_detection && m.geoms_type[ga] == GEOM_BOX && m.geoms_type[gb] == GEOM_BOX) box_box_contact(e, ga, gb, i);  // NP:2175-2189
+    }
+    for (int i = 0; i < e.n_broad; i++) {  // NP:2193-2239 func_narrow_phase_any_vs_terrain
+      int ga = e.broad_pairs[2 * i], gb = e.broad_pairs[2 * i + 1];
+      if (m.geoms_type[ga] == GEOM_TERRAIN) std::swap(ga, gb);
+      if (m.geoms_type[gb] == GEOM_TERRAIN) terrain_contact(e, ga, gb);
     }
     if (has_cc && cfg.sort_contacts) sort_contacts(e);  // collider.py:804-808 (GPU split path)
   }

@@ -241,6 +241,30 @@ def case_boxbox_pile():
     return s, m, dict(qpos=np.asarray(m.qpos0, float)[None].copy(), vel=np.zeros((1, m.n_dofs))), 4, dict(box_box_detection=True)
 
 
+def terrain_height_field(rows=16, cols=14, seed=11):
+    """A bumpy height field in units of vertical_scale = 0.005 m: smooth hills plus integer noise (deterministic)."""
+    r, c = np.meshgrid(np.arange(rows), np.arange(cols), indexing="ij")
+    hills = 30.0 * np.sin(0.55 * r) * np.cos(0.4 * c) + 12.0 * np.cos(0.9 * r + 0.3 * c)
+    return np.round(hills + _rng(seed).integers(-4, 5, (rows, cols))).astype(np.int32) + 40
+
+
+def terrain_morphs():
+    """Height-field terrain (narrowphase.py:346-517 func_contact_mpr_terrain) under a box, a sphere and a Go2-sized capsule."""
+    return [gs.morphs.Terrain(height_field=terrain_height_field(), horizontal_scale=0.25, vertical_scale=0.005, pos=(-1.0, -1.2, 0.0)),
+            gs.morphs.Box(size=(0.3, 0.22, 0.12), pos=(0.1, 0.0, 0.5), quat=(0.96, 0.1, -0.2, 0.15)),
+            gs.morphs.Sphere(radius=0.09, pos=(0.8, 0.6, 0.5)), gs.morphs.Box(size=(0.5, 0.08, 0.08), pos=(-0.3, 0.9, 0.5), quat=(0.9, 0.3, 0.1, -0.3))]
+
+
+def case_terrain_primitives():
+    s, m = _scene(morphs=terrain_morphs())
+    q = np.asarray(m.qpos0, float)[None].repeat(2, 0).copy()
+    for k in range(3):
+        q[:, 7 * k + 3: 7 * k + 7] /= np.linalg.norm(q[:, 7 * k + 3: 7 * k + 7], axis=1, keepdims=True)
+    q[1, 0::7][:3] += [0.13, -0.21, 0.17]; q[1, 1::7][:3] += [0.06, 0.11, -0.14]   # a second set of cells
+    q[:, 2::7] = [[0.30, 0.345, 0.165], [0.315, 0.335, 0.175]]                      # about a centimetre above the ground
+    return s, m, dict(qpos=q, vel=np.zeros((2, m.n_dofs))), 10, {}
+
+
 def case_go2_drop_sap():
     """The same drop with the sweep-and-prune broad phase of the CPU backend (broadphase.py:142-396): the insertion sort is warm-started
     from the previous step, the candidate pairs come out in sweep order."""

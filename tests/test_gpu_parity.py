@@ -489,6 +489,34 @@ def test_box_box_detection_contact_records_and_stack():
     assert float(ent.get_dofs_velocity().abs().max()) <= 0.5
 
 
+def test_go2_on_height_field_terrain():
+    """Height-field terrain (scope row f4, narrowphase.py:346-517): Go2 robots with randomised joints dropped on a bumpy height field
+    follow the oracle (itself pinned to the reference's func_contact_mpr_terrain by tests/golden/ref_terrain_primitives.npz): same
+    contact sets, trajectories within the contact tolerances, nobody falls through the ground."""
+    import ref_cases
+
+    B, K = 32, 80
+    hf = ref_cases.terrain_height_field(rows=24, cols=24, seed=5)
+    scene, robot = make_go2(B, seed=9, terrain=(hf, 0.25, 0.004, (-3.0, -3.0, 0.0)))
+    s = scene.rigid_solver
+    q = s.field("qpos").clone()
+    g = torch.Generator(device="cpu").manual_seed(1)
+    q[:, 0:2] += (1.5 * (torch.rand((B, 2), generator=g) - 0.5)).to(gs.device)   # different cells under every robot
+    q[:, 2] += 0.25                                                            # above the highest bump
+    s.set_qpos(q)
+    orc = mirror_oracle(scene)
+    for _ in range(K):
+        scene.step()
+    orc.step(K)
+    dq = np.abs(gpu_field(scene, "qpos") - orc.qpos()).max(axis=1)
+    assert (dq <= TRAJ_QPOS_CONTACT).mean() >= 0.9, f"qpos outliers: {np.sort(dq)[-5:]}"
+    a, b = contact_set(scene, B), contact_set(orc, B)
+    assert len(b) >= 2 * B and jaccard(a, b) >= 0.95, (len(a), len(b), jaccard(a, b))
+    assert int(s.field("errno_").max()) == 0
+    z = gpu_field(scene, "qpos")[:, 2]
+    assert (z > 0.05).all() and (z < 1.0).all()  # the trunk rests on the ground (heights 0.05 .. 0.35 m), it has not fallen through
+
+
 def test_double_pendulum_link_accelerations():
     """The reference's double pendulum (tests/test_rigid_physics.py:230-297, 955-1020: massless arms, fixed links kept, CG +
     Euler) on the CUDA path: a 50-step swing and the link accelerations (`get_links_acc_ang`, `cacc_lin`) against the oracle,
