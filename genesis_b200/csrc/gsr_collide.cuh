@@ -333,9 +333,10 @@ struct PairDet {
 };
 
 // one detection at the (possibly perturbed) poses in P: analytic capsule pairs, plane support query, or MPR with warm start
-// MPR = false compiles the portal refinement and the EPA fallback out: models without a convex-convex pair that needs them
+// MPR is a level: 0 compiles the portal refinement and the GJK / EPA fallback out, 1 = the default, 2 = the full variant (GJK-first mode)
+// MPR = 0 compiles the portal refinement and the EPA fallback out: models without a convex-convex pair that needs them
 // (gsr_host.h has_mpr; e.g. a robot without self-collision on a plane) run a kernel a few thousand instructions shorter
-template <int G, bool MPR>
+template <int G, int MPR>
 __device__ __forceinline__ void dev_detect(const Ctx<G>& C, const PairDet& D, const PairPose& P, int i_det, bool& is_col, f3& normal, float& pen, f3& cpos) {
   const float EPS = c_m.eps;
   const int ga = D.ga, gb = D.gb;
@@ -353,35 +354,42 @@ __device__ __forceinline__ void dev_detect(const Ctx<G>& C, const PairDet& D, co
   } else if constexpr (!MPR) {
     is_col = false; normal = f3(); pen = 0.f; cpos = f3();  // unreachable: the host launches this variant only without such pairs
   } else {
-    // the perturbed detections read the normal the unperturbed one has just cached (same as the sequential reference flow)
-    int* cvalid = reinterpret_cast<int*>(C.cache) + c_h.cache_valid;
-    f3 normal_ws;
-    const bool valid = (cvalid[D.p >> 5] >> (D.p & 31)) & 1;
-    if (valid) normal_ws = ld3(C.cache, D.p);
-    const bool guess = fabsf(normal_ws.x) > EPS || fabsf(normal_ws.y) > EPS || fabsf(normal_ws.z) > EPS;
-    Simplex sx;
-    bool tetra = false, guess_used = guess;
-    dev_mpr_contact(C, P, normal_ws, is_col, normal, pen, cpos, sx, tetra);
-    if (i_det == 0 && !is_col && guess) { dev_mpr_contact(C, P, f3(), is_col, normal, pen, cpos, sx, tetra); guess_used = false; }
-    // NP:726-733: MPR's answer is replaced by the exact one when the overlap is large or no direction was cached
-    if (c_m.gjk_fallback && is_col && pen > D.tolerance && (!guess_used || c_m.mc_tolerance * pen >= 0.25f * D.tolerance)) {
-      if (c_m.gjk_fallback == 2) {  // round-1 approximation (EPA seeded with MPR's final portal), kept for A/B runs
-        if (tetra) {
-          const GroupSupport<G> sup{C, P};
-          f3 n2, c2;
-          float p2 = 0.f;
-          if (epa_penetration(sx.v, sx.v1, sx.v2, sup, n2, p2, c2)) { normal = n2; pen = p2; cpos = c2; is_col = p2 > 0.f; }
+    bool run_gjk = false;  // RigidOptions.use_gjk_collision: no MPR at all (NP:604-607); compiled into the full variants (level 2) only
+    if constexpr (MPR == 2) run_gjk = c_m.use_gjk != 0;
+    if (!run_gjk) {
+      // the perturbed detections read the normal the unperturbed one has just cached (same as the sequential reference flow)
+      int* cvalid = reinterpret_cast<int*>(C.cache) + c_h.cache_valid;
+      f3 normal_ws;
+      const bool valid = (cvalid[D.p >> 5] >> (D.p & 31)) & 1;
+      if (valid) normal_ws = ld3(C.cache, D.p);
+      const bool guess = fabsf(normal_ws.x) > EPS || fabsf(normal_ws.y) > EPS || fabsf(normal_ws.z) > EPS;
+      Simplex sx;
+      bool tetra = false, guess_used = guess;
+      dev_mpr_contact(C, P, normal_ws, is_col, normal, pen, cpos, sx, tetra);
+      if (i_det == 0 && !is_col && guess) { dev_mpr_contact(C, P, f3(), is_col, normal, pen, cpos, sx, tetra); guess_used = false; }
+      // NP:726-733: MPR's answer is replaced by the exact one when the overlap is large or no direction was cached
+      if (c_m.gjk_fallback && is_col && pen > D.tolerance && (!guess_used || c_m.mc_tolerance * pen >= 0.25f * D.tolerance)) {
+        if (c_m.gjk_fallback == 2) {  // round-1 approximation (EPA seeded with MPR's final portal), kept for A/B runs
+          if (tetra) {
+            const GroupSupport<G> sup{C, P};
+            f3 n2, c2;
+            float p2 = 0.f;
+            if (epa_penetration(sx.v, sx.v1, sx.v2, sup, n2, p2, c2)) { normal = n2; pen = p2; cpos = c2; is_col = p2 > 0.f; }
+          }
+        } else {
+          run_gjk = true;
         }
-      } else {  // the reference's path: a fresh safe-GJK query and safe EPA from its tetrahedron (gsr_gjk.cuh)
-        const GroupGeo<G> geo{C, P, D.ta, D.tb};
-        gjk_contact(geo, is_col, normal, pen, cpos);
       }
+    }
+    if (run_gjk) {  // the reference's path: a fresh safe-GJK query and safe EPA from its tetrahedron (gsr_gjk.cuh)
+      const GroupGeo<G> geo{C, P, D.ta, D.tb};
+      gjk_contact(geo, is_col, normal, pen, cpos);
     }
   }
 }
 
 // unperturbed detection of a pair: contact 0, warm-start cache update, perturbation axes
-template <int G, bool MPR>
+template <int G, int MPR>
 __device__ __noinline__ void dev_pair_det0(const Ctx<G>& C, LaneContacts& out, PairDet& D) {
   const float EPS = c_m.eps;
   const int ga = D.ga, gb = D.gb;
@@ -426,7 +434,7 @@ __device__ __noinline__ void dev_pair_det0(const Ctx<G>& C, LaneContacts& out, P
 }
 
 // perturbed detection i_det (1..4) of a colliding pair, corrected back to the unperturbed frame (NP:889-936)
-template <int G, bool MPR>
+template <int G, int MPR>
 __device__ __noinline__ void dev_pair_perturbed(const Ctx<G>& C, const PairDet& D, int i_det, bool& is_col, f3& normal, float& pen, f3& cpos) {
   const float EPS = c_m.eps;
   const f3 axis = D.axis_0 * (float)(2 * (i_det % 2) - 1) + D.axis_1 * (float)(1 - 2 * ((i_det / 2) % 2));
@@ -506,7 +514,7 @@ __device__ int narrow_batch(const Ctx<G>& C, const int* queue, int n_batch, int 
     if (is_plane_box) dev_plane_box(C, out, ga, gb);
     else if (is_box_box) { if constexpr (BB) dev_box_box(C, out, ga, gb); }
     else if (is_terrain) { if constexpr (BB) dev_terrain(C, out, ga, gb); }
-    else { D.ga = ga; D.gb = gb; D.p = p; dev_pair_det0<G, MPR>(C, out, D); }
+    else { D.ga = ga; D.gb = gb; D.p = p; dev_pair_det0<G, (MPR ? (BB ? 2 : 1) : 0)>(C, out, D); }
   }
   // ---- perturbed detections: task (pair k of the colliding multi-contact pairs, i_det) -> lane, results through the
   // staging area behind the contact staging records, then every pair lane applies the de-duplication in detection order
@@ -536,7 +544,7 @@ __device__ int narrow_batch(const Ctx<G>& C, const int* queue, int n_batch, int 
       bool is_col;
       f3 normal, cpos;
       float pen = 0.f;
-      dev_pair_perturbed<G, MPR>(C, T, i_det, is_col, normal, pen, cpos);
+      dev_pair_perturbed<G, (MPR ? (BB ? 2 : 1) : 0)>(C, T, i_det, is_col, normal, pen, cpos);
       float* r = stage + ((size_t)src * 4 + (i_det - 1)) * 8;
       r[0] = is_col ? 1.f : 0.f; r[1] = normal.x; r[2] = normal.y; r[3] = normal.z; r[4] = cpos.x; r[5] = cpos.y; r[6] = cpos.z; r[7] = pen;
     }

@@ -186,6 +186,7 @@ static inline int gsr_fill_model(GsrSpec* h) {
   m.has_box_box = 0;
   const bool box_box_detection = h->S("cfg_box_box_detection", 0) != 0;  // options/solvers.py:511
   m.box_box_detection = box_box_detection ? 1 : 0;
+  m.use_gjk = h->S("cfg_use_gjk_collision", 0) != 0 ? 1 : 0;
   {
     const int* pr = IV("pairs", 2 * (size_t)m.nP);
     for (int p = 0; p < m.nP; p++) {
@@ -195,7 +196,7 @@ static inline int gsr_fill_model(GsrSpec* h) {
       if (box_box || tb == GEOM_TERRAIN) { m.has_box_box = 1; continue; }  // terrain: not convex, its own narrow-phase pass
       if (!(ta == GEOM_PLANE && tb == GEOM_BOX)) m.has_cc = 1;
       const bool analytic = (ta == GEOM_CAPSULE && tb == GEOM_CAPSULE) || (ta == GEOM_SPHERE && tb == GEOM_CAPSULE) || (ta == GEOM_CAPSULE && tb == GEOM_SPHERE);
-      if (ta != GEOM_PLANE && tb != GEOM_PLANE && !analytic) m.has_mpr = 1;
+      if (ta != GEOM_PLANE && tb != GEOM_PLANE && !analytic) { m.has_mpr = 1; if (m.use_gjk) m.has_box_box = 1; }  // GJK-first lives in the full variant
     }
   }
 

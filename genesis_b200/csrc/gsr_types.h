@@ -49,6 +49,7 @@ struct DevModel {
   int has_box_box;        // a box-box pair under RigidOptions.box_box_detection or a terrain pair: the "full" variant (func_box_box_contact,
                           // func_contact_mpr_terrain compiled in)
   int box_box_detection;  // options/solvers.py:511
+  int use_gjk;            // RigidOptions.use_gjk_collision: convex pairs through GJK + EPA only
   // height-field terrain (collider.py:541-561): scaled heights (rows x cols, device), cell size, [x_max, y_max, z_max, x_min, y_min, z_min - 1]
   const float* terrain_hf;
   int terrain_rows, terrain_cols;

@@ -128,11 +128,13 @@ class RigidSolver:
             raise GenesisException("batch_dofs_info / batch_links_info need the lane-group step kernel (unset GSR_GROUP_SIZE=1).")
         if self.tuning.get("group_size") == 1 and (o.box_box_detection or any(isinstance(e.morph, _morphs.Terrain) for e in self._entities)):
             raise GenesisException("box_box_detection / Terrain need the lane-group step kernel (unset GSR_GROUP_SIZE=1).")
-        if o.use_contact_island or o.use_hibernation or o.enable_mujoco_compatibility or o.use_gjk_collision:
+        if o.use_contact_island or o.use_hibernation or o.enable_mujoco_compatibility:
             raise GenesisException(
-                "contact islands, hibernation, mujoco-compatibility and GJK-first collision are outside the "
-                "hot-path scope of this build (DESIGN.md 'Out of scope')."
+                "contact islands, hibernation and mujoco-compatibility are outside the hot-path scope of this build "
+                "(DESIGN.md 'Out of scope')."
             )
+        if o.use_gjk_collision and self.tuning.get("group_size") == 1:
+            raise GenesisException("use_gjk_collision needs the lane-group step kernel (unset GSR_GROUP_SIZE=1).")
         b = ModelBuilder(
             dt=self._substep_dt, gravity=self._gravity, constraint_timeconst=o.constraint_timeconst,
             enable_self_collision=o.enable_self_collision, enable_adjacent_collision=o.enable_adjacent_collision,
@@ -159,7 +161,7 @@ class RigidSolver:
                     enable_joint_limit=int(o.enable_joint_limit), enable_multi_contact=int(o.enable_multi_contact),
                     noslip_iterations=int(o.noslip_iterations), noslip_tolerance=float(o.noslip_tolerance),
                     batch_dofs_info=int(bool(o.batch_dofs_info)), disable_constraint=int(bool(o.disable_constraint)),
-                    box_box_detection=int(bool(o.box_box_detection)),
+                    box_box_detection=int(bool(o.box_box_detection)), use_gjk_collision=int(bool(o.use_gjk_collision)),
                     sort_contacts=1, **self.tuning)
 
     def build(self, n_envs, device):

@@ -110,6 +110,7 @@ static void load_cfg(const RawModel& r, Config& c) {
   c.gjk_fallback = (int)S("cfg_gjk_fallback", 1);
   c.broadphase_sap = (int)S("cfg_broadphase_sap", 0);
   c.box_box_detection = (int)S("cfg_box_box_detection", 0);
+  c.use_gjk_collision = (int)S("cfg_use_gjk_collision", 0);
   c.noslip_iterations = (int)S("cfg_noslip_iterations", 0); c.noslip_tolerance = S("cfg_noslip_tolerance", c.noslip_tolerance);
 }
 

@@ -122,6 +122,7 @@ struct Config {
   int ccd_iterations = 50;
   int broadphase_sap = 0;     // 1: sweep-and-prune traversal of the CPU backend (BP:142-396); 0: all-vs-all over the valid-pair table (BP:400-460)
   int gjk_fallback = 1;       // exact-penetration fallback after MPR (NP:726-733); 0 keeps MPR's answer (A/B tests)
+  int use_gjk_collision = 0;  // options/solvers.py use_gjk_collision: convex pairs through GJK + EPA, no MPR (NP:604-607, 736-850)
   int box_box_detection = 0;  // options/solvers.py:511: box-box pairs through func_box_box_contact (BOX:100-785) instead of MPR
   int noslip_iterations = 0;  // options/solvers.py:506-507
   double noslip_tolerance = 1e-6;
@@ -1613,28 +1614,30 @@ struct Oracle {
           cpos = v1 - normal * (T(0.5) * pen);
           is_col = pen > 0;
         } else {
-          V normal_ws = e.contact_cache_normal[i_pair];
-          bool guess = std::abs(normal_ws.x) > EPS || std::abs(normal_ws.y) > EPS || std::abs(normal_ws.z) > EPS;
-          bool updated = false;
-          Simplex last_simplex;
-          bool last_simplex_valid = false;
-          for (int i_mpr = 0; i_mpr < 2; i_mpr++) {
-            if (i_mpr == 1 && i_det == 0 && !is_col && guess) { normal_ws = V(); guess = false; updated = false; }
-            if (!updated) { mpr_contact(ga, gb, normal_ws, ga_pos, ga_quat, gb_pos, gb_quat, is_col, normal, pen, cpos, last_simplex, last_simplex_valid); updated = true; }
-          }
-          // NP:726-733: MPR's answer is replaced by the exact one when the overlap is large or no direction was cached
-          if (cfg.gjk_fallback && is_col && pen > tolerance) {
-            const bool prefer_gjk = !guess || (T(cfg.mc_tolerance) * pen >= T(cfg.mpr_to_gjk_overlap_ratio) * tolerance);
-            if (prefer_gjk) {
-              if (cfg.gjk_fallback == 2) {  // round-1 approximation kept for A/B: EPA seeded with MPR's final portal
+          bool prefer_gjk = cfg.use_gjk_collision != 0;  // NP:604-607
+          if (!prefer_gjk) {
+            V normal_ws = e.contact_cache_normal[i_pair];
+            bool guess = std::abs(normal_ws.x) > EPS || std::abs(normal_ws.y) > EPS || std::abs(normal_ws.z) > EPS;
+            bool updated = false;
+            Simplex last_simplex;
+            bool last_simplex_valid = false;
+            for (int i_mpr = 0; i_mpr < 2; i_mpr++) {
+              if (i_mpr == 1 && i_det == 0 && !is_col && guess) { normal_ws = V(); guess = false; updated = false; }
+              if (!updated) { mpr_contact(ga, gb, normal_ws, ga_pos, ga_quat, gb_pos, gb_quat, is_col, normal, pen, cpos, last_simplex, last_simplex_valid); updated = true; }
+            }
+            // NP:726-733: MPR's answer is replaced by the exact one when the overlap is large or no direction was cached
+            if (cfg.gjk_fallback && is_col && pen > tolerance) {
+              prefer_gjk = !guess || (T(cfg.mc_tolerance) * pen >= T(cfg.mpr_to_gjk_overlap_ratio) * tolerance);
+              if (prefer_gjk && cfg.gjk_fallback == 2) {  // round-1 approximation kept for A/B: EPA seeded with MPR's final portal
                 V n2, c2;
                 T p2 = 0;
                 if (epa_penetration(last_simplex, ga, gb, ga_pos, ga_quat, gb_pos, gb_quat, n2, p2, c2)) { normal = n2; pen = p2; cpos = c2; is_col = p2 > 0; }
-              } else {          // the reference's path: a fresh GJK distance query, then EPA from its tetrahedron (NP:756-850)
-                gjk_contact(ga, gb, ga_pos, ga_quat, gb_pos, gb_quat, is_col, normal, pen, cpos);
+                prefer_gjk = false;
               }
             }
           }
+          // the reference's path: a fresh GJK distance query, then EPA from its tetrahedron (NP:736-850)
+          if (prefer_gjk) gjk_contact(ga, gb, ga_pos, ga_quat, gb_pos, gb_quat, is_col, normal, pen, cpos);
         }
       }
       if (i_det == 0) {

@@ -265,6 +265,21 @@ def case_terrain_primitives():
     return s, m, dict(qpos=q, vel=np.zeros((2, m.n_dofs))), 10, {}
 
 
+def case_jumble_gjk():
+    """RigidOptions.use_gjk_collision: every convex pair through the GJK distance query + EPA, no MPR (narrowphase.py:604-607, 736-850;
+    gjk.py:170-446): boxes, a capsule and a cylinder touching and overlapping, multi-contact perturbations included."""
+    s, m = _scene(xml=JUMBLE_XML, use_gjk_collision=True)
+    return s, m, dict(qpos=np.asarray(m.qpos0, float)[None].copy(), vel=np.zeros((1, m.n_dofs))), 3, dict(use_gjk_collision=True)
+
+
+def case_box_box_gjk():
+    """The reference's box_box fixture in GJK mode (test_many_boxes_dynamics parametrises gjk_collision, tests/test_rigid_physics.py:1059-1066)."""
+    s, m = _scene(xml=BOX_BOX_XML, use_gjk_collision=True)
+    q = box_box_qpos(2, seed=3)
+    q[:, 9] = [0.595, 0.59]
+    return s, m, dict(qpos=q, vel=np.zeros((2, 12))), 4, dict(use_gjk_collision=True)
+
+
 def case_go2_drop_sap():
     """The same drop with the sweep-and-prune broad phase of the CPU backend (broadphase.py:142-396): the insertion sort is warm-started
     from the previous step, the candidate pairs come out in sweep order."""

@@ -489,6 +489,23 @@ def test_box_box_detection_contact_records_and_stack():
     assert float(ent.get_dofs_velocity().abs().max()) <= 0.5
 
 
+def test_gjk_first_collision_mode():
+    """RigidOptions.use_gjk_collision=True (scope row a17, the `gjk=` argument of the reference's benchmark factories): every convex
+    pair through the GJK distance query + EPA instead of MPR.  The grasp cluster (fingertip boxes / pads against cubes, a stacked
+    pair) follows the oracle, whose GJK-first path is pinned by tests/golden/ref_jumble_gjk.npz and ref_box_box_gjk.npz."""
+    B, K = 16, 30
+    scene, franka, boxes = make_franka_grasp(B, use_gjk_collision=True)
+    orc = mirror_oracle(scene)
+    for _ in range(K):
+        scene.step()
+    orc.step(K)
+    dq = np.abs(gpu_field(scene, "qpos") - orc.qpos()).max(axis=1)
+    assert (dq <= TRAJ_QPOS_CONTACT).mean() >= 0.9, f"qpos outliers: {np.sort(dq)[-5:]}"
+    a, b = contact_set(scene, B), contact_set(orc, B)
+    assert len(b) >= 4 * B and jaccard(a, b) >= 0.95, (len(a), len(b), jaccard(a, b))
+    assert int(scene.rigid_solver.field("errno_").max()) == 0
+
+
 def test_go2_on_height_field_terrain():
     """Height-field terrain (scope row f4, narrowphase.py:346-517): Go2 robots with randomised joints dropped on a bumpy height field
     follow the oracle (itself pinned to the reference's func_contact_mpr_terrain by tests/golden/ref_terrain_primitives.npz): same
