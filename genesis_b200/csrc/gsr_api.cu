@@ -12,7 +12,9 @@
 
 #include "gsr_host.h"
 #include "gsr_kernels.cuh"
+#ifndef GSR_DEV_ONLY_G  // developer builds (-DGSR_DEV_ONLY_G=32): one group size, no lane kernel -- a third of the compile time
 #include "gsr_lane.cuh"
+#endif
 
 namespace {
 
@@ -101,7 +103,9 @@ static int activate(gsr_handle_t h, cudaStream_t st) {
     CUDA_OK(cudaMemcpyToSymbolAsync(c_m, &h->hm, sizeof(DevModel), 0, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemcpyToSymbolAsync(c_h, &h->lay, sizeof(HotLayout), 0, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemcpyToSymbolAsync(c_s, &h->sl, sizeof(SmemLayout), 0, cudaMemcpyHostToDevice, st));
+#ifndef GSR_DEV_ONLY_G
     CUDA_OK(cudaMemcpyToSymbolAsync(c_l, &h->ll, sizeof(LaneLayout), 0, cudaMemcpyHostToDevice, st));
+#endif
     CUDA_OK(cudaMemcpyAsync(h->d_model, &h->hm, sizeof(DevModel), cudaMemcpyHostToDevice, st));
     g_active[h->device] = h;
   }
@@ -258,6 +262,9 @@ static cudaError_t set_smem(K kernel, size_t bytes) {
 }
 // lane-per-environment step kernel: one warp = 32 environments, interleaved workspace (gsr_lane.cuh)
 static int lane_launch(gsr_handle_t h, cudaStream_t st, int clear_ext) {
+#ifdef GSR_DEV_ONLY_G
+  return fail(h, GSR_ESTATE, "developer build without the lane kernel");
+#else
   const size_t warp_bytes = (size_t)h->ll.env_words * GSR_LANE_STRIDE_DEV * sizeof(float);
   if (warp_bytes > 227 * 1024) return fail(h, GSR_ELIMIT, "lane kernel: per-warp workspace exceeds 227 KB (use cfg_group_size 8/16/32)");
   int warps = h->warps_per_cta > 0 ? h->warps_per_cta : 1;  // independent warps: small CTAs balance best
@@ -273,6 +280,7 @@ static int lane_launch(gsr_handle_t h, cudaStream_t st, int clear_ext) {
   }
   CUDA_OK(cudaGetLastError());
   return GSR_OK;
+#endif
 }
 
 // order[B] = 1 when the most expensive environment costs at least 1.5x the median one
@@ -412,7 +420,12 @@ static int group_launch(gsr_handle_t h, int which, cudaStream_t st, const uint8_
     Bracket br_(h, K_FORWARD, st);                                                                       \
     k_forward<GG><<<grid, block, smem, st>>>(h->state, h->B, h->d_model, mask, clear_ext);               \
   }
+#ifdef GSR_DEV_ONLY_G
+  if (G != GSR_DEV_ONLY_G) return fail(h, GSR_ESTATE, "developer build for one group size only");
+  LAUNCH(GSR_DEV_ONLY_G)
+#else
   if (G == 32) { LAUNCH(32) } else if (G == 16) { LAUNCH(16) } else { LAUNCH(8) }
+#endif
 #undef LAUNCH
   CUDA_OK(cudaGetLastError());
   return GSR_OK;

@@ -12,7 +12,6 @@
 //                 against the others and writes it to its final slot of the CONTACT record (and of the on-chip copy).
 #pragma once
 #include "gsr_group.cuh"
-#include "gsr_epa.cuh"
 #include "gsr_gjk.cuh"
 #undef IN
 #undef WK
@@ -369,22 +368,17 @@ __device__ __forceinline__ void dev_detect(const Ctx<G>& C, const PairDet& D, co
       if (i_det == 0 && !is_col && guess) { dev_mpr_contact(C, P, f3(), is_col, normal, pen, cpos, sx, tetra); guess_used = false; }
       // NP:726-733: MPR's answer is replaced by the exact one when the overlap is large or no direction was cached
       if (c_m.gjk_fallback && is_col && pen > D.tolerance && (!guess_used || c_m.mc_tolerance * pen >= 0.25f * D.tolerance)) {
-        if (c_m.gjk_fallback == 2) {  // round-1 approximation (EPA seeded with MPR's final portal), kept for A/B runs
-          if (tetra) {
-            const GroupSupport<G> sup{C, P};
-            f3 n2, c2;
-            float p2 = 0.f;
-            if (epa_penetration(sx.v, sx.v1, sx.v2, sup, n2, p2, c2)) { normal = n2; pen = p2; cpos = c2; is_col = p2 > 0.f; }
-          }
-        } else {
-          run_gjk = true;
-        }
+#ifndef GSR_DEV_NO_GJK  // developer A/B builds: what does compiling the exact-penetration path in cost a scene that never runs it?
+        run_gjk = true;  // (the round-1 approximation, EPA seeded with MPR's portal, is gone from this kernel: carrying it cost Go2 time)
+#endif
       }
     }
+#ifndef GSR_DEV_NO_GJK
     if (run_gjk) {  // the reference's path: a fresh safe-GJK query and safe EPA from its tetrahedron (gsr_gjk.cuh)
       const GroupGeo<G> geo{C, P, D.ta, D.tb};
       gjk_contact(geo, is_col, normal, pen, cpos);
     }
+#endif
   }
 }
 
