@@ -290,9 +290,13 @@ __host__ __device__ void bb_contacts(f3 pos1, const mat3& mat1, f3 size1, f3 pos
 template <int G>
 __device__ __noinline__ void dev_box_box(const Ctx<G>& C, LaneContacts& out, int ga, int gb) {
   const float EPS = c_m.eps;
-  const mat3 mat1 = quat_to_R(ld4(WK(gquat), ga), EPS), mat2 = quat_to_R(ld4(WK(gquat), gb), EPS);
+  f3 pos1, pos2;
+  f4 quat1, quat2;
+  geom_pose(C, ga, pos1, quat1);
+  geom_pose(C, gb, pos2, quat2);
+  const mat3 mat1 = quat_to_R(quat1, EPS), mat2 = quat_to_R(quat2, EPS);
   const f3 size1 = f3(GM(g_data[ga][0]), GM(g_data[ga][1]), GM(g_data[ga][2])) * 0.5f;
   const f3 size2 = f3(GM(g_data[gb][0]), GM(g_data[gb][1]), GM(g_data[gb][2])) * 0.5f;
-  bb_contacts(ld3(WK(gpos), ga), mat1, size1, ld3(WK(gpos), gb), mat2, size2, EPS, min(c_m.n_contacts_per_pair, 5), out);
+  bb_contacts(pos1, mat1, size1, pos2, mat2, size2, EPS, min(c_m.n_contacts_per_pair, 5), out);
 }
 #endif

@@ -390,8 +390,8 @@ __device__ __noinline__ void dev_pair_det0(const Ctx<G>& C, LaneContacts& out, P
   D.ta = GM(g_type[ga]); D.tb = GM(g_type[gb]);
   D.multi = c_m.enable_multi_contact && D.ta != GEOM_SPHERE && D.ta != GEOM_ELLIPSOID && D.tb != GEOM_SPHERE && D.tb != GEOM_ELLIPSOID;
   D.tolerance = dev_tolerance(C, ga, gb);
-  D.pa0 = ld3(WK(gpos), ga); D.pb0 = ld3(WK(gpos), gb);
-  D.qa0 = ld4(WK(gquat), ga); D.qb0 = ld4(WK(gquat), gb);
+  geom_pose(C, ga, D.pa0, D.qa0);
+  geom_pose(C, gb, D.pb0, D.qb0);
   PairPose P;
   P.ga = ga; P.gb = gb; P.pa = D.pa0; P.pb = D.pb0; P.qa = D.qa0; P.qb = D.qb0;
   bool is_col;
@@ -457,8 +457,10 @@ __device__ __noinline__ void dev_pair_perturbed(const Ctx<G>& C, const PairDet& 
 // BOX:24-96 func_plane_box_contact
 template <int G>
 __device__ __noinline__ void dev_plane_box(const Ctx<G>& C, LaneContacts& out, int ga, int gb) {
-  const f3 pa = ld3(WK(gpos), ga), pb = ld3(WK(gpos), gb);
-  const f4 qa = ld4(WK(gquat), ga), qb = ld4(WK(gquat), gb);
+  f3 pa, pb;
+  f4 qa, qb;
+  geom_pose(C, ga, pa, qa);
+  geom_pose(C, gb, pb, qb);
   const f3 normal = -normalized(rotate(f3(GM(g_data[ga][0]), GM(g_data[ga][1]), GM(g_data[ga][2])), qa));
   const f3 v1 = dev_support(C, normal, gb, pb, qb);
   float pen = dot(normal, v1 - pa);

@@ -235,20 +235,34 @@ __device__ void phase_kinematics(const Ctx<G>& C) {
   C.sync();
 }
 
-// geom poses from link poses (FK:828-864) and world AABBs (FK:1297-1319) into the collision scratch
+// geom pose from its link's pose (FK:828-864)
+template <int G>
+__device__ __forceinline__ void geom_pose_from_link(const Ctx<G>& C, int g, f3& gp, f4& gq) {
+  const int l = GM(g_link[g]);
+  const f3 lp = ld3(IN(links_pos), l);
+  const f4 lq = ld4(IN(links_quat), l);
+  gp = lp + rotate(f3(GM(g_pos[g][0]), GM(g_pos[g][1]), GM(g_pos[g][2])), lq);
+  gq = quat_compose(f4(GM(g_quat[g][0]), GM(g_quat[g][1]), GM(g_quat[g][2]), GM(g_quat[g][3])), lq);
+}
+// ... as the narrow phase reads it: from the collision scratch (models whose layout keeps the poses: c_s.gpos >= 0) or recomputed
+// with the same arithmetic (small-group models, where 7 words per geom of workspace cost resident environments)
+template <int G>
+__device__ __forceinline__ void geom_pose(const Ctx<G>& C, int g, f3& gp, f4& gq) {
+  if (c_s.gpos >= 0) { gp = ld3(WK(gpos), g); gq = ld4(WK(gquat), g); }
+  else geom_pose_from_link(C, g, gp, gq);
+}
+
+// geom poses (collision scratch, when kept) and world AABBs (FK:1297-1319)
 template <int G>
 __device__ void phase_geoms(const Ctx<G>& C) {
   const int nG = CM(nG);
-  float* gpos = WK(gpos);
-  float* gquat = WK(gquat);
   float* aabb = WK(aabb);
+  const bool keep = c_s.gpos >= 0;
   for (int g = C.lane; g < nG; g += G) {
-    const int l = GM(g_link[g]);
-    const f3 lp = ld3(IN(links_pos), l);
-    const f4 lq = ld4(IN(links_quat), l);
-    const f3 gp = lp + rotate(f3(GM(g_pos[g][0]), GM(g_pos[g][1]), GM(g_pos[g][2])), lq);
-    const f4 gq = quat_compose(f4(GM(g_quat[g][0]), GM(g_quat[g][1]), GM(g_quat[g][2]), GM(g_quat[g][3])), lq);
-    st3(gpos, g, gp); st4(gquat, g, gq);
+    f3 gp;
+    f4 gq;
+    geom_pose_from_link(C, g, gp, gq);
+    if (keep) { st3(WK(gpos), g, gp); st4(WK(gquat), g, gq); }
     // the reference transforms the 8 corners of the rest-pose box and takes min / max; the identical box is
     // centre +- |R| * half-extent
     const mat3 R = quat_to_R(gq, 0.f);
@@ -399,7 +413,7 @@ __device__ void phase_dynamics(const Ctx<G>& C) {
   float* M = WK(M);
   float* L = WK(L);
   const int ntri = nD * (nD + 1) / 2;
-  const int* mode = C.SI() + c_h.ctrl_mode;
+  const int* mode = reinterpret_cast<const int*>(C.rec) + c_h.ctrl_mode;  // PRE block: read from the record
   for (int t = lane; t < ntri; t += G) {
     int i, j;
     tri_decode(t, i, j);
@@ -412,7 +426,14 @@ __device__ void phase_dynamics(const Ctx<G>& C) {
         if (mode[i] <= CTRL_VELOCITY) v -= dof_bias(C, i, 2) * dt;
       }
     }
-    M[i * MS + j] = v; M[j * MS + i] = v; L[i * MS + j] = v;
+    M[t] = v;  // M: packed lower triangle in task order (gsr_group.cuh sym_row_dot)
+  }
+  C.sync();
+  // the factorisation works on a copy, in the square layout of the dense-algebra routines (f_d may have lived in that slot until now)
+  for (int t = lane; t < ntri; t += G) {
+    int i, j;
+    tri_decode(t, i, j);
+    L[i * MS + j] = M[t];
   }
   C.sync();
   mass_factor(C);
@@ -428,11 +449,11 @@ __device__ void phase_dynamics(const Ctx<G>& C) {
     const float v = vel[d], dp = dofs_pos[d];
     const float kp = dof_kp(C, d), b0 = dof_bias(C, d, 0), b1 = dof_bias(C, d, 1), b2 = dof_bias(C, d, 2);
     float force = 0.f;
-    if (md == CTRL_FORCE) force = IN(ctrl_force)[d];
-    else if (md == CTRL_VELOCITY) force = -b2 * (IN(ctrl_vel)[d] - v);
+    if (md == CTRL_FORCE) force = C.rec[c_h.ctrl_force + d];
+    else if (md == CTRL_VELOCITY) force = -b2 * (C.rec[c_h.ctrl_vel + d] - v);
     else if (md == CTRL_POSITION) {
       if (!(jt == JOINT_FREE && d >= ds + 3)) {
-        force = kp * (IN(ctrl_pos)[d] - dp) + b0 + (kp + b1) * dp + b2 * (v - IN(ctrl_vel)[d]);
+        force = kp * (IN(ctrl_pos)[d] - dp) + b0 + (kp + b1) * dp + b2 * (v - C.rec[c_h.ctrl_vel + d]);
       }
     }
     if (jt == JOINT_FREE && d >= ds + 3 && (mode[ds + 3] == CTRL_POSITION || mode[ds + 4] == CTRL_POSITION || mode[ds + 5] == CTRL_POSITION)) {
@@ -440,9 +461,11 @@ __device__ void phase_dynamics(const Ctx<G>& C) {
       const f3 xyz(dofs_pos[ds + 3], dofs_pos[ds + 4], dofs_pos[ds + 5]);
       const f3 cxyz(IN(ctrl_pos)[ds + 3], IN(ctrl_pos)[ds + 4], IN(ctrl_pos)[ds + 5]);
       const f3 rv = quat_to_rotvec(quat_compose(xyz_to_quat(cxyz), quat_inv(xyz_to_quat(xyz))), CM(eps));
-      force = kp * comp(rv, d - ds - 3) + b0 + (kp + b1) * dp + b2 * (v - IN(ctrl_vel)[d]);
+      force = kp * comp(rv, d - ds - 3) + b0 + (kp + b1) * dp + b2 * (v - C.rec[c_h.ctrl_vel + d]);
     }
-    qf_applied[d] = fminf(fmaxf(force, dof_force_range(C, d, 0)), dof_force_range(C, d, 1));
+    const float applied = fminf(fmaxf(force, dof_force_range(C, d, 0)), dof_force_range(C, d, 1));
+    qf_applied[d] = applied;                // workspace slot shared with `acc` (free until the solver ends), read back below
+    C.rec[c_h.qf_applied + d] = applied;    // accessor-visible copy
     float passive = -dof_damping(C, d) * v;
     if (jt != JOINT_FREE && jt != JOINT_FIXED) passive += -dp * dof_stiffness(C, d);
     qf_passive[d] = passive;
@@ -517,7 +540,7 @@ __device__ void phase_integrate(const Ctx<G>& C) {
   }
   if (CM(integrator) != INTEGRATOR_APPROX_IMPLICITFAST) {
     // FD:1787-1859 func_implicit_damping: refactor M + dt (damping - d act / d vel) and re-solve acc = M'^-1 force
-    const int* mode = C.SI() + c_h.ctrl_mode;
+    const int* mode = reinterpret_cast<const int*>(C.rec) + c_h.ctrl_mode;  // PRE block: read from the record
     auto dof_damped = [&](int k) {
       return dof_damping(C, k) > EPS || (CM(integrator) != INTEGRATOR_EULER && mode[k] <= CTRL_VELOCITY && fabsf(dof_bias(C, k, 2)) > EPS);
     };
@@ -538,7 +561,7 @@ __device__ void phase_integrate(const Ctx<G>& C) {
       for (int t = lane; t < ntri; t += G) {
         int i, j;
         tri_decode(t, i, j);
-        float v = M[i * MS + j];
+        float v = M[t];
         if (i == j && ent_active(GM(d_entity[i]))) {
           v += dof_damping(C, i) * dt;
           if (CM(integrator) == INTEGRATOR_IMPLICITFAST && mode[i] <= CTRL_VELOCITY) v -= dof_bias(C, i, 2) * dt;

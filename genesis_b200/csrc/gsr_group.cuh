@@ -68,6 +68,18 @@ __device__ __forceinline__ bool bit64(unsigned long long m, int i) { return (m >
 // lower-triangle task decode: t = i (i + 1) / 2 + j, j <= i (table built on the host, read through the L1 read-only path)
 #define tri_decode(t, i, j) { const unsigned tr_ = GM(tri[t]); i = (int)(tr_ >> 8); j = (int)(tr_ & 255u); }
 
+// The mass matrix lives in the workspace as a PACKED lower triangle: entry (i, j), j <= i, at i (i + 1) / 2 + j -- the order of the
+// `tri` task table, so the assembly loops address it by their task index.  Row i times a vector, terms in ascending j like a dense row:
+__device__ __forceinline__ float sym_row_dot(const float* Mp, int i, const float* x, int n) {
+  float s = 0.f;
+  const float* r = Mp + i * (i + 1) / 2;
+  for (int j = 0; j <= i; j++) s += r[j] * x[j];
+  int idx = (i + 1) * (i + 2) / 2 + i;
+  for (int j = i + 1; j < n; j++) { s += Mp[idx] * x[j]; idx += j + 1; }
+  return s;
+}
+__device__ __forceinline__ float sym_get(const float* Mp, int i, int j) { return i >= j ? Mp[i * (i + 1) / 2 + j] : Mp[j * (j + 1) / 2 + i]; }
+
 // per-environment inertial parameters: model value plus the domain-randomisation shift of the record (FK:377-382, 437)
 template <int G>
 __device__ __forceinline__ float link_mass(const Ctx<G>& C, int l, bool shifted) {

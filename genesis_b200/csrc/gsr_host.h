@@ -228,6 +228,9 @@ static inline int gsr_compute_layouts(GsrSpec* h, int n_envs) {
     h->fields.push_back(GsrFieldInfo{#name, is_int, 0, 0, off, it_, cp_, cp_});                            \
     off += (it_ * cp_ > 0 ? it_ * cp_ : 1);                                                             \
   }
+  GSR_HOT_PRE_FIELDS(X)
+  off = gsr_round4(off);
+  L.in_start = (int)off;
   GSR_HOT_IN_FIELDS(X)
   off = gsr_round4(off);
   L.n_in = (int)off;
@@ -271,32 +274,49 @@ static inline int gsr_compute_layouts(GsrSpec* h, int n_envs) {
   SmemLayout& s = h->sl;
   memset(&s, 0, sizeof(s));
   s.MS = MS; s.JS = JS;
-  int NCS = (int)S("cfg_smem_rows", nD > 12 ? 32 : 16);  // rows kept on chip (more => SPILL record): 16 lets 13 Franka CTAs fit an SM,
+  int NCS = (int)S("cfg_smem_rows", nD > 12 ? 32 : 12);  // rows kept on chip (more => SPILL record): 12 lets 17 Franka CTAs fit an SM,
   // 32 covers 99.9 % of the Go2 env-steps and leaves twice the L1 for the model tables (profiles/README.md, r1c sweeps)
   if (NCS > lenC) NCS = lenC;
   if (NCS < 4) NCS = 4;
   s.NCS = NCS;
   s.NCC = NCS / 4 > 0 ? NCS / 4 : 1;
-  // scratch of the dynamics / collision / integrate+FK phases starts after the IN mirror
+  // scratch of the dynamics / collision / integrate+FK phases starts after the IN mirror.  Dynamics: the composite inertias and
+  // f_d = crb * cdof are dead once the mass matrix is assembled, so the bias-force scratch (cdd, cfrc) overlays them; the smooth
+  // force terms that only the diagnostics read after the phase (qf_passive, qf_bias) and D^-1 (needed after the phase only by the
+  // CG solver, noslip, the implicit integrators and the diagnostics) follow them inside the pool when nothing reads them later.
+  const bool newton = m.solver_type == SOLVER_NEWTON;
+  const bool dyn_terms_live = m.diagnostics != 0;
+  const bool dinv_live = m.diagnostics != 0 || !newton || m.noslip_iterations > 0 || m.integrator != INTEGRATOR_APPROX_IMPLICITFAST;
   int x = L.n_in, xmax = x;
-  s.crb = x; x += 10 * nL; s.fdof = x; x += 6 * nD; s.cdd = x; x += 6 * nL; s.cfrc = x; x += 6 * nL;
+  const bool fdof_on_L = 6 * nD <= nD * MS;  // f_d = crb * cdof waits in L's slot: the factorisation copies M there afterwards
+  s.crb = x; x += 10 * nL;
+  if (!fdof_on_L) { s.fdof = x; x += 6 * nD; }
+  if (x > xmax) xmax = x;
+  x = L.n_in;
+  s.cdd = x; x += 6 * nL; s.cfrc = x; x += 6 * nL;
+  if (!dyn_terms_live) { s.qf_passive = x; x += nD; s.qf_bias = x; x += nD; }
+  if (!dinv_live) { s.Dinv = x; x += nD; }
   if (x > xmax) xmax = x;
   x = L.n_in;
   // the broad-phase work queue holds at most 2 G - 1 candidates (a full batch is flushed as soon as G are queued)
-  s.gpos = x; x += 3 * nG; s.gquat = x; x += 4 * nG; s.aabb = x; x += 6 * nG; s.queue = x; x += 2 * (h->group == 1 ? 32 : h->group);
+  // geom poses are kept for full-warp models; small-group models recompute them per pair (gsr_dynamics.cuh geom_pose)
+  if (h->group == 32 || h->group == 1) { s.gpos = x; x += 3 * nG; s.gquat = x; x += 4 * nG; } else { s.gpos = -1; s.gquat = -1; }
+  s.aabb = x; x += 6 * nG; s.queue = x; x += 2 * (h->group == 1 ? 32 : h->group);
   if (x > xmax) xmax = x;
   // integration scratch (link accelerations, next velocity / position): written out by the epilogue before the kinematics
-  // of the new configuration start, whose scratch (joint anchors / axes, the two scan buffers) therefore overlays it
+  // of the new configuration start, whose scratch (joint anchors / axes, the two scan buffers) therefore overlays it.  The second
+  // scan buffer goes on top of M / L (dead whenever the kinematics run: k_step's epilogue, k_forward, k_set_state) when it fits there.
   x = L.n_in;
   s.cacc = x; x += 6 * nL; s.vel_next = x; x += nD; s.qpos_next = x; x += nQ;
   if (x > xmax) xmax = x;
   x = L.n_in;
-  s.xanchor = x; x += 3 * m.nJ; s.xaxis = x; x += 3 * m.nJ; s.pose_a = x; x += 8 * nL; s.pose_b = x; x += 8 * nL;
+  s.xanchor = x; x += 3 * m.nJ; s.xaxis = x; x += 3 * m.nJ; s.pose_a = x; x += 8 * nL;
+  const bool pose_b_on_M = 8 * nL <= nD * (nD + 1) / 2 + nD * MS;
+  if (!pose_b_on_M) { s.pose_b = x; x += 8 * nL; }
   if (x > xmax) xmax = x;
   // solver arrays overlay the dead part of the kinematic cache and the phase scratch
   x = L.kin_dead;
   s.contacts = x; x += s.NCC * GSR_CONTACT_WORDS;
-  const bool newton = m.solver_type == SOLVER_NEWTON;
   const bool h_own = !newton || m.noslip_iterations > 0;  // noslip solves with the L^T D L factor after the Newton solve
   if (h_own) { s.H = x; x += nD * MS; }  // otherwise H overlays the L^T D L factor, which is dead once acc_smooth is known
   s.Hinv = x; x += nD; s.tmpv = x; x += nD;
@@ -308,11 +328,21 @@ static inline int gsr_compute_layouts(GsrSpec* h, int n_envs) {
   if (x > xmax) xmax = x;
   // always-live block
   x = (int)gsr_round4(xmax);
-  s.M = x; x += nD * MS; s.L = x; x += nD * MS; s.Dinv = x; x += nD;
+  s.M = x; x += nD * (nD + 1) / 2;  // packed lower triangle (gsr_group.cuh sym_row_dot)
+  s.L = x; x += nD * MS;
+  if (fdof_on_L) s.fdof = s.L;
+  if (pose_b_on_M) s.pose_b = s.M;
+  if (dinv_live) { s.Dinv = x; x += nD; }
   if (!h_own) s.H = s.L;
   s.force = x; x += nD; s.acc_smooth = x; x += nD;
-  s.acc = x; x += nD; s.qf_applied = x; x += nD; s.qf_passive = x; x += nD; s.qf_bias = x; x += nD; s.qfrc_c = x; x += nD;
-  s.env_words = (int)gsr_round4(x);
+  // acc is written when the solver ends, after the last read of acc_smooth (cost evaluations), element by element: one slot, unless
+  // the diagnostics read acc_smooth in the epilogue.  qf_applied waits in acc's slot from the actuation loop to the end of the phase.
+  // (noslip reads acc_smooth after the solver has committed acc: no sharing then)
+  if (dyn_terms_live || m.noslip_iterations > 0) { s.acc = x; x += nD; } else s.acc = s.acc_smooth;
+  s.qf_applied = s.acc;
+  if (dyn_terms_live) { s.qf_passive = x; x += nD; s.qf_bias = x; x += nD; }
+  s.qfrc_c = x; x += nD;
+  s.env_words = (int)gsr_round4(x) - L.in_start;  // the PRE block of the record is not mirrored
 
 
   // ---- lane-per-environment kernel (group == 1): interleaved workspace, word w of lane t at S[w * 33 + t] (gsr_lane.cuh)

@@ -41,7 +41,7 @@ __device__ __forceinline__ bool make_ctx(Ctx<G>& C, float* state, int B, const D
   C.env = env;
   C.lane = lane32 % G;
   C.gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (sub * G));
-  C.S = smem + (size_t)slot * c_s.env_words;
+  C.S = smem + (size_t)slot * c_s.env_words - c_h.in_start;  // record-relative workspace offsets (SmemLayout)
   C.rec = state + (size_t)env * c_h.hot_stride;
   C.contacts = state + c_h.contact_base + (size_t)env * c_h.contact_stride;
   C.cache = state + c_h.cache_base + (size_t)env * c_h.cache_stride;
@@ -61,14 +61,14 @@ __device__ __forceinline__ void bulk_load_in(float* state, int B, float* smem, u
   const int warp = threadIdx.x >> 5, lane32 = threadIdx.x & 31;
   const int env0 = (blockIdx.x * (blockDim.x >> 5) + warp) * EPW;
   const int n_live = min(EPW, B - env0);  // > 0 for a live warp
-  const uint32_t bytes = (uint32_t)c_h.n_in * 4u;
+  const uint32_t bytes = (uint32_t)(c_h.n_in - c_h.in_start) * 4u;
   const uint32_t b = smem_u32(bar);
   if (lane32 == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b), "r"(1) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes * (uint32_t)n_live) : "memory");
     for (int e = 0; e < n_live; e++) {
-      const float* src = state + (size_t)(order ? __ldg(order + env0 + e) : env0 + e) * c_h.hot_stride;
+      const float* src = state + (size_t)(order ? __ldg(order + env0 + e) : env0 + e) * c_h.hot_stride + c_h.in_start;
       const uint32_t dst = smem_u32(smem + (size_t)(warp * EPW + e) * c_s.env_words);
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                    ::"r"(dst), "l"(src), "r"(bytes), "r"(b) : "memory");
@@ -86,12 +86,12 @@ __device__ __forceinline__ void bulk_store_in(float* state, int B, float* smem, 
   const int warp = threadIdx.x >> 5, lane32 = threadIdx.x & 31;
   const int env0 = (blockIdx.x * (blockDim.x >> 5) + warp) * EPW;
   const int n_live = min(EPW, B - env0);
-  const uint32_t bytes = (uint32_t)c_h.n_in * 4u;
+  const uint32_t bytes = (uint32_t)(c_h.n_in - c_h.in_start) * 4u;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the async proxy
   __syncwarp();
   if (lane32 == 0) {
     for (int e = 0; e < n_live; e++) {
-      float* dst = state + (size_t)(order ? __ldg(order + env0 + e) : env0 + e) * c_h.hot_stride;
+      float* dst = state + (size_t)(order ? __ldg(order + env0 + e) : env0 + e) * c_h.hot_stride + c_h.in_start;
       const uint32_t src = smem_u32(smem + (size_t)(warp * EPW + e) * c_s.env_words);
       asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
     }
@@ -115,12 +115,17 @@ struct HostIO {
 
 // launch bounds of the step kernel (developer builds may override: ptxas fits the kernel into 96 registers without spilling, so
 // shared memory, not registers, bounds the number of resident CTAs)
+// Full-warp groups run multi-warp CTAs (one big CTA or a few per SM); small groups run one-warp CTAs, as many as the workspace
+// lets an SM hold -- 17 for Franka-sized models, which needs <= 120 registers per thread.
 #ifndef GSR_LB_T
-#define GSR_LB_T (GSR_MAX_WARPS_PER_CTA * 32)
-#define GSR_LB_B 1
+#define GSR_LB_T(G) ((G) == 32 ? GSR_MAX_WARPS_PER_CTA * 32 : 32)
+#ifndef GSR_DEV_SMALL_BLOCKS
+#define GSR_DEV_SMALL_BLOCKS 17
+#endif
+#define GSR_LB_B(G) ((G) == 32 ? 1 : GSR_DEV_SMALL_BLOCKS)
 #endif
 template <int G, bool MPR, bool BB = false>
-__global__ void __launch_bounds__(GSR_LB_T, GSR_LB_B) k_step(float* state, int B, const DevModel* gm, int clear_ext, const int* order,
+__global__ void __launch_bounds__(GSR_LB_T(G), GSR_LB_B(G)) k_step(float* state, int B, const DevModel* gm, int clear_ext, const int* order,
                                                                         unsigned long long* trace, HostIO io) {
   extern __shared__ __align__(16) float smem[];
   Ctx<G> C;
@@ -205,7 +210,7 @@ __device__ __forceinline__ void write_dynamics_diagnostics(const Ctx<G>& C) {
     rec[c_h.mass_Dinv + d] = WK(Dinv)[d];
   }
   for (int i = 0; i < nD; i++)
-    for (int j = lane; j < nD; j += G) rec[c_h.mass_mat + i * nD + j] = WK(M)[i * MS + j];
+    for (int j = lane; j < nD; j += G) rec[c_h.mass_mat + i * nD + j] = sym_get(WK(M), i, j);
 }
 template <int G>
 __device__ __forceinline__ void write_geom_poses(const Ctx<G>& C) {
@@ -228,7 +233,6 @@ __device__ __forceinline__ void step_epilogue(const Ctx<G>& C, int clear_ext) {
   for (int d = lane; d < nD; d += G) {
     rec[c_h.acc + d] = WK(acc)[d];
     rec[c_h.force + d] = WK(force)[d] + WK(qfrc_c)[d];
-    rec[c_h.qf_applied + d] = WK(qf_applied)[d];
     rec[c_h.qf_constraint + d] = WK(qfrc_c)[d];
   }
   for (int l = lane; l < nL; l += G) {
@@ -258,17 +262,17 @@ __global__ void __launch_bounds__(GSR_MAX_WARPS_PER_CTA * 32) k_forward(float* s
   {  // masked environments are few: plain vector copies
     const float4* src = reinterpret_cast<const float4*>(C.rec);
     float4* dst = reinterpret_cast<float4*>(C.S);
-    for (int i = C.lane; i < c_h.n_in / 4; i += G) dst[i] = src[i];
+    for (int i = c_h.in_start / 4 + C.lane; i < c_h.n_in / 4; i += G) dst[i] = src[i];
     C.sync();
   }
   phase_kinematics(C);
   phase_geoms(C);
-  if (C.lane == 0) C.SI()[c_h.fk_dirty] = 0;
+  if (C.lane == 0) reinterpret_cast<int*>(C.rec)[c_h.fk_dirty] = 0;  // PRE block: lives in the record only
   C.sync();
   {
     float4* dst = reinterpret_cast<float4*>(C.rec);
     const float4* src = reinterpret_cast<const float4*>(C.S);
-    for (int i = C.lane; i < c_h.n_in / 4; i += G) dst[i] = src[i];
+    for (int i = c_h.in_start / 4 + C.lane; i < c_h.n_in / 4; i += G) dst[i] = src[i];
   }
 }
 
@@ -336,7 +340,7 @@ __global__ void __launch_bounds__(GSR_MAX_WARPS_PER_CTA * 32) k_set_state(float*
   {
     const float4* src = reinterpret_cast<const float4*>(rec);
     float4* dst = reinterpret_cast<float4*>(C.S);
-    for (int i = lane; i < c_h.n_in / 4; i += G) dst[i] = src[i];
+    for (int i = c_h.in_start / 4 + lane; i < c_h.n_in / 4; i += G) dst[i] = src[i];
     C.sync();
   }
   phase_kinematics(C);
@@ -345,7 +349,7 @@ __global__ void __launch_bounds__(GSR_MAX_WARPS_PER_CTA * 32) k_set_state(float*
   {
     float4* dst = reinterpret_cast<float4*>(rec);
     const float4* src = reinterpret_cast<const float4*>(C.S);
-    for (int i = lane; i < c_h.n_in / 4; i += G) dst[i] = src[i];
+    for (int i = c_h.in_start / 4 + lane; i < c_h.n_in / 4; i += G) dst[i] = src[i];
   }
 }
 
@@ -381,7 +385,7 @@ __global__ void __launch_bounds__(GSR_MAX_WARPS_PER_CTA * 32) k_diag(float* stat
   {
     const float4* src = reinterpret_cast<const float4*>(C.rec);
     float4* dst = reinterpret_cast<float4*>(C.S);
-    for (int i = C.lane; i < c_h.n_in / 4; i += G) dst[i] = src[i];
+    for (int i = c_h.in_start / 4 + C.lane; i < c_h.n_in / 4; i += G) dst[i] = src[i];
     C.sync();
   }
   phase_dynamics(C);

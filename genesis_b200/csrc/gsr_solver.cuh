@@ -383,7 +383,7 @@ __device__ __noinline__ void hessian_cholesky(const Ctx<G>& C, const Rows& R, lo
 #pragma unroll
     for (int e = 0; e < NE; e++) {
       const int t = t0 + e * G + lane;
-      if (t < ntri) H[oi[e] * MS + oj[e]] = acc[e] + M[oi[e] * MS + oj[e]];
+      if (t < ntri) H[oi[e] * MS + oj[e]] = acc[e] + M[t];  // packed M in task order
     }
   }
   C.sync();
@@ -703,8 +703,7 @@ __device__ float linesearch(const Ctx<G>& C, const Rows& R, SolverState& X) {
   for (int i = lane; i < nD; i += G) {
     const float s = search[i];
     sn += s * s;
-    float m = 0.f;
-    for (int j = 0; j < nD; j++) m += M[i * MS + j] * search[j];
+    const float m = sym_row_dot(M, i, search, nD);
     mv[i] = m;
     qg1 += s * WK(Ma)[i] - s * WK(force)[i];
     qg2 += 0.5f * s * m;
@@ -903,8 +902,7 @@ __device__ void phase_constraints(const Ctx<G>& C) {
     const float* M = WK(M);
     for (int i = lane; i < nD; i += G) {  // CS:2910-2929
       float s = 0.f;
-      for (int j = 0; j < nD; j++) s += M[i * MS + j] * qacc[j];
-      Ma[i] = s;
+      Ma[i] = sym_row_dot(M, i, qacc, nD);
     }
     for (int c = lane; c < n_con; c += G) {  // CS:2887-2907
       float s = -R.aref[c];

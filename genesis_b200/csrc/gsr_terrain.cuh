@@ -26,8 +26,10 @@ struct TerrainSupport {
 
 template <int G>
 __device__ __noinline__ void dev_terrain(const Ctx<G>& C, LaneContacts& out, int ga, int gb) {
-  const f3 ga_pos = ld3(WK(gpos), ga), gb_pos = ld3(WK(gpos), gb);
-  const f4 ga_quat = ld4(WK(gquat), ga), gb_quat = ld4(WK(gquat), gb);
+  f3 ga_pos, gb_pos;
+  f4 ga_quat, gb_quat;
+  geom_pose(C, ga, ga_pos, ga_quat);
+  geom_pose(C, gb, gb_pos, gb_quat);
   const float tolerance = dev_tolerance(C, ga, gb);
   const f4 inv_b = quat_inv(gb_quat);
   const f3 pa = rotate(ga_pos - gb_pos, inv_b);

@@ -114,12 +114,15 @@ struct DevModel {
 // ---- HOT segment fields: X(name, is_int, items, comps).  Everything up to `kin_end` is the IN part (same offsets in the
 // shared-memory workspace); the rest is OUT.
 // nL/nD/... are the model counts; "items x comps" words, item-major.
+// The record starts with the PRE block: inputs the step reads once, straight from the record (they are never written by the
+// kernel, so mirroring them in shared memory and storing them back would only cost workspace and HBM traffic).
+#define GSR_HOT_PRE_FIELDS(X)                                                                                      \
+  X(ctrl_vel, 0, nD, 1) X(ctrl_force, 0, nD, 1) X(ctrl_mode, 1, nD, 1) X(fk_dirty, 1, 1, 1)
 #define GSR_HOT_IN_FIELDS(X)                                                                                       \
-  /* persistent state (rigid_global_info.qpos, dofs_state.vel / ctrl_*, constraint_state.qacc_ws) */               \
-  X(qpos, 0, nQ, 1) X(vel, 0, nD, 1) X(ctrl_pos, 0, nD, 1) X(ctrl_vel, 0, nD, 1) X(ctrl_force, 0, nD, 1)           \
-  X(ctrl_mode, 1, nD, 1) X(qacc_ws, 0, nD, 1)                                                                      \
+  /* persistent state (rigid_global_info.qpos, dofs_state.vel / ctrl_pos, constraint_state.qacc_ws) */             \
+  X(qpos, 0, nQ, 1) X(vel, 0, nD, 1) X(ctrl_pos, 0, nD, 1) X(qacc_ws, 0, nD, 1)                                    \
   X(is_warmstart, 1, 1, 1) X(errno_, 1, 1, 1) X(n_contacts, 1, 1, 1) X(n_broad, 1, 1, 1)                           \
-  X(has_ext_force, 1, 1, 1) X(has_shift, 1, 1, 1) X(n_dyn_eq, 1, 1, 1) X(fk_dirty, 1, 1, 1)                                           \
+  X(has_ext_force, 1, 1, 1) X(has_shift, 1, 1, 1) X(n_dyn_eq, 1, 1, 1)                                           \
   /* kinematic cache written by the FK at the end of a step and consumed by the next step */                       \
   X(dofs_pos, 0, nD, 1) X(root_COM, 0, nL, 3) X(cdof_ang, 0, nD, 3) X(cdof_vel, 0, nD, 3) X(cdofd_ang, 0, nD, 3)   \
   X(cdofd_vel, 0, nD, 3) X(links_pos, 0, nL, 3) X(links_quat, 0, nL, 4) X(cinr_I, 0, nL, 6) X(cinr_pos, 0, nL, 3)  \
@@ -147,10 +150,12 @@ struct DevModel {
 
 struct HotLayout {
 #define X(name, is_int, items, comps) int name;
+  GSR_HOT_PRE_FIELDS(X)
   GSR_HOT_IN_FIELDS(X)
   GSR_HOT_OUT_FIELDS(X)
 #undef X
-  int n_in;        // words of the IN part (multiple of 4)
+  int in_start;    // first word of the IN part = size of the PRE block (multiple of 4)
+  int n_in;        // end of the IN part (multiple of 4): record words [in_start, n_in) are mirrored in shared memory
   int kin_dead;    // first word of the IN part that is dead after collision detection (links_pos ...)
   int hot_stride;  // words per env in the HOT segment (multiple of 4)
   int contact_stride, cache_stride, spill_stride;
@@ -159,7 +164,9 @@ struct HotLayout {
   int spill_minvjt;                                // noslip: offset of the M^-1 J^T rows inside a SPILL record
 };
 
-// Shared-memory workspace of one environment (word offsets from the env's base).  Words [0, n_in) mirror the record's IN
+// Shared-memory workspace of one environment.  Offsets are RECORD-RELATIVE: word w of the layout sits at shared-memory word
+// w - in_start of the environment's slot (the kernels bias the slot pointer once, make_ctx), so that the IN part keeps the
+// record's own offsets.  Words [in_start, n_in) mirror the record's IN
 // part.  Regions are overlaid by liveness: the dynamics scratch and the kinematic cache that is dead after collision
 // detection are reused by the collision scratch and then by the solver rows.
 struct SmemLayout {

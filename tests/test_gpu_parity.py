@@ -562,6 +562,32 @@ def test_double_pendulum_link_accelerations():
     np.testing.assert_allclose(acc_ang[:, -1, 0], acc[:, 0] + acc[:, 1], atol=1e-4)
 
 
+@pytest.mark.parametrize("model", ["franka", "go2", "grasp", "franka_cg_euler"])
+def test_workspace_layouts_give_identical_steps(model, monkeypatch):
+    """The shared-memory workspace has two layouts: with cfg_diagnostics = 1 (what most parity tests run) the smooth force terms and
+    D^-1 stay live until the epilogue; with the default cfg_diagnostics = 0 they live in the phase scratch that later phases recycle
+    (gsr_host.h).  Both must produce bit-identical steps, so the parity established with diagnostics on carries over."""
+    def make():
+        if model == "go2":
+            return make_go2(64, seed=4)[0]
+        if model == "grasp":
+            return make_franka_grasp(32)[0]
+        if model == "franka_cg_euler":
+            return make_franka(64, randomized=True, seed=2, constraint_solver=gs.constraint_solver.CG, integrator=gs.integrator.Euler)[0]
+        return make_franka(128, randomized=True, seed=2)[0]
+
+    scene_a = make()
+    monkeypatch.setenv("GSR_DIAGNOSTICS", "0")
+    scene_b = make()
+    sa, sb = scene_a.rigid_solver, scene_b.rigid_solver
+    assert sa.tuning["diagnostics"] == 1 and sb.tuning["diagnostics"] == 0
+    assert sb.launch_info["smem_bytes_per_env"] <= sa.launch_info["smem_bytes_per_env"]
+    for _ in range(30):
+        scene_a.step(); scene_b.step()
+    for k in ("qpos", "vel", "acc", "force", "qf_applied", "qf_constraint", "n_contacts", "contact_pos", "links_pos", "links_contact_force", "cacc_lin"):
+        assert torch.equal(sa.field(k), sb.field(k)), k
+
+
 def test_lazy_diagnostics_match_per_step_diagnostics(monkeypatch):
     """cfg_diagnostics = 0 (the default): get_mass_mat / geoms poses / qf_* are recomputed on demand for the current state by
     k_diag.  They must equal what a cfg_diagnostics = 1 scene writes during the step that starts from the same state."""
