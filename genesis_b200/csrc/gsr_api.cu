@@ -387,7 +387,7 @@ static int group_launch(gsr_handle_t h, int which, cudaStream_t st, const uint8_
   if (h->auto_warps == 0) h->auto_warps = G == 32 ? auto_warps_per_cta(h, warp_bytes) : 1;  // G < 32: 1-warp CTAs measured best
   int warps = h->warps_per_cta > 0 ? h->warps_per_cta : h->auto_warps;
   if (warps > GSR_MAX_WARPS_PER_CTA) warps = GSR_MAX_WARPS_PER_CTA;
-  if (G < 32 && which == K_STEP) warps = 1;  // the small-group step kernels are compiled for one-warp CTAs (launch bounds, gsr_kernels.cuh)
+  if (G < 32 && which == K_STEP && warps > GSR_DEV_SMALL_WARPS) warps = GSR_DEV_SMALL_WARPS;  // the small-group step kernels are compiled for one-warp CTAs (launch bounds, gsr_kernels.cuh)
   while (warps > 1 && warps * (warp_bytes + 8) > 224 * 1024) warps--;  // one big CTA per SM, its warps in phase lockstep
   const int envs_per_cta = warps * EPW;
   const size_t smem = (size_t)warps * warp_bytes + (size_t)warps * 8;  // + one mbarrier per warp (TMA staging)

@@ -118,7 +118,10 @@ struct HostIO {
 // Full-warp groups run multi-warp CTAs (one big CTA or a few per SM); small groups run one-warp CTAs, as many as the workspace
 // lets an SM hold -- 17 for Franka-sized models, which needs <= 120 registers per thread.
 #ifndef GSR_LB_T
-#define GSR_LB_T(G) ((G) == 32 ? GSR_MAX_WARPS_PER_CTA * 32 : 32)
+#ifndef GSR_DEV_SMALL_WARPS
+#define GSR_DEV_SMALL_WARPS 1
+#endif
+#define GSR_LB_T(G) ((G) == 32 ? GSR_MAX_WARPS_PER_CTA * 32 : 32 * GSR_DEV_SMALL_WARPS)
 #ifndef GSR_DEV_SMALL_BLOCKS
 #define GSR_DEV_SMALL_BLOCKS 17
 #endif

@@ -467,6 +467,9 @@ __device__ __noinline__ bool hessian_incremental(const Ctx<G>& C, const Rows& R)
           bad |= fabsf(vk) > EPS && tmp < EPS;
           const float rinv = rsqrtf(fmaxf(tmp, EPS)), r = tmp * rinv;
           const float cc = r * Linv, cinv = Lkk * rinv, s_ = vk * Linv;
+          // every lane has read the pivot of column k + 1 (one column ahead, above) before its owner may overwrite it in the next
+          // trip: the shuffle orders the instruction streams, this barrier makes the order part of the memory model (racecheck)
+          C.sync();
           if (fabsf(vk) > EPS) {
             if (own && lane > k) {
               const float Lik = (hik + s_ * v * sign) * cinv;
