@@ -209,7 +209,9 @@ class Leg:
         self.workload, self.rank, self.world, self.clocks = workload, rank, world, clocks
         self.barrier, self.max_over_ranks = barrier, max_over_ranks
         if workload == "mixed":
-            per = 32768 // world
+            # both models step back to back on ONE stream: libgsrigid keeps the active model in __constant__ memory (per device), so
+            # two different models cannot run concurrently on one GPU (measured: a second stream faults on the constant upload)
+            per = envs_per_gpu // 2 if envs_per_gpu else 32768 // world
             self.parts = [("franka", per), ("go2", per)]
         else:
             self.parts = [(workload, envs_per_gpu)]
