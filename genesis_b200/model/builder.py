@@ -85,6 +85,10 @@ def _geom_inertial(g, rho):
         r = g["data"][0]
         m = rho * 4.0 / 3.0 * np.pi * r**3
         return m, np.zeros(3), 0.4 * m * r * r * np.eye(3)
+    if t == GEOM_TYPE.ELLIPSOID:
+        a, b, c = g["data"][:3]
+        m = rho * 4.0 / 3.0 * np.pi * a * b * c
+        return m, np.zeros(3), 0.2 * m * np.diag([b * b + c * c, a * a + c * c, a * a + b * b])
     if t == GEOM_TYPE.CYLINDER:
         r, h = g["data"][:2]
         m = rho * np.pi * r * r * h

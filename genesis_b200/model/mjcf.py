@@ -243,6 +243,11 @@ def parse_mjcf(path, default_armature=0.1, scale=1.0):
             elif gtype == "sphere":
                 verts, faces = meshio.icosphere(size[0] * scale, 2)
                 g_info.update(type=GEOM_TYPE.SPHERE, data=np.concatenate([[size[0] * scale], np.zeros(6)]), verts=verts, faces=faces)
+            elif gtype == "ellipsoid":  # semi-axes in geoms_info.data (support_field.py _func_support_ellipsoid)
+                semi = size[:3] * scale
+                verts, faces = meshio.icosphere(1.0, 2)
+                verts = np.asarray(verts) * semi[None, :]
+                g_info.update(type=GEOM_TYPE.ELLIPSOID, data=np.concatenate([semi, np.zeros(4)]), verts=verts, faces=faces)
             elif gtype == "capsule":
                 if "fromto" in attrs:  # segment end points instead of pos / quat / half length
                     ft = _floats(attrs["fromto"], 6) * scale

@@ -9,6 +9,8 @@ class Morph:
     quat: tuple | None = None
     collision: bool = True
     visualization: bool = False
+    contype: int = 0xFFFF       # options/morphs.py:171-183: two geoms collide when contype_a & conaffinity_b or contype_b & conaffinity_a
+    conaffinity: int = 0xFFFF
 
 
 @dataclass

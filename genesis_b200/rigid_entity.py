@@ -35,6 +35,20 @@ class RigidJoint:
         return list(range(self.dof_start - self.entity.dof_start, self.dof_start - self.entity.dof_start + self.n_dofs))
 
 
+class RigidGeom:
+    """rigid_geom.py: the part of a geom the step depends on and a user may change after build."""
+
+    def __init__(self, entity, idx, idx_local):
+        self.entity, self.idx, self.idx_local = entity, idx, idx_local
+
+    @property
+    def sol_params(self):
+        return self.entity._solver.get_geoms_sol_params([self.idx])[0]
+
+    def set_sol_params(self, sol_params):
+        self.entity._solver.set_geoms_sol_params(sol_params, [self.idx])
+
+
 class Material:
     """genesis/engine/materials/rigid.py: only the parameters that reach the rigid step."""
 
@@ -112,6 +126,10 @@ class RigidEntity:
             nq = {0: 0, 1: 1, 2: 1, 3: 4, 4: 7}[int(m.joints_type[j])]
             out.append(RigidJoint(self, e.joint_names[i], j, int(m.joints_dof_start[j]), nd, int(m.joints_q_start[j]), nq, int(m.joints_type[j])))
         return out
+
+    @property
+    def geoms(self):
+        return [RigidGeom(self, self.geom_start + i, i) for i in range(self.n_geoms)]
 
     def get_link(self, name):
         for l in self.links:

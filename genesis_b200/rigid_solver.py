@@ -25,8 +25,22 @@ class GenesisException(Exception):
     pass
 
 
+def _with_masks(l_infos, morph):
+    for l in l_infos:
+        for g in l["geoms"]:
+            g["contype"], g["conaffinity"] = int(morph.contype), int(morph.conaffinity)
+    return l_infos
+
+
 def _morph_to_infos(morph):
     """Returns (l_infos, eqs_info, is_robot, local_collision_mask)."""
+    if isinstance(morph, (_morphs.Plane, _morphs.Box, _morphs.Sphere, _morphs.Terrain)) and (morph.contype != 0xFFFF or morph.conaffinity != 0xFFFF):
+        import copy
+
+        plain = copy.copy(morph)
+        plain.contype = plain.conaffinity = 0xFFFF
+        l_infos, eqs, is_robot, local = _morph_to_infos(plain)
+        return _with_masks(l_infos, morph), eqs, is_robot, local
     if isinstance(morph, _morphs.Plane):
         return plane_l_infos(morph.pos or (0, 0, 0), morph.quat or (1, 0, 0, 0), morph.normal, morph.plane_size), [], False, False
     if isinstance(morph, _morphs.Box):
@@ -597,6 +611,27 @@ class RigidSolver:
         L = _lib.lib()
         L.gsr_model_set_f32(self._handle, name.encode(), a.ctypes.data, a.size)
         _lib.check(self._handle, L.gsr_model_refresh(self._handle))
+
+    def set_geoms_sol_params(self, sol_params, geoms_idx=None):
+        """RigidGeom.set_sol_params (rigid_geom.py; sanitised like rigid_solver.py:187-218: timeconst >= 2 dt, impedances in
+        [1e-4, 1 - 1e-4], width >= 0, power >= 1).  Contacts take the mean of both geoms' parameters (contact.py:181-222)."""
+        from .model.builder import sanitize_sol_params
+
+        m = self.model
+        idx = np.arange(m.n_geoms) if geoms_idx is None else np.atleast_1d(np.asarray(geoms_idx, dtype=np.int64))
+        vals = np.asarray(torch.as_tensor(sol_params).detach().cpu().numpy(), dtype=np.float64)
+        sp = sanitize_sol_params(np.broadcast_to(vals, (len(idx), 7)), 2.0 * self._substep_dt,
+                                 max(self._options.constraint_timeconst, 2.0 * self._substep_dt))
+        m.geoms_sol_params[idx] = sp
+        a = np.ascontiguousarray(m.geoms_sol_params, dtype=np.float32)
+        L = _lib.lib()
+        L.gsr_model_set_f32(self._handle, b"geoms_sol_params", a.ctypes.data, a.size)
+        _lib.check(self._handle, L.gsr_model_refresh(self._handle))
+
+    def get_geoms_sol_params(self, geoms_idx=None):
+        m = self.model
+        idx = np.arange(m.n_geoms) if geoms_idx is None else np.atleast_1d(np.asarray(geoms_idx, dtype=np.int64))
+        return torch.tensor(m.geoms_sol_params[idx], dtype=torch.float32, device=self.device)
 
     # per-dof parameters: model constants shared by every environment (default), or -- RigidOptions.batch_dofs_info -- fields of each
     # environment's record (dofs_info of shape (n_dofs, B) in the reference, array_class.py:1347-1364)
