@@ -12,7 +12,7 @@ _lib = None
 EXPORTS = (
     "gsr_model_begin", "gsr_model_set_f32", "gsr_model_set_i32", "gsr_model_set_scalar", "gsr_model_commit", "gsr_model_refresh",
     "gsr_state_words", "gsr_field_count", "gsr_field_info", "gsr_bind", "gsr_launch_info", "gsr_init_state", "gsr_step",
-    "gsr_forward_kinematics", "gsr_forward_kinematics_dirty", "gsr_reset_envs", "gsr_compute_diagnostics", "gsr_set_state", "gsr_gather_fields", "gsr_step_host", "gsr_launch_count", "gsr_kernel_info",
+    "gsr_forward_kinematics", "gsr_forward_kinematics_dirty", "gsr_set_kinematics_policy", "gsr_kinematics_valid", "gsr_reset_envs", "gsr_compute_diagnostics", "gsr_set_state", "gsr_gather_fields", "gsr_step_host", "gsr_launch_count", "gsr_kernel_info",
     "gsr_set_profiling", "gsr_kernel_time_ms", "gsr_debug_trace", "gsr_debug_trace_read",
     "gsr_last_error", "gsr_version", "gsr_destroy",
 )
@@ -54,6 +54,8 @@ def lib():
         L.gsr_forward_kinematics.argtypes = [vp, vp, vp]
         L.gsr_reset_envs.argtypes = [vp, vp, vp]
         L.gsr_forward_kinematics_dirty.argtypes = [vp, vp]
+        L.gsr_set_kinematics_policy.argtypes = [vp, i]
+        L.gsr_kinematics_valid.argtypes = [vp]
         L.gsr_compute_diagnostics.argtypes = [vp, vp]
         L.gsr_set_state.argtypes = [vp] + [vp] * 9 + [i, vp]
         L.gsr_gather_fields.argtypes = [vp, i, ctypes.POINTER(cp), ctypes.POINTER(vp), vp]

@@ -53,6 +53,9 @@ struct gsr_handle_s : GsrSpec {
   cudaEvent_t rows_event = nullptr;
   bool rows_pending = false, adaptive_rows = true;
   int rows_default = 0, rows_changes = 0;
+  // kinematic-cache policy (gsr_set_kinematics_policy): eager = every step leaves a valid cache (reference behaviour, default);
+  // lazy = steps recompute it on chip and never store it; cache_valid tracks what the records currently hold
+  bool eager_fk = true, cache_valid = false;
   int host_io_mode = 2;  // cfg_host_io: 0 = staged copies + k_scatter / k_gather, 1 = k_step reads / writes dense device staging, 2 = 1 + results posted straight into page-locked caller buffers
   KernelStat stats[K_COUNT] = {{"k_step", 0}, {"k_forward", 0}, {"k_reset", 0}, {"k_init", 0}, {"k_scatter", 0}, {"k_gather", 0},
                               {"k_gather_cost", 0}, {"k_order_flag", 0}, {"k_diag", 0}, {"k_set_state", 0}, {"k_gather_fields", 0}};
@@ -380,7 +383,7 @@ static int auto_warps_per_cta(const gsr_handle_t h, size_t warp_bytes) {
 }
 
 static int group_launch(gsr_handle_t h, int which, cudaStream_t st, const uint8_t* mask, int clear_ext, HostIO io = HostIO{nullptr, nullptr, nullptr},
-                        StateIO sio = StateIO{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}) {
+                        StateIO sio = StateIO{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, int fk_flags = 2) {
   if (h->group == 1 && which == K_STEP) return lane_launch(h, st, clear_ext);
   const int G = h->group == 1 ? 8 : h->group, EPW = 32 / G;  // the (cold) forward-kinematics paths of a lane model use the group kernel
   const size_t warp_bytes = (size_t)EPW * h->sl.env_words * sizeof(float);
@@ -398,15 +401,15 @@ static int group_launch(gsr_handle_t h, int which, cudaStream_t st, const uint8_
     if (h->hm.has_box_box) {                                                                             \
       CUDA_OK((set_smem(k_step<GG, true, true>, smem)));                                                 \
       Bracket br_(h, K_STEP, st);                                                                        \
-      k_step<GG, true, true><<<grid, block, smem, st>>>(h->state, h->B, h->d_model, clear_ext, h->d_order, h->d_trace, io);      \
+      k_step<GG, true, true><<<grid, block, smem, st>>>(h->state, h->B, h->d_model, clear_ext, h->d_order,  h->d_trace, io, fk_flags);      \
     } else if (h->hm.has_mpr) {                                                                          \
       CUDA_OK((set_smem(k_step<GG, true>, smem)));                                                       \
       Bracket br_(h, K_STEP, st);                                                                        \
-      k_step<GG, true><<<grid, block, smem, st>>>(h->state, h->B, h->d_model, clear_ext, h->d_order, h->d_trace, io);            \
+      k_step<GG, true><<<grid, block, smem, st>>>(h->state, h->B, h->d_model, clear_ext, h->d_order,  h->d_trace, io, fk_flags);            \
     } else {                                                                                             \
       CUDA_OK((set_smem(k_step<GG, false>, smem)));                                                      \
       Bracket br_(h, K_STEP, st);                                                                        \
-      k_step<GG, false><<<grid, block, smem, st>>>(h->state, h->B, h->d_model, clear_ext, h->d_order, h->d_trace, io);           \
+      k_step<GG, false><<<grid, block, smem, st>>>(h->state, h->B, h->d_model, clear_ext, h->d_order,  h->d_trace, io, fk_flags);           \
     }                                                                                                    \
   } else if (which == K_SET_STATE) {                                                                     \
     CUDA_OK(set_smem(k_set_state<GG>, smem));                                                            \
@@ -445,8 +448,13 @@ static int step_impl(gsr_handle_t h, int n_substeps, void* cuda_stream, HostIO i
       if (rc) return rc;
     }
     const bool last = s == n_substeps - 1;
-    rc = group_launch(h, K_STEP, st, nullptr, last, HostIO{s == 0 ? io.ctrl_pos : nullptr, last ? io.qpos : nullptr, last ? io.vel : nullptr});
+    // the lane kernel recomputes and writes the kinematics itself; diagnostics (geom poses of the new configuration) need them too
+    const bool end_fk = h->eager_fk || h->group == 1 || h->hm.diagnostics != 0;
+    const int fk_flags = (h->cache_valid ? 0 : 1) | (end_fk ? 2 : 0);
+    rc = group_launch(h, K_STEP, st, nullptr, last, HostIO{s == 0 ? io.ctrl_pos : nullptr, last ? io.qpos : nullptr, last ? io.vel : nullptr},
+                      StateIO{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, fk_flags);
     if (rc) return rc;
+    h->cache_valid = end_fk;
   }
   return GSR_OK;
 }
@@ -471,8 +479,17 @@ int gsr_init_state(gsr_handle_t h, void* cuda_stream) {
     k_init<<<(h->B + 127) / 128, 128, 0, st>>>(h->state, h->B);
   }
   CUDA_OK(cudaGetLastError());
-  return group_launch(h, K_FORWARD, st, nullptr, 0);
+  rc = group_launch(h, K_FORWARD, st, nullptr, 0);
+  h->cache_valid = rc == GSR_OK;
+  return rc;
 }
+
+int gsr_set_kinematics_policy(gsr_handle_t h, int eager) {
+  if (!h || !h->committed) return fail(h, GSR_ESTATE, "model not committed");
+  h->eager_fk = eager != 0;
+  return GSR_OK;
+}
+int gsr_kinematics_valid(gsr_handle_t h) { return (h && h->cache_valid) ? 1 : 0; }
 
 int gsr_step(gsr_handle_t h, int n_substeps, void* cuda_stream) { return step_impl(h, n_substeps, cuda_stream, HostIO{nullptr, nullptr, nullptr}); }
 
@@ -481,7 +498,9 @@ int gsr_forward_kinematics(gsr_handle_t h, const uint8_t* env_mask_dev, void* cu
   cudaStream_t st = (cudaStream_t)cuda_stream;
   int rc = activate(h, st);
   if (rc) return rc;
-  return group_launch(h, K_FORWARD, st, env_mask_dev, 0);
+  rc = group_launch(h, K_FORWARD, st, env_mask_dev, 0);
+  if (rc == GSR_OK && !env_mask_dev) h->cache_valid = true;  // a masked pass refreshes its environments only
+  return rc;
 }
 
 int gsr_set_state(gsr_handle_t h, const uint8_t* env_mask_dev, const float* qpos, const float* dofs_vel, const float* dofs_acc,

@@ -84,7 +84,7 @@ __device__ __noinline__ void fk_link(const Ctx<G>& C, int l, bool has_parent, f3
 // Kinematics of the whole environment from qpos / vel (FK:580-736, FK:337-576, FK:993-1116): rebuilds the kinematic cache.
 // ---------------------------------------------------------------------------------------------------------------------
 template <int G>
-__device__ void phase_kinematics(const Ctx<G>& C) {
+__device__ __noinline__ void phase_kinematics(const Ctx<G>& C) {  // one copy for its two call sites in k_step (start / epilogue)
   const int nL = CM(nL), nD = CM(nD), nJ = CM(nJ);
   const float EPS = CM(eps);
   const int lane = C.lane;

@@ -231,7 +231,10 @@ static inline int gsr_compute_layouts(GsrSpec* h, int n_envs) {
   GSR_HOT_PRE_FIELDS(X)
   off = gsr_round4(off);
   L.in_start = (int)off;
-  GSR_HOT_IN_FIELDS(X)
+  GSR_HOT_STATE_FIELDS(X)
+  off = gsr_round4(off);
+  L.n_state = (int)off;
+  GSR_HOT_CACHE_FIELDS(X)
   off = gsr_round4(off);
   L.n_in = (int)off;
   L.kin_dead = L.cinr_I;

@@ -56,12 +56,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 // Loads the IN parts of the (up to 32 / G) live environments of this warp; `bar` is this warp's mbarrier (one phase per launch).
 template <int G>
-__device__ __forceinline__ void bulk_load_in(float* state, int B, float* smem, uint64_t* bar, const int* order) {
+__device__ __forceinline__ void bulk_load_in(float* state, int B, float* smem, uint64_t* bar, const int* order, int n_end) {
   constexpr int EPW = 32 / G;
   const int warp = threadIdx.x >> 5, lane32 = threadIdx.x & 31;
   const int env0 = (blockIdx.x * (blockDim.x >> 5) + warp) * EPW;
   const int n_live = min(EPW, B - env0);  // > 0 for a live warp
-  const uint32_t bytes = (uint32_t)(c_h.n_in - c_h.in_start) * 4u;
+  const uint32_t bytes = (uint32_t)(n_end - c_h.in_start) * 4u;
   const uint32_t b = smem_u32(bar);
   if (lane32 == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b), "r"(1) : "memory");
@@ -81,12 +81,12 @@ __device__ __forceinline__ void bulk_load_in(float* state, int B, float* smem, u
 }
 // Stores the IN parts back (smem -> global bulk copies); returns after the TMA has finished reading shared memory.
 template <int G>
-__device__ __forceinline__ void bulk_store_in(float* state, int B, float* smem, const int* order) {
+__device__ __forceinline__ void bulk_store_in(float* state, int B, float* smem, const int* order, int n_end) {
   constexpr int EPW = 32 / G;
   const int warp = threadIdx.x >> 5, lane32 = threadIdx.x & 31;
   const int env0 = (blockIdx.x * (blockDim.x >> 5) + warp) * EPW;
   const int n_live = min(EPW, B - env0);
-  const uint32_t bytes = (uint32_t)(c_h.n_in - c_h.in_start) * 4u;
+  const uint32_t bytes = (uint32_t)(n_end - c_h.in_start) * 4u;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the async proxy
   __syncwarp();
   if (lane32 == 0) {
@@ -102,7 +102,7 @@ __device__ __forceinline__ void bulk_store_in(float* state, int B, float* smem, 
 }
 
 template <int G>
-__device__ __forceinline__ void step_epilogue(const Ctx<G>& C, int clear_ext);
+__device__ __forceinline__ void step_epilogue(const Ctx<G>& C, int clear_ext, bool end_fk);
 
 // gsr_step_host: the step kernel itself reads this step's control targets from a dense (B, nD) device staging buffer and
 // writes the new qpos / vel to dense (B, n) buffers -- device staging, or the device-side aliases of the caller's PAGE-LOCKED
@@ -129,7 +129,7 @@ struct HostIO {
 #endif
 template <int G, bool MPR, bool BB = false>
 __global__ void __launch_bounds__(GSR_LB_T(G), GSR_LB_B(G)) k_step(float* state, int B, const DevModel* gm, int clear_ext, const int* order,
-                                                                        unsigned long long* trace, HostIO io) {
+                                                                        unsigned long long* trace, HostIO io, int fk_flags) {
   extern __shared__ __align__(16) float smem[];
   Ctx<G> C;
   // order[B] tells whether the measured costs are spread enough for the permutation to pay (uniform batches keep the
@@ -148,7 +148,21 @@ __global__ void __launch_bounds__(GSR_LB_T(G), GSR_LB_B(G)) k_step(float* state,
   // a warp is live when its first environment exists; its mbarrier sits after the workspaces
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)(blockDim.x >> 5) * (32 / G) * c_s.env_words);
   const bool warp_live = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (32 / G) < B;
-  if (warp_live) bulk_load_in<G>(state, B, smem, bars + (threadIdx.x >> 5), order);
+  // fk_flags: bit 0 = the kinematic cache of the records is stale: load the state block only and run the kinematics first; bit 1 =
+  // leave a valid cache behind (kinematics of the new configuration in the epilogue, whole IN part stored).  Eager stepping is
+  // (0, 1): what the reference does (FK at the end of kernel_step_2).  Lazy stepping is (1, 0): the same arithmetic per step, but the
+  // cache never travels through HBM -- the host asks for it (k_forward) only when an accessor needs link poses / velocities.
+  const bool start_fk = fk_flags & 1, end_fk = (fk_flags & 2) != 0;
+  if (warp_live) bulk_load_in<G>(state, B, smem, bars + (threadIdx.x >> 5), order, start_fk ? c_h.n_state : c_h.n_in);
+  if (start_fk && live) {  // group-uniform: fixed roots keep a user-set pose (state, not cache), everything else follows from qpos / vel
+    for (int l = C.lane; l < CM(nL); l += G)
+      if (GM(l_parent[l]) == -1 && GM(l_is_fixed[l])) {
+        for (int k = 0; k < 3; k++) IN(links_pos)[3 * l + k] = C.rec[c_h.links_pos + 3 * l + k];
+        for (int k = 0; k < 4; k++) IN(links_quat)[4 * l + k] = C.rec[c_h.links_quat + 4 * l + k];
+      }
+    C.sync();
+    phase_kinematics(C);
+  }
   if (io.ctrl_pos && live) {  // this step's control targets from the dense staging buffer
     const int nD = CM(nD);
     const float* src = io.ctrl_pos + (size_t)C.env * nD;
@@ -176,7 +190,7 @@ __global__ void __launch_bounds__(GSR_LB_T(G), GSR_LB_B(G)) k_step(float* state,
   TRACE_MARK(4);
   PHASE_BARRIER(4);
   PHASE_BEGIN();
-  if (live) step_epilogue(C, clear_ext);
+  if (live) step_epilogue(C, clear_ext, end_fk);
   PHASE_END();
   if (live && C.lane == 0) reinterpret_cast<int*>(C.rec)[c_h.step_cost] = (int)min(busy, (long long)0x7fffffff);
   if (live && (io.qpos || io.vel)) {  // results into dense staging or straight into the caller's pinned buffers (posted PCIe writes)
@@ -185,7 +199,7 @@ __global__ void __launch_bounds__(GSR_LB_T(G), GSR_LB_B(G)) k_step(float* state,
     if (io.vel) for (int d = C.lane; d < nD; d += G) __stcs(io.vel + (size_t)C.env * nD + d, IN(vel)[d]);
   }
   __syncwarp();
-  if (warp_live) bulk_store_in<G>(state, B, smem, order);
+  if (warp_live) bulk_store_in<G>(state, B, smem, order, end_fk ? c_h.n_in : c_h.n_state);
   if (trace && live && C.lane == 0) {
     unsigned smid;
     TRACE_MARK(5);
@@ -229,7 +243,7 @@ __device__ __forceinline__ void write_geom_poses(const Ctx<G>& C) {
 }
 
 template <int G>
-__device__ __forceinline__ void step_epilogue(const Ctx<G>& C, int clear_ext) {
+__device__ __forceinline__ void step_epilogue(const Ctx<G>& C, int clear_ext, bool end_fk) {
   // ---- outputs that live in scratch recycled by the kinematics
   const int nD = CM(nD), nL = CM(nL), MS = c_s.MS, lane = C.lane;
   float* rec = C.rec;
@@ -244,7 +258,7 @@ __device__ __forceinline__ void step_epilogue(const Ctx<G>& C, int clear_ext) {
   }
   if (CM(diagnostics)) write_dynamics_diagnostics(C);
   C.sync();
-  phase_kinematics(C);
+  if (end_fk) phase_kinematics(C);
   if (CM(diagnostics)) write_geom_poses(C);  // geoms_state.pos / quat of the post-integration configuration (FK:828-864)
   if (clear_ext && C.SI()[c_h.has_ext_force]) {  // RS:2603-2612 clear_external_force
     for (int i = lane; i < 3 * nL; i += G) { rec[c_h.cfrc_applied_vel + i] = 0.f; rec[c_h.cfrc_applied_ang + i] = 0.f; }

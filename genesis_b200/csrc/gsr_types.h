@@ -118,15 +118,18 @@ struct DevModel {
 // kernel, so mirroring them in shared memory and storing them back would only cost workspace and HBM traffic).
 #define GSR_HOT_PRE_FIELDS(X)                                                                                      \
   X(ctrl_vel, 0, nD, 1) X(ctrl_force, 0, nD, 1) X(ctrl_mode, 1, nD, 1) X(fk_dirty, 1, 1, 1)
-#define GSR_HOT_IN_FIELDS(X)                                                                                       \
-  /* persistent state (rigid_global_info.qpos, dofs_state.vel / ctrl_pos, constraint_state.qacc_ws) */             \
+#define GSR_HOT_STATE_FIELDS(X)                                                                                    \
+  /* persistent state (rigid_global_info.qpos, dofs_state.vel / ctrl_pos, constraint_state.qacc_ws) and dofs_state.pos */ \
   X(qpos, 0, nQ, 1) X(vel, 0, nD, 1) X(ctrl_pos, 0, nD, 1) X(qacc_ws, 0, nD, 1)                                    \
   X(is_warmstart, 1, 1, 1) X(errno_, 1, 1, 1) X(n_contacts, 1, 1, 1) X(n_broad, 1, 1, 1)                           \
-  X(has_ext_force, 1, 1, 1) X(has_shift, 1, 1, 1) X(n_dyn_eq, 1, 1, 1)                                           \
-  /* kinematic cache written by the FK at the end of a step and consumed by the next step */                       \
-  X(dofs_pos, 0, nD, 1) X(root_COM, 0, nL, 3) X(cdof_ang, 0, nD, 3) X(cdof_vel, 0, nD, 3) X(cdofd_ang, 0, nD, 3)   \
+  X(has_ext_force, 1, 1, 1) X(has_shift, 1, 1, 1) X(n_dyn_eq, 1, 1, 1) X(dofs_pos, 0, nD, 1)
+#define GSR_HOT_CACHE_FIELDS(X)                                                                                    \
+  /* kinematic cache: a pure function of (qpos, vel, poses of the fixed roots).  Written by the FK at the end of a step and   \
+     consumed by the next one (eager), or recomputed at the start of every step and never stored (lazy, gsr_set_kinematics_policy) */ \
+  X(root_COM, 0, nL, 3) X(cdof_ang, 0, nD, 3) X(cdof_vel, 0, nD, 3) X(cdofd_ang, 0, nD, 3)                         \
   X(cdofd_vel, 0, nD, 3) X(links_pos, 0, nL, 3) X(links_quat, 0, nL, 4) X(cinr_I, 0, nL, 6) X(cinr_pos, 0, nL, 3)  \
   X(cd_vel, 0, nL, 3) X(cd_ang, 0, nL, 3)
+#define GSR_HOT_IN_FIELDS(X) GSR_HOT_STATE_FIELDS(X) GSR_HOT_CACHE_FIELDS(X)
 #define GSR_HOT_OUT_FIELDS(X)                                                                                      \
   /* rarely used inputs, read from the record on demand: per-geom friction scale (set_friction_ratio) and the external  \
      wrenches of apply_links_external_force (only read and cleared when has_ext_force is set) */                       \
@@ -155,6 +158,7 @@ struct HotLayout {
   GSR_HOT_OUT_FIELDS(X)
 #undef X
   int in_start;    // first word of the IN part = size of the PRE block (multiple of 4)
+  int n_state;     // end of the state block of the IN part (multiple of 4): all a lazy-kinematics step loads and stores
   int n_in;        // end of the IN part (multiple of 4): record words [in_start, n_in) are mirrored in shared memory
   int kin_dead;    // first word of the IN part that is dead after collision detection (links_pos ...)
   int hot_stride;  // words per env in the HOT segment (multiple of 4)

@@ -106,8 +106,13 @@ class RigidSolver:
         self._handle = None
         self._n_substeps_total = 0
         self._errno_host = self._errno_event = None
-        self._obs_valid, self._obs = False, None
+        self._obs_valid, self._obs, self._obs_have = False, None, set()
         self._fk_dirty_any = False
+        self._kin_valid, self._kin_requested, self._eager_fk = True, False, True
+        import os as _os
+        # GSR_LAZY_FK=1: adaptive kinematics (see _apply_kinematics_policy).  Off by default: it halves the HBM traffic of a pure
+        # stepping loop but measured slower for Franka-sized models (profiles/README.md item 16)
+        self._adaptive_fk = _os.environ.get("GSR_LAZY_FK", "0") == "1"
         self._errno_pending = False
         # launch tuning of libgsrigid (0 = library default): lanes per environment, constraint rows kept in shared
         # memory, and whether the diagnostic fields (mass_mat, qf_*, acc_smooth, geom poses) are written every step
@@ -211,6 +216,7 @@ class RigidSolver:
             self._fields[name.value.decode()] = torch.as_strided(buf, shape, strides, seg + off)
         _lib.check(h, L.gsr_init_state(h, self._stream()))
         self._is_built = True
+        self.launch_info_cached = self.launch_info
         self._init_qpos = self._fields["qpos"].clone()  # (B, nQ)
         self._envs_all = torch.arange(self._B, device=self.device)
         m_ = self.model
@@ -236,24 +242,53 @@ class RigidSolver:
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    # fields that are a function of (qpos, vel): valid in the records only after an eager step or a forward-kinematics pass
+    KIN_FIELDS = frozenset(("dofs_pos", "root_COM", "cdof_ang", "cdof_vel", "cdofd_ang", "cdofd_vel", "links_pos", "links_quat", "cinr_I",
+                            "cinr_pos", "cd_vel", "cd_ang"))
+
+    def _ensure_kinematics(self):
+        """Lazy kinematics (see `substep`): the records hold no link poses / velocities after a lazy step; the first accessor
+        that needs them runs one forward-kinematics pass over all environments and makes the next steps eager."""
+        self._kin_requested = True
+        if not self._kin_valid:
+            _lib.check(self._handle, _lib.lib().gsr_forward_kinematics(self._handle, None, self._stream()))
+            self._kin_valid = True
+            self._fk_dirty_any = False
+
     def field(self, name):
         """Zero-copy torch view of a state field, (B, items) or (B, items, comps): the reference's transposed zero-copy
         qd_to_torch views (genesis/utils/misc.py:415-536) are plain strided views of the env-major records here."""
+        if name in self.KIN_FIELDS:
+            self._ensure_kinematics()
         return self._fields[name]
 
     def rows(self, name):
         """(B, items * comps) copy-free when possible: every scalar of a field, one row per environment."""
-        return self._fields[name].reshape(self._B, -1)
+        return self.field(name).reshape(self._B, -1)
 
     # ------------------------------------------------------------------ stepping
     def _flush_deferred_fk(self):
-        if self._fk_dirty_any:
+        if self._fk_dirty_any and self._kin_valid:
             _lib.check(self._handle, _lib.lib().gsr_forward_kinematics_dirty(self._handle, self._stream()))
-            self._fk_dirty_any = False
+        self._fk_dirty_any = False  # with a stale cache the step recomputes the kinematics of every environment anyway
+
+    def _apply_kinematics_policy(self):
+        """Adaptive kinematics: a step leaves link poses / velocities in the records (eager, what the reference does at the end of
+        kernel_step_2) only if an accessor asked for them since the previous step -- an RL loop reading observations every step
+        stays eager, a pure stepping loop runs lazy: the same arithmetic, but the kinematic cache never travels through HBM.
+        Opt-in (GSR_LAZY_FK=1); the default is the reference's eager behaviour."""
+        eager = self._kin_requested or not self._adaptive_fk or bool(self.tuning.get("diagnostics")) or self.launch_info_cached["group_size"] == 1
+        if eager != self._eager_fk:
+            _lib.check(self._handle, _lib.lib().gsr_set_kinematics_policy(self._handle, int(eager)))
+            self._eager_fk = eager
+        self._kin_requested = False
+        return eager
 
     def substep(self, n=1):
         self._flush_deferred_fk()
+        eager = self._apply_kinematics_policy()
         _lib.check(self._handle, _lib.lib().gsr_step(self._handle, n, self._stream()))
+        self._kin_valid = eager
         self._n_substeps_total += n
         self._obs_valid = False
 
@@ -268,6 +303,8 @@ class RigidSolver:
         """Reference-facing host-buffer call (bench.py e2e): numpy (B, n) float32 arrays in / out."""
         p = lambda a: ctypes.c_void_p(a.ctypes.data) if a is not None else None
         self._flush_deferred_fk()
+        eager = self._apply_kinematics_policy()
+        self._kin_valid = eager
         _lib.check(self._handle, _lib.lib().gsr_step_host(self._handle, n, p(ctrl_pos_host), p(qpos_host), p(vel_host), self._stream()))
         self._n_substeps_total += n
         self._obs_valid = False
@@ -357,15 +394,25 @@ class RigidSolver:
 
     # fields the observation getters of an RL loop read: gathered into dense (B, n) tensors by ONE launch the first time any of them
     # is asked for after a step / setter (k_gather_fields); the getters then return copies of those dense tensors
-    OBS_FIELDS = ("qpos", "dofs_pos", "vel", "links_pos", "links_quat", "cd_vel", "cd_ang", "root_COM", "acc", "force", "qf_applied",
-                  "cacc_lin", "cacc_ang", "links_contact_force")
+    OBS_STATE = ("qpos", "vel", "acc", "force", "qf_applied", "cacc_lin", "cacc_ang", "links_contact_force")
+    OBS_KIN = ("dofs_pos", "links_pos", "links_quat", "cd_vel", "cd_ang", "root_COM")
+    OBS_FIELDS = OBS_STATE + OBS_KIN
 
     def _observed(self, name):
+        """Dense (B, n) snapshot of an observation field.  Two groups, each gathered by ONE launch the first time one of its fields
+        is asked for after a step / setter: plain state (never forces kinematics) and kinematic quantities (forces a valid cache)."""
         if name not in self.OBS_FIELDS:
-            return self._fields[name]
+            return self.field(name)
         if not self._obs_valid:
-            self._obs = self.gather_fields(list(self.OBS_FIELDS), out=self._obs)
+            self._obs_have = set()
             self._obs_valid = True
+        if name not in self._obs_have:
+            if self._kin_valid and not self._obs_have:
+                group = self.OBS_FIELDS  # the records hold everything: one launch serves every getter of this step
+            else:
+                group = self.OBS_KIN if name in self.OBS_KIN else self.OBS_STATE
+            self._obs = {**(self._obs or {}), **self.gather_fields(list(group), out=self._obs)}
+            self._obs_have.update(group)
         return self._obs[name]
 
     def _get(self, name, idx, envs_idx, n, comps=1):
@@ -442,6 +489,10 @@ class RigidSolver:
         return mask
 
     def _forward(self, envs_idx=None):
+        if envs_idx is None:
+            self._kin_valid = True
+        elif not self._kin_valid:
+            return  # the cache is stale for every environment: the next step (or the next accessor) recomputes all of it
         mask = self._env_mask(envs_idx)
         ptr = ctypes.c_void_p(mask.data_ptr()) if mask is not None else None
         _lib.check(self._handle, _lib.lib().gsr_forward_kinematics(self._handle, ptr, self._stream()))
@@ -490,7 +541,7 @@ class RigidSolver:
         envs = self._envs(envs_idx)
         nb = self._B if envs is None else len(envs)
         pos = torch.broadcast_to(torch.as_tensor(position, dtype=torch.float32, device=self.device), (nb, len(dofs)))
-        cur = self._fields["dofs_pos"].clone()  # (B, nD)
+        cur = self.field("dofs_pos").clone()  # (B, nD)
         sel = cur if envs is None else cur[envs]
         sel[:, dofs] = pos
         qpos = self._fields["qpos"].clone()
@@ -548,13 +599,13 @@ class RigidSolver:
         sel = (lambda f: f[:, links]) if envs is None else (lambda f: f[envs][:, links])
         if local:
             iq = torch.tensor(m.links_inertial_quat, dtype=torch.float32, device=self.device)[links]
-            quat = sel(self._fields["links_quat"])
+            quat = sel(self.field("links_quat"))
             force = _rotate_torch(force, _quat_mul_torch(quat, iq[None].expand(quat.shape[0], -1, -1)))
-        root = sel(self._fields["root_COM"])
+        root = sel(self.field("root_COM"))
         if ref == "link_com":
             arm = self._get_links_com(links, envs) - root
         elif ref == "link_origin":
-            arm = sel(self._fields["links_pos"]) - root
+            arm = sel(self.field("links_pos")) - root
         else:
             arm = torch.zeros_like(force)
         torque = torch.cross(arm, force, dim=-1)
@@ -572,7 +623,7 @@ class RigidSolver:
         nb = self._B if envs is None else len(envs)
         torque = torch.broadcast_to(torch.as_tensor(torque, dtype=torch.float32, device=self.device), (nb, len(links), 3))
         if local:
-            quat = self._fields["links_quat"][:, links]
+            quat = self.field("links_quat")[:, links]
             quat = quat if envs is None else quat[envs]
             if ref == "link_com":  # inertial frame: link quat (x) inertial quat
                 iq = torch.tensor(m.links_inertial_quat, dtype=torch.float32, device=self.device)[links]
@@ -585,8 +636,8 @@ class RigidSolver:
 
     def _get_links_com(self, links, envs):
         m = self.model
-        pos = self._fields["links_pos"][:, links]
-        quat = self._fields["links_quat"][:, links]
+        pos = self.field("links_pos")[:, links]
+        quat = self.field("links_quat")[:, links]
         if envs is not None:
             pos, quat = pos[envs], quat[envs]
         ipos = torch.tensor(m.links_inertial_pos, dtype=torch.float32, device=self.device)[links]
@@ -817,8 +868,8 @@ class RigidSolver:
         n = self._fields["n_dyn_eq"][e, 0]
         if int(n.max()) >= self.MAX_DYN_EQ:
             raise GenesisException("Exceeding max number of dynamic equality constraints (max_dynamic_constraints).")
-        p1, q1 = self._fields["links_pos"][e, link1_idx], self._fields["links_quat"][e, link1_idx]
-        p2, q2 = self._fields["links_pos"][e, link2_idx], self._fields["links_quat"][e, link2_idx]
+        p1, q1 = self.field("links_pos")[e, link1_idx], self.field("links_quat")[e, link1_idx]
+        p2, q2 = self.field("links_pos")[e, link2_idx], self.field("links_quat")[e, link2_idx]
         q2c = torch.cat([q2[:, :1], -q2[:, 1:]], dim=-1)
         q1c = torch.cat([q1[:, :1], -q1[:, 1:]], dim=-1)
         pos1 = torch.zeros_like(p1)                      # the shared point is link1's origin
@@ -899,6 +950,7 @@ class RigidSolver:
         acc_smooth, geoms_pos / quat); the accessors that expose them recompute them for the CURRENT state on demand (k_diag).
         With GSR_DIAGNOSTICS=1 they are written every step with the reference's timing and this is a no-op."""
         if not self.tuning.get("diagnostics"):
+            self._ensure_kinematics()
             _lib.check(self._handle, _lib.lib().gsr_compute_diagnostics(self._handle, self._stream()))
 
     def get_geoms_pos(self, geoms_idx=None, envs_idx=None):
@@ -969,6 +1021,8 @@ class RigidSolver:
         """{name: dense (B, items[, comps]) tensor} of several record fields in ONE launch (gsr_gather_fields)."""
         out = out or {}
         bufs = []
+        if any(nme in self.KIN_FIELDS for nme in names):
+            self._ensure_kinematics()
         for nme in names:
             f = self._fields[nme]
             t = out.get(nme)

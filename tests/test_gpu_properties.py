@@ -145,3 +145,31 @@ def test_step_host_after_device_steps_keeps_adaptive_rows_alive():
     if mean_rows > rows0:  # the batch needs more rows than the default capacity: the adaptation must have happened and survived
         assert sb.launch_info["smem_rows"] > rows0, (rows0, sb.launch_info, mean_rows)
     assert sb.launch_info == sa.launch_info
+
+
+@pytest.mark.parametrize("model", ["go2", "franka"])
+def test_lazy_kinematics_equals_eager(model, monkeypatch):
+    """Adaptive kinematics (RigidSolver.substep, opt-in with GSR_LAZY_FK=1): a loop that only steps runs `lazy` -- every step recomputes the kinematic cache
+    on chip from qpos / vel and stores the state block only -- while a loop that reads link poses stays `eager` (the reference's
+    FK at the end of kernel_step_2).  Same arithmetic either way: trajectories, contacts and the link poses an accessor finally
+    asks for are bit-identical, and mode switches in the middle of a run change nothing."""
+    from genesis_b200 import _lib
+
+    make = (lambda: make_go2(256, seed=11)) if model == "go2" else (lambda: make_franka(256, self_collision=True, randomized=True, controlled=False, seed=11))
+    monkeypatch.setenv("GSR_LAZY_FK", "0")
+    scene_e, robot_e = make()
+    monkeypatch.setenv("GSR_LAZY_FK", "1")
+    scene_l, robot_l = make()
+    se, sl = scene_e.rigid_solver, scene_l.rigid_solver
+    for k in range(40):
+        scene_e.step(); scene_l.step()
+        if k in (9, 25):  # an accessor in the middle of the run: one forward pass, then eager for the following step
+            assert torch.equal(robot_l.get_links_pos(), robot_e.get_links_pos())
+    assert sl._eager_fk is False and _lib.lib().gsr_kinematics_valid(sl._handle) == 0, "the stepping-only loop did not run lazy"
+    assert se._eager_fk is True and _lib.lib().gsr_kinematics_valid(se._handle) == 1
+    assert torch.equal(se.field("qpos"), sl.field("qpos")) and torch.equal(se.field("vel"), sl.field("vel"))
+    assert torch.equal(se.field("n_contacts"), sl.field("n_contacts"))
+    assert torch.equal(se.field("contact_pos"), sl.field("contact_pos"))
+    for name in ("links_pos", "links_quat", "cd_vel", "cd_ang", "root_COM", "dofs_pos", "cdof_ang", "cinr_I"):
+        assert torch.equal(se.field(name), sl.field(name)), name
+    assert sl.kernel_launches()["k_forward"] > se.kernel_launches()["k_forward"]
