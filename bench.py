@@ -209,8 +209,8 @@ class Leg:
         self.workload, self.rank, self.world, self.clocks = workload, rank, world, clocks
         self.barrier, self.max_over_ranks = barrier, max_over_ranks
         if workload == "mixed":
-            # both models step back to back on ONE stream: libgsrigid keeps the active model in __constant__ memory (per device), so
-            # two different models cannot run concurrently on one GPU (measured: a second stream faults on the constant upload)
+            # two models on one GPU: each scene gets its own copy of the library (its own CUDA module and __constant__ model,
+            # genesis_b200/_lib.py), so they step concurrently on two streams and share the SMs
             per = envs_per_gpu // 2 if envs_per_gpu else 32768 // world
             self.parts = [("franka", per), ("go2", per)]
         else:
@@ -218,14 +218,44 @@ class Leg:
         self.scenes = [build_scene(w, b, seed=rank)[0] for w, b in self.parts]
         self.B = sum(b for _, b in self.parts)
         self.settled = False
+        self.streams = None
+        if len(self.scenes) > 1 and len({s.rigid_solver._lib_instance for s in self.scenes}) == len(self.scenes) \
+                and os.environ.get("GSR_BENCH_SERIAL_SCENES", "0") != "1":
+            import torch
+
+            self.streams = [torch.cuda.Stream() for _ in self.scenes]
 
     @property
     def solvers(self):
         return [s.rigid_solver for s in self.scenes]
 
     def step(self):
-        for s in self.scenes:
-            s.step()
+        if self.streams is None:
+            for s in self.scenes:
+                s.step()
+            return
+        import torch
+
+        for s, st in zip(self.scenes, self.streams):
+            with torch.cuda.stream(st):
+                s.step()
+
+    def fork_streams(self):
+        """The per-scene streams start after everything already enqueued on the current stream (the timing event included)."""
+        if self.streams is not None:
+            import torch
+
+            cur = torch.cuda.current_stream()
+            for st in self.streams:
+                st.wait_stream(cur)
+
+    def join_streams(self):
+        if self.streams is not None:
+            import torch
+
+            cur = torch.cuda.current_stream()
+            for st in self.streams:
+                cur.wait_stream(st)
 
     def settle(self):
         if not self.settled:
@@ -236,16 +266,20 @@ class Leg:
     def time_resident(self, K, W):
         import torch
 
+        self.fork_streams()
         self.settle()
         for _ in range(W):
             self.step()
+        self.join_streams()
         l0 = sum(s.launch_count() for s in self.solvers)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         self.barrier()
         self.clocks.mark(True)
         e0.record()
+        self.fork_streams()
         for _ in range(K):
             self.step()
+        self.join_streams()
         e1.record()
         self.barrier()
         self.clocks.mark(False)

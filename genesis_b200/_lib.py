@@ -8,6 +8,12 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GSR_LIB") or os.path.join(_HERE, "csrc", "libgsrigid.so")  # GSR_LIB: developer builds (make trace)
 _lib = None
+# A second copy of the library (libgsrigid.1.so, made by the Makefile) gives a second scene on the same GPU its own CUDA module and
+# with it its own __constant__ model: two different models then neither re-upload their constants at every step nor race when they
+# run on two streams.  Scenes beyond N_INSTANCES alive at once share instance 0 (one stream, constants re-uploaded on every switch).
+N_INSTANCES = 2
+_libs = {}
+_slots = {}  # device index -> [owner id or None] * N_INSTANCES
 
 EXPORTS = (
     "gsr_model_begin", "gsr_model_set_f32", "gsr_model_set_i32", "gsr_model_set_scalar", "gsr_model_commit", "gsr_model_refresh",
@@ -29,14 +35,35 @@ def build(force=False):
     return LIB_PATH
 
 
-def lib():
+def instance_path(instance):
+    return LIB_PATH if instance == 0 else LIB_PATH[:-3] + f".{instance}.so"
+
+
+def acquire_instance(device_index, owner):
+    """Lowest library instance no live solver uses on this device (0 when all are taken or the extra copy was not built)."""
+    slots = _slots.setdefault(device_index, [None] * N_INSTANCES)
+    for k in range(N_INSTANCES):
+        if slots[k] is None and (k == 0 or os.path.exists(instance_path(k))):
+            slots[k] = id(owner)
+            return k
+    return 0
+
+
+def release_instance(device_index, instance, owner):
+    slots = _slots.get(device_index)
+    if slots is not None and slots[instance] == id(owner):
+        slots[instance] = None
+
+
+def lib(instance=0):
     global _lib
-    if _lib is None:
-        if not os.path.exists(LIB_PATH):
+    if instance not in _libs:
+        path = instance_path(instance)
+        if not os.path.exists(path):
             raise GsrError(
-                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)"
+                f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)"
             )
-        L = ctypes.CDLL(LIB_PATH)
+        L = ctypes.CDLL(path)
         vp, cp, i, sz = ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_size_t
         L.gsr_model_begin.argtypes = [ctypes.POINTER(vp)]
         L.gsr_model_set_f32.argtypes = [vp, cp, vp, sz]
@@ -71,11 +98,13 @@ def lib():
         L.gsr_last_error.restype = cp
         L.gsr_version.restype = cp
         L.gsr_destroy.argtypes = [vp]
-        _lib = L
-    return _lib
+        _libs[instance] = L
+        if instance == 0:
+            _lib = L
+    return _libs[instance]
 
 
 def check(handle, rc):
     if rc != 0:
-        msg = lib().gsr_last_error(handle)
+        msg = lib().gsr_last_error(handle)  # reads the handle's own message buffer: any instance's code can do it
         raise GsrError(f"gsrigid error {rc}: {msg.decode() if msg else ''}")

@@ -190,7 +190,10 @@ class RigidSolver:
         self._B = max(1, n_envs)
         self.device = torch.device(device)
         m = self.model if self.model is not None else self.build_model()
-        L = _lib.lib()
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self._lib_instance = _lib.acquire_instance(dev_index, self)  # its own CUDA module (constant memory) when another scene is alive
+        self._lib_device = dev_index
+        L = self._L = _lib.lib(self._lib_instance)
         h = ctypes.c_void_p()
         _lib.check(None, L.gsr_model_begin(ctypes.byref(h)))
         self._handle = h
@@ -223,7 +226,7 @@ class RigidSolver:
         self._dofs_limit = torch.tensor(m_.dofs_limit, dtype=torch.float32, device=self.device).reshape(-1, 2)
 
     def _upload_model_arrays(self):
-        L, h, m = _lib.lib(), self._handle, self.model
+        L, h, m = self._L, self._handle, self.model
         self._model_keepalive = []
         for k, v in m.__dict__.items():
             if isinstance(v, np.ndarray):
@@ -251,7 +254,7 @@ class RigidSolver:
         that needs them runs one forward-kinematics pass over all environments and makes the next steps eager."""
         self._kin_requested = True
         if not self._kin_valid:
-            _lib.check(self._handle, _lib.lib().gsr_forward_kinematics(self._handle, None, self._stream()))
+            _lib.check(self._handle, self._L.gsr_forward_kinematics(self._handle, None, self._stream()))
             self._kin_valid = True
             self._fk_dirty_any = False
 
@@ -269,7 +272,7 @@ class RigidSolver:
     # ------------------------------------------------------------------ stepping
     def _flush_deferred_fk(self):
         if self._fk_dirty_any and self._kin_valid:
-            _lib.check(self._handle, _lib.lib().gsr_forward_kinematics_dirty(self._handle, self._stream()))
+            _lib.check(self._handle, self._L.gsr_forward_kinematics_dirty(self._handle, self._stream()))
         self._fk_dirty_any = False  # with a stale cache the step recomputes the kinematics of every environment anyway
 
     def _apply_kinematics_policy(self):
@@ -279,7 +282,7 @@ class RigidSolver:
         Opt-in (GSR_LAZY_FK=1); the default is the reference's eager behaviour."""
         eager = self._kin_requested or not self._adaptive_fk or bool(self.tuning.get("diagnostics")) or self.launch_info_cached["group_size"] == 1
         if eager != self._eager_fk:
-            _lib.check(self._handle, _lib.lib().gsr_set_kinematics_policy(self._handle, int(eager)))
+            _lib.check(self._handle, self._L.gsr_set_kinematics_policy(self._handle, int(eager)))
             self._eager_fk = eager
         self._kin_requested = False
         return eager
@@ -287,7 +290,7 @@ class RigidSolver:
     def substep(self, n=1):
         self._flush_deferred_fk()
         eager = self._apply_kinematics_policy()
-        _lib.check(self._handle, _lib.lib().gsr_step(self._handle, n, self._stream()))
+        _lib.check(self._handle, self._L.gsr_step(self._handle, n, self._stream()))
         self._kin_valid = eager
         self._n_substeps_total += n
         self._obs_valid = False
@@ -296,7 +299,7 @@ class RigidSolver:
     def launch_info(self):
         """Launch geometry of the step kernel as of now (the on-chip row capacity follows the workload, gsr_api.cu adapt_rows)."""
         gi = [ctypes.c_int() for _ in range(4)]
-        _lib.check(self._handle, _lib.lib().gsr_launch_info(self._handle, *[ctypes.byref(x) for x in gi]))
+        _lib.check(self._handle, self._L.gsr_launch_info(self._handle, *[ctypes.byref(x) for x in gi]))
         return dict(group_size=gi[0].value, smem_bytes_per_env=gi[1].value, smem_rows=gi[2].value, smem_contacts=gi[3].value)
 
     def step_host(self, ctrl_pos_host, qpos_host, vel_host, n=1):
@@ -305,32 +308,32 @@ class RigidSolver:
         self._flush_deferred_fk()
         eager = self._apply_kinematics_policy()
         self._kin_valid = eager
-        _lib.check(self._handle, _lib.lib().gsr_step_host(self._handle, n, p(ctrl_pos_host), p(qpos_host), p(vel_host), self._stream()))
+        _lib.check(self._handle, self._L.gsr_step_host(self._handle, n, p(ctrl_pos_host), p(qpos_host), p(vel_host), self._stream()))
         self._n_substeps_total += n
         self._obs_valid = False
 
     def launch_count(self):
-        return int(_lib.lib().gsr_launch_count(self._handle))
+        return int(self._L.gsr_launch_count(self._handle))
 
     def kernel_launches(self):
         out = {}
         name, cnt = ctypes.c_char_p(), ctypes.c_longlong()
         i = 0
-        while _lib.lib().gsr_kernel_info(self._handle, i, ctypes.byref(name), ctypes.byref(cnt)) == 0:
+        while self._L.gsr_kernel_info(self._handle, i, ctypes.byref(name), ctypes.byref(cnt)) == 0:
             out[name.value.decode()] = cnt.value
             i += 1
         return out
 
     def set_profiling(self, enabled):
-        _lib.check(self._handle, _lib.lib().gsr_set_profiling(self._handle, int(bool(enabled))))
+        _lib.check(self._handle, self._L.gsr_set_profiling(self._handle, int(bool(enabled))))
 
     def kernel_times(self):
         """{kernel name: (total ms, timed launches)} recorded with CUDA events while profiling was enabled."""
         out = {}
         name, cnt, ms, n = ctypes.c_char_p(), ctypes.c_longlong(), ctypes.c_double(), ctypes.c_longlong()
         i = 0
-        while _lib.lib().gsr_kernel_info(self._handle, i, ctypes.byref(name), ctypes.byref(cnt)) == 0:
-            _lib.check(self._handle, _lib.lib().gsr_kernel_time_ms(self._handle, i, ctypes.byref(ms), ctypes.byref(n)))
+        while self._L.gsr_kernel_info(self._handle, i, ctypes.byref(name), ctypes.byref(cnt)) == 0:
+            _lib.check(self._handle, self._L.gsr_kernel_time_ms(self._handle, i, ctypes.byref(ms), ctypes.byref(n)))
             out[name.value.decode()] = (ms.value, n.value)
             i += 1
         return out
@@ -495,7 +498,7 @@ class RigidSolver:
             return  # the cache is stale for every environment: the next step (or the next accessor) recomputes all of it
         mask = self._env_mask(envs_idx)
         ptr = ctypes.c_void_p(mask.data_ptr()) if mask is not None else None
-        _lib.check(self._handle, _lib.lib().gsr_forward_kinematics(self._handle, ptr, self._stream()))
+        _lib.check(self._handle, self._L.gsr_forward_kinematics(self._handle, ptr, self._stream()))
 
     # ------------------------------------------------------------------ setters (rigid_solver.py:1902-2287)
     def set_qpos(self, qpos, qs_idx=None, envs_idx=None, *, skip_forward=False):
@@ -558,7 +561,7 @@ class RigidSolver:
     def _reset_warmstart(self, envs_idx):
         mask = self._env_mask(envs_idx)
         ptr = ctypes.c_void_p(mask.data_ptr()) if mask is not None else None
-        _lib.check(self._handle, _lib.lib().gsr_reset_envs(self._handle, ptr, self._stream()))
+        _lib.check(self._handle, self._L.gsr_reset_envs(self._handle, ptr, self._stream()))
 
     def control_dofs_position(self, position, dofs_idx=None, envs_idx=None):
         n = self.model.n_dofs
@@ -659,7 +662,7 @@ class RigidSolver:
         else:
             arr[idx, width] = vals
         a = np.ascontiguousarray(arr, dtype=np.float32)
-        L = _lib.lib()
+        L = self._L
         L.gsr_model_set_f32(self._handle, name.encode(), a.ctypes.data, a.size)
         _lib.check(self._handle, L.gsr_model_refresh(self._handle))
 
@@ -675,7 +678,7 @@ class RigidSolver:
                                  max(self._options.constraint_timeconst, 2.0 * self._substep_dt))
         m.geoms_sol_params[idx] = sp
         a = np.ascontiguousarray(m.geoms_sol_params, dtype=np.float32)
-        L = _lib.lib()
+        L = self._L
         L.gsr_model_set_f32(self._handle, b"geoms_sol_params", a.ctypes.data, a.size)
         _lib.check(self._handle, L.gsr_model_refresh(self._handle))
 
@@ -951,7 +954,7 @@ class RigidSolver:
         With GSR_DIAGNOSTICS=1 they are written every step with the reference's timing and this is a no-op."""
         if not self.tuning.get("diagnostics"):
             self._ensure_kinematics()
-            _lib.check(self._handle, _lib.lib().gsr_compute_diagnostics(self._handle, self._stream()))
+            _lib.check(self._handle, self._L.gsr_compute_diagnostics(self._handle, self._stream()))
 
     def get_geoms_pos(self, geoms_idx=None, envs_idx=None):
         self.refresh_diagnostics()
@@ -1033,7 +1036,7 @@ class RigidSolver:
             chunk, cb = names[k: k + 16], bufs[k: k + 16]
             arr_n = (ctypes.c_char_p * len(chunk))(*[c.encode() for c in chunk])
             arr_p = (ctypes.c_void_p * len(chunk))(*[b.data_ptr() for b in cb])
-            _lib.check(self._handle, _lib.lib().gsr_gather_fields(self._handle, len(chunk), arr_n, arr_p, self._stream()))
+            _lib.check(self._handle, self._L.gsr_gather_fields(self._handle, len(chunk), arr_n, arr_p, self._stream()))
         return dict(zip(names, bufs))
 
     def get_state(self, f=None):
@@ -1067,7 +1070,7 @@ class RigidSolver:
             ptrs.append(ctypes.c_void_p(t.data_ptr()))
         mask = self._env_mask(envs_idx)
         mptr = ctypes.c_void_p(mask.data_ptr()) if mask is not None else None
-        _lib.check(self._handle, _lib.lib().gsr_set_state(self._handle, mptr, *ptrs, int(bool(partial)), self._stream()))
+        _lib.check(self._handle, self._L.gsr_set_state(self._handle, mptr, *ptrs, int(bool(partial)), self._stream()))
         self._obs_valid = False
         if partial:
             self._fk_dirty_any = True
@@ -1092,8 +1095,9 @@ class RigidSolver:
 
     def destroy(self):
         if self._handle is not None:
-            _lib.lib().gsr_destroy(self._handle)
+            self._L.gsr_destroy(self._handle)
             self._handle = None
+            _lib.release_instance(self._lib_device, self._lib_instance, self)
 
     def __del__(self):
         try:
@@ -1123,8 +1127,8 @@ class _QdFieldFacade:
         else:
             getattr(s.model, self._model_name)[...] = arr.reshape(np.shape(getattr(s.model, self._model_name)))
             a = np.ascontiguousarray(getattr(s.model, self._model_name), dtype=np.float32)
-            _lib.lib().gsr_model_set_f32(s._handle, self._model_name.encode(), a.ctypes.data, a.size)
-            _lib.check(s._handle, _lib.lib().gsr_model_refresh(s._handle))
+            s._L.gsr_model_set_f32(s._handle, self._model_name.encode(), a.ctypes.data, a.size)
+            _lib.check(s._handle, s._L.gsr_model_refresh(s._handle))
 
 
 class _DofsInfoFacade:

@@ -165,8 +165,8 @@ def test_lazy_kinematics_equals_eager(model, monkeypatch):
         scene_e.step(); scene_l.step()
         if k in (9, 25):  # an accessor in the middle of the run: one forward pass, then eager for the following step
             assert torch.equal(robot_l.get_links_pos(), robot_e.get_links_pos())
-    assert sl._eager_fk is False and _lib.lib().gsr_kinematics_valid(sl._handle) == 0, "the stepping-only loop did not run lazy"
-    assert se._eager_fk is True and _lib.lib().gsr_kinematics_valid(se._handle) == 1
+    assert sl._eager_fk is False and sl._L.gsr_kinematics_valid(sl._handle) == 0, "the stepping-only loop did not run lazy"
+    assert se._eager_fk is True and se._L.gsr_kinematics_valid(se._handle) == 1
     assert torch.equal(se.field("qpos"), sl.field("qpos")) and torch.equal(se.field("vel"), sl.field("vel"))
     assert torch.equal(se.field("n_contacts"), sl.field("n_contacts"))
     assert torch.equal(se.field("contact_pos"), sl.field("contact_pos"))

@@ -16,7 +16,7 @@ for _ in range(warm):
     scene.step()
 torch.cuda.synchronize()
 out = np.zeros((n, 16), dtype=np.uint64)
-L = _lib.lib()
+L = s._L
 L.gsr_debug_solver_read.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
 _lib.check(s._handle, L.gsr_debug_solver_read(s._handle, out.ctypes.data, n))
 d = out.astype(np.float64)

@@ -13,7 +13,7 @@ scene = {"go2": lambda: make_go2(n), "grasp": lambda: make_franka_grasp(n)}.get(
 s = scene.rigid_solver
 for _ in range(int(os.environ.get("TRACE_WARMUP", 400))):
     scene.step()
-L = _lib.lib()
+L = s._L
 _lib.check(s._handle, L.gsr_debug_trace(s._handle, 1))
 for _ in range(3):
     scene.step()
