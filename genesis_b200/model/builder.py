@@ -516,6 +516,35 @@ def box_l_infos(size, pos, quat=(1.0, 0.0, 0.0, 0.0), fixed=False):
                  geoms=[geom], inertial_mass=None, inertial_pos=None, inertial_quat=None, inertial_i=None, invweight=None)]
 
 
+def _primitive_l_infos(name, geom, pos, quat, fixed):
+    from .urdf import _free_joint
+
+    joints = []
+    if not fixed:
+        j = _free_joint(f"{name}_baselink_joint")
+        j["init_qpos"] = np.concatenate([np.asarray(pos, float), np.asarray(quat, float)])
+        joints = [j]
+    return [dict(name=f"{name}_baselink", pos=np.asarray(pos, float), quat=np.asarray(quat, float), parent_idx=-1, joints=joints,
+                 geoms=[geom], inertial_mass=None, inertial_pos=None, inertial_quat=None, inertial_i=None, invweight=None)]
+
+
+def cylinder_l_infos(radius, height, pos, quat=(1.0, 0.0, 0.0, 0.0), fixed=False):
+    """Free (or fixed) cylinder entity: mesh-backed like the reference's (support field), data = (radius, height)."""
+    verts, faces = meshio.cylinder_mesh(radius, height)
+    geom = dict(type=GEOM_TYPE.CYLINDER, pos=np.zeros(3), quat=np.array([1.0, 0, 0, 0]), data=np.array([radius, height, 0, 0, 0, 0, 0.0]),
+                verts=verts, faces=faces, friction=1.0, contype=0xFFFF, conaffinity=0xFFFF,
+                sol_params=np.array([0.0, 1.0, 0.9, 0.95, 0.001, 0.5, 2.0]))
+    return _primitive_l_infos("cylinder", geom, pos, quat, fixed)
+
+
+def capsule_l_infos(radius, length, pos, quat=(1.0, 0.0, 0.0, 0.0), fixed=False):
+    verts, faces = meshio.capsule_mesh(radius, length)
+    geom = dict(type=GEOM_TYPE.CAPSULE, pos=np.zeros(3), quat=np.array([1.0, 0, 0, 0]), data=np.array([radius, length, 0, 0, 0, 0, 0.0]),
+                verts=verts, faces=faces, friction=1.0, contype=0xFFFF, conaffinity=0xFFFF,
+                sol_params=np.array([0.0, 1.0, 0.9, 0.95, 0.001, 0.5, 2.0]))
+    return _primitive_l_infos("capsule", geom, pos, quat, fixed)
+
+
 def terrain_l_infos(height_field, horizontal_scale, vertical_scale, pos, quat=(1.0, 0.0, 0.0, 0.0)):
     """Fixed height-field terrain entity (rigid_entity.py `_load_terrain`; collider.py:541-561 keeps the scaled heights, the
     grid shape and the scales for func_contact_mpr_terrain).  The geom's vertices are the grid points (AABB, centre)."""

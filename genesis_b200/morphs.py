@@ -33,6 +33,22 @@ class Sphere(Morph):
 
 
 @dataclass
+class Cylinder(Morph):
+    """options/morphs.py Cylinder: axis along z; collides through its mesh / support field like the reference's cylinders."""
+    radius: float = 0.5
+    height: float = 1.0
+    fixed: bool = False
+
+
+@dataclass
+class Capsule(Morph):
+    """A capsule along z: `length` is the cylindrical part, analytic capsule pairs apply (capsule_contact.py)."""
+    radius: float = 0.5
+    length: float = 1.0
+    fixed: bool = False
+
+
+@dataclass
 class Terrain(Morph):
     """Height-field terrain (genesis/options/morphs.py:916+, the `height_field` form): `height_field[r, c]` in units of
     vertical_scale at x = r * horizontal_scale, y = c * horizontal_scale in the terrain's frame.  The procedural sub-terrain

@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 from .constants import CTRL_MODE, ErrorCode
-from .model import ModelBuilder, box_l_infos, parse_mjcf, parse_urdf, plane_l_infos, sphere_l_infos, terrain_l_infos
+from .model import ModelBuilder, box_l_infos, parse_mjcf, parse_urdf, plane_l_infos, sphere_l_infos, terrain_l_infos, cylinder_l_infos, capsule_l_infos
 from .model.compiled import load_compiled, resolve_asset
 from . import morphs as _morphs
 
@@ -34,7 +34,7 @@ def _with_masks(l_infos, morph):
 
 def _morph_to_infos(morph):
     """Returns (l_infos, eqs_info, is_robot, local_collision_mask)."""
-    if isinstance(morph, (_morphs.Plane, _morphs.Box, _morphs.Sphere, _morphs.Terrain)) and (morph.contype != 0xFFFF or morph.conaffinity != 0xFFFF):
+    if isinstance(morph, (_morphs.Plane, _morphs.Box, _morphs.Sphere, _morphs.Terrain, _morphs.Cylinder, _morphs.Capsule)) and (morph.contype != 0xFFFF or morph.conaffinity != 0xFFFF):
         import copy
 
         plain = copy.copy(morph)
@@ -48,6 +48,10 @@ def _morph_to_infos(morph):
     if isinstance(morph, _morphs.Terrain):
         return terrain_l_infos(morph.height_field, morph.horizontal_scale, morph.vertical_scale, morph.pos or (0, 0, 0),
                                morph.quat or (1, 0, 0, 0)), [], False, False
+    if isinstance(morph, _morphs.Cylinder):
+        return cylinder_l_infos(morph.radius, morph.height, morph.pos or (0, 0, 0), morph.quat or (1, 0, 0, 0), morph.fixed), [], False, False
+    if isinstance(morph, _morphs.Capsule):
+        return capsule_l_infos(morph.radius, morph.length, morph.pos or (0, 0, 0), morph.quat or (1, 0, 0, 0), morph.fixed), [], False, False
     if isinstance(morph, _morphs.Sphere):
         return sphere_l_infos(morph.radius, morph.pos or (0, 0, 0), morph.fixed), [], False, False
     if isinstance(morph, (_morphs.MJCF, _morphs.URDF)):

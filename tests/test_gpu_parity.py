@@ -183,9 +183,13 @@ def test_contact_records_match():
         np.testing.assert_allclose(con["force"][b, : n[b]].cpu().numpy(), f, atol=2e-2 * max(1.0, np.abs(f).max()))
 
 
-@pytest.mark.parametrize("shape", ["box", "sphere", "stack"])
+@pytest.mark.parametrize("shape", ["box", "sphere", "stack", "cylinder_capsule"])
 def test_primitives_on_plane(shape):
-    if shape == "box":
+    if shape == "cylinder_capsule":  # gs.morphs.Cylinder (mesh-backed support field) and gs.morphs.Capsule (analytic pairs) over a sphere
+        morphs = [gs.morphs.Plane(), gs.morphs.Cylinder(radius=0.06, height=0.3, pos=(0, 0, 0.2), quat=(0.9, 0.3, 0.2, 0.1)),
+                  gs.morphs.Capsule(radius=0.05, length=0.2, pos=(0.5, 0, 0.2), quat=(0.8, 0.1, 0.55, 0.1)),
+                  gs.morphs.Sphere(radius=0.05, pos=(0.5, 0.02, 0.4))]
+    elif shape == "box":
         morphs = [gs.morphs.Plane(), gs.morphs.Box(size=(0.2, 0.3, 0.1), pos=(0, 0, 0.3), quat=(0.9, 0.1, 0.3, 0.2))]
     elif shape == "sphere":
         morphs = [gs.morphs.Plane(), gs.morphs.Sphere(radius=0.1, pos=(0, 0, 0.3))]
@@ -195,7 +199,7 @@ def test_primitives_on_plane(shape):
     scene, ents = scene_from_morphs(morphs, dt=0.01)
     scene.build(n_envs=4)
     orc = mirror_oracle(scene)
-    K = 120
+    K = 60 if shape == "cylinder_capsule" else 120  # tumbling round bodies: a shorter horizon keeps fp32 round-off below the tolerance
     for _ in range(K):
         scene.step()
     orc.step(K)
@@ -205,7 +209,7 @@ def test_primitives_on_plane(shape):
     # the body came to rest on the plane and the contact force carries its weight
     m = scene.rigid_solver.model
     f = gpu_field(scene, "links_contact_force").reshape(4, m.n_links, 3)
-    if shape != "stack":
+    if shape not in ("stack", "cylinder_capsule"):
         assert f[0, 1, 2] == pytest.approx(m.links_inertial_mass[1] * 9.81, rel=5e-3)
 
 
