@@ -17,7 +17,7 @@ _slots = {}  # device index -> [owner id or None] * N_INSTANCES
 
 EXPORTS = (
     "gsr_model_begin", "gsr_model_set_f32", "gsr_model_set_i32", "gsr_model_set_scalar", "gsr_model_commit", "gsr_model_refresh",
-    "gsr_state_words", "gsr_field_count", "gsr_field_info", "gsr_bind", "gsr_launch_info", "gsr_init_state", "gsr_step",
+    "gsr_model_spec_header", "gsr_is_specialised", "gsr_state_words", "gsr_field_count", "gsr_field_info", "gsr_bind", "gsr_launch_info", "gsr_init_state", "gsr_step",
     "gsr_forward_kinematics", "gsr_forward_kinematics_dirty", "gsr_set_kinematics_policy", "gsr_kinematics_valid", "gsr_reset_envs", "gsr_compute_diagnostics", "gsr_set_state", "gsr_gather_fields", "gsr_step_host", "gsr_launch_count", "gsr_kernel_info",
     "gsr_set_profiling", "gsr_kernel_time_ms", "gsr_debug_trace", "gsr_debug_trace_read",
     "gsr_last_error", "gsr_version", "gsr_destroy",
@@ -33,6 +33,33 @@ def build(force=False):
     if force or not os.path.exists(LIB_PATH):
         subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc")] + (["-B"] if force else []))
     return LIB_PATH
+
+
+def source_digest():
+    """Digest of the CUDA / C++ sources a specialised copy was compiled from: a copy built from other sources is never picked up."""
+    import hashlib
+
+    h = hashlib.sha256()
+    d = os.path.join(_HERE, "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def spec_path(header_text):
+    """Where the copy specialised for the model described by `header_text` (gsr_model_spec_header) lives, if it was built."""
+    import hashlib
+
+    tag = hashlib.sha256((source_digest() + header_text).encode()).hexdigest()[:12]
+    return os.path.join(_HERE, "csrc", f"libgsrigid.spec_{tag}.so")
+
+
+def lib_at(path):
+    """A library copy by path (model-specialised builds); bound like the generic one."""
+    if path not in _libs:
+        _libs[path] = _bind(ctypes.CDLL(path))
+    return _libs[path]
 
 
 def instance_path(instance):
@@ -51,7 +78,7 @@ def acquire_instance(device_index, owner):
 
 def release_instance(device_index, instance, owner):
     slots = _slots.get(device_index)
-    if slots is not None and slots[instance] == id(owner):
+    if slots is not None and isinstance(instance, int) and slots[instance] == id(owner):
         slots[instance] = None
 
 
@@ -63,7 +90,14 @@ def lib(instance=0):
             raise GsrError(
                 f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)"
             )
-        L = ctypes.CDLL(path)
+        _libs[instance] = _bind(ctypes.CDLL(path))
+        if instance == 0:
+            _lib = _libs[instance]
+    return _libs[instance]
+
+
+def _bind(L):
+    if True:
         vp, cp, i, sz = ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_size_t
         L.gsr_model_begin.argtypes = [ctypes.POINTER(vp)]
         L.gsr_model_set_f32.argtypes = [vp, cp, vp, sz]
@@ -71,6 +105,8 @@ def lib(instance=0):
         L.gsr_model_set_scalar.argtypes = [vp, cp, ctypes.c_double]
         L.gsr_model_commit.argtypes = [vp, i, i]
         L.gsr_model_refresh.argtypes = [vp]
+        L.gsr_model_spec_header.argtypes = [vp, i, vp, sz]
+        L.gsr_model_spec_header.restype = ctypes.c_longlong
         L.gsr_state_words.argtypes = [vp, ctypes.POINTER(sz)]
         L.gsr_field_count.argtypes = [vp]
         L.gsr_field_info.argtypes = [vp, i, ctypes.POINTER(cp), ctypes.POINTER(i)] + [ctypes.POINTER(sz)] * 6
@@ -98,10 +134,7 @@ def lib(instance=0):
         L.gsr_last_error.restype = cp
         L.gsr_version.restype = cp
         L.gsr_destroy.argtypes = [vp]
-        _libs[instance] = L
-        if instance == 0:
-            _lib = L
-    return _libs[instance]
+    return L
 
 
 def check(handle, rc):

@@ -104,8 +104,13 @@ static int activate(gsr_handle_t h, cudaStream_t st) {
   if (g_active[h->device] != h) {
     // constant memory is per device: re-upload when another model (e.g. a second scene on this GPU) ran last
     CUDA_OK(cudaMemcpyToSymbolAsync(c_m, &h->hm, sizeof(DevModel), 0, cudaMemcpyHostToDevice, st));
+#ifdef GSR_SPEC_HEADER
+    CUDA_OK(cudaMemcpyToSymbolAsync(c_h_rt, &h->lay, sizeof(HotLayout), 0, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyToSymbolAsync(c_s_rt, &h->sl, sizeof(SmemLayout), 0, cudaMemcpyHostToDevice, st));
+#else
     CUDA_OK(cudaMemcpyToSymbolAsync(c_h, &h->lay, sizeof(HotLayout), 0, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemcpyToSymbolAsync(c_s, &h->sl, sizeof(SmemLayout), 0, cudaMemcpyHostToDevice, st));
+#endif
 #ifndef GSR_DEV_ONLY_G
     CUDA_OK(cudaMemcpyToSymbolAsync(c_l, &h->ll, sizeof(LaneLayout), 0, cudaMemcpyHostToDevice, st));
 #endif
@@ -179,10 +184,17 @@ int gsr_model_commit(gsr_handle_t h, int device, int n_envs) {
   m.terrain_hf = h->d_terrain;
 
   { int rc_lay = gsr_compute_layouts(h, n_envs); if (rc_lay) return rc_lay; }
+#ifdef GSR_SPEC_HEADER
+  if (!gsr_spec_matches(h->lay, h->sl, h->hm) || h->group != GSR_SPEC_GROUP)
+    return fail(h, GSR_EINVAL, "this copy of the library was specialised for another model / option set (tools/specialize.py)");
+#endif
   h->reorder_period = (int)h->S("cfg_reorder_period", 16);
   h->host_io_mode = (int)h->S("cfg_host_io", 2);
   // the caller fixing cfg_smem_rows switches the adaptation off (sweeps); the lane kernel has its own layout
   h->adaptive_rows = h->S("cfg_adaptive_rows", h->s.count("cfg_smem_rows") ? 0 : 1) != 0 && h->group != 1;
+#ifdef GSR_SPEC_HEADER
+  h->adaptive_rows = false;  // the workspace layout is part of the build
+#endif
   // every buffer of the cost-ordered launch, the adaptive row capacity and gsr_step_host is allocated here: nothing on the
   // step path calls cudaMalloc / cudaHostAlloc / cudaEventCreate (those serialise the device and used to land inside timed loops)
   if (h->group != 1) {
@@ -208,6 +220,58 @@ int gsr_model_commit(gsr_handle_t h, int device, int n_envs) {
   h->committed = true;
   g_active[device] = nullptr;
   return GSR_OK;
+}
+
+// ---- model-specialised builds (tools/specialize.py) ------------------------------------------------------------------
+// Host-only: fills the model and the layouts from the arrays / scalars set so far (no CUDA call) and writes the header a
+// specialised build includes: every layout offset and every build-time count / option of the model as a literal.
+long long gsr_model_spec_header(gsr_handle_t h, int n_envs, char* buf, size_t cap) {
+  if (!h) return GSR_EINVAL;
+  int rc = gsr_fill_model(h);
+  if (rc) return rc;
+  rc = gsr_compute_layouts(h, n_envs);
+  if (rc) return rc;
+  std::string o = "// GENERATED by gsr_model_spec_header (tools/specialize.py): layouts and build-time scalars of ONE model as literals\n#pragma once\n";
+  o += "struct SpecH {\n";
+#define X(name, is_int, items, comps) o += "  static constexpr int " #name " = " + std::to_string(h->lay.name) + ";\n";
+  GSR_HOT_PRE_FIELDS(X) GSR_HOT_IN_FIELDS(X) GSR_HOT_OUT_FIELDS(X)
+#undef X
+#define X(name) o += "  static constexpr int " #name " = " + std::to_string(h->lay.name) + ";\n";
+  GSR_HOT_SCALAR_FIELDS(X)
+#undef X
+  o += "};\nstruct SpecS {\n";
+#define X(name) o += "  static constexpr int " #name " = " + std::to_string(h->sl.name) + ";\n";
+  GSR_SMEM_FIELDS(X)
+#undef X
+  o += "};\n";
+#define X(name) o += "#define CMX_" #name " " + std::to_string(h->hm.name) + "\n";
+  GSR_MODEL_SPEC_SCALARS(X)
+#undef X
+  o += "#define GSR_SPEC_GROUP " + std::to_string(h->group) + "\n";
+  o += "static inline bool gsr_spec_matches(const HotLayout& L, const SmemLayout& S, const DevModel& m) {\n  return true";
+#define X(name, is_int, items, comps) o += " && L." #name " == SpecH::" #name;
+  GSR_HOT_PRE_FIELDS(X) GSR_HOT_IN_FIELDS(X) GSR_HOT_OUT_FIELDS(X)
+#undef X
+#define X(name) o += " && L." #name " == SpecH::" #name;
+  GSR_HOT_SCALAR_FIELDS(X)
+#undef X
+#define X(name) o += " && S." #name " == SpecS::" #name;
+  GSR_SMEM_FIELDS(X)
+#undef X
+#define X(name) o += " && m." #name " == " + std::to_string(h->hm.name);
+  GSR_MODEL_SPEC_SCALARS(X)
+#undef X
+  o += ";\n}\n";
+  if (buf && cap > o.size()) memcpy(buf, o.c_str(), o.size() + 1);
+  return (long long)o.size() + 1;
+}
+/* 1 when this library was built for one model (GSR_SPEC_HEADER): gsr_model_commit then refuses any other */
+int gsr_is_specialised(void) {
+#ifdef GSR_SPEC_HEADER
+  return 1;
+#else
+  return 0;
+#endif
 }
 
 int gsr_model_refresh(gsr_handle_t h) {

@@ -4,12 +4,27 @@
 #include "gsr_math.cuh"
 
 __constant__ DevModel c_m;     // warp-uniform reads (scalars, loop bounds, tables indexed by a uniform loop variable)
+#ifdef GSR_SPEC_HEADER
+// Model-specialised build (tools/specialize.py): the record / workspace layouts and the model's counts and options are literals of
+// the generated header -- offsets become immediates, loop bounds and option branches fold.  The library only accepts the model
+// it was built for (gsr_api.cu checks the layouts at commit).  The run-time copies stay for the batch-dependent segment bases.
+#include GSR_SPEC_HEADER
+__constant__ HotLayout c_h_rt;
+__constant__ SmemLayout c_s_rt;
+#define c_h SpecH()
+#define c_s SpecS()
+#define c_hb c_h_rt
+#else
 __constant__ HotLayout c_h;
 __constant__ SmemLayout c_s;
+#define c_hb c_h
+#endif
 
 // Lane-varying table reads go to a global-memory copy of the model (read-only path, L1 resident): constant memory
 // serialises divergent addresses.
-#define CM(x) (c_m.x)
+#define CM(x) CMX_##x
+#define CMI(x) CMX_##x  // the same, for a use nested inside CM(...) (a macro does not expand inside itself)
+#include "gsr_cm_fields.h"
 #define GM(x) (__ldg(&(C.gm->x)))
 
 template <int G>

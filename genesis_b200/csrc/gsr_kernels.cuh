@@ -43,9 +43,9 @@ __device__ __forceinline__ bool make_ctx(Ctx<G>& C, float* state, int B, const D
   C.gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (sub * G));
   C.S = smem + (size_t)slot * c_s.env_words - c_h.in_start;  // record-relative workspace offsets (SmemLayout)
   C.rec = state + (size_t)env * c_h.hot_stride;
-  C.contacts = state + c_h.contact_base + (size_t)env * c_h.contact_stride;
-  C.cache = state + c_h.cache_base + (size_t)env * c_h.cache_stride;
-  C.spill = state + c_h.spill_base + (size_t)env * c_h.spill_stride;
+  C.contacts = state + c_hb.contact_base + (size_t)env * c_h.contact_stride;
+  C.cache = state + c_hb.cache_base + (size_t)env * c_h.cache_stride;
+  C.spill = state + c_hb.spill_base + (size_t)env * c_h.spill_stride;
   C.gm = gm;
   return true;
 }
@@ -420,9 +420,9 @@ __global__ void k_reset(float* state, int B, const uint8_t* mask) {
   int* reci = reinterpret_cast<int*>(rec);
   for (int d = 0; d < c_m.nD; d++) rec[c_h.qacc_ws + d] = 0.f;
   reci[c_h.is_warmstart] = 0;
-  int* cv = reinterpret_cast<int*>(state + c_h.cache_base + (size_t)env * c_h.cache_stride) + c_h.cache_valid;
+  int* cv = reinterpret_cast<int*>(state + c_hb.cache_base + (size_t)env * c_h.cache_stride) + c_h.cache_valid;
   for (int w = 0; w < c_m.n_cache_words; w++) cv[w] = 0;
-  float* ct = state + c_h.contact_base + (size_t)env * c_h.contact_stride;
+  float* ct = state + c_hb.contact_base + (size_t)env * c_h.contact_stride;
   const int nc = reci[c_h.n_contacts];
   for (int c = 0; c < nc; c++) {
     float* r = ct + (size_t)c * GSR_CONTACT_WORDS;

@@ -382,7 +382,7 @@ LHD __noinline__ void lane_dynamics(const LaneCtx& C) {
     const int p = CM(l_parent[l]);
     f3 dv, da;
     if (p >= 0) { dv = ld3(cdd_v, p); da = ld3(cdd_a, p); }
-    else dv = -grav * (1.0f - CM(e_gravcomp[CM(l_entity[l])]));
+    else dv = -grav * (1.0f - CM(e_gravcomp[CMI(l_entity[l])]));
     for (int d = CM(l_dof_start[l]); d < CM(l_dof_end[l]); d++) { const float w = vel[d]; dv += ld3(cddv, d) * w; da += ld3(cdda, d) * w; }
     st3(cdd_v, l, dv); st3(cdd_a, l, da);
     sym3 I;
@@ -1113,7 +1113,7 @@ LHD __noinline__ void lane_build_rows(const LaneCtx& C, LRows& R) {
     for (int d = 0; d < nD; d++)
       if (CM(d_frictionloss[d]) > EPS) {
         float imp, aref;
-        imp_aref(CM(j_sol[CM(d_joint[d])]), 0.f, vel[d], 0.f, imp, aref);
+        imp_aref(CM(j_sol[CMI(d_joint[d])]), 0.f, vel[d], 0.f, imp, aref);
         const float diag = fmaxf(CM(d_invweight[d]) * (1.0f - imp) / imp, EPS);
         R.R[r] = diag; R.aref[r] = aref; R.D[r] = 1.0f / diag; R.floss[r] = CM(d_frictionloss[d]);
         J[r * JS + d] = 1.0f;
@@ -1667,7 +1667,7 @@ LHD __noinline__ void lane_integrate(const LaneCtx& C) {
   for (int l = 0; l < nL; l++) {
     const int ds = CM(l_dof_start[l]), de = CM(l_dof_end[l]), qs = CM(l_q_start[l]), qe = CM(l_q_end[l]);
     if (de - ds <= 0) continue;
-    const int jt = CM(j_type[CM(l_joint_start[l])]);
+    const int jt = CM(j_type[CMI(l_joint_start[l])]);
     if (jt == JOINT_FREE)
       for (int k = 0; k < 3; k++) qn[qs + k] = qpos[qs + k] + vn[ds + k] * dt;
     if (jt == JOINT_FREE || jt == JOINT_SPHERICAL) {

@@ -202,7 +202,7 @@ __device__ __noinline__ void build_rows(const Ctx<G>& C, Rows& R) {
     for (int d = 0; d < nD; d++)
       if (dof_frictionloss(C, d) > EPS) {
         float imp, aref;
-        imp_aref(CM(j_sol[CM(d_joint[d])]), 0.f, vel[d], 0.f, imp, aref);
+        { const int jd_ = CM(d_joint[d]); imp_aref(CM(j_sol[jd_]), 0.f, vel[d], 0.f, imp, aref); }
         const float diag = fmaxf(dof_invweight(C, d) * (1.0f - imp) / imp, EPS);
         R.R[r] = diag; R.aref[r] = aref; R.D[r] = 1.0f / diag; R.floss[r] = dof_frictionloss(C, d);
         J[r * JS + d] = 1.0f;

@@ -191,6 +191,21 @@ struct SmemLayout {
   int env_words;  // total words per env (multiple of 4, ≡ 8 mod 32 is not required)
 };
 
+// field lists for the model-specialised builds (gsr_model_spec_header writes them out as literals, gsr_spec_matches compares them)
+#define GSR_SMEM_FIELDS(X)                                                                                                      \
+  X(M) X(L) X(Dinv) X(Hinv) X(force) X(acc_smooth) X(acc) X(qf_applied) X(qf_passive) X(qf_bias) X(qfrc_c) X(MS) X(crb) X(fdof)   \
+  X(cdd) X(cfrc) X(gpos) X(gquat) X(aabb) X(queue) X(contacts) X(NCC) X(H) X(qacc) X(Ma) X(grad) X(Mgrad) X(search) X(mv)         \
+  X(prev_grad) X(prev_Mgrad) X(tmpv) X(J) X(JS) X(NCS) X(r_aref) X(r_D) X(r_R) X(r_floss) X(r_Jaref) X(r_jv) X(r_force)           \
+  X(r_active) X(xanchor) X(xaxis) X(cacc) X(vel_next) X(qpos_next) X(pose_a) X(pose_b) X(env_words)
+#define GSR_HOT_SCALAR_FIELDS(X)                                                                                                \
+  X(in_start) X(n_state) X(n_in) X(kin_dead) X(hot_stride) X(contact_stride) X(cache_stride) X(spill_stride) X(cache_valid)       \
+  X(spill_minvjt)
+#define GSR_MODEL_SPEC_SCALARS(X)                                                                                               \
+  X(nL) X(nJ) X(nD) X(nQ) X(nG) X(nE) X(nEq) X(nP) X(max_contact_pairs) X(max_broad_pairs) X(n_contacts_per_pair)                 \
+  X(len_constraints) X(iterations) X(ls_iterations) X(integrator) X(solver_type) X(noslip_iterations) X(box_box_detection)        \
+  X(use_gjk) X(gjk_fallback) X(enable_collision) X(enable_joint_limit) X(enable_multi_contact) X(sort_contacts) X(has_cc)         \
+  X(n_cache_words) X(diagnostics) X(batch_dofs) X(disable_constraint) X(n_roots) X(max_depth) X(phase_barriers)
+
 // Workspace of the lane-per-environment kernel (gsr_lane.cuh), word offsets per environment.  Words [0, n_head) mirror the
 // head of the record (qpos .. dofs_pos, same offsets as HotLayout).  The pool is overlaid phase by phase.
 struct LaneLayout {

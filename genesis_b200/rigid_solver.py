@@ -8,6 +8,7 @@ returned tensors are (B, n) copies on `gs.device`.  There is no CPU path: buildi
 """
 
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -198,13 +199,34 @@ class RigidSolver:
         self._lib_instance = _lib.acquire_instance(dev_index, self)  # its own CUDA module (constant memory) when another scene is alive
         self._lib_device = dev_index
         L = self._L = _lib.lib(self._lib_instance)
-        h = ctypes.c_void_p()
-        _lib.check(None, L.gsr_model_begin(ctypes.byref(h)))
-        self._handle = h
-        self._upload_model_arrays()
-        for k, v in self.model_options().items():
-            L.gsr_model_set_scalar(h, f"cfg_{k}".encode(), float(v))
-        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+
+        def describe(lib_):
+            h_ = ctypes.c_void_p()
+            _lib.check(None, lib_.gsr_model_begin(ctypes.byref(h_)))
+            self._handle, self._L = h_, lib_
+            self._upload_model_arrays()
+            for k, v in self.model_options().items():
+                lib_.gsr_model_set_scalar(h_, f"cfg_{k}".encode(), float(v))
+            return h_
+
+        h = describe(L)
+        # a copy of the library compiled for exactly this model and option set (tools/specialize.py; layouts and counts are literals
+        # there) is used when it was built: the generic library describes the model, the description names the file
+        self.specialised = False
+        if os.environ.get("GSR_NO_SPEC", "0") != "1" and not os.environ.get("GSR_LIB"):
+            n = L.gsr_model_spec_header(h, self._B, None, 0)
+            if n > 0:
+                buf = ctypes.create_string_buffer(n)
+                L.gsr_model_spec_header(h, self._B, buf, n)
+                path = _lib.spec_path(buf.value.decode())
+                if os.path.exists(path):
+                    Ls = _lib.lib_at(path)
+                    L.gsr_destroy(h)
+                    _lib.release_instance(dev_index, self._lib_instance, self)
+                    self._lib_instance = path  # a specialised copy is its own CUDA module as well
+                    h = describe(Ls)
+                    L = Ls
+                    self.specialised = True
         _lib.check(h, L.gsr_model_commit(h, dev_index, self._B))
         nw = ctypes.c_size_t()
         _lib.check(h, L.gsr_state_words(h, ctypes.byref(nw)))

@@ -173,3 +173,25 @@ def test_lazy_kinematics_equals_eager(model, monkeypatch):
     for name in ("links_pos", "links_quat", "cd_vel", "cd_ang", "root_COM", "dofs_pos", "cdof_ang", "cinr_I"):
         assert torch.equal(se.field(name), sl.field(name)), name
     assert sl.kernel_launches()["k_forward"] > se.kernel_launches()["k_forward"]
+
+
+@pytest.mark.parametrize("model", ["franka", "go2"])
+def test_specialised_library_is_used_and_bit_identical(model, monkeypatch):
+    """Model-specialised builds (tools/specialize.py, built by __graft_entry__.build() for the two benchmark models): the benchmark
+    scene picks the copy compiled for it (layouts, counts and options as literals), any other option set runs the generic library,
+    and both give bit-identical steps (the arithmetic is the same source; only address computations and loop bounds fold)."""
+    make = (lambda: make_go2(128, seed=3)) if model == "go2" else (lambda: make_franka(256, randomized=True, seed=3))
+    scene_s, _ = make()
+    monkeypatch.setenv("GSR_NO_SPEC", "1")
+    scene_g, _ = make()
+    ss, sg = scene_s.rigid_solver, scene_g.rigid_solver
+    assert ss.specialised and ss._L.gsr_is_specialised() == 1, "the specialised copy was not built / not found (run __graft_entry__.build())"
+    assert not sg.specialised and sg._L.gsr_is_specialised() == 0
+    for _ in range(40):
+        scene_s.step(); scene_g.step()
+    for k in ("qpos", "vel", "acc", "force", "n_contacts", "contact_pos", "links_pos", "links_contact_force", "n_constraints", "solver_iters"):
+        assert torch.equal(ss.field(k), sg.field(k)), k
+    monkeypatch.delenv("GSR_NO_SPEC")
+    other, _ = (make_go2(16, seed=3, noslip_iterations=2) if model == "go2" else make_franka(16, randomized=True, seed=3, iterations=40))
+    assert not other.rigid_solver.specialised  # another option set: the generic library
+    other.step()
