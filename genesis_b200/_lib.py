@@ -47,11 +47,17 @@ def source_digest():
     return h.hexdigest()[:16]
 
 
+# extra flags of a model-specialised build: with a quarter less code than the generic kernels, inlining the kinematics, the small
+# math helpers (rotate, quat_compose, quat_to_R, rotvec_to_quat), fk_link and the Hessian factorisation pays (Franka 87 -> 103 M
+# env-steps/s, measured variant by variant: profiles/README.md item 22); in the generic kernels they stay real functions
+SPEC_NVCC_FLAGS = ("-DGSR_KIN_INLINE=__forceinline__", "-DGSR_MATH_NOINLINE=", "-DGSR_FK_NOINLINE=", "-DGSR_HESS_NOINLINE=")
+
+
 def spec_path(header_text):
     """Where the copy specialised for the model described by `header_text` (gsr_model_spec_header) lives, if it was built."""
     import hashlib
 
-    tag = hashlib.sha256((source_digest() + header_text).encode()).hexdigest()[:12]
+    tag = hashlib.sha256((source_digest() + " ".join(SPEC_NVCC_FLAGS) + header_text).encode()).hexdigest()[:12]
     return os.path.join(_HERE, "csrc", f"libgsrigid.spec_{tag}.so")
 
 

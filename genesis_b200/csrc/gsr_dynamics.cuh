@@ -23,7 +23,7 @@
 // FK:580-736 one link's pose from its parent's world pose (pp, pq); also joint anchors / axes and dofs_pos when `final`.
 // ---------------------------------------------------------------------------------------------------------------------
 template <int G>
-__device__ __noinline__ void fk_link(const Ctx<G>& C, int l, bool has_parent, f3 pp, f4 pq, const float* qpos, f3& pos, f4& quat, bool final) {
+__device__ GSR_FK_NOINLINE void fk_link(const Ctx<G>& C, int l, bool has_parent, f3 pp, f4 pq, const float* qpos, f3& pos, f4& quat, bool final) {
   const float EPS = CM(eps);
   pos = f3(GM(l_pos[l][0]), GM(l_pos[l][1]), GM(l_pos[l][2]));
   quat = f4(GM(l_quat[l][0]), GM(l_quat[l][1]), GM(l_quat[l][2]), GM(l_quat[l][3]));
@@ -81,10 +81,13 @@ __device__ __noinline__ void fk_link(const Ctx<G>& C, int l, bool has_parent, f3
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+#ifndef GSR_KIN_INLINE
+#define GSR_KIN_INLINE __noinline__
+#endif
 // Kinematics of the whole environment from qpos / vel (FK:580-736, FK:337-576, FK:993-1116): rebuilds the kinematic cache.
 // ---------------------------------------------------------------------------------------------------------------------
 template <int G>
-__device__ __noinline__ void phase_kinematics(const Ctx<G>& C) {  // one copy for its two call sites in k_step (start / epilogue)
+__device__ GSR_KIN_INLINE void phase_kinematics(const Ctx<G>& C) {  // one copy for its two call sites in k_step (start / epilogue)
   const int nL = CM(nL), nD = CM(nD), nJ = CM(nJ);
   const float EPS = CM(eps);
   const int lane = C.lane;
@@ -286,7 +289,7 @@ __device__ void phase_geoms(const Ctx<G>& C) {
 // L^T D L solve (FD:813-894) of the vector x (shared memory, in place): x <- L^-1 D^-1 L^-T x
 // ---------------------------------------------------------------------------------------------------------------------
 template <int G>
-__device__ __noinline__ void mass_solve(const Ctx<G>& C, float* x) {
+__device__ GSR_MASS_NOINLINE void mass_solve(const Ctx<G>& C, float* x) {
   const int nD = CM(nD), MS = c_s.MS;
   const float* L = WKS(L);
   const float* Dinv = WKS(Dinv);
@@ -347,7 +350,7 @@ __device__ __noinline__ void mass_solve(const Ctx<G>& C, float* x) {
 
 // FD:545-602 factor of the matrix stored in WK(L) (lower part), in place; D^-1 to WK(Dinv)
 template <int G>
-__device__ __noinline__ void mass_factor(const Ctx<G>& C) {
+__device__ GSR_MASS_NOINLINE void mass_factor(const Ctx<G>& C) {
   const int nD = CM(nD), MS = c_s.MS;
   float* L = WKS(L);
   float* Dinv = WKS(Dinv);

@@ -2,6 +2,32 @@
 // Conventions follow the reference's device helpers (genesis/utils/geom.py:18-426): quaternions are (w,x,y,z),
 // spatial quantities are (ang, vel) pairs expressed about the subtree COM in world axes.
 #pragma once
+// the small math helpers are real functions in the generic kernels (code size: instruction fetch is a contended resource there); the
+// model-specialised builds are a quarter smaller and inline them (GSR_MATH_NOINLINE / GSR_ROUTINE_NOINLINE empty)
+#ifndef GSR_MATH_NOINLINE
+#define GSR_MATH_NOINLINE __noinline__
+#endif
+#ifndef GSR_ROUTINE_NOINLINE
+#define GSR_ROUTINE_NOINLINE __noinline__
+#endif
+#ifndef GSR_ROWS_NOINLINE
+#define GSR_ROWS_NOINLINE GSR_ROUTINE_NOINLINE
+#endif
+#ifndef GSR_UPD_NOINLINE
+#define GSR_UPD_NOINLINE GSR_ROUTINE_NOINLINE
+#endif
+#ifndef GSR_HESS_NOINLINE
+#define GSR_HESS_NOINLINE GSR_ROUTINE_NOINLINE
+#endif
+#ifndef GSR_GRAD_NOINLINE
+#define GSR_GRAD_NOINLINE GSR_ROUTINE_NOINLINE
+#endif
+#ifndef GSR_FK_NOINLINE
+#define GSR_FK_NOINLINE GSR_ROUTINE_NOINLINE
+#endif
+#ifndef GSR_MASS_NOINLINE
+#define GSR_MASS_NOINLINE GSR_ROUTINE_NOINLINE
+#endif
 #include <cuda_runtime.h>
 #include <math.h>
 
@@ -47,13 +73,13 @@ __host__ __device__ __forceinline__ f4 quat_mul_axis(f4 q, f3 a) {
   return f4(-q.x * a.x - q.y * a.y - q.z * a.z, q.w * a.x + q.y * a.z - q.z * a.y, q.w * a.y + q.z * a.x - q.x * a.z, q.w * a.z + q.x * a.y - q.y * a.x);
 }
 // geom.py:245-252: transform_quat_by_quat(v, u) = normalize(u * v)
-__host__ __device__ __noinline__ f4 quat_compose(f4 v, f4 u) {
+__host__ __device__ GSR_MATH_NOINLINE f4 quat_compose(f4 v, f4 u) {
   f4 r = quat_mul(u, v);
   float n = 1.0f / sqrtf(r.w * r.w + r.x * r.x + r.y * r.y + r.z * r.z);
   return f4(r.w * n, r.x * n, r.y * n, r.z * n);
 }
 // geom.py:255-270
-__host__ __device__ __noinline__ f3 rotate(f3 v, f4 q) {
+__host__ __device__ GSR_MATH_NOINLINE f3 rotate(f3 v, f4 q) {
   float xx = q.x * q.x, xy = q.x * q.y, xz = q.x * q.z, wx = q.x * q.w;
   float yy = q.y * q.y, yz = q.y * q.z, wy = q.y * q.w;
   float zz = q.z * q.z, wz = q.z * q.w, ww = q.w * q.w;
@@ -69,7 +95,7 @@ struct mat3 {
   float m[3][3];
 };
 // geom.py:136-161
-__host__ __device__ __noinline__ mat3 quat_to_R(f4 q, float eps) {
+__host__ __device__ GSR_MATH_NOINLINE mat3 quat_to_R(f4 q, float eps) {
   mat3 R;
   R.m[0][0] = 1.f; R.m[0][1] = 0.f; R.m[0][2] = 0.f; R.m[1][0] = 0.f; R.m[1][1] = 1.f; R.m[1][2] = 0.f;
   R.m[2][0] = 0.f; R.m[2][1] = 0.f; R.m[2][2] = 1.f;
@@ -89,7 +115,7 @@ __host__ __device__ __noinline__ mat3 quat_to_R(f4 q, float eps) {
 __host__ __device__ __forceinline__ f3 mat_col(const mat3& R, int j) { return f3(R.m[0][j], R.m[1][j], R.m[2][j]); }
 
 // geom.py:110-133
-__host__ __device__ __noinline__ f4 rotvec_to_quat(f3 rv, float eps) {
+__host__ __device__ GSR_MATH_NOINLINE f4 rotvec_to_quat(f3 rv, float eps) {
   f4 q(0.f, 0.f, 0.f, 0.f);
   float thetasq = norm_sqr(rv);
   if (thetasq > eps * eps) {

@@ -79,7 +79,7 @@ __device__ __noinline__ void weld_rows(const Ctx<G>& C, Rows& R, int row, int l1
 // Row assembly (CS:579-1286), row order [equality | frictionloss | 4 x contacts | joint limits]
 // ---------------------------------------------------------------------------------------------------------------------
 template <int G>
-__device__ __noinline__ void build_rows(const Ctx<G>& C, Rows& R) {
+__device__ GSR_ROWS_NOINLINE void build_rows(const Ctx<G>& C, Rows& R) {
   const int nD = CM(nD), nJ = CM(nJ), lane = C.lane;
   const float EPS = CM(eps);
   const float* qpos = IN(qpos);
@@ -298,7 +298,7 @@ __device__ __noinline__ void build_rows(const Ctx<G>& C, Rows& R) {
 // ---------------------------------------------------------------------------------------------------------------------
 // CS:2619-2694 func_update_constraint_batch
 template <int G>
-__device__ __noinline__ void update_constraint(const Ctx<G>& C, const Rows& R, SolverState& X, bool track_prev) {
+__device__ GSR_UPD_NOINLINE void update_constraint(const Ctx<G>& C, const Rows& R, SolverState& X, bool track_prev) {
   const int nD = CM(nD), lane = C.lane;
   X.prev_cost = X.cost;
   float cost = 0.f;
@@ -336,7 +336,7 @@ __device__ __noinline__ void update_constraint(const Ctx<G>& C, const Rows& R, S
 
 // CS:1394-1452 + CS:1594-1621: H = M + J^T (D active) J (lower), then in-place Cholesky (1 / L_ii kept in WK(Hinv))
 template <int G>
-__device__ __noinline__ void hessian_cholesky(const Ctx<G>& C, const Rows& R, long long* t_split = nullptr) {
+__device__ GSR_HESS_NOINLINE void hessian_cholesky(const Ctx<G>& C, const Rows& R, long long* t_split = nullptr) {
   const int nD = CM(nD), MS = c_s.MS, lane = C.lane;
   const float EPS = CM(eps);
   float* H = WKS(H);
@@ -525,7 +525,7 @@ __device__ __noinline__ bool hessian_incremental(const Ctx<G>& C, const Rows& R)
 
 // CS:2721-2750 gradient and preconditioned gradient (Newton: Cholesky solve CS:1892-1910; CG: M^-1 via L^T D L)
 template <int G>
-__device__ __noinline__ void update_gradient(const Ctx<G>& C, bool solve = true) {
+__device__ GSR_GRAD_NOINLINE void update_gradient(const Ctx<G>& C, bool solve = true) {
   const int nD = CM(nD), MS = c_s.MS, lane = C.lane;
   float* grad = WK(grad);
   float* Mgrad = WK(Mgrad);

@@ -580,6 +580,7 @@ def test_workspace_layouts_give_identical_steps(model, monkeypatch):
             return make_franka(64, randomized=True, seed=2, constraint_solver=gs.constraint_solver.CG, integrator=gs.integrator.Euler)[0]
         return make_franka(128, randomized=True, seed=2)[0]
 
+    monkeypatch.setenv("GSR_NO_SPEC", "1")  # both in the generic library: a model-specialised copy inlines differently (other FMA contractions)
     scene_a = make()
     monkeypatch.setenv("GSR_DIAGNOSTICS", "0")
     scene_b = make()
@@ -595,6 +596,7 @@ def test_workspace_layouts_give_identical_steps(model, monkeypatch):
 def test_lazy_diagnostics_match_per_step_diagnostics(monkeypatch):
     """cfg_diagnostics = 0 (the default): get_mass_mat / geoms poses / qf_* are recomputed on demand for the current state by
     k_diag.  They must equal what a cfg_diagnostics = 1 scene writes during the step that starts from the same state."""
+    monkeypatch.setenv("GSR_NO_SPEC", "1")        # one binary for both scenes (bit-exact comparison)
     scene_a, fa = make_go2(16, seed=3)            # diagnostics on (fixture)
     monkeypatch.setenv("GSR_DIAGNOSTICS", "0")
     scene_b, fb = make_go2(16, seed=3)

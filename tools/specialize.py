@@ -74,6 +74,7 @@ def main():
             return
         cmd = ["/usr/local/cuda/bin/nvcc", "-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a", "-prec-div=false",
                "-prec-sqrt=false", "-Xcompiler", "-fPIC", "-shared", f"-DGSR_SPEC_HEADER=\"spec/spec_{name}.h\"", f"-DGSR_DEV_ONLY_G={group}",
+               *_lib.SPEC_NVCC_FLAGS,
                "-o", out, "gsr_api.cu", "-lcudart"]
         subprocess.check_call(cmd, cwd=CSRC)
         print(out)
