@@ -14,6 +14,8 @@ for W in franka go2; do
 done
 for R in franka go2; do
   K=k_stepILi8ELb0; [ $R = go2 ] && K=k_stepILi32ELb1
+  export GSR_PROF_LIB=$(python tools/which_lib.py $R 2>/dev/null | tail -1)   # the copy that ran (model-specialised for the bench scenes)
+  echo "$R: $GSR_PROF_LIB" >> $O/prof_libs.txt
   ncu -i $O/prof_$R.ncu-rep --page raw --csv > $O/prof_$R.raw.csv 2>/dev/null
   python tools/ncu_funcs.py $O/prof_$R.ncu-rep $K > $O/prof_$R.funcs.txt 2>&1
   python tools/ncu_lines.py $O/prof_$R.ncu-rep $K 60 > $O/prof_$R.lines.txt 2>&1

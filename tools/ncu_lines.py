@@ -6,7 +6,7 @@ import csv, io, os, re, subprocess, sys, collections
 
 rep, kname = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "genesis_b200", "csrc", "libgsrigid.so")
+so = os.environ.get("GSR_PROF_LIB") or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "genesis_b200", "csrc", "libgsrigid.so")  # GSR_PROF_LIB: the copy that ran (a model-specialised one)
 tmp = "/tmp/ncu_lines"
 os.makedirs(tmp, exist_ok=True)
 subprocess.run(f"cd {tmp} && rm -f *.cubin && cuobjdump -xelf all {so} > /dev/null && nvdisasm -g *.cubin > all.sass 2>/dev/null", shell=True, check=True)
