@@ -2,7 +2,7 @@
 """Model-specialised builds of libgsrigid (the reference specialises its kernels per scene through its JIT, rigid_solver.py:187-218,
 380-400; here it is an ahead-of-time build per model).
 
-    python tools/specialize.py franka|go2 [--build]
+    python tools/specialize.py franka|go2|grasp [--build]
 
 Builds the scene's model on the host (no GPU needed), asks the library for the specialisation header (gsr_model_spec_header: every
 record / workspace offset and every build-time count / option as a literal) and, with --build, compiles
@@ -20,13 +20,15 @@ CSRC = os.path.join(ROOT, "genesis_b200", "csrc")
 
 def scene_for(name, n_envs):
     import genesis_b200 as gs
-    from genesis_b200.bench_scenes import make_franka, make_go2
+    from genesis_b200.bench_scenes import make_franka, make_franka_grasp, make_go2
 
     gs.init(backend=gs.gpu, seed=0)
     if name == "franka":
         return make_franka(n_envs, randomized=True, build=False)[0]
     if name == "go2":
         return make_go2(n_envs, build=False)[0]
+    if name == "grasp":
+        return make_franka_grasp(n_envs, build=False)[0]
     raise SystemExit(f"unknown model {name}")
 
 
@@ -55,7 +57,7 @@ def spec_header(solver, n_envs):
 
 def main():
     name = sys.argv[1]
-    n_envs = {"franka": 30000, "go2": 4096}.get(name, 1024)
+    n_envs = {"franka": 30000, "go2": 4096, "grasp": 8192}.get(name, 1024)
     scene = scene_for(name, n_envs)
     text = spec_header(scene.rigid_solver, n_envs)
     from genesis_b200 import _lib
