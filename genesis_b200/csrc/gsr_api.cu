@@ -121,6 +121,7 @@ static int activate(gsr_handle_t h, cudaStream_t st) {
 }
 
 #define GSR_ROWS_BINS 32  // rows per environment in buckets of 8 (the last bucket collects everything above 240)
+#define GSR_ROWS_GROW_MAX 96  // adapt_rows never raises the on-chip row capacity beyond this (see there)
 __global__ void k_iota(int* v, int n) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) v[t] = t;
@@ -374,14 +375,19 @@ static int adapt_rows(gsr_handle_t h, cudaStream_t st) {
   for (int b = 0; b < GSR_ROWS_BINS; b++) if (8 * b > cur) spilled += h->h_rows_hist[b];
   for (int b = 0; b < GSR_ROWS_BINS; b++) { cum += h->h_rows_hist[b]; if (100LL * cum >= 97LL * B) { b97 = b; break; } }
   int want = 8 * b97;
-  if (b97 == GSR_ROWS_BINS - 1) want = cur;  // beyond the histogram: leave as is
+  if (b97 == GSR_ROWS_BINS - 1) want = lenC;  // beyond the histogram: out of reach (below)
   if (want < h->rows_default) want = h->rows_default;
   if (want > lenC) want = lenC;
   const size_t env_bytes_now = (size_t)h->sl.env_words * 4;
   const size_t env_bytes_want = env_bytes_now + (size_t)(want - cur) * (h->sl.JS + 8 + GSR_CONTACT_WORDS / 4) * 4;
   const size_t per_warp = env_bytes_want * (32 / h->group);
-  const bool grow = want > cur && 4LL * spilled >= B && per_warp * 4 <= 220 * 1024;  // keep at least four warps per SM
-  const bool shrink = want + 16 <= cur;
+  // Raising the capacity trades residency for on-chip rows; it pays while the rows stay moderate (72 rows, above) and loses
+  // badly when they do not: grasp with three boxes, 200 rows per environment -- 232 rows on chip 1.48 M env-steps/s against
+  // 2.44 M with the default 32 (every environment in the SPILL record, but four times the residency; 64 / 96 / 128 rows:
+  // 2.16 / 1.97 / 1.49 M).  So: never beyond GSR_ROWS_GROW_MAX rows, and never below four warps per SM.
+  const bool grow = want > cur && want <= GSR_ROWS_GROW_MAX && 4LL * spilled >= B && per_warp * 4 <= 220 * 1024;
+  bool shrink = want + 16 <= cur;
+  if (want > GSR_ROWS_GROW_MAX && cur > h->rows_default) { want = h->rows_default; shrink = true; }  // out of reach: back to full residency
   if (!grow && !shrink) return GSR_OK;
   h->s["cfg_smem_rows"] = want;
   int rc = gsr_compute_layouts(h, B);

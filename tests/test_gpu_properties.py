@@ -119,16 +119,18 @@ def test_grasp_8192_determinism_launch_order_and_sanity():
     assert float(outs[0][1].float().mean()) > 20.0  # four boxes x four corner contacts + finger-box and box-box contacts
 
 
-def test_step_host_after_device_steps_keeps_adaptive_rows_alive():
+def test_step_host_after_device_steps_keeps_adaptive_rows_alive(monkeypatch):
     """Regression for the use-after-free of round 1 (gsr_api.cu: the first gsr_step_host after >= 16 device steps freed the row
-    histogram of the adaptive on-chip capacity).  Grasp scene: 40 device steps (two reorder periods: the histogram exists and
-    the capacity has been raised once), then 64 host-buffer steps; the capacity must still follow the workload and the results
-    must equal a scene that only ever took device steps."""
+    histogram of the adaptive on-chip capacity).  Grasp scene with one box (a few dozen rows: within reach of the adaptation,
+    gsr_api.cu adapt_rows; the generic library, the model-specialised copies fix the capacity): 40 device steps (two reorder
+    periods: the histogram exists and the capacity has been raised once), then 64 host-buffer steps; the capacity must still
+    follow the workload and the results must equal a scene that only ever took device steps."""
     from helpers import make_franka_grasp
 
+    monkeypatch.setenv("GSR_NO_SPEC", "1")
     B = 2048
-    scene_a, fa, _ = make_franka_grasp(B)
-    scene_b, fb, _ = make_franka_grasp(B)
+    scene_a, fa, _ = make_franka_grasp(B, n_boxes=1)
+    scene_b, fb, _ = make_franka_grasp(B, n_boxes=1)
     sa, sb = scene_a.rigid_solver, scene_b.rigid_solver
     rows0 = sb.launch_info["smem_rows"]
     for _ in range(40):
@@ -141,10 +143,29 @@ def test_step_host_after_device_steps_keeps_adaptive_rows_alive():
         sb.step_host(ctrl, qpos, vel)
     assert np.array_equal(sa.field("qpos").cpu().numpy(), qpos) and np.array_equal(sa.field("vel").cpu().numpy(), vel)
     assert int(sb.field("errno_").max()) == 0
-    mean_rows = float(sb.field("n_constraints").float().mean())
-    if mean_rows > rows0:  # the batch needs more rows than the default capacity: the adaptation must have happened and survived
-        assert sb.launch_info["smem_rows"] > rows0, (rows0, sb.launch_info, mean_rows)
+    rows = sb.field("n_constraints").float()
+    print("rows: default", rows0, "mean", float(rows.mean()), "max", float(rows.max()), "now", sb.launch_info)
+    if rows0 + 8 <= float(rows.min()) and float(rows.max()) <= 88:
+        # every environment needs more rows than the default capacity and the need is within reach (GSR_ROWS_GROW_MAX = 96):
+        # the adaptation must have happened and survived
+        assert sb.launch_info["smem_rows"] > rows0, (rows0, sb.launch_info)
     assert sb.launch_info == sa.launch_info
+
+
+def test_adaptive_rows_stay_at_full_residency_when_out_of_reach(monkeypatch):
+    """The full grasp cluster carries about 200 rows per environment: raising the on-chip capacity that far costs three quarters
+    of the residency (measured 1.48 M against 2.44 M env-steps/s, profiles/README.md), so the capacity stays at its default."""
+    from helpers import make_franka_grasp
+
+    monkeypatch.setenv("GSR_NO_SPEC", "1")
+    scene, _, _ = make_franka_grasp(1024)
+    s = scene.rigid_solver
+    rows0 = s.launch_info["smem_rows"]
+    for _ in range(72):
+        scene.step()
+    assert float(s.field("n_constraints").float().mean()) > 96
+    assert s.launch_info["smem_rows"] == rows0
+    assert int(s.field("errno_").max()) == 0
 
 
 @pytest.mark.parametrize("model", ["go2", "franka"])
