@@ -705,6 +705,13 @@ int gsr_step_host(gsr_handle_t h, int n_substeps, const float* ctrl_pos_host, fl
   return GSR_OK;
 }
 
+#ifdef GSR_NARROW_TRACE
+extern "C" int gsr_debug_narrow(unsigned long long* out16) {  // developer build only: read and clear the counters of gsr_gjk.cuh
+  if (cudaMemcpyFromSymbol(out16, g_narrow, sizeof(unsigned long long) * 16) != cudaSuccess) return GSR_ECUDA;
+  unsigned long long z[16] = {0};
+  return cudaMemcpyToSymbol(g_narrow, z, sizeof(z)) == cudaSuccess ? GSR_OK : GSR_ECUDA;
+}
+#endif
 #ifdef GSR_SOLVER_TRACE
 int gsr_debug_solver_read(gsr_handle_t h, unsigned long long* out, int n_envs) {  // developer build only (make trace)
   CUDA_OK(cudaDeviceSynchronize());

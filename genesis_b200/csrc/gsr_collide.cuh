@@ -225,7 +225,10 @@ template <int G, class Sup>
 __device__ __forceinline__ void dev_mpr_from_centers(const Ctx<G>& C, const Sup& sup, f3 ca, f3 cb, bool& is_col, f3& normal, float& pen, f3& pos,
                                                      Simplex& s, bool& tetra) {
   const float CE = c_m.ccd_eps;
+  const long long mt0 = NARROW_CLOCK();
+  int n_refine = 0;
   int res = discover_portal(C, s, sup, ca, cb);
+  const long long mt1 = NARROW_CLOCK();
   is_col = false; pos = f3(); normal = f3(); pen = 0.f;
   tetra = false;  // true when s ends as the interior point + final portal, a tetrahedron around the origin (EPA seed)
   if (res == 1) { is_col = true; normal = -normalized(s.v[0]); pos = (s.v1[1] + s.v2[1]) * 0.5f; }
@@ -238,6 +241,7 @@ __device__ __forceinline__ void dev_mpr_from_centers(const Ctx<G>& C, const Sup&
       sup(dir, v, v1, v2);
       if (!(dot(v, dir) > -CE) || reach_tolerance(s, v, dir)) { res = -1; break; }
       expand_portal(s, v, v1, v2);
+      n_refine++;
     }
     if (res >= 0) {
       int it = 0;
@@ -260,8 +264,13 @@ __device__ __forceinline__ void dev_mpr_from_centers(const Ctx<G>& C, const Sup&
         expand_portal(s, v, v1, v2);
         it++;
       }
+      NARROW_ADD(5, it); NARROW_MAX(6, it);
     }
   }
+  // developer counters (GSR_NARROW_TRACE, tools/go2_tail.py): queries, cycles, portal discovery cycles, refinement / penetration iterations
+  NARROW_ADD(0, 1); NARROW_ADD(1, NARROW_CLOCK() - mt0); NARROW_MAX(2, NARROW_CLOCK() - mt0); NARROW_ADD(3, n_refine); NARROW_MAX(4, n_refine);
+  NARROW_ADD(7, mt1 - mt0); NARROW_MAX(8, mt1 - mt0);
+  (void)mt0; (void)mt1; (void)n_refine;
 }
 
 // MPR:601-819 func_mpr_contact (centre guess + portal discovery/refinement + penetration)
@@ -494,6 +503,7 @@ __device__ int narrow_batch(const Ctx<G>& C, const int* queue, int n_batch, int 
   const int lane = C.lane;
   LaneContacts out;
   out.n = 0;
+  const long long nb0 = NARROW_CLOCK();
   int ga = 0, gb = 0, p = 0, plane_box = 0;
   PairDet D;
   D.multi = false; D.is_col_0 = false;
@@ -520,6 +530,8 @@ __device__ int narrow_batch(const Ctx<G>& C, const int* queue, int n_batch, int 
   float* stage = C.spill + (size_t)CM(max_contact_pairs) * GSR_CONTACT_WORDS;  // [lane][4][8]
   __threadfence_block();
   C.sync();
+  const long long nb1 = NARROW_CLOCK();
+  if (lane == 0) { NARROW_MAX(12, nb1 - nb0); NARROW_ADD(14, nb1 - nb0); }
   for (int base = 0; base < n_task; base += G) {
     const int tt = base + lane;
     const bool active = tt < n_task;
@@ -547,6 +559,7 @@ __device__ int narrow_batch(const Ctx<G>& C, const int* queue, int n_batch, int 
   }
   __threadfence_block();
   C.sync();
+  if (lane == 0) { NARROW_MAX(13, NARROW_CLOCK() - nb1); NARROW_ADD(15, NARROW_CLOCK() - nb1); }
   if (want) {
     for (int i_det = 1; i_det < 5; i_det++) {
       const float* r = stage + ((size_t)lane * 4 + (i_det - 1)) * 8;

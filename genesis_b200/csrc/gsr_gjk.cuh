@@ -40,6 +40,7 @@ struct GjkSolver {
   GjkVert sv[4];
   int nverts;
   int last_searched;
+  int n_search = 0, n_iter = 0;  // developer counters (GSR_NARROW_TRACE): candidates walked by search_valid_vertex, GJK iterations
   __host__ __device__ GjkSolver(const Geo& g) : geo(g), nverts(0), last_searched(0) {}
 
   __host__ __device__ bool duplicate(int id1, int id2) const {  // gjk.py:1451-1470
@@ -92,12 +93,38 @@ struct GjkSolver {
   __host__ __device__ bool search_valid_vertex(GjkVert& r) {  // gjk.py:1545-1645
     r.o1 = f3(); r.o2 = f3(); r.id1 = r.id2 = -1;
     if (geo.discrete()) {
+      // Exhaustive walk over the vertex pairs (i of A, j of B) from where the last search stopped, first valid pair wins.
+      // Minkowski differences of boxes / hulls put long runs of candidates on a common plane with the simplex, so the walk
+      // is the hot loop of the exact-penetration path (Go2 self-contacts: two thirds of its instructions before this
+      // rewrite): the indices advance incrementally (no division), A's vertex is fetched once per row, and the parts of the
+      // validity test (`valid`: duplicate + degenerate) that do not depend on the candidate are evaluated once.
       const int n1 = geo.n_verts(1), num = geo.n_verts(0) * n1;
+      if (num <= 0) return false;
+      const float deg2 = 1e-5f * 1e-5f;
+      f3 m0, m1, m2, e1, n;  // (explicit names, not an array: the simplex stays in registers)
+      float e1e1 = 0.f, nn = 0.f;
+      if (nverts > 0) m0 = sv[0].mink();
+      if (nverts > 1) m1 = sv[1].mink();
+      if (nverts > 2) m2 = sv[2].mink();
+      if (nverts == 2) { e1 = m1 - m0; e1e1 = dot(e1, e1); }
+      if (nverts == 3) { n = cross(normalized(m1 - m0), normalized(m2 - m0)); nn = dot(n, n); }
+      int mm = last_searched % num, i = mm / n1, j = mm - i * n1;
+      geo.vertex(0, i, r.o1, r.id1);
       for (int k = 0; k < num; k++) {
-        const int mm = (k + last_searched) % num, i = mm / n1, j = mm % n1;
-        geo.vertex(0, i, r.o1, r.id1);
+        n_search++;
         geo.vertex(1, j, r.o2, r.id2);
-        if (valid(r)) { last_searched = (mm + 1) % num; return true; }
+        bool ok = !duplicate(r.id1, r.id2);
+        if (ok) {
+          const f3 mk = r.mink();
+          if (nverts > 0) { const f3 d = m0 - mk; if (dot(d, d) < deg2) ok = false; }
+          if (nverts > 1) { const f3 d = m1 - mk; if (dot(d, d) < deg2) ok = false; }
+          if (nverts > 2) { const f3 d = m2 - mk; if (dot(d, d) < deg2) ok = false; }
+          if (ok && nverts == 2) { const f3 e2 = mk - m0, c = cross(e1, e2); ok = !(dot(c, c) < deg2 * e1e1 * dot(e2, e2)); }
+          if (ok && nverts == 3) { const f3 diff = mk - m0; const float nd = dot(n, diff); ok = !(nd * nd < deg2 * nn * dot(diff, diff)); }
+        }
+        mm++; j++;
+        if (ok) { last_searched = mm == num ? 0 : mm; return true; }
+        if (j == n1) { j = 0; i++; if (mm == num) { mm = 0; i = 0; } geo.vertex(0, i, r.o1, r.id1); }
       }
       return false;
     }
@@ -126,6 +153,7 @@ struct GjkSolver {
     if (!init_ok) return false;
     int si[4] = {0, 1, 2, 3};
     for (int it = 0; it < 50; it++) {
+      n_iter++;
       f3 min_normal;
       float min_sd = 0.f;
       int min_i = 0;
@@ -204,12 +232,30 @@ __host__ __device__ __forceinline__ bool gjk_project_origin(f3 v1, f3 v2, f3 v3,
   return true;
 }
 
+#if defined(GSR_NARROW_TRACE) && defined(__CUDACC__)  // developer build (tools/go2_tail.py): where does one exact-penetration query spend its time?
+__device__ unsigned long long g_narrow[16];
+#endif
+#if defined(GSR_NARROW_TRACE) && defined(__CUDA_ARCH__)
+#define NARROW_CLOCK() clock64()
+#define NARROW_ADD(k, v) atomicAdd(&g_narrow[k], (unsigned long long)(v))
+#define NARROW_MAX(k, v) atomicMax(&g_narrow[k], (unsigned long long)(v))
+#else
+#define NARROW_CLOCK() 0ll
+#define NARROW_ADD(k, v)
+#define NARROW_MAX(k, v)
+#endif
+
 #pragma nv_exec_check_disable
 template <class Geo>
 __host__ __device__ __noinline__ void gjk_contact(const Geo& geo, bool& is_col, f3& normal, float& pen, f3& pos) {
   is_col = false; pen = 0.f;
   GjkSolver<Geo> gs(geo);
-  if (!gs.safe_gjk()) return;
+  const long long nt0 = NARROW_CLOCK();
+  const bool gjk_inside = gs.safe_gjk();
+  const long long nt1 = NARROW_CLOCK();
+  NARROW_ADD(9, 1); NARROW_ADD(10, nt1 - nt0); NARROW_ADD(11, gs.n_search);  // exact-penetration queries, GJK cycles, candidates walked
+  (void)nt0; (void)nt1;
+  if (!gjk_inside) return;
   // ---- safe EPA (epa.py:970-1183) from the GJK tetrahedron (epa.py:1251-1301)
   const float EPS = geo.eps(), FMAX = 1e15f;
   GjkVert pv[GSR_GJK_MAXV];

@@ -29,6 +29,8 @@ rows = list(csv.reader(io.StringIO(out)))
 hi = next(i for i, r in enumerate(rows) if "Instructions Executed" in r)
 hdr = rows[hi]
 ca, ci, cs = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("# Samples")
+ct = hdr.index("Thread Instructions Executed") if "Thread Instructions Executed" in hdr else None
+t_line = collections.Counter()
 base = None
 by_line, by_file = collections.Counter(), collections.Counter()
 s_line, s_file = collections.Counter(), collections.Counter()
@@ -43,6 +45,8 @@ for r in rows[hi + 1:]:
     n, s = int(r[ci] or 0), int(r[cs] or 0)
     loc = off2line.get(a - base, (None, ""))[0] or ("?", 0)
     by_line[loc] += n; by_file[loc[0]] += n; s_line[loc] += s; s_file[loc[0]] += s
+    if ct is not None:
+        t_line[loc] += int(r[ct] or 0)
     tot += n; stot += s
 print(f"total warp instructions {tot}, stall samples {stot}")
 for f, n in by_file.most_common():
@@ -56,3 +60,17 @@ for loc, s in s_line.most_common(top):
         srcs[f] = open(p).read().split("\n") if os.path.exists(p) else []
     text = srcs[f][l - 1].strip()[:110] if 0 < l <= len(srcs[f]) else ""
     print(f"  {f}:{l:<4d} samples {100 * s / max(stot, 1):5.1f}%  inst {100 * by_line[loc] / tot:5.1f}%  | {text}")
+
+flt = os.environ.get("GSR_LINES_FILTER")  # e.g. gsr_collide.cuh: the hottest lines of one file, with the lanes active on them
+if flt:
+    print(f"top lines of {flt} by samples (active lanes = thread instructions / warp instructions):")
+    rows_f = [(loc, s) for loc, s in s_line.most_common() if loc[0] == flt][:top]
+    for loc, s in rows_f:
+        f, l = loc
+        text = srcs.get(f, [])
+        if f not in srcs:
+            pth = os.path.join(os.path.dirname(so), f)
+            srcs[f] = open(pth).read().split("\n") if os.path.exists(pth) else []
+        text = srcs[f][l - 1].strip()[:100] if 0 < l <= len(srcs[f]) else ""
+        lanes = t_line[loc] / by_line[loc] if by_line[loc] else 0.0
+        print(f"  {f}:{l:<4d} samples {100 * s / max(stot, 1):5.2f}%  inst {100 * by_line[loc] / tot:5.2f}%  lanes {lanes:4.1f} | {text}")
