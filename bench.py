@@ -389,7 +389,11 @@ class Leg:
                "errno_max": errno, "internal_warmup_steps": SETTLE_STEPS.get(self.workload, INTERNAL_WARMUP),
                "errno_poll": "every 10 substeps inside the timed loop (asynchronous reduction, no host sync)",
                "l2": f"per-GPU state {sum(s._F.numel() for s in self.solvers) * 4 / 2**20:.0f} MiB > 126 MB L2 (no flush needed)",
-               "parallelism": f"env-sharded x{self.world}, no step-path collective"}
+               "parallelism": f"env-sharded x{self.world}, no step-path collective",
+               "kinematics": ("lazy: the forward kinematics of every configuration run at the start of the next step instead of the end of this one "
+                              "(same arithmetic per step; accessors that need link poses trigger them on demand)") if not s0._eager_fk else
+                             "eager: forward kinematics at the end of every step (reference order)",
+               "specialised_library": bool(s0.specialised)}
         if len(self.parts) == 1:
             cfg.update({"n_dofs": m.n_dofs, "n_links": m.n_links, "n_geoms": m.n_geoms, "launch": s0.launch_info,
                         "mean_contacts_per_env": roof["mean_contacts_per_env"]})

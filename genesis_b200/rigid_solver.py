@@ -115,8 +115,9 @@ class RigidSolver:
         self._fk_dirty_any = False
         self._kin_valid, self._kin_requested, self._eager_fk = True, False, True
         import os as _os
-        # GSR_LAZY_FK=1: adaptive kinematics (see _apply_kinematics_policy).  Off by default: it halves the HBM traffic of a pure
-        # stepping loop but measured slower for Franka-sized models (profiles/README.md item 16)
+        # Adaptive kinematics (see _apply_kinematics_policy): a pure stepping loop keeps the kinematic cache out of HBM.  Default:
+        # on with a model-specialised library copy (Franka 30000: 103 -> 118 M env-steps/s, a third of the DRAM traffic), off with
+        # the generic library (measured slower there: profiles/README.md items 16 and 25); GSR_LAZY_FK=0 / 1 forces either.
         self._adaptive_fk = _os.environ.get("GSR_LAZY_FK", "0") == "1"
         self._errno_pending = False
         # launch tuning of libgsrigid (0 = library default): lanes per environment, constraint rows kept in shared
@@ -227,6 +228,8 @@ class RigidSolver:
                     h = describe(Ls)
                     L = Ls
                     self.specialised = True
+        if "GSR_LAZY_FK" not in os.environ:
+            self._adaptive_fk = self.specialised
         _lib.check(h, L.gsr_model_commit(h, dev_index, self._B))
         nw = ctypes.c_size_t()
         _lib.check(h, L.gsr_state_words(h, ctypes.byref(nw)))
@@ -305,7 +308,7 @@ class RigidSolver:
         """Adaptive kinematics: a step leaves link poses / velocities in the records (eager, what the reference does at the end of
         kernel_step_2) only if an accessor asked for them since the previous step -- an RL loop reading observations every step
         stays eager, a pure stepping loop runs lazy: the same arithmetic, but the kinematic cache never travels through HBM.
-        Opt-in (GSR_LAZY_FK=1); the default is the reference's eager behaviour."""
+        Default with a model-specialised library copy; the generic library keeps the reference's eager behaviour (GSR_LAZY_FK=0 / 1 forces either)."""
         eager = self._kin_requested or not self._adaptive_fk or bool(self.tuning.get("diagnostics")) or self.launch_info_cached["group_size"] == 1
         if eager != self._eager_fk:
             _lib.check(self._handle, self._L.gsr_set_kinematics_policy(self._handle, int(eager)))

@@ -269,13 +269,16 @@ def _accessor_step(scene, franka, state0, mask, qpos0, vel0, stiff, damp):
     franka.set_qpos(qpos0, envs_idx=mask, zero_velocity=False, skip_forward=True)
 
 
-def test_franka_accessors_reference_step_body_runs_and_resets():
+def test_franka_accessors_reference_step_body_runs_and_resets(monkeypatch):
     """RL-loop boundary (scope row f3): the reference's franka_accessors step body runs unmodified -- RigidSolverState from
     get_state(), set_state(f, state, envs_idx=<bool mask>, partial=True), masked setters with skip_forward=True (the forward
     kinematics of the reset environments are deferred to the next step) -- and the reset environments then replay the trajectory
     of the initial state bit for bit, while the others are untouched."""
     from helpers import make_franka
 
+    # bit-for-bit replay: both scenes keep the reference's eager kinematics (with a model-specialised library copy the lazy and
+    # the eager order run two inlined copies of the kinematics, equal to round-off only: test_kinematics_policy_defaults)
+    monkeypatch.setenv("GSR_LAZY_FK", "0")
     B = 64
     scene, franka = make_franka(B, randomized=True, seed=5)
     s = scene.rigid_solver

@@ -197,6 +197,36 @@ def test_lazy_kinematics_equals_eager(model, monkeypatch):
     assert sl.kernel_launches()["k_forward"] > se.kernel_launches()["k_forward"]
 
 
+def test_kinematics_policy_defaults(monkeypatch):
+    """Default kinematics policy (RigidSolver._apply_kinematics_policy): a model-specialised library copy steps lazily -- measured
+    faster there, profiles/README.md item 25 --, the generic library eagerly like the reference; GSR_LAZY_FK forces either.  An
+    accessor that needs link poses gets them either way (one forward pass, then one eager step), and the specialised copy's lazy
+    and eager trajectories agree to round-off (its kinematics are inlined at both call sites: same source, two code copies)."""
+    monkeypatch.delenv("GSR_LAZY_FK", raising=False)
+    scene_l, robot_l = make_franka(256, randomized=True, seed=3)
+    monkeypatch.setenv("GSR_LAZY_FK", "0")
+    scene_e, robot_e = make_franka(256, randomized=True, seed=3)
+    monkeypatch.delenv("GSR_LAZY_FK")
+    monkeypatch.setenv("GSR_NO_SPEC", "1")
+    scene_g, robot_g = make_franka(256, randomized=True, seed=3)
+    monkeypatch.delenv("GSR_NO_SPEC")
+    sl, se, sg = scene_l.rigid_solver, scene_e.rigid_solver, scene_g.rigid_solver
+    assert sl.specialised and se.specialised and not sg.specialised
+    for _ in range(40):
+        scene_l.step(); scene_e.step(); scene_g.step()
+    assert sl._eager_fk is False and sl._L.gsr_kinematics_valid(sl._handle) == 0, "the specialised copy did not step lazily by default"
+    assert se._eager_fk is True and se._L.gsr_kinematics_valid(se._handle) == 1
+    assert sg._eager_fk is True and sg._L.gsr_kinematics_valid(sg._handle) == 1, "the generic library must keep the reference's eager order"
+    np.testing.assert_allclose(sl.field("qpos").cpu().numpy(), se.field("qpos").cpu().numpy(), atol=2e-6)
+    np.testing.assert_allclose(robot_l.get_links_pos().cpu().numpy(), robot_e.get_links_pos().cpu().numpy(), atol=2e-6)
+    np.testing.assert_allclose(robot_l.get_links_pos().cpu().numpy(), robot_g.get_links_pos().cpu().numpy(), atol=1e-5)
+    scene_l.step()
+    assert sl._eager_fk is True, "the step after an accessor that needed link poses leaves them in the records"
+    scene_l.step()
+    assert sl._eager_fk is False
+    assert int(sl.field("errno_").max()) == 0
+
+
 @pytest.mark.parametrize("model", ["franka", "go2"])
 def test_specialised_library_is_used_and_matches(model, monkeypatch):
     """Model-specialised builds (tools/specialize.py, built by __graft_entry__.build() for the two benchmark models): the benchmark
