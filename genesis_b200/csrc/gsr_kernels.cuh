@@ -193,10 +193,26 @@ __global__ void __launch_bounds__(GSR_LB_T(G), GSR_LB_B(G)) k_step(float* state,
   if (live) step_epilogue(C, clear_ext, end_fk);
   PHASE_END();
   if (live && C.lane == 0) reinterpret_cast<int*>(C.rec)[c_h.step_cost] = (int)min(busy, (long long)0x7fffffff);
-  if (live && (io.qpos || io.vel)) {  // results into dense staging or straight into the caller's pinned buffers (posted PCIe writes)
+  if (io.qpos || io.vel) {  // results into dense staging or straight into the caller's pinned buffers (posted PCIe writes)
     const int nQ = CM(nQ), nD = CM(nD);
-    if (io.qpos) for (int q = C.lane; q < nQ; q += G) __stcs(io.qpos + (size_t)C.env * nQ + q, IN(qpos)[q]);
-    if (io.vel) for (int d = C.lane; d < nD; d += G) __stcs(io.vel + (size_t)C.env * nD + d, IN(vel)[d]);
+    if (G < 32 && !order) {
+      // Small groups in launch order: the 32 / G environments of a warp are neighbours in the dense (B, n) buffers, so the warp
+      // writes ONE contiguous run per buffer (full sectors) instead of 32 / G short rows -- posted writes over PCIe are paid
+      // per transaction (tools/e2e_breakdown.py: 42 us of a 332 us Franka call went into them).
+      constexpr int EPW = 32 / G;
+      __syncwarp();
+      const int lane32 = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      const int env0 = (blockIdx.x * (blockDim.x >> 5) + warp) * EPW;
+      const int n_live = min(EPW, B - env0);
+      if (n_live > 0) {
+        const float* s0 = smem + (size_t)(warp * EPW) * c_s.env_words - c_h.in_start;  // workspace of the warp's first environment
+        if (io.qpos) for (int t = lane32; t < n_live * nQ; t += 32) { const int e = t / nQ, q = t - e * nQ; __stcs(io.qpos + (size_t)env0 * nQ + t, s0[(size_t)e * c_s.env_words + c_h.qpos + q]); }
+        if (io.vel) for (int t = lane32; t < n_live * nD; t += 32) { const int e = t / nD, d = t - e * nD; __stcs(io.vel + (size_t)env0 * nD + t, s0[(size_t)e * c_s.env_words + c_h.vel + d]); }
+      }
+    } else if (live) {
+      if (io.qpos) for (int q = C.lane; q < nQ; q += G) __stcs(io.qpos + (size_t)C.env * nQ + q, IN(qpos)[q]);
+      if (io.vel) for (int d = C.lane; d < nD; d += G) __stcs(io.vel + (size_t)C.env * nD + d, IN(vel)[d]);
+    }
   }
   __syncwarp();
   if (warp_live) bulk_store_in<G>(state, B, smem, order, end_fk ? c_h.n_in : c_h.n_state);
